@@ -1,0 +1,116 @@
+"""ctypes binding of the C-ABI library ``libfiberis_b200.so`` (declared in ``include/fiberis_b200.h``).
+
+There is no CPU fallback: if the shared library has not been built (``python -c "import
+__graft_entry__ as g; g.build()"`` or ``make -C fiberis_b200/csrc``) every compute entry point
+raises ``RuntimeError``.  PyTorch tensors are used only as device buffers; this module passes
+their ``data_ptr()`` and the current CUDA stream to the library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfiberis_b200.so")
+
+FBR_OK, FBR_ERR_BAD_ARG, FBR_ERR_UNSUPPORTED, FBR_ERR_CUDA = 0, -1, -2, -3
+BC_CODES = {"None": 0, "Dirichlet": 1, "Neumann": 2}
+SOLVER_AUTO, SOLVER_THOMAS, SOLVER_PCR = 0, 1, 2
+
+_p = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int
+_f64 = C.c_double
+
+# name -> (restype, argtypes); mirrors include/fiberis_b200.h one to one
+SIGNATURES = {
+    "fbr_version": (_i32, []),
+    "fbr_last_error": (C.c_char_p, []),
+    "fbr_last_launch_count": (_i32, []),
+    "fbr_device_info": (_i32, [C.POINTER(_i32)] * 3 + [C.POINTER(_i64)] * 3),
+    "fbr_assemble_f64": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
+    "fbr_assemble_zonal_f64": (_i32, [_p, _p, _i32, _p, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
+    "fbr_pml_sigma_f64": (_i32, [_p, _i64, _f64, _f64, _p, _p]),
+    "fbr_factorize_f64": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
+    "fbr_run_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "fbr_run_f32": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "fbr_run_max_nx": (_i64, []),
+    "fbr_solve_tridiag_work_bytes": (_i64, [_i64, _i64, _i32]),
+    "fbr_solve_tridiag_f64": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p]),
+    "fbr_rhs_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _i32, _p, _p, _p]),
+    "fbr_error_norms_f64": (_i32, [_p, _p, _i64, _i64, _p, _p]),
+    "fbr_jacobi_f64": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _f64, _i32, _p, _p]),
+}
+
+_lib = None
+
+
+class FbrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once; fail loudly when it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"fiberis_b200: CUDA library not built ({LIB_PATH} missing). Build it with "
+            "`make -C fiberis_b200/csrc` (needs nvcc, targets sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    """Map an fbr_status to the exception type the reference raises for the same condition."""
+    if rc == FBR_OK:
+        return
+    msg = load().fbr_last_error().decode("utf-8", "replace")
+    if rc == FBR_ERR_BAD_ARG:
+        raise ValueError(msg)
+    if rc == FBR_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise FbrError(msg)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device buffers must be contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("fiberis_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    load()
+
+
+def launch_count() -> int:
+    return int(load().fbr_last_launch_count())
+
+
+def device_info() -> dict:
+    lib = load()
+    a, b, c = _i32(), _i32(), _i32()
+    d, e, f = _i64(), _i64(), _i64()
+    check(lib.fbr_device_info(C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e), C.byref(f)))
+    return dict(sm_count=a.value, cc=(b.value, c.value), smem_optin=d.value, l2_bytes=e.value, hbm_bytes=f.value)
+
+
+def as_f64(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))

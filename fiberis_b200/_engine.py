@@ -1,0 +1,178 @@
+"""Device-side operations of the diffusion path: thin Python over the C ABI.
+
+Every function takes / returns torch CUDA tensors (used purely as device buffers) and calls one
+entry point of ``libfiberis_b200.so`` on the current CUDA stream.  Nothing here computes on the
+host; without a CUDA device or without the built library the calls raise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import BC_CODES, check, current_stream, ptr
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def device(dev=None):
+    torch = _torch()
+    _cabi.require_cuda()
+    if dev is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(dev)
+
+
+def to_device(x, dtype=np.float64, dev=None, pinned=False):
+    """Host array -> device tensor (one H2D copy)."""
+    torch = _torch()
+    a = np.ascontiguousarray(np.asarray(x, dtype=dtype))
+    t = torch.from_numpy(a)
+    if pinned:
+        t = t.pin_memory()
+    return t.to(device(dev), non_blocking=pinned)
+
+
+def index_tensor(idx, dev=None):
+    idx = np.atleast_1d(np.asarray(idx)).astype(np.int64)
+    if idx.size == 0:
+        return None, 0
+    return to_device(idx, np.int64, dev), int(idx.size)
+
+
+def raise_if_singular(flags, what="matrix"):
+    """Zero pivot -> the exception scipy.linalg.solve raises in the reference
+    (src/fiberis/simulator/solver/PDESolver_IMP.py:28)."""
+    bad = flags.nonzero()
+    if bad.numel():
+        m = int(bad[0, 0])
+        row = int(flags[m]) - 1
+        raise np.linalg.LinAlgError(f"Matrix is singular ({what} {m}: zero pivot at row {row}).")
+
+
+def assemble(mesh, diffusivity, M, nx, dt, lbc, rbc, src_idx, n_src, pml_thickness=0.0, sigma_max=2.0):
+    """K1: (dl, d, du), each (M, nx).  mesh / diffusivity are (nx,) shared or (M, nx) tensors."""
+    torch = _torch()
+    lib = _cabi.load()
+    out = torch.empty((3, M, nx), dtype=torch.float64, device=mesh.device)
+    ms = 0 if mesh.dim() == 1 else nx
+    ds = 0 if diffusivity.dim() == 1 else nx
+    check(lib.fbr_assemble_f64(ptr(mesh), ms, ptr(diffusivity), ds, M, nx, float(dt), BC_CODES[lbc], BC_CODES[rbc],
+                               ptr(src_idx), n_src, float(pml_thickness), float(sigma_max),
+                               ptr(out[0]), ptr(out[1]), ptr(out[2]), current_stream()))
+    return out[0], out[1], out[2]
+
+
+def assemble_zonal(mesh, zone_value, zone_of_cell, M, nx, dt, lbc, rbc, src_idx, n_src, pml_thickness=0.0,
+                   sigma_max=2.0):
+    torch = _torch()
+    lib = _cabi.load()
+    out = torch.empty((3, M, nx), dtype=torch.float64, device=mesh.device)
+    check(lib.fbr_assemble_zonal_f64(ptr(mesh), ptr(zone_value), int(zone_value.shape[1]), ptr(zone_of_cell), M, nx,
+                                     float(dt), BC_CODES[lbc], BC_CODES[rbc], ptr(src_idx), n_src,
+                                     float(pml_thickness), float(sigma_max), ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                     current_stream()))
+    return out[0], out[1], out[2]
+
+
+def pml_sigma(mesh, pml_thickness, sigma_max):
+    torch = _torch()
+    out = torch.empty_like(mesh)
+    check(_cabi.load().fbr_pml_sigma_f64(ptr(mesh), mesh.numel(), float(pml_thickness), float(sigma_max), ptr(out),
+                                         current_stream()))
+    return out
+
+
+def factorize(dl, d, du, check_singular=True):
+    """K1b: time-invariant factors (fl, fr, fg); raises LinAlgError on a zero pivot."""
+    torch = _torch()
+    lib = _cabi.load()
+    M, nx = d.shape
+    out = torch.empty((3, M, nx), dtype=torch.float64, device=d.device)
+    flags = torch.zeros(M, dtype=torch.int32, device=d.device)
+    check(lib.fbr_factorize_f64(ptr(dl), ptr(d), ptr(du), M, nx, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(flags),
+                                current_stream()))
+    if check_singular:
+        raise_if_singular(flags, "model")
+    return out[0], out[1], out[2]
+
+
+def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, snap_models=None,
+        n_snap_models=None, want_final=False, obs_idx=None, n_obs=0, obs=None, obs_w=None, dtype="float64",
+        snap_out=None, misfit_out=None):
+    """K3: persistent on-chip integration.  Returns (snap | None, p_final | None, misfit | None)."""
+    torch = _torch()
+    lib = _cabi.load()
+    fl, fr, fg = factors
+    dev = fl.device
+    tdt = torch.float64 if dtype == "float64" else torch.float32
+    fn = lib.fbr_run_f64 if dtype == "float64" else lib.fbr_run_f32
+    snap = snap_out
+    n_rows = n_steps // snapshot_every if snapshot_every else 0
+    if snap is None and snapshot_every and n_rows > 0:
+        ns = M if snap_models is None else n_snap_models
+        snap = torch.empty((n_rows, ns, nx), dtype=tdt, device=dev)
+        n_snap_models = ns
+    p_final = torch.empty((M, nx), dtype=tdt, device=dev) if want_final else None
+    misfit = misfit_out
+    if misfit is None and obs_idx is not None:
+        misfit = torch.empty(M, dtype=torch.float64, device=dev)
+    p0_stride = 0 if p0.dim() == 1 else nx
+    check(fn(ptr(fl), ptr(fr), ptr(fg), ptr(p0), p0_stride, M, nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
+             ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), ptr(snap_models),
+             int(n_snap_models or 0), ptr(snap), ptr(p_final), ptr(obs_idx), int(n_obs), ptr(obs), ptr(obs_w),
+             ptr(misfit), current_stream()))
+    return snap, p_final, misfit
+
+
+def run_max_nx() -> int:
+    return int(_cabi.load().fbr_run_max_nx())
+
+
+def rhs(p, lbc, rbc, src_idx, n_src, src_val, out=None):
+    torch = _torch()
+    lib = _cabi.load()
+    M, nx = p.shape
+    b = torch.empty_like(p) if out is None else out
+    check(lib.fbr_rhs_f64(ptr(p), M, nx, BC_CODES[lbc], BC_CODES[rbc], ptr(src_idx), n_src, ptr(src_val), ptr(b),
+                          current_stream()))
+    return b
+
+
+def solve_tridiag(dl, d, du, b, variant=_cabi.SOLVER_AUTO, check_singular=True):
+    """K2: bare batched solve (dl, d, du, b) -> x, all (M, nx)."""
+    torch = _torch()
+    lib = _cabi.load()
+    M, nx = d.shape
+    x = torch.empty_like(b)
+    flags = torch.zeros(M, dtype=torch.int32, device=d.device)
+    work = None
+    if variant == _cabi.SOLVER_THOMAS or (variant == _cabi.SOLVER_AUTO and (nx < 32 or nx > 4096 or M >= 16384)):
+        work = torch.empty((M, nx), dtype=torch.float64, device=d.device)
+    check(lib.fbr_solve_tridiag_f64(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(x), M, nx, int(variant), ptr(work),
+                                    ptr(flags), current_stream()))
+    if check_singular:
+        raise_if_singular(flags, "system")
+    return x
+
+
+def error_norms(u1, u2):
+    torch = _torch()
+    lib = _cabi.load()
+    M, nx = u1.shape
+    err = torch.empty(M, dtype=torch.float64, device=u1.device)
+    check(lib.fbr_error_norms_f64(ptr(u1), ptr(u2), M, nx, ptr(err), current_stream()))
+    return err
+
+
+def jacobi(dl, d, du, b, tol=1e-10, max_iter=1000):
+    torch = _torch()
+    lib = _cabi.load()
+    M, nx = d.shape
+    x = torch.empty_like(b)
+    iters = torch.zeros(M, dtype=torch.int32, device=d.device)
+    check(lib.fbr_jacobi_f64(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(x), M, nx, float(tol), int(max_iter), ptr(iters),
+                             current_stream()))
+    return x, iters

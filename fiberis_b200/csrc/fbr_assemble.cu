@@ -1,0 +1,280 @@
+// K1 fused coefficient assembly, K1b time-invariant factorisation, right-hand side, K5 error norms.
+// All bandwidth-trivial one-off kernels (they run once per dt, the time loop is in fbr_run_onchip.cu).
+#include <stdarg.h>
+
+#include "fbr_common.cuh"
+
+namespace fbr {
+
+std::string &last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+int &launch_count_ref() {
+    static thread_local int n = 0;
+    return n;
+}
+
+int device_facts(DeviceFacts *out) {
+    static thread_local DeviceFacts cached;
+    int dev = 0;
+    FBR_CUDA(cudaGetDevice(&dev));
+    if (cached.device != dev) {
+        cudaDeviceProp p;
+        FBR_CUDA(cudaGetDeviceProperties(&p, dev));
+        cached.device = dev;
+        cached.sm_count = p.multiProcessorCount;
+        cached.cc_major = p.major;
+        cached.cc_minor = p.minor;
+        cached.smem_optin = (int64_t)p.sharedMemPerBlockOptin;
+        cached.l2_bytes = (int64_t)p.l2CacheSize;
+        cached.hbm_bytes = (int64_t)p.totalGlobalMem;
+    }
+    *out = cached;
+    return FBR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: one thread per (model, cell).  The arithmetic follows the NumPy expression order of
+// matbuilder.py:21-28 with round-to-nearest intrinsics so that nvcc cannot contract a*b+c into an
+// FMA: the three diagonals are bit-identical to the reference's dense A.
+// ------------------------------------------------------------------------------------------------
+struct DiffusivityDense {
+    const double *D;
+    int64_t stride;
+    __device__ double at(int64_t m, int64_t i) const { return D[m * stride + i]; }
+};
+struct DiffusivityZonal {
+    const double *zone_value;  // (M, n_zones) = 10 ** theta, expanded by the host
+    const int32_t *zone_of_cell;
+    int n_zones;
+    __device__ double at(int64_t m, int64_t i) const { return zone_value[m * n_zones + zone_of_cell[i]]; }
+};
+
+// PML ramp of matbuilder.py:170-196 for one node (pml > 0).
+__device__ __forceinline__ double pml_sigma_at(const double *__restrict__ x, int64_t i, int64_t nx, double pml,
+                                               double sigma_max) {
+    const double dist_left = __dsub_rn(x[i], x[0]), dist_right = __dsub_rn(x[nx - 1], x[i]);
+    double sigma = 0.0;
+    if (dist_left < pml) sigma = __dmul_rn(sigma_max, __ddiv_rn(__dsub_rn(pml, dist_left), pml));
+    if (dist_right < pml) sigma = fmax(sigma, __dmul_rn(sigma_max, __ddiv_rn(__dsub_rn(pml, dist_right), pml)));
+    return sigma;
+}
+
+__global__ void __launch_bounds__(256) pml_sigma_kernel(const double *__restrict__ mesh, int64_t nx, double pml,
+                                                        double sigma_max, double *__restrict__ sigma) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nx; i += (int64_t)gridDim.x * blockDim.x)
+        sigma[i] = pml != 0.0 ? pml_sigma_at(mesh, i, nx, pml, sigma_max) : 0.0;
+}
+
+template <class Diff>
+__global__ void __launch_bounds__(256) assemble_kernel(const double *__restrict__ mesh, int64_t mesh_stride,
+                                                       Diff diff, int64_t M, int64_t nx, double dt, int lbc,
+                                                       int rbc, const int64_t *__restrict__ src_idx, int n_src,
+                                                       double pml, double sigma_max, double *__restrict__ dl,
+                                                       double *__restrict__ d, double *__restrict__ du) {
+    const int64_t total = M * nx;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = e / nx, i = e - m * nx;
+        const double *x = mesh + m * mesh_stride;
+        double a = 0.0, b = 0.0, c = 0.0;
+        if (i > 0 && i < nx - 1) {
+            const double xm = x[i - 1], x0 = x[i], xp = x[i + 1];
+            const double Dm = diff.at(m, i - 1), D0 = diff.at(m, i), Dp = diff.at(m, i + 1);
+            const double dxm = __dsub_rn(x0, xm), dxp = __dsub_rn(xp, x0);
+            const double dem = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, Dm), D0), __dadd_rn(Dm, D0));
+            const double dep = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, D0), Dp), __dadd_rn(D0, Dp));
+            const double sum = __dadd_rn(dxm, dxp);
+            const double al = __ddiv_rn(__dmul_rn(dem, dt), __ddiv_rn(__dmul_rn(dxm, sum), 2.0));
+            const double ar = __ddiv_rn(__dmul_rn(dep, dt), __ddiv_rn(__dmul_rn(dxp, sum), 2.0));
+            a = -al;
+            b = __dadd_rn(__dadd_rn(1.0, al), ar);
+            c = -ar;
+        }
+        if (i == 0) {  // matbuilder.py:49-57
+            if (lbc == FBR_BC_DIRICHLET) b = 1.0;
+            else if (lbc == FBR_BC_NEUMANN) { b = -1.0; c = 1.0; }
+        }
+        if (i == nx - 1) {  // matbuilder.py:60-69
+            if (rbc == FBR_BC_DIRICHLET) b = 1.0;
+            else if (rbc == FBR_BC_NEUMANN) { b = -1.0; a = 1.0; }
+        }
+        for (int k = 0; k < n_src; ++k)  // matbuilder.py:73-76 / 156-161
+            if (src_idx[k] == i) { a = 0.0; b = 1.0; c = 0.0; }
+        if (pml != 0.0)  // matbuilder.py:79-81
+            b = __dadd_rn(b, __dmul_rn(dt, pml_sigma_at(x, i, nx, pml, sigma_max)));
+        if (i == 0) a = 0.0;
+        if (i == nx - 1) c = 0.0;
+        dl[e] = a;
+        d[e] = b;
+        du[e] = c;
+    }
+}
+
+// K1b: one thread per model, sequential elimination (run once per dt).
+__global__ void __launch_bounds__(128) factorize_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                        const double *__restrict__ du, int64_t M, int64_t nx,
+                                                        double *__restrict__ fl, double *__restrict__ fr,
+                                                        double *__restrict__ fg, int32_t *__restrict__ singular) {
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t o = m * nx;
+    double u_prev = 1.0, c_prev = 0.0;
+    int32_t bad = 0;
+    for (int64_t i = 0; i < nx; ++i) {
+        const double a = dl[o + i], b = d[o + i], c = du[o + i];
+        const double l = (i == 0) ? 0.0 : a / u_prev;
+        const double u = b - l * c_prev;
+        if (!bad && (u == 0.0 || !isfinite(u))) bad = (int32_t)(i + 1);
+        fl[o + i] = l;
+        fr[o + i] = 1.0 / u;
+        fg[o + i] = c / u;
+        u_prev = u;
+        c_prev = c;
+    }
+    if (singular) singular[m] = bad;
+}
+
+__global__ void __launch_bounds__(256) rhs_kernel(const double *__restrict__ p, int64_t M, int64_t nx, int lbc,
+                                                  int rbc, const int64_t *__restrict__ src_idx, int n_src,
+                                                  const double *__restrict__ src_val, double *__restrict__ b) {
+    const int64_t total = M * nx;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % nx;
+        double v = p[e];
+        if (i == 0 && lbc != FBR_BC_NONE) v = 0.0;
+        if (i == nx - 1 && rbc != FBR_BC_NONE) v = 0.0;
+        for (int k = 0; k < n_src; ++k)
+            if (src_idx[k] == i) v = src_val[k];
+        b[e] = v;
+    }
+}
+
+// K5: one CTA per model; fixed-order tree reduction (deterministic).
+__global__ void __launch_bounds__(256) error_norms_kernel(const double *__restrict__ u1,
+                                                          const double *__restrict__ u2, int64_t nx,
+                                                          double *__restrict__ err) {
+    __shared__ double s_num[8], s_den[8];
+    const int64_t o = blockIdx.x * nx;
+    double num = 0.0, den = 0.0;
+    for (int64_t i = threadIdx.x; i < nx; i += blockDim.x) {
+        const double a = u1[o + i], df = a - u2[o + i];
+        num += df * df;
+        den += a * a;
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        num += __shfl_xor_sync(0xffffffffu, num, s);
+        den += __shfl_xor_sync(0xffffffffu, den, s);
+    }
+    if ((threadIdx.x & 31) == 0) { s_num[threadIdx.x >> 5] = num; s_den[threadIdx.x >> 5] = den; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double n2 = 0.0, d2 = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { n2 += s_num[w]; d2 += s_den[w]; }
+        err[blockIdx.x] = sqrt(n2) / sqrt(d2);  // 0/0 -> nan, as numpy (tso.py:18)
+    }
+}
+
+static inline int grid_for(int64_t total, int block, int sm_count) {
+    int64_t g = (total + block - 1) / block;
+    const int64_t cap = (int64_t)sm_count * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace fbr
+
+using namespace fbr;
+
+static int check_common(int64_t M, int64_t nx, int lbc, int rbc, int n_src, const void *src_idx) {
+    FBR_REQUIRE(M >= 1 && nx >= 2, "M (%lld) must be >= 1 and nx (%lld) >= 2", (long long)M, (long long)nx);
+    FBR_REQUIRE(lbc >= 0 && lbc <= 2 && rbc >= 0 && rbc <= 2, "boundary codes must be 0 (None), 1 (Dirichlet) or 2 (Neumann)");
+    FBR_REQUIRE(n_src >= 0 && (n_src == 0 || src_idx), "n_src=%d but src_idx is NULL", n_src);
+    return FBR_OK;
+}
+
+extern "C" int fbr_assemble_f64(const double *mesh, int64_t mesh_stride, const double *diffusivity,
+                                int64_t diff_stride, int64_t M, int64_t nx, double dt, int lbc, int rbc,
+                                const int64_t *src_idx, int n_src, double pml_thickness, double sigma_max,
+                                double *dl, double *d, double *du, void *stream) {
+    if (int rc = check_common(M, nx, lbc, rbc, n_src, src_idx)) return rc;
+    FBR_REQUIRE(mesh && diffusivity && dl && d && du, "NULL array argument");
+    FBR_REQUIRE((mesh_stride == 0 || mesh_stride >= nx) && (diff_stride == 0 || diff_stride >= nx), "bad stride");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    DiffusivityDense diff{diffusivity, diff_stride};
+    assemble_kernel<<<grid_for(M * nx, 256, f.sm_count), 256, 0, as_stream(stream)>>>(
+        mesh, mesh_stride, diff, M, nx, dt, lbc, rbc, src_idx, n_src, pml_thickness, sigma_max, dl, d, du);
+    return check_launch("fbr_assemble_f64");
+}
+
+extern "C" int fbr_assemble_zonal_f64(const double *mesh, const double *zone_value, int n_zones,
+                                      const int32_t *zone_of_cell, int64_t M, int64_t nx, double dt, int lbc,
+                                      int rbc, const int64_t *src_idx, int n_src, double pml_thickness,
+                                      double sigma_max, double *dl, double *d, double *du, void *stream) {
+    if (int rc = check_common(M, nx, lbc, rbc, n_src, src_idx)) return rc;
+    FBR_REQUIRE(mesh && zone_value && zone_of_cell && dl && d && du, "NULL array argument");
+    FBR_REQUIRE(n_zones >= 1, "n_zones must be >= 1");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    DiffusivityZonal diff{zone_value, zone_of_cell, n_zones};
+    assemble_kernel<<<grid_for(M * nx, 256, f.sm_count), 256, 0, as_stream(stream)>>>(
+        mesh, 0, diff, M, nx, dt, lbc, rbc, src_idx, n_src, pml_thickness, sigma_max, dl, d, du);
+    return check_launch("fbr_assemble_zonal_f64");
+}
+
+extern "C" int fbr_pml_sigma_f64(const double *mesh, int64_t nx, double pml_thickness, double sigma_max,
+                                 double *sigma, void *stream) {
+    FBR_REQUIRE(mesh && sigma && nx >= 1, "bad argument");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    pml_sigma_kernel<<<grid_for(nx, 256, f.sm_count), 256, 0, as_stream(stream)>>>(mesh, nx, pml_thickness, sigma_max,
+                                                                                 sigma);
+    return check_launch("fbr_pml_sigma_f64");
+}
+
+extern "C" int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64_t M, int64_t nx,
+                                 double *fl, double *fr, double *fg, int32_t *singular, void *stream) {
+    FBR_REQUIRE(M >= 1 && nx >= 1, "M and nx must be >= 1");
+    FBR_REQUIRE(dl && d && du && fl && fr && fg, "NULL array argument");
+    const int block = M >= 128 * 148 ? 128 : 32;
+    factorize_kernel<<<(unsigned)((M + block - 1) / block), block, 0, as_stream(stream)>>>(dl, d, du, M, nx, fl, fr,
+                                                                                          fg, singular);
+    return check_launch("fbr_factorize_f64");
+}
+
+extern "C" int fbr_rhs_f64(const double *p, int64_t M, int64_t nx, int lbc, int rbc, const int64_t *src_idx,
+                           int n_src, const double *src_val, double *b, void *stream) {
+    if (int rc = check_common(M, nx, lbc, rbc, n_src, src_idx)) return rc;
+    FBR_REQUIRE(p && b && (n_src == 0 || src_val), "NULL array argument");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    rhs_kernel<<<grid_for(M * nx, 256, f.sm_count), 256, 0, as_stream(stream)>>>(p, M, nx, lbc, rbc, src_idx, n_src,
+                                                                              src_val, b);
+    return check_launch("fbr_rhs_f64");
+}
+
+extern "C" int fbr_error_norms_f64(const double *u1, const double *u2, int64_t M, int64_t nx, double *err,
+                                   void *stream) {
+    FBR_REQUIRE(M >= 1 && nx >= 1 && u1 && u2 && err, "bad argument");
+    error_norms_kernel<<<(unsigned)M, 256, 0, as_stream(stream)>>>(u1, u2, nx, err);
+    return check_launch("fbr_error_norms_f64");
+}
+
+extern "C" int fbr_version(void) { return FBR_VERSION; }
+extern "C" const char *fbr_last_error(void) { return last_error_ref().c_str(); }
+extern "C" int fbr_last_launch_count(void) { return launch_count_ref(); }
+
+extern "C" int fbr_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_per_block_optin,
+                               int64_t *l2_bytes, int64_t *hbm_bytes) {
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    if (sm_count) *sm_count = f.sm_count;
+    if (cc_major) *cc_major = f.cc_major;
+    if (cc_minor) *cc_minor = f.cc_minor;
+    if (smem_per_block_optin) *smem_per_block_optin = f.smem_optin;
+    if (l2_bytes) *l2_bytes = f.l2_bytes;
+    if (hbm_bytes) *hbm_bytes = f.hbm_bytes;
+    return FBR_OK;
+}

@@ -1,0 +1,198 @@
+// K2  bare batched tridiagonal solves (matrix changes every call: adaptive time stepping) and the
+// Jacobi "explicit" mode.  Two variants, chosen by shape (north_star: "variant chosen by mesh length"):
+//   THOMAS  one thread per system, sequential elimination      -> many systems
+//   PCR     one CTA per system, shared-memory parallel cyclic reduction, log2(nx) levels -> few, longer systems
+#include "fbr_common.cuh"
+
+namespace fbr {
+
+constexpr int kPcrMaxNx = 4096;
+constexpr int kJacobiMaxNx = 8192;
+
+// ---- THOMAS: thread per system; work holds the modified super-diagonal ----
+__global__ void __launch_bounds__(128) thomas_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                     const double *__restrict__ du, const double *b, double *x,
+                                                     int64_t M, int64_t nx, double *__restrict__ work,
+                                                     int32_t *__restrict__ singular) {
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t o = m * nx;
+    double cp = 0.0, xp = 0.0;
+    int32_t bad = 0;
+    for (int64_t i = 0; i < nx; ++i) {
+        const double a = dl[o + i];
+        const double den = d[o + i] - a * cp;
+        if (!bad && (den == 0.0 || !isfinite(den))) bad = (int32_t)(i + 1);
+        cp = du[o + i] / den;
+        xp = (b[o + i] - a * xp) / den;
+        work[o + i] = cp;
+        x[o + i] = xp;
+    }
+    for (int64_t i = nx - 2; i >= 0; --i) {
+        xp = x[o + i] - work[o + i] * xp;
+        x[o + i] = xp;
+    }
+    if (singular) singular[m] = bad;
+}
+
+// ---- PCR: CTA per system; every level halves the coupling distance ----
+template <int CELLS>
+__global__ void __launch_bounds__(1024) pcr_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                   const double *__restrict__ du, const double *b, double *x,
+                                                   int64_t nx64, int32_t *__restrict__ singular) {
+    extern __shared__ double sm[];
+    const int n = (int)nx64;
+    double *sa = sm, *sb = sm + n, *sc = sm + 2 * n, *sr = sm + 3 * n;
+    __shared__ int s_bad;
+    const int64_t o = blockIdx.x * nx64;
+    if (threadIdx.x == 0) s_bad = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        sa[i] = dl[o + i];
+        sb[i] = d[o + i];
+        sc[i] = du[o + i];
+        sr[i] = b[o + i];
+    }
+    __syncthreads();
+    for (int s = 1; s < n; s <<= 1) {
+        double na[CELLS], nb[CELLS], nc[CELLS], nr[CELLS];
+#pragma unroll
+        for (int k = 0; k < CELLS; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < n) {
+                const int im = i - s, ip = i + s;
+                double a = sa[i], bb = sb[i], c = sc[i], r = sr[i];
+                double xa = 0.0, xc = 0.0;
+                if (im >= 0) {
+                    const double piv = sb[im];
+                    if (piv == 0.0) s_bad = im + 1;
+                    const double k1 = a / piv;
+                    xa = -sa[im] * k1;
+                    bb -= sc[im] * k1;
+                    r -= sr[im] * k1;
+                }
+                if (ip < n) {
+                    const double piv = sb[ip];
+                    if (piv == 0.0) s_bad = ip + 1;
+                    const double k2 = c / piv;
+                    xc = -sc[ip] * k2;
+                    bb -= sa[ip] * k2;
+                    r -= sr[ip] * k2;
+                }
+                na[k] = xa; nb[k] = bb; nc[k] = xc; nr[k] = r;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CELLS; ++k) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < n) { sa[i] = na[k]; sb[i] = nb[k]; sc[i] = nc[k]; sr[i] = nr[k]; }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double piv = sb[i];
+        if (piv == 0.0 || !isfinite(piv)) s_bad = i + 1;
+        x[o + i] = sr[i] / piv;
+    }
+    __syncthreads();
+    if (singular && threadIdx.x == 0) singular[blockIdx.x] = s_bad;
+}
+
+// ---- Jacobi (PDESolver_EXP.py:5-39): CTA per system, iterate in shared memory ----
+__global__ void __launch_bounds__(1024) jacobi_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                      const double *__restrict__ du, const double *__restrict__ b,
+                                                      double *__restrict__ x, int64_t nx64, double tol, int max_iter,
+                                                      int32_t *__restrict__ iters) {
+    extern __shared__ double sm[];
+    const int n = (int)nx64;
+    double *cur = sm, *nxt = sm + n;
+    __shared__ double s_red[32];
+    __shared__ int s_done;
+    const int64_t o = blockIdx.x * nx64;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cur[i] = 0.0;
+    if (threadIdx.x == 0) s_done = 0;
+    __syncthreads();
+    int used = -max_iter;
+    for (int it = 0; it < max_iter; ++it) {
+        double dmax = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const double di = d[o + i], x0 = cur[i];
+            double s = __dmul_rn(di, x0);
+            if (i > 0) s = __dadd_rn(__dmul_rn(dl[o + i], cur[i - 1]), s);
+            if (i < n - 1) s = __dadd_rn(s, __dmul_rn(du[o + i], cur[i + 1]));
+            const double except_i = __dsub_rn(s, __dmul_rn(di, x0));
+            const double v = __ddiv_rn(__dsub_rn(b[o + i], except_i), di);
+            nxt[i] = v;
+            dmax = fmax(dmax, fabs(v - x0));
+        }
+        for (int s = 16; s > 0; s >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, s));
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = dmax;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double mx = 0.0;
+            for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) mx = fmax(mx, s_red[w]);
+            if (mx < tol) s_done = 1;
+        }
+        __syncthreads();
+        double *t = cur; cur = nxt; nxt = t;
+        if (s_done) { used = it + 1; break; }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x[o + i] = cur[i];
+    if (iters && threadIdx.x == 0) iters[blockIdx.x] = used;
+}
+
+}  // namespace fbr
+
+using namespace fbr;
+
+extern "C" int64_t fbr_solve_tridiag_work_bytes(int64_t M, int64_t nx, int variant) {
+    if (variant == FBR_SOLVER_PCR) return 0;
+    return M * nx * (int64_t)sizeof(double);
+}
+
+extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, const double *b,
+                                     double *x, int64_t M, int64_t nx, int variant, double *work,
+                                     int32_t *singular, void *stream) {
+    FBR_REQUIRE(M >= 1 && nx >= 1 && dl && d && du && b && x, "bad argument");
+    FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_PCR, "unknown solver variant %d", variant);
+    if (variant == FBR_SOLVER_AUTO)
+        variant = (nx <= kPcrMaxNx && nx >= 32 && (M < 16384 || !work)) ? FBR_SOLVER_PCR : FBR_SOLVER_THOMAS;
+    if (variant == FBR_SOLVER_PCR) {
+        if (nx > kPcrMaxNx)
+            return fail(FBR_ERR_UNSUPPORTED, "PCR variant covers nx <= %d (got %lld)", kPcrMaxNx, (long long)nx);
+        int threads = (int)((nx + 31) / 32) * 32;
+        if (threads > 1024) threads = 1024;
+        const int cells = (int)((nx + threads - 1) / threads);
+        const size_t smem = 4 * (size_t)nx * sizeof(double);
+        auto go = [&](auto kern) -> int {
+            if (smem > 48 * 1024)
+                FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)M, threads, smem, as_stream(stream)>>>(dl, d, du, b, x, nx, singular);
+            return check_launch("fbr_solve_tridiag_f64 (PCR)");
+        };
+        switch (cells) {
+            case 1: return go(pcr_kernel<1>);
+            case 2: return go(pcr_kernel<2>);
+            default: return go(pcr_kernel<4>);
+        }
+    }
+    FBR_REQUIRE(work, "the THOMAS variant needs a work array of fbr_solve_tridiag_work_bytes()");
+    const int block = M >= 128 * 148 ? 128 : 32;
+    thomas_kernel<<<(unsigned)((M + block - 1) / block), block, 0, as_stream(stream)>>>(dl, d, du, b, x, M, nx, work,
+                                                                                       singular);
+    return check_launch("fbr_solve_tridiag_f64 (Thomas)");
+}
+
+extern "C" int fbr_jacobi_f64(const double *dl, const double *d, const double *du, const double *b, double *x,
+                              int64_t M, int64_t nx, double tol, int max_iter, int32_t *iters, void *stream) {
+    FBR_REQUIRE(M >= 1 && nx >= 1 && dl && d && du && b && x && max_iter >= 0, "bad argument");
+    if (nx > kJacobiMaxNx)
+        return fail(FBR_ERR_UNSUPPORTED, "Jacobi mode covers nx <= %d (got %lld)", kJacobiMaxNx, (long long)nx);
+    int threads = (int)((nx + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
+    const size_t smem = 2 * (size_t)nx * sizeof(double);
+    if (smem > 48 * 1024)
+        FBR_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jacobi_kernel<<<(unsigned)M, threads, smem, as_stream(stream)>>>(dl, d, du, b, x, nx, tol, max_iter, iters);
+    return check_launch("fbr_jacobi_f64");
+}

@@ -1,0 +1,229 @@
+"""``PDS1D_Ensemble`` — many independent diffusion models stepped on one GPU (new capability).
+
+The reference has no batched driver (``fiberis.simulator.optimizer`` only holds the adaptive-dt
+controller); ensembles are what BASELINE.json's configs C3/C4 call "optimizer parameter sweep" /
+"ensemble sweep".  Each member is exactly a ``PDS1D_MultiSource`` problem
+(/root/reference/src/fiberis/simulator/core/pds.py:432-610) and its pressures are pinned by looping
+the reference over members.  Members share mesh, sources, boundary conditions and time axis; they
+differ in diffusivity (dense ``(M, nx)`` or zonal ``zone_value[m, zone_of_cell]``) and optionally in
+the initial state.
+
+Outputs: ``misfit`` (M,) — sum over steps and observation cells of w_k (p - obs)^2, accumulated on
+the fly inside the time-stepping kernel so member snapshots never leave the chip — and full
+snapshots of the few ``audit_models`` asked for.  The misfit definition is this package's own
+(parity unpinned; the reference has none in ``fiberis.simulator``).
+
+Multi-GPU: members are sharded contiguously over the ranks of a ``torch.distributed`` process
+group (``shard_bounds``); the only collective is an all-gather of the per-member misfits.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from fiberis_b200 import _engine
+from fiberis_b200.simulator.core.pds import PDS1D_MultiSource, _ALLOWED_BC
+
+
+def shard_bounds(n_models: int, world_size: int, rank: int):
+    """Contiguous block [lo, hi) of members owned by ``rank`` (sizes differ by at most one)."""
+    base, extra = divmod(n_models, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class PDS1D_Ensemble:
+    def __init__(self):
+        self.mesh = None
+        self.source = None           # list of Data1D-like, shared by all members
+        self.sourceidx = None
+        self.lbc = self.rbc = None
+        self.t0 = 0
+        self.initial = None          # (nx,) shared or (M, nx)
+        self.diffusivity = None      # (M, nx) or None when zonal
+        self.zone_value = None       # (M, Z)
+        self.zone_of_cell = None     # (nx,) int
+        self.obs_idx = None
+        self.obs = None              # (n_steps + 1, n_obs), row 0 unused
+        self.obs_weights = None
+        self.misfit = None
+        self.snapshot = None         # (n_audit, n_t, nx)
+        self.taxis = None
+        self.audit_models = None
+        self.history = []
+
+    # -- configuration (same vocabulary as PDS1D_*) ------------------------------------------------
+    def set_mesh(self, mesh):
+        if not isinstance(mesh, np.ndarray) or mesh.ndim != 1 or len(mesh) < 2:
+            raise ValueError("Mesh must be a 1D numpy array with at least 2 points.")
+        self.mesh = mesh
+
+    def set_source(self, source):
+        if not isinstance(source, list):
+            raise ValueError("Source term must be a list.")
+        self.source = source
+
+    def set_sourceidx(self, sourceidx):
+        self.sourceidx = np.atleast_1d(np.asarray(sourceidx)).astype(np.int64)
+
+    def set_bcs(self, lbc="Neumann", rbc="Neumann"):
+        if lbc not in _ALLOWED_BC or rbc not in _ALLOWED_BC:
+            raise ValueError(f"Boundary conditions must be in {_ALLOWED_BC}.")
+        self.lbc, self.rbc = lbc, rbc
+
+    def set_t0(self, t0):
+        self.t0 = t0
+
+    def set_initial(self, initial):
+        self.initial = np.asarray(initial, dtype=np.float64)
+
+    def set_diffusivity(self, diffusivity):
+        """Dense per-member diffusivity (M, nx)."""
+        d = np.asarray(diffusivity, dtype=np.float64)
+        if d.ndim != 2 or self.mesh is None or d.shape[1] != len(self.mesh):
+            raise ValueError("Ensemble diffusivity must be an (M, nx) array; set the mesh first.")
+        self.diffusivity, self.zone_value, self.zone_of_cell = d, None, None
+
+    def set_zonal_diffusivity(self, zone_value, zone_of_cell):
+        """D_m(x) = zone_value[m, zone_of_cell[x]] (e.g. zone_value = 10 ** theta)."""
+        zv = np.asarray(zone_value, dtype=np.float64)
+        zc = np.asarray(zone_of_cell)
+        if zv.ndim != 2 or self.mesh is None or zc.shape != (len(self.mesh),):
+            raise ValueError("zone_value must be (M, Z) and zone_of_cell (nx,); set the mesh first.")
+        if zc.min() < 0 or zc.max() >= zv.shape[1]:
+            raise ValueError("zone_of_cell refers to a zone outside zone_value.")
+        self.zone_value, self.zone_of_cell, self.diffusivity = zv, zc.astype(np.int32), None
+
+    def set_observations(self, obs_idx, obs, weights=None):
+        """obs[n, k]: observed pressure at cell obs_idx[k] at time taxis[n] (row 0 is not used)."""
+        idx = np.atleast_1d(np.asarray(obs_idx)).astype(np.int64)
+        if len(np.unique(idx)) != len(idx):
+            raise ValueError("Observation cells must be distinct.")
+        obs = np.asarray(obs, dtype=np.float64)
+        if obs.ndim != 2 or obs.shape[1] != len(idx):
+            raise ValueError("obs must have shape (n_steps + 1, n_obs).")
+        self.obs_idx, self.obs = idx, obs
+        self.obs_weights = None if weights is None else np.asarray(weights, dtype=np.float64)
+
+    @property
+    def n_models(self):
+        if self.diffusivity is not None:
+            return self.diffusivity.shape[0]
+        if self.zone_value is not None:
+            return self.zone_value.shape[0]
+        return 0
+
+    def member(self, m):
+        """Member ``m`` as a stand-alone ``PDS1D_MultiSource`` (the parity cross-check uses this)."""
+        p = PDS1D_MultiSource()
+        p.set_mesh(self.mesh)
+        p.set_source(self.source)
+        p.set_bcs(self.lbc, self.rbc)
+        init = self.initial if self.initial.ndim == 1 else self.initial[m]
+        p.set_initial(init)
+        D = self.diffusivity[m] if self.diffusivity is not None else self.zone_value[m][self.zone_of_cell]
+        p.set_diffusivity(np.array(D))
+        p.set_sourceidx(list(self.sourceidx))
+        p.set_t0(self.t0)
+        return p
+
+    # -- solve ------------------------------------------------------------------------------------
+    def solve(self, dt, t_total=None, audit_models=(), snapshot_every=1, dtype="float64", models=None,
+              process_group=None, gather=True):
+        """Integrate every member with a fixed ``dt``.
+
+        ``models=(lo, hi)`` restricts the run to a contiguous block (multi-GPU sharding does this
+        per rank when ``process_group`` / an initialised default group is given); ``misfit`` is then
+        gathered over ranks unless ``gather=False``.
+        """
+        M_all = self.n_models
+        if M_all == 0:
+            raise ValueError("No diffusivity set.")
+        nx = len(self.mesh)
+        if t_total is None:
+            t_total = self.source[0].taxis[-1] + self.t0
+        taxis = [self.t0]
+        while taxis[-1] < t_total:  # same fp64 accumulation as the single-model path
+            taxis.append(taxis[-1] + dt)
+        n_steps = len(taxis) - 1
+
+        dist = _dist(process_group)
+        if models is None and dist is not None:
+            models = shard_bounds(M_all, dist.get_world_size(process_group), dist.get_rank(process_group))
+        lo, hi = (0, M_all) if models is None else models
+        M = hi - lo
+
+        proto = PDS1D_MultiSource()
+        proto.source, proto.t0 = self.source, self.t0
+        table = proto._source_table(taxis[:-1])
+
+        mesh_d = _engine.to_device(self.mesh)
+        sidx_d, n_src = _engine.index_tensor(self.sourceidx)
+        if self.diffusivity is not None:
+            diag = _engine.assemble(mesh_d, _engine.to_device(self.diffusivity[lo:hi]), M, nx, dt, self.lbc, self.rbc,
+                                    sidx_d, n_src)
+        else:
+            diag = _engine.assemble_zonal(mesh_d, _engine.to_device(self.zone_value[lo:hi]),
+                                          _engine.to_device(self.zone_of_cell, np.int32), M, nx, dt, self.lbc,
+                                          self.rbc, sidx_d, n_src)
+        factors = _engine.factorize(*diag)
+        del diag
+        init = self.initial if self.initial.ndim == 1 else self.initial[lo:hi]
+        p0_d = _engine.to_device(init)
+        table_d = _engine.to_device(table)
+
+        audit = [int(a) for a in audit_models if lo <= int(a) < hi]
+        snap_models_d, n_audit = _engine.index_tensor(np.asarray(audit, dtype=np.int64) - lo) if audit else (None, 0)
+        obs_idx_d = obs_d = w_d = None
+        n_obs = 0
+        if self.obs_idx is not None:
+            if self.obs.shape[0] != n_steps + 1:
+                raise ValueError(f"obs has {self.obs.shape[0]} rows, the run has {n_steps + 1} time samples.")
+            obs_idx_d, n_obs = _engine.index_tensor(self.obs_idx)
+            obs_d = _engine.to_device(self.obs)
+            w_d = None if self.obs_weights is None else _engine.to_device(self.obs_weights)
+
+        snap_d, _, misfit_d = _engine.run(
+            factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+            snapshot_every=snapshot_every if n_audit else 0, snap_models=snap_models_d, n_snap_models=n_audit,
+            obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, obs_w=w_d, dtype=dtype)
+
+        self.taxis = np.array(taxis)
+        self.audit_models = audit
+        if n_audit and snap_d is not None:
+            rows = snap_d.permute(1, 0, 2).cpu().numpy().astype(np.float64, copy=False)
+            first = np.stack([(self.initial if self.initial.ndim == 1 else self.initial[a]) for a in audit])
+            self.snapshot = np.concatenate([first[:, None, :], rows], axis=1)
+        else:
+            self.snapshot = None
+        if misfit_d is not None:
+            if dist is not None and gather:
+                misfit_d = gather_misfit(misfit_d, M_all, process_group)
+            self.misfit = misfit_d.cpu().numpy()
+        self.history.append(f"{M} members x {nx} cells x {n_steps} steps solved on device (dt={dt}).")
+        return self.misfit
+
+
+def _dist(process_group):
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None
+    if dist.is_available() and dist.is_initialized():
+        return dist
+    return None
+
+
+def gather_misfit(local, n_models, process_group=None):
+    """All-gather the per-member misfits of every rank's contiguous block into one (n_models,)
+    tensor (NCCL over NVLink on GPUs; gloo in the CPU tests).  Block sizes may differ by one, so
+    blocks are padded to the largest and trimmed after the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(process_group)
+    sizes = [shard_bounds(n_models, world, r) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
+    padded[: local.numel()] = local
+    out = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=process_group)
+    return torch.cat([out[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])

@@ -1,0 +1,455 @@
+"""1D pressure-diffusion models: the reference's ``PDS1D_SingleSource`` / ``PDS1D_MultiSource`` API
+(/root/reference/src/fiberis/simulator/core/pds.py:17-610) on a B200-native engine.
+
+What stays on the host (cheap, sequential, and it has to be bit-identical):
+  * validation and ``history`` bookkeeping;
+  * the time axis — ``while taxis[-1] < t_total: taxis.append(taxis[-1] + dt)`` with fp64
+    accumulation (reference :287,309), so the number of steps and every ``taxis`` entry are equal
+    bit for bit;
+  * sampling the sources at the start of every step (``np.interp``, reference core1D.py:247).
+
+What runs on the GPU through the C ABI (``include/fiberis_b200.h``):
+  * K1 fused coefficient assembly + K1b one-off factorisation (A is time-invariant for fixed dt);
+  * K3 the whole time loop in ONE persistent kernel (pressure and factors resident on chip,
+    snapshots streamed out as they are produced);
+  * for ``optimizer=True``: per iteration assembly, three batched tridiagonal solves (K2) and the
+    step-doubling error reduction (K5); only the 8-byte error crosses to the host, where the
+    reference's scalar accept/reject logic runs unchanged.
+
+Additive keyword arguments of ``solve`` (defaults keep the reference behaviour):
+  ``dtype='float64'|'float32'``, ``snapshot_every=1``, ``pml_thickness=0.0``, ``sigma_max``.
+"""
+from __future__ import annotations
+
+from datetime import datetime
+
+import numpy as np
+
+from fiberis_b200 import _engine
+from fiberis_b200.simulator.optimizer import tso
+
+_ALLOWED_BC = ["Dirichlet", "Neumann", "None"]
+
+
+def _uses_stock_interp(src) -> bool:
+    """True when ``src`` samples with plain np.interp on (taxis, data), so a whole step table can
+    be produced by one vectorised np.interp call with identical results."""
+    from fiberis_b200.analyzer.Data1D.core1D import Data1D
+    fn = getattr(type(src), "get_value_by_time", None)
+    if fn is Data1D.get_value_by_time:
+        return src.data is not None and src.taxis is not None and np.size(src.data) > 0
+    # the reference's own Data1D (same np.interp semantics) when scripts mix the two packages
+    mod = getattr(type(src), "__module__", "")
+    return mod.startswith("fiberis.analyzer.Data1D") and isinstance(getattr(src, "taxis", None), np.ndarray) \
+        and np.size(src.taxis) > 1
+
+
+class PDS1D_SingleSource:
+    """One mesh, one pressure source pinned at ``sourceidx`` (a Dirichlet-in-time row)."""
+
+    _multi = False
+
+    def __init__(self):
+        self.mesh = None
+        self.source = None
+        self.lbc = None
+        self.rbc = None
+        self.initial = None
+        self.diffusivity = None
+        self.t0 = 0
+        self.taxis = None
+        self.sourceidx = None
+        self.snapshot = None
+        self.history = []
+
+    # ------------------------------------------------------------------ configuration
+    def _log_check(self, result):
+        self.history.append(result[1])
+
+    def set_mesh(self, mesh):
+        self.mesh = mesh
+        self._log_check(self._check_mesh())
+
+    def set_source(self, source):
+        self.source = source
+        self._log_check(self._check_source())
+
+    def set_bcs(self, lbc="Neumann", rbc="Neumann"):
+        self.lbc, self.rbc = lbc, rbc
+        self._log_check(self._check_bc())
+
+    def set_initial(self, initial):
+        self.initial = initial  # kept by reference, like the original
+        self._log_check(self._check_initial())
+
+    def set_diffusivity(self, diffusivity):
+        """Scalar (broadcast over the mesh, which must be set first) or a per-node array."""
+        if isinstance(diffusivity, (int, float)):
+            self.diffusivity = np.full(len(self.mesh), diffusivity)
+            print("Diffusivity is a single scalar value, broadcasted to the mesh length.")
+        elif isinstance(diffusivity, (list, np.ndarray)) and len(diffusivity) == len(self.mesh):
+            self.diffusivity = np.array(diffusivity)
+        else:
+            raise ValueError(
+                "Diffusivity must be either a single scalar value or an array of the same length as the mesh.")
+        self._log_check(self._check_diffusivity())
+
+    def set_t0(self, t0):
+        self.t0 = t0
+        self.history.append(f"Initial time set done. \nThe simulation starts at {t0}.")
+
+    def set_sourceidx(self, sourceidx):
+        self.sourceidx = sourceidx
+        self._log_check(self._check_sourceidx())
+
+    def print(self):
+        bar = "=" * 41
+        print(bar)
+        print(f"{type(self).__name__ + ' Info':^41}")
+        print(bar)
+        for key, value in self.__dict__.items():
+            if isinstance(value, np.ndarray):
+                print(f"{key:>15}: shape={value.shape}, unique={np.unique(value)}")
+            else:
+                print(f"{key:>15}: {value}")
+        print(bar)
+
+    # ------------------------------------------------------------------ checks
+    def _check_mesh(self):
+        if self.mesh is None:
+            return False, "Mesh is not set."
+        if not isinstance(self.mesh, np.ndarray):
+            return False, "Mesh must be a numpy array."
+        if len(self.mesh) < 2:
+            return False, "Mesh must have at least 2 points."
+        return True, "Mesh is properly set."
+
+    def _check_source(self):
+        if self.source is None:
+            return False, "Source term is not set."
+        return True, "Source term is properly set."
+
+    def _check_bc(self):
+        if self.lbc is None or self.rbc is None:
+            return False, "Boundary condition(s) (lbc/rbc) not set."
+        if self.lbc not in _ALLOWED_BC:
+            return False, f"Invalid left BC: {self.lbc}. Must be {_ALLOWED_BC}."
+        if self.rbc not in _ALLOWED_BC:
+            return False, f"Invalid right BC: {self.rbc}. Must be {_ALLOWED_BC}."
+        return True, "Boundary conditions are properly set."
+
+    def _check_initial(self):
+        if self.initial is None:
+            return False, "Initial condition is not set."
+        if self.mesh is None:
+            return False, "Mesh is not set. Please set the mesh first."
+        if len(self.initial) != len(self.mesh):
+            return False, "Length of initial condition array must match mesh length."
+        return True, "Initial condition is properly set."
+
+    def _check_diffusivity(self):
+        if self.diffusivity is None:
+            return False, "Diffusivity is not set."
+        if not isinstance(self.diffusivity, np.ndarray):
+            return False, "Diffusivity must be a numpy array or the pds frame is failed to init the diffusivity."
+        if len(self.diffusivity) != len(self.mesh):
+            return False, "Diffusivity array length must match mesh length."
+        return True, "Diffusivity is properly set."
+
+    def _check_sourceidx(self):
+        if self.sourceidx is None:
+            return False, "Source index is not set."
+        if self.sourceidx not in np.arange(len(self.mesh)):
+            return False, "Source index is not in the mesh."
+        return True, "Source index is properly set."
+
+    def self_check(self, params=None):
+        """True when every requested check passes; failures are printed (never raised)."""
+        checks = {"mesh": self._check_mesh, "source": self._check_source, "bc": self._check_bc,
+                  "initial": self._check_initial, "diffusivity": self._check_diffusivity,
+                  "sourceidx": self._check_sourceidx}
+        if params is None:
+            params = list(checks)
+        elif isinstance(params, str):
+            params = [params]
+        ok_all = True
+        for name in params:
+            if name not in checks:
+                print(f"Parameter '{name}' is not recognized. Skipping.")
+                ok_all = False
+                continue
+            ok, msg = checks[name]()
+            if not ok:
+                print(msg)
+                ok_all = False
+        return ok_all
+
+    # ------------------------------------------------------------------ source helpers
+    def _sources(self):
+        return list(self.source) if self._multi else [self.source]
+
+    def _source_indices(self):
+        return np.atleast_1d(np.asarray(self.sourceidx)).astype(np.int64)
+
+    def _source_values_at(self, t_rel):
+        return [s.get_value_by_time(t_rel) for s in self._sources()]
+
+    def _source_table(self, step_starts):
+        """(n_steps, n_src): value of every source at the start of every step."""
+        rel = np.asarray(step_starts, dtype=np.float64) - self.t0
+        cols = []
+        for s in self._sources():
+            if _uses_stock_interp(s):
+                cols.append(np.interp(rel, s.taxis, s.data))
+            else:
+                cols.append(np.array([s.get_value_by_time(float(t)) for t in rel], dtype=np.float64))
+        return np.ascontiguousarray(np.stack(cols, axis=1)) if cols else np.zeros((len(rel), 0))
+
+    def _end_time(self, kwargs):
+        if "t_total" in kwargs:
+            print("Time array generated using t_total.")
+            return kwargs["t_total"], "Time array generated using t_total."
+        first = self.source[0] if self._multi else self.source
+        print("Time array generated using the source term.")
+        return first.taxis[-1] + self.t0, "Time array generated using the source term."
+
+    # ------------------------------------------------------------------ solve
+    def solve(self, optimizer=False, **kwargs):
+        """Integrate to ``t_total`` (default: end of the source record).
+
+        ``optimizer=False``: fixed ``dt`` (required).  ``optimizer=True``: adaptive step doubling
+        starting at ``dt_init`` with the ``tso`` keyword arguments.  Returns ``None``; results are
+        left in ``snapshot`` ((n_t, nx) ndarray, row 0 = initial) and ``taxis``.
+        """
+        if not self.self_check():
+            print("Self check failed. Please check the parameters.")
+            return None
+        if optimizer:
+            dt_init = kwargs["dt_init"]
+            t_total, _ = self._end_time(kwargs)
+            self._solve_adaptive(dt_init, t_total, kwargs)
+        else:
+            dt = kwargs["dt"]  # required for fixed stepping (KeyError otherwise, as in the reference)
+            t_total, note = self._end_time(kwargs)
+            if not self._multi:
+                self.history.append(note)
+            self._solve_fixed(dt, t_total, kwargs)
+        self.record_log("Problem solved")
+        print("Problem solved.")
+        return None
+
+    def _device_model(self, kwargs):
+        nx = len(self.mesh)
+        sidx = self._source_indices()
+        sidx = np.where(sidx < 0, sidx + nx, sidx)
+        mesh_d = _engine.to_device(self.mesh)
+        diff_d = _engine.to_device(self.diffusivity)
+        sidx_d, n_src = _engine.index_tensor(sidx)
+        pml = float(kwargs.get("pml_thickness", 0.0))
+        smax = float(kwargs.get("sigma_max", 10 if self._multi else 2))
+        return nx, mesh_d, diff_d, sidx_d, n_src, pml, smax
+
+    def _solve_fixed(self, dt, t_total, kwargs):
+        mode = kwargs.get("mode", "implicit")
+        dtype = kwargs.get("dtype", "float64")
+        every = int(kwargs.get("snapshot_every", 1))
+        if dtype not in ("float64", "float32"):
+            raise ValueError("dtype must be 'float64' or 'float32'.")
+        if every < 1:
+            raise ValueError("snapshot_every must be >= 1.")
+        # exact replica of the reference's time axis (fp64 accumulation decides the step count)
+        taxis = [self.t0]
+        while taxis[-1] < t_total:
+            taxis.append(taxis[-1] + dt)
+        n_steps = len(taxis) - 1
+        self.record_log("Start to solve the problem.")
+        initial = np.asarray(self.initial, dtype=np.float64)
+        if n_steps == 0:
+            self.snapshot = np.array([self.initial])
+            self.taxis = np.array(taxis)
+            return
+        nx, mesh_d, diff_d, sidx_d, n_src, pml, smax = self._device_model(kwargs)
+        table = self._source_table(taxis[:-1])
+        dl, d, du = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
+        p0_d = _engine.to_device(initial[None, :])
+        if mode == "implicit":
+            if nx > _engine.run_max_nx():
+                raise NotImplementedError(
+                    f"nx={nx}: meshes longer than {_engine.run_max_nx()} cells need the long-mesh kernel "
+                    "(not built yet in this round).")
+            factors = _engine.factorize(dl, d, du)
+            table_d = _engine.to_device(table)
+            snap_d, _, _ = _engine.run(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                       snapshot_every=every, dtype=dtype)
+            rows = snap_d[:, 0, :].cpu().numpy().astype(np.float64, copy=False)
+        else:
+            rows = self._jacobi_loop(dl, d, du, p0_d, sidx_d, n_src, table, n_steps, every)
+        self.snapshot = np.concatenate([initial[None, :], rows], axis=0)
+        kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
+        self.taxis = np.array(taxis)[kept] if every > 1 else np.array(taxis)
+        self.record_log(f"{n_steps} full steps solved on device (dt={dt}, mode={mode}, dtype={dtype}). "
+                        f"taxis[-1]=", taxis[-1])
+        if kwargs.get("print_progress"):
+            for n in range(n_steps):
+                vals = table[n].tolist()
+                print("Time:", taxis[n + 1], "Source term:", vals if self._multi else vals[0])
+
+    def _jacobi_loop(self, dl, d, du, p_d, sidx_d, n_src, table, n_steps, every):
+        """mode != 'implicit': one Jacobi solve per step (reference pds.py:296-300)."""
+        import torch
+        table_d = _engine.to_device(table)
+        rows = []
+        bad = 0
+        for n in range(n_steps):
+            b = _engine.rhs(p_d, self.lbc, self.rbc, sidx_d, n_src, table_d[n])
+            p_d, iters = _engine.jacobi(dl, d, du, b)
+            bad += int((iters <= 0).sum().item())
+            if (n + 1) % every == 0:
+                rows.append(p_d[0])
+        if bad:
+            print("Warning: Maximum iterations reached without convergence.")
+        return torch.stack(rows).cpu().numpy() if rows else np.zeros((0, dl.shape[1]))
+
+    def _solve_adaptive(self, dt_init, t_total, kwargs):
+        """Step-doubling loop of reference pds.py:312-336 with device-resident states."""
+        import torch
+        nx, mesh_d, diff_d, sidx_d, n_src, pml, smax = self._device_model(kwargs)
+        self.snapshot = [self.initial]
+        self.taxis = [self.t0]
+        self.record_log("Start to solve the problem.")
+        accepted = []  # device rows of the accepted states
+        p_d = _engine.to_device(np.asarray(self.initial, dtype=np.float64)[None, :])
+        dt = dt_init
+        max_iter = kwargs.get("max_iterations")  # additive safety valve (the reference can spin forever)
+        it = 0
+        while self.taxis[-1] < t_total:
+            if max_iter is not None and it >= max_iter:
+                break
+            it += 1
+            vals = self._source_values_at(self.taxis[-1] - self.t0)
+            self.record_log("Time:", self.taxis[-1], "Source term:", vals if self._multi else vals[0])
+            vals_d = _engine.to_device(np.asarray(vals, dtype=np.float64))
+            b = _engine.rhs(p_d, self.lbc, self.rbc, sidx_d, n_src, vals_d)
+            full = _engine.solve_tridiag(
+                *_engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax), b)
+            half_sys = _engine.assemble(mesh_d, diff_d, 1, nx, dt / 2, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
+            mid = _engine.solve_tridiag(*half_sys, b)
+            half = _engine.solve_tridiag(*half_sys, _engine.rhs(mid, self.lbc, self.rbc, sidx_d, n_src, vals_d))
+            error = tso.step_error(full, half)
+            n_before = len(self.taxis)
+            marker = _DeviceRow(len(accepted))
+            dt = tso.decide(self, marker, error, dt, **kwargs)
+            if len(self.taxis) > n_before:  # accepted: the FULL-step state becomes the new state
+                accepted.append(full[0])
+                p_d = full
+            if kwargs.get("print_progress"):
+                print("Time:", self.taxis[-1], "Source term:", vals if self._multi else vals[0])
+        rows = torch.stack(accepted).cpu().numpy() if accepted else np.zeros((0, nx))
+        self.snapshot = np.concatenate([np.asarray(self.initial, dtype=np.float64)[None, :], rows], axis=0)
+        self.taxis = np.array(self.taxis)
+
+    # ------------------------------------------------------------------ logging / results
+    def record_log(self, *args):
+        self.history.append(" ".join(map(str, args)) + f" | Time: {datetime.now()}")
+
+    def print_log(self):
+        for msg in self.history:
+            print(msg)
+
+    def get_solution(self):
+        return self.snapshot, self.taxis
+
+    def get_val_at_source_idx(self):
+        return self.snapshot[:, self.sourceidx]
+
+    def get_val_at_idx(self, idx):
+        return self.snapshot[:, idx]
+
+    def get_val_at_time(self, time):
+        k = np.argmin(np.abs(self.taxis - time))
+        print("Closest time = ", self.taxis[k])
+        return self.snapshot[k]
+
+    def plot_solution(self, **kwargs):
+        method = kwargs.get("method", "imshow")
+        if method not in ("imshow", "pcolormesh"):
+            raise ValueError("Method must be 'imshow' or 'pcolormesh'.")
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as exc:  # plotting is optional tooling, not part of the compute path
+            raise RuntimeError("plot_solution needs matplotlib, which is not installed.") from exc
+        cmap = kwargs.get("cmap", "bwr")
+        plt.figure()
+        if method == "imshow":
+            plt.imshow(self.snapshot.T, aspect="auto", cmap=cmap,
+                       extent=[self.taxis[0], self.taxis[-1], self.mesh[0], self.mesh[-1]])
+            plt.gca().invert_yaxis()
+        else:
+            plt.pcolormesh(self.taxis, self.mesh, self.snapshot.T, cmap=cmap)
+            plt.colorbar()
+        plt.xlabel("Time/s")
+        plt.ylabel("Distance/ft")
+        plt.show()
+
+    def pack_result(self, **kwargs):
+        """npz in the layout ``Data2D.load_npz`` reads: data is (distance, time)."""
+        filename = kwargs.get("filename", "result.npz")
+        if kwargs.get("mode", "fiberis") != "fiberis":
+            raise ValueError("Mode must be 'fiberis' data format.")
+        first = self.source[0] if isinstance(self.source, list) else self.source
+        np.savez(filename, daxis=self.mesh, taxis=self.taxis, data=self.snapshot.T, start_time=first.start_time)
+
+    def to_data2d(self, name=None):
+        """The result as a ``Data2D`` object without the npz round trip (additive helper)."""
+        from fiberis_b200.analyzer.Data2D.core2D import Data2D
+        first = self.source[0] if isinstance(self.source, list) else self.source
+        return Data2D(data=np.ascontiguousarray(self.snapshot.T), taxis=np.asarray(self.taxis, dtype=float),
+                      daxis=np.asarray(self.mesh, dtype=float), start_time=getattr(first, "start_time", None),
+                      name=name)
+
+    def reset(self):
+        self.taxis = None
+        self.snapshot = None
+        self.history = []
+
+
+class _DeviceRow:
+    """Placeholder appended to ``snapshot`` by ``tso.decide`` while the accepted state stays on the
+    device; replaced by the real rows when the loop ends."""
+
+    def __init__(self, k):
+        self.k = k
+
+
+class PDS1D_MultiSource(PDS1D_SingleSource):
+    """Several independent pressure sources: ``source`` is a list, ``sourceidx`` a list of nodes."""
+
+    _multi = True
+
+    def set_sourceidx(self, sourceidx):
+        super().set_sourceidx(sourceidx)
+        self.sourceidx = np.array(self.sourceidx)
+
+    def _check_source(self):
+        if self.source is None:
+            return False, "Source term is not set."
+        if not isinstance(self.source, list):
+            return False, "Source term must be a list."
+        return True, "Source term is properly set."
+
+    def _check_sourceidx(self):
+        if self.sourceidx is None:
+            return False, "Source index is not set."
+        if isinstance(self.sourceidx, int):
+            return False, ("Source index must be a list of integers. If you want to set a single source index, "
+                           "please use PDS1D_SingleSource.")
+        for idx in self.sourceidx:  # reference quirk: a raw list of Python ints is rejected; the setter
+            if isinstance(idx, int):  # converts to an ndarray afterwards, whose entries are np.int64
+                return False, "Source index must be a list of integers."
+        nodes = np.arange(len(self.mesh))
+        for idx in self.sourceidx:
+            if idx not in nodes:
+                return False, "Source index is not in the mesh."
+        if self.source is not None and len(self.sourceidx) != len(self.source):
+            return False, "Source index and source term length do not match."
+        return True, "Source index is properly set."

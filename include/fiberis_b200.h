@@ -1,0 +1,177 @@
+/*
+ * fiberis_b200 — C ABI of the B200-native 1D pressure-diffusion hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names: the part of
+ * fibeRIS's `fiberis.simulator` that assembles the implicit (backward-Euler) tridiagonal system,
+ * solves it once per time step and collects the snapshots.  The reference has no FFI for this path
+ * (it is pure Python); the entry points below are what a ctypes binding added to the reference's
+ * own modules would call (see INTEGRATION.md for that binding).  Reference paths are relative to
+ * /root/reference/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with `h_`; the caller owns all
+ *     memory (the library allocates nothing that outlives a call);
+ *   - arrays of batched systems are model-major: element (m, i) of an (M, nx) array is at
+ *     m * nx + i.  A "shared" per-cell array (one mesh for all models) is passed with stride 0;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream) and returns an fbr_status; FBR_OK only means "enqueued" — device-side findings
+ *     (zero pivots, Jacobi non-convergence) are written to the status arrays the call documents;
+ *   - on error the thread-local message is available from fbr_last_error(); the library never
+ *     aborts or exits;
+ *   - boundary-condition codes: 0 = 'None', 1 = 'Dirichlet', 2 = 'Neumann'
+ *     (src/fiberis/simulator/core/pds.py:137).
+ */
+#ifndef FIBERIS_B200_H
+#define FIBERIS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBR_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    FBR_OK = 0,
+    FBR_ERR_BAD_ARG = -1,      /* -> ValueError on the Python side */
+    FBR_ERR_UNSUPPORTED = -2,  /* shape outside what the selected kernel variant covers */
+    FBR_ERR_CUDA = -3          /* a CUDA runtime call failed; message has the cudaError string */
+} fbr_status;
+
+enum { FBR_BC_NONE = 0, FBR_BC_DIRICHLET = 1, FBR_BC_NEUMANN = 2 };
+
+/* Solver variants for fbr_solve_tridiag_* (north_star: "variant chosen by mesh length"). */
+enum {
+    FBR_SOLVER_AUTO = 0,
+    FBR_SOLVER_THOMAS = 1, /* one thread per system (many small systems)            */
+    FBR_SOLVER_PCR = 2     /* one CTA per system, shared-memory parallel cyclic reduction */
+};
+
+int fbr_version(void);
+const char *fbr_last_error(void);
+
+/* Device facts the host layer sizes launches with.  Any out pointer may be NULL. */
+int fbr_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_per_block_optin,
+                    int64_t *l2_bytes, int64_t *hbm_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  fused coefficient assembly.
+ * Replaces matrix_builder_1d_single_source / _multi_source
+ * (src/fiberis/simulator/solver/matbuilder.py:6-83, 86-167) and build_pml_sigma (:170-196),
+ * producing the three diagonals of the reference's dense A instead of the dense matrix:
+ * harmonic-mean interface diffusivity, non-uniform 3-point stencil, boundary rows, source rows
+ * (which win over boundary rows), PML added to every diagonal entry.  Bit-identical to the NumPy
+ * arithmetic of the reference (same operation order, IEEE division, no FMA contraction).
+ *   mesh, diffusivity : (M, nx) with stride nx, or one shared (nx) row with stride 0
+ *   src_idx           : (n_src) int64 DEVICE array of source rows (may be NULL when n_src == 0)
+ *   dl, d, du         : (M, nx) out; dl[m,0] = du[m,nx-1] = 0
+ * ------------------------------------------------------------------------------------------ */
+int fbr_assemble_f64(const double *mesh, int64_t mesh_stride, const double *diffusivity,
+                     int64_t diff_stride, int64_t M, int64_t nx, double dt, int lbc, int rbc,
+                     const int64_t *src_idx, int n_src, double pml_thickness, double sigma_max,
+                     double *dl, double *d, double *du, void *stream);
+
+/* Zonal ensembles: D_m(x) = zone_value[m, zone_of_cell[x]],
+ * gathered on the fly (the (M, nx) diffusivity array is never materialised); mesh is shared.
+ * zone_value: (M, n_zones), e.g. 10 ** theta computed by the host; zone_of_cell: (nx) int32. */
+int fbr_assemble_zonal_f64(const double *mesh, const double *zone_value, int n_zones,
+                           const int32_t *zone_of_cell, int64_t M, int64_t nx, double dt, int lbc,
+                           int rbc, const int64_t *src_idx, int n_src, double pml_thickness,
+                           double sigma_max, double *dl, double *d, double *du, void *stream);
+
+/* PML ramp alone: sigma (nx) = build_pml_sigma(mesh, pml_thickness, sigma_max)
+ * (src/fiberis/simulator/solver/matbuilder.py:170-196); all zeros when pml_thickness == 0. */
+int fbr_pml_sigma_f64(const double *mesh, int64_t nx, double pml_thickness, double sigma_max,
+                      double *sigma, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1b time-invariant factorisation.  A is constant for a fixed dt (only b changes,
+ * src/fiberis/simulator/core/pds.py:287-310), so the elimination is done once:
+ *   u_0 = d_0, l_i = dl_i / u_{i-1}, u_i = d_i - l_i du_{i-1}
+ *   fl = l, fr = 1 / u, fg = du / u            (each (M, nx))
+ * singular[m] (int32, may be NULL) receives 1 + the first row with a zero/non-finite pivot, or 0.
+ * The Python layer maps a non-zero flag to numpy.linalg.LinAlgError, the exception
+ * scipy.linalg.solve raises in the reference (src/fiberis/simulator/solver/PDESolver_IMP.py:28).
+ * ------------------------------------------------------------------------------------------ */
+int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64_t M, int64_t nx,
+                      double *fl, double *fr, double *fg, int32_t *singular, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  persistent multi-step integration — replaces the time loop
+ * `while taxis[-1] < t_total` of PDS1D_*.solve (src/fiberis/simulator/core/pds.py:287-310)
+ * for a fixed dt.  Pressure and the factors stay on chip for all n_steps; per step
+ *     b = p^n ; b[0] = 0 unless lbc == None ; b[nx-1] = 0 unless rbc == None ;
+ *     b[src_idx[k]] = src_table[n, k]  (k ascending: later duplicates win) ; p^{n+1} = A^-1 b
+ * (src/fiberis/simulator/solver/matbuilder.py:45-76).
+ *   p0          : (M, nx) with stride nx or shared (nx) with p0_stride 0
+ *   src_table   : (n_steps, n_src) value of source k at the START of step n (host: np.interp)
+ *   snap        : NULL, or ((n_steps / snapshot_every), n_snap_models, nx): state after steps
+ *                 snapshot_every, 2*snapshot_every, ... of the models listed in snap_models
+ *                 (int64 (n_snap_models); NULL = all M models, n_snap_models must then be M)
+ *   p_final     : NULL or (M, nx): state after the last step
+ *   obs_idx/obs/obs_w/misfit : fused objective (NULL obs_idx disables it):
+ *                 misfit[m] = sum_{n=1..n_steps} sum_k obs_w[k] (p^n[m, obs_idx[k]] - obs[n, k])^2
+ *                 obs: (n_steps + 1, n_obs), row 0 unused; obs_w may be NULL (all ones)
+ * The _f32 variant keeps state and factors in float (fp32 mode of north_star, gated at 1e-5).
+ * Limits of this on-chip variant: nx <= fbr_run_max_nx(), n_src <= 64, n_obs <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,
+                int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
+                const int64_t *src_idx, int n_src, const double *src_table,
+                int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
+                double *snap, double *p_final, const int64_t *obs_idx, int n_obs,
+                const double *obs, const double *obs_w, double *misfit, void *stream);
+
+int fbr_run_f32(const double *fl, const double *fr, const double *fg, const double *p0,
+                int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
+                const int64_t *src_idx, int n_src, const double *src_table,
+                int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
+                float *snap, float *p_final, const int64_t *obs_idx, int n_obs,
+                const double *obs, const double *obs_w, double *misfit, void *stream);
+
+int64_t fbr_run_max_nx(void);
+
+/* Running count of kernels this thread has launched through the library (bench.py's
+ * gpu_launches is a difference of two readings). */
+int fbr_last_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  bare batched tridiagonal solve  dl, d, du, b -> x  (no reuse of factors).
+ * Replaces solver_implicit(A, b, solver='numpy') = scipy.linalg.solve
+ * (src/fiberis/simulator/solver/PDESolver_IMP.py:9-34) for tridiagonal A; used by the adaptive
+ * time-step loop where A changes every iteration (src/fiberis/simulator/core/pds.py:312-336).
+ * x may alias b.  singular as in fbr_factorize_f64.  work: (M, nx) scratch needed by the THOMAS
+ * variant (fbr_solve_tridiag_work_bytes); may be NULL for PCR.  PCR covers 1 <= nx <= 4096.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fbr_solve_tridiag_work_bytes(int64_t M, int64_t nx, int variant);
+int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, const double *b,
+                          double *x, int64_t M, int64_t nx, int variant, double *work,
+                          int32_t *singular, void *stream);
+
+/* Right-hand side of one step, b = p with boundary / source overrides
+ * (src/fiberis/simulator/solver/matbuilder.py:45-76).  src_val: (n_src) DEVICE values shared by
+ * all models.  b may alias p. */
+int fbr_rhs_f64(const double *p, int64_t M, int64_t nx, int lbc, int rbc, const int64_t *src_idx,
+                int n_src, const double *src_val, double *b, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5  step-doubling error of the adaptive controller: err[m] = ||u1 - u2||_2 / ||u1||_2
+ * (src/fiberis/simulator/optimizer/tso.py:18).  u1, u2: (M, nx); err: (M).
+ * ------------------------------------------------------------------------------------------ */
+int fbr_error_norms_f64(const double *u1, const double *u2, int64_t M, int64_t nx, double *err,
+                        void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * "explicit" mode = Jacobi iteration from x = 0 on A x = b, stop when ||dx||_inf < tol or after
+ * max_iter sweeps (src/fiberis/simulator/solver/PDESolver_EXP.py:5-39).  iters[m] (int32, may be
+ * NULL) receives the sweeps used, or -max_iter when it did not converge (the reference is silent).
+ * ------------------------------------------------------------------------------------------ */
+int fbr_jacobi_f64(const double *dl, const double *d, const double *du, const double *b, double *x,
+                   int64_t M, int64_t nx, double tol, int max_iter, int32_t *iters, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIBERIS_B200_H */
