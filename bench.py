@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native fibeRIS 1D pressure-diffusion path.
+
+Metric (BASELINE.json): cell-updates/sec in fp64.  One "step" of this benchmark is one full pass of
+the hot path over one ensemble batch: BASELINE.json configs[2] ("optimizer parameter sweep: 4096
+independent models x 1024 cells x 5000 steps on 1 B200", SURVEY.md 8(d) recipe C3, seed 303) =
+2.097e10 cell-updates: K1 zonal assembly + K1b factorisation + K3 persistent time integration with
+the fused misfit and full snapshots of 4 audit members.  With --gpus N every rank runs one such
+batch of its own members (weak scaling) and the per-member misfits are all-gathered over NCCL.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c4|c1]
+
+  value ....... whole-job cell-updates/s, inputs resident in HBM, CUDA events around the three kernels
+  e2e ......... the same through the public API (PDS1D_Ensemble.solve) with HOST arrays in and out
+  roofline .... K3 alone: 16 B/cell-update (read p^n + write p^{n+1}) / measured launch time vs the
+                measured HBM copy peak (MEASURED_PEAKS.json).  K3 keeps pressure and factors on chip,
+                so this ALGORITHMIC figure can exceed 1: `traffic` is the ncu-measured DRAM bytes.
+  cpu_baseline  the banded C oracle (OpenMP over members) on a bounded sample of the same workload
+  --impl reference : the reference's algorithm (dense nx*nx matrix per step + scipy.linalg.solve)
+                restated in oracle/pds_oracle.py, one member per host core, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (models per GPU, cells, steps, description)
+    "c3": (4096, 1024, 5000, "C3: 4096 models x 1024 cells x 5000 steps per GPU (BASELINE.json configs[2])"),
+    "c4": (125000, 512, 2000, "C4 shard: 125000 models x 512 cells x 2000 steps per GPU (configs[3] at 8 GPUs)"),
+    "c1": (1, 200, 1000, "C1: single model, 200 cells x 1000 steps (configs[0])"),
+}
+B_ALG = 16.0  # bytes per cell-update, fp64: read p^n + write p^{n+1}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_workload(name, world=1):
+    """Synthetic inputs of SURVEY.md 8(d) (C3 recipe; C4 is the same recipe at 512 cells).  With
+    world > 1 the ensemble has world x (members per GPU) members; rank r owns the r-th block."""
+    M, nx, n_steps, desc = WORKLOADS[name]
+    M_per_gpu = M
+    M = M * world
+    seed = {"c3": 303, "c4": 404, "c1": 101}[name]
+    rng = np.random.default_rng(seed)
+    if name == "c1":
+        mesh = np.linspace(0, 199, 200)
+        return dict(name=name, desc=desc, M=world, M_per_gpu=1, nx=nx, n_steps=n_steps, dt=1.0, mesh=mesh, zones=1,
+                    zone=np.zeros(nx, np.int32), zv=np.ones((world, 1)), sidx=np.array([100]),
+                    srcs=[(np.array([0.0, 500.0, 1000.0]), np.array([0.0, 10.0, 10.0]))],
+                    obs_idx=np.array([50, 150]), audit=[0], seed=seed)
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    T = float(n_steps)
+    srcs = [(np.linspace(0, T, 64), rng.uniform(1.0, 10.0, 64)) for _ in range(2)]
+    zone = ((np.arange(nx) * 8) // nx).astype(np.int32)
+    theta = rng.uniform(-1, 1, (M, 8))
+    return dict(name=name, desc=desc, M=M, M_per_gpu=M_per_gpu, nx=nx, n_steps=n_steps, dt=1.0, mesh=mesh, zones=8, zone=zone,
+                zv=10.0 ** theta, sidx=np.array([nx // 4, 3 * nx // 4]), srcs=srcs,
+                obs_idx=np.linspace(1, nx - 2, 16).astype(np.int64),
+                # 4 audited members (full snapshots every step) in every rank's block
+                audit=[r * M_per_gpu + a for r in range(world)
+                       for a in (0, M_per_gpu // 3, (2 * M_per_gpu) // 3, M_per_gpu - 1)],
+                seed=seed)
+
+
+def build_ensemble(w):
+    from fiberis_b200.analyzer.Data1D.core1D import Data1D
+    from fiberis_b200.simulator.core.ensemble import PDS1D_Ensemble
+    e = PDS1D_Ensemble()
+    e.set_mesh(w["mesh"])
+    e.set_source([Data1D(data=d, taxis=t) for t, d in w["srcs"]])
+    e.set_sourceidx(w["sidx"])
+    e.set_bcs("Neumann", "Neumann")
+    e.set_initial(np.zeros(w["nx"]))
+    e.set_zonal_diffusivity(w["zv"], w["zone"])
+    return e
+
+
+def source_table(w):
+    t = np.arange(w["n_steps"], dtype=np.float64) * w["dt"]
+    return np.ascontiguousarray(np.stack([np.interp(t, st, sd) for st, sd in w["srcs"]], axis=1))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per K3 launch from the committed ncu --set full capture (None if not captured)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(w, budget_s=12.0):
+    """Banded C oracle, OpenMP over members, on a bounded sample sized for ~budget_s of CPU time."""
+    from oracle import c_oracle as CO
+    threads = CO.max_threads()
+    table = source_table(w)
+    obs = np.zeros((w["n_steps"] + 1, len(w["obs_idx"])))
+    steps = min(w["n_steps"], 200)
+    members = min(w["M"], threads)
+
+    def go(mm, ss):
+        t = time.perf_counter()
+        CO.run_ensemble(w["mesh"], w["zv"][:mm], w["zone"], np.zeros(w["nx"]), ss, w["dt"], "Neumann", "Neumann",
+                        w["sidx"], table[:ss], w["obs_idx"], obs[: ss + 1], None, threads=threads)
+        return time.perf_counter() - t
+
+    t_cal = go(members, steps)
+    rate = members * steps * w["nx"] / t_cal
+    if w["M"] > members:
+        mm = int(min(w["M"], max(members, (budget_s * rate / (w["nx"] * w["n_steps"])) // threads * threads)))
+        ss = w["n_steps"]
+        if mm * w["nx"] * ss / rate > 2.5 * budget_s:
+            ss = max(steps, int(budget_s * rate / (mm * w["nx"])))
+    else:
+        mm, ss = members, w["n_steps"]
+    dt_s = go(mm, ss)
+    return {"value": mm * ss * w["nx"] / dt_s, "unit": "cell-updates/s", "cores": threads, "kind": "port",
+            "sample": f"{mm} members x {w['nx']} cells x {ss} steps of the same workload, banded C oracle "
+                      f"(LAPACK-style pivoted gttrf once + gttrs per step), OpenMP {threads} threads, {dt_s:.1f} s"}
+
+
+def _ref_member(args):
+    """One member through the reference's algorithm: dense (nx, nx) matrix + scipy.linalg.solve per step."""
+    from oracle import pds_oracle as O
+    mesh, D, sidx, srcs, dt, steps = args
+    t = time.perf_counter()
+    O.solve_fixed(mesh, D, np.zeros(len(mesh)), "Neumann", "Neumann", sidx, srcs, 0.0, dt, steps * dt, dense=True,
+                  rebuild_every_step=True)
+    return time.perf_counter() - t
+
+
+def run_reference_arm(args):
+    """--impl reference: rank 0 only; every 'step' is a bounded sample (one member per host core,
+    ref_steps time steps each) of the same workload, through the reference's dense algorithm."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    w = make_workload(args.workload)
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64, w["M"]))
+    ref_steps = 12 if w["nx"] >= 1024 else (40 if w["nx"] >= 512 else w["n_steps"])
+    jobs = [(w["mesh"], w["zv"][m % w["M"]][w["zone"]], w["sidx"], w["srcs"], w["dt"], ref_steps) for m in range(procs)]
+    times = []
+    with mp.get_context("fork").Pool(procs) as pool:
+        for it in range(args.warmup + args.steps):
+            t = time.perf_counter()
+            pool.map(_ref_member, jobs)
+            if it >= args.warmup:
+                times.append(time.perf_counter() - t)
+    work = procs * ref_steps * w["nx"]
+    ms = 1e3 * float(np.mean(times))
+    value = work / (ms / 1e3)
+    sample = (f"{procs} members (one per process) x {w['nx']} cells x {ref_steps} steps per step; reference "
+              f"algorithm restated in oracle/pds_oracle.py: dense (nx,nx) A rebuilt every step + scipy.linalg.solve")
+    line = {"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "seed": w["seed"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from fiberis_b200 import _cabi, _engine as E
+    from fiberis_b200.simulator.core.ensemble import gather_misfit, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _cabi.require_cuda()
+
+    w = make_workload(args.workload, world)
+    M, nx, n_steps, dt = w["M_per_gpu"], w["nx"], w["n_steps"], w["dt"]
+    lo, hi = shard_bounds(w["M"], world, rank)
+    assert hi - lo == M
+    work = float(M) * nx * n_steps  # cell-updates per rank per step
+    table = source_table(w)
+    my_audit = [a - lo for a in w["audit"] if lo <= a < hi]
+
+    # ---- resident inputs for the device-timed leg -------------------------------------------------
+    mesh_d = E.to_device(w["mesh"])
+    zv_d = E.to_device(w["zv"][lo:hi])
+    zv0_d = E.to_device(w["zv"][:1])  # global member 0 generates the observations on every rank
+    zone_d = E.to_device(w["zone"], np.int32)
+    sidx_d, n_src = E.index_tensor(w["sidx"])
+    table_d = E.to_device(table)
+    p0_d = E.to_device(np.zeros(nx))
+    obs_idx_d, n_obs = E.index_tensor(w["obs_idx"])
+    audit_d, n_audit = E.index_tensor(np.asarray(my_audit, dtype=np.int64))
+    # observations = member 0's pressure at the observation cells (untimed set-up run on the device)
+    f0 = E.factorize(*E.assemble_zonal(mesh_d, zv0_d, zone_d, 1, nx, dt, "Neumann", "Neumann", sidx_d, n_src))
+    snap0, _, _ = E.run(f0, p0_d, 1, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1)
+    obs_d = torch.zeros((n_steps + 1, n_obs), dtype=torch.float64, device=mesh_d.device)
+    obs_d[1:] = snap0[:, 0, :][:, obs_idx_d]
+    obs_host = obs_d.cpu().numpy()
+    del snap0, f0
+    snap_d = torch.empty((n_steps, n_audit, nx), dtype=torch.float64, device=mesh_d.device)
+    misfit_d = torch.empty(M, dtype=torch.float64, device=mesh_d.device)
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=mesh_d.device)  # > 126 MB L2
+
+    def hot_path(ev=None):
+        diag = E.assemble_zonal(mesh_d, zv_d, zone_d, M, nx, dt, "Neumann", "Neumann", sidx_d, n_src)
+        fac = E.factorize(*diag, check_singular=False)
+        if ev:
+            ev[0].record()
+        E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1,
+              snap_models=audit_d, n_snap_models=n_audit, obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d,
+              snap_out=snap_d, misfit_out=misfit_d)
+        if ev:
+            ev[1].record()
+        return gather_misfit(misfit_d, M * world) if world > 1 else misfit_d
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        hot_path()
+    sync_all()
+
+    # ---- leg 1: device-resident inputs, CUDA events ------------------------------------------------
+    step_ms, k3_ms = [], []
+    launches0 = _cabi.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            hot_path((k0, k1))
+            e1.record()
+            sync_all()
+            step_ms.append(e0.elapsed_time(e1))
+            k3_ms.append(k0.elapsed_time(k1))
+    launches = (_cabi.launch_count() - launches0) // max(args.steps, 1)
+    total_ms = float(np.sum(step_ms))
+    t = torch.tensor([total_ms, float(np.sum(k3_ms))], dtype=torch.float64, device=mesh_d.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, k3_total_ms = float(t[0]), float(t[1])
+    misfit_resident = misfit_d.cpu().numpy().copy()
+
+    # ---- leg 2: end to end through the public API, host arrays in and out ----------------------------
+    ens = build_ensemble(w)
+    ens.set_observations(w["obs_idx"], obs_host)
+    h2d = (w["mesh"].nbytes + w["zv"].nbytes + w["zone"].nbytes + table.nbytes + obs_host.nbytes + 8 * nx
+           + 8 * len(w["sidx"]) + 8 * len(w["obs_idx"]) + 8 * len(w["audit"]))
+    d2h = 8 * M * world + 8 * n_steps * n_audit * nx
+    del snap_d
+    e2e_s = []
+    for it in range(2 + args.steps):
+        flush.zero_()
+        sync_all()
+        t0 = time.perf_counter()
+        mis = ens.solve(dt=dt, t_total=n_steps * dt, audit_models=w["audit"])
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if it >= 2:
+            e2e_s.append(t1 - t0)
+    assert np.array_equal(mis[lo:hi], misfit_resident), "e2e and resident legs disagree"
+    assert mis[0] == 0.0 and np.all(np.isfinite(mis)), "member 0 generated the observations: misfit must be 0"
+    t = torch.tensor([float(np.sum(e2e_s))], dtype=torch.float64, device=mesh_d.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_total_s = float(t[0])
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        k3_s = k3_total_ms / 1e3 / args.steps
+        achieved = work * B_ALG / k3_s / 1e9
+        line = {
+            "metric": "cell-updates/sec (fp64)",
+            "value": work * world * args.steps / (total_ms / 1e3),
+            "unit": "cell-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["desc"], "seed": w["seed"], "members_per_gpu": M, "cells": nx, "time_steps": n_steps,
+                       "diffusivity": "zonal, 8 zones, 10**U(-1,1)", "sources": 2, "obs_cells": int(n_obs),
+                       "audit_members_with_full_snapshots": n_audit, "bc": "Neumann/Neumann",
+                       "l2": "flushed between timed iterations (512 MiB memset)",
+                       "timed_kernels": "K1 assemble_zonal + K1b factorize + K3 run_onchip"
+                                        + (" + NCCL all-gather of misfits" if world > 1 else "")},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(args.workload), "kernel": "run_onchip_kernel<double,8>",
+                         "kernel_ms": k3_s * 1e3, "peak_source": peak_src,
+                         "note": "algorithmic 16 B/cell-update; K3 keeps pressure+factors on chip for all time "
+                                 "steps, so frac > 1 is expected - see traffic (ncu DRAM bytes per launch)"},
+            "e2e": {"value": work * world * args.steps / e2e_total_s, "unit": "cell-updates/s",
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "PDS1D_Ensemble.solve(host arrays) -> misfit + audit snapshots as numpy"},
+            "gpu_launches": int(launches) * args.steps,
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:  # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,15 +18,13 @@
 //   (3) a carry across the warps of the team through shared memory (W-1 FMAs),
 //   (4) a second local pass with the true carry-in.
 // No divisions, no HBM traffic and two __syncthreads per step (none for single-warp teams).
-#include <cuda_pipeline.h>
-#include <stdarg.h>
-
+// Source values and observations are read by the one thread that owns the cell, prefetched one
+// step ahead straight from global memory (L2), so the time loop has no staging code at all.
 #include "fbr_common.cuh"
 
 namespace fbr {
 
-constexpr int kTileSteps = 16;    // steps of source / observation values staged per smem tile
-constexpr int kMaxThreads = 512;  // per team
+constexpr int kMaxWarps = 16;  // per team
 constexpr int kMaxSrc = 64;
 constexpr int kMaxObs = 64;
 constexpr unsigned kFull = 0xffffffffu;
@@ -56,56 +54,105 @@ template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 
-// slot codes packed one byte per owned cell
+// x[j] = v / v = x[j] for a run-time j without dynamic register indexing (a short branch tree)
+template <typename T, int CPT>
+__device__ __forceinline__ void set_at(T (&x)[CPT], int j, T v) {
+    switch (j) {
+        case 0: x[0] = v; break;
+        case 1: if (CPT > 1) x[CPT > 1 ? 1 : 0] = v; break;
+        case 2: if (CPT > 2) x[CPT > 2 ? 2 : 0] = v; break;
+        case 3: if (CPT > 3) x[CPT > 3 ? 3 : 0] = v; break;
+        case 4: if (CPT > 4) x[CPT > 4 ? 4 : 0] = v; break;
+        case 5: if (CPT > 5) x[CPT > 5 ? 5 : 0] = v; break;
+        case 6: if (CPT > 6) x[CPT > 6 ? 6 : 0] = v; break;
+        default: if (CPT > 7) x[CPT > 7 ? 7 : 0] = v; break;
+    }
+}
+template <typename T, int CPT>
+__device__ __forceinline__ T get_at(const T (&x)[CPT], int j) {
+    switch (j) {
+        case 0: return x[0];
+        case 1: return x[CPT > 1 ? 1 : 0];
+        case 2: return x[CPT > 2 ? 2 : 0];
+        case 3: return x[CPT > 3 ? 3 : 0];
+        case 4: return x[CPT > 4 ? 4 : 0];
+        case 5: return x[CPT > 5 ? 5 : 0];
+        case 6: return x[CPT > 6 ? 6 : 0];
+        default: return x[CPT > 7 ? 7 : 0];
+    }
+}
+
+// per-thread bookkeeping modes
+enum { kNone = 0, kFastZero = 1, kFast = 2, kSlow = 3 };
 constexpr unsigned kSlotNone = 0xFF, kSlotZero = 0xFE;
 
-template <typename T, int CPT>
-__global__ void __launch_bounds__(kMaxThreads, 1) run_onchip_kernel(const RunArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+template <typename T, int CPT, int W>
+__global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchip_kernel(const RunArgs a) {
+    static_assert(CPT <= 8, "slot bytes are packed into one 64-bit word");
+    // [0] forward {T_w, E_w} pairs, [1] backward pairs; T = warp-total multiplier (time-invariant),
+    // E = this step's zero-carry warp-end value
+    __shared__ T s_pair[2][W][2];
+    __shared__ double s_red[W];
+    __shared__ long long s_snap_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int W = blockDim.x >> 5;
-    // smem carve-up: [Tf W][Tb W][Ef W][Eb W] of T, misfit scratch W doubles, snap slot, tiles
-    T *Tf = reinterpret_cast<T *>(smem_raw);
-    T *Tb = Tf + W;
-    T *Ef = Tb + W;
-    T *Eb = Ef + W;
-    double *red = reinterpret_cast<double *>(smem_raw + ((4 * W * sizeof(T) + 15) / 16) * 16);
-    long long *snap_slot_s = reinterpret_cast<long long *>(red + W);
-    const int tile_row = a.n_src + a.n_obs;  // doubles per staged step
-    double *tile = reinterpret_cast<double *>(snap_slot_s + 2);  // [2][kTileSteps][tile_row]
-    double *wobs = tile + 2 * kTileSteps * tile_row;             // [n_obs] observation weights
-
     const int64_t nx = a.nx;
     const int64_t cell0 = (int64_t)tid * CPT;
 
     for (int64_t m = blockIdx.x; m < a.M; m += gridDim.x) {
         // ---------------- per-model setup ----------------
         T l[CPT], r[CPT], g[CPT], x[CPT];
-        uint64_t ov = ~0ull, ob = ~0ull;  // override / observation slot per owned cell
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             const int64_t i = cell0 + j;
             if (i < nx) {
-                l[j] = (T)a.fl[m * nx + i];
-                r[j] = (T)a.fr[m * nx + i];
-                g[j] = (T)a.fg[m * nx + i];
-                x[j] = (T)a.p0[m * a.p0_stride + i];
-                unsigned slot = kSlotNone;
-                if ((i == 0 && a.lbc != FBR_BC_NONE) || (i == nx - 1 && a.rbc != FBR_BC_NONE)) slot = kSlotZero;
-                for (int k = 0; k < a.n_src; ++k)
-                    if (a.src_idx[k] == i) slot = (unsigned)k;
-                ov = (ov & ~(0xFFull << (8 * j))) | ((uint64_t)slot << (8 * j));
-                unsigned oslot = kSlotNone;
-                for (int k = 0; k < a.n_obs; ++k)
-                    if (a.obs_idx[k] == i) oslot = (unsigned)k;
-                ob = (ob & ~(0xFFull << (8 * j))) | ((uint64_t)oslot << (8 * j));
+                l[j] = (T)__ldg(a.fl + m * nx + i);
+                r[j] = (T)__ldg(a.fr + m * nx + i);
+                g[j] = (T)__ldg(a.fg + m * nx + i);
+                x[j] = (T)__ldg(a.p0 + m * a.p0_stride + i);
             } else {  // padding cell: identity row, decoupled
                 l[j] = (T)0; r[j] = (T)1; g[j] = (T)0; x[j] = (T)0;
             }
         }
-        const bool has_ov = ov != ~0ull, has_ob = ob != ~0ull;
+        // Which of my cells are overridden in the right-hand side / observed?  The common case — at
+        // most one of each per thread — is handled with one register index (ov_j / ob_j); threads
+        // owning several (adjacent sources, a source next to a boundary) take a slow generic path.
+        int ov_mode = kNone, ov_j = 0, ob_mode = kNone, ob_j = 0;
+        const double *ovp = a.src_table, *obp = a.obs;
+        if (cell0 < nx) {
+            uint64_t ov = ~0ull;  // one slot byte per owned cell
+            if (cell0 == 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~0xFFull) | kSlotZero;
+            const int64_t jl = nx - 1 - cell0;
+            if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE)
+                ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kSlotZero << (8 * jl));
+#pragma unroll 1
+            for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win (matbuilder.py:156-161)
+                const int64_t jj = a.src_idx[k] - cell0;
+                if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)k << (8 * jj));
+            }
+            int n_ov = 0, n_ob = 0;
+#pragma unroll 1
+            for (int j = 0; j < CPT; ++j) {
+                const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
+                if (so != kSlotNone) {
+                    ++n_ov; ov_j = j;
+                    ov_mode = so == kSlotZero ? kFastZero : kFast;
+                    if (so != kSlotZero) ovp = a.src_table + so;
+                }
+            }
+#pragma unroll 1
+            for (int k = 0; k < a.n_obs; ++k) {
+                const int64_t jj = a.obs_idx[k] - cell0;
+                if (jj >= 0 && jj < CPT && a.obs_idx[k] < nx) {
+                    ++n_ob; ob_j = (int)jj; ob_mode = kFast;
+                    obp = a.obs + a.n_obs + k;  // row 1 = state after the first step
+                }
+            }
+            if (n_ov > 1) ov_mode = kSlow;
+            if (n_ob > 1) ob_mode = kSlow;
+        }
 
-        // scan multipliers (time-invariant): stage products of the chunk multipliers
+        // scan multipliers (time-invariant): stage products of the chunk multipliers; lanes that a
+        // stage does not touch get a zero multiplier so the time loop needs no predicates
         T PfL[5], PbL[5], PfEx, PbEx;
         {
             T pf = (T)1, pb = (T)1;
@@ -113,12 +160,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) run_onchip_kernel(const RunArg
             for (int j = 0; j < CPT; ++j) { pf *= -l[j]; pb *= -g[j]; }
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
-                PfL[s] = pf;
-                PbL[s] = pb;
+                const bool fa = lane >= (1 << s), ba = lane + (1 << s) < 32;
+                PfL[s] = fa ? pf : (T)0;
+                PbL[s] = ba ? pb : (T)0;
                 const T upf = __shfl_up_sync(kFull, pf, 1 << s);
                 const T dnb = __shfl_down_sync(kFull, pb, 1 << s);
-                if (lane >= (1 << s)) pf *= upf;
-                if (lane + (1 << s) < 32) pb *= dnb;
+                if (fa) pf *= upf;
+                if (ba) pb *= dnb;
             }
             // pf = product over lanes 0..lane, pb = product over lanes lane..31
             PfEx = __shfl_up_sync(kFull, pf, 1);
@@ -126,9 +174,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) run_onchip_kernel(const RunArg
             if (lane == 0) PfEx = (T)1;
             if (lane == 31) PbEx = (T)1;
             if (W > 1) {
-                __syncthreads();  // previous model's readers are done with Tf/Tb
-                if (lane == 31) Tf[warp] = pf;
-                if (lane == 0) Tb[warp] = pb;
+                __syncthreads();  // previous model's readers are done with the shared scratch
+                if (lane == 31) s_pair[0][warp][0] = pf;
+                if (lane == 0) s_pair[1][warp][0] = pb;
             }
         }
         // snapshot slot of this model (-1: not recorded)
@@ -140,69 +188,57 @@ __global__ void __launch_bounds__(kMaxThreads, 1) run_onchip_kernel(const RunArg
                     for (int64_t q = 0; q < a.n_snap_models; ++q)
                         if (a.snap_models[q] == m) slot = q;
             }
-            snap_slot_s[0] = slot;
+            s_snap_slot = slot;
         }
-        // first tile of staged per-step values
-        auto stage_tile = [&](int64_t tile_idx) {
-            if (tile_row == 0) return;
-            double *dst = tile + (tile_idx & 1) * (kTileSteps * tile_row);
-            const int64_t n0 = tile_idx * kTileSteps;
-            for (int e = tid; e < kTileSteps * tile_row; e += blockDim.x) {
-                const int s = e / tile_row, c = e - s * tile_row;
-                const int64_t n = n0 + s;
-                if (n < a.n_steps) {
-                    const double *src = c < a.n_src ? a.src_table + n * a.n_src + c
-                                                    : a.obs + (n + 1) * a.n_obs + (c - a.n_src);
-                    __pipeline_memcpy_async(dst + e, src, sizeof(double));
-                }
-            }
-            __pipeline_commit();
-        };
-        stage_tile(0);
-        for (int k = tid; k < a.n_obs; k += blockDim.x) wobs[k] = a.obs_w ? a.obs_w[k] : 1.0;
         __syncthreads();
-        const long long snap_slot = snap_slot_s[0];
+        const long long snap_slot = s_snap_slot;
         double acc = 0.0;
-        int64_t snap_countdown = a.snapshot_every, snap_row = 0;
-        int in_tile = 0;
-        int64_t tile_idx = 0;
+        const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
+        int snap_countdown = snap_every;
+        T *snap_dst = snap_slot >= 0 ? reinterpret_cast<T *>(a.snap) + snap_slot * nx + cell0 : nullptr;
+        const int64_t snap_stride = a.n_snap_models * nx;
+        // per-step scalars are prefetched one step ahead straight from global memory by the (few)
+        // threads that own an overridden / observed cell
+        double ov_val = (ov_mode == kFast && a.n_steps > 0) ? __ldg(ovp) : 0.0;
+        double ob_val = (ob_mode == kFast && a.n_steps > 0) ? __ldg(obp) : 0.0;
 
         // ---------------- time loop ----------------
         for (int64_t n = 0; n < a.n_steps; ++n) {
-            if (in_tile == kTileSteps) { in_tile = 0; ++tile_idx; }
-            if (in_tile == 0) {
-                __pipeline_wait_prior(0);
-                __syncthreads();  // tile tile_idx is visible; the other buffer is free
-                stage_tile(tile_idx + 1);
-            }
-            const double *row = tile + (tile_idx & 1) * (kTileSteps * tile_row) + in_tile * tile_row;
-            ++in_tile;
+            const bool more = n + 1 < a.n_steps;
+            double ov_next = 0.0, ob_next = 0.0;
+            if (ov_mode == kFast && more) { ovp += a.n_src; ov_next = __ldg(ovp); }
+            if (ob_mode == kFast && more) { obp += a.n_obs; ob_next = __ldg(obp); }
 
             // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
-            if (has_ov) {
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    const unsigned slot = (unsigned)(ov >> (8 * j)) & 0xFF;
-                    if (slot == kSlotZero) x[j] = (T)0;
-                    else if (slot != kSlotNone) x[j] = (T)row[slot];
+            if (ov_mode != kNone) {
+                if (ov_mode != kSlow) {
+                    set_at<T, CPT>(x, ov_j, (T)ov_val);
+                } else {  // several overridden cells in this thread: re-derive them (rare, slow)
+                    if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (T)0;
+                    const int64_t jl = nx - 1 - cell0;
+                    if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) set_at<T, CPT>(x, (int)jl, (T)0);
+#pragma unroll 1
+                    for (int k = 0; k < a.n_src; ++k) {
+                        const int64_t jj = a.src_idx[k] - cell0;
+                        if (jj >= 0 && jj < CPT) set_at<T, CPT>(x, (int)jj, (T)__ldg(a.src_table + n * a.n_src + k));
+                    }
                 }
             }
-            // ---- forward sweep ----
+            // ---- forward sweep: y_i = b_i - l_i y_{i-1} ----
             T y = (T)0;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) y = fma_t<T>(-l[j], y, x[j]);
 #pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                const T up = __shfl_up_sync(kFull, y, 1 << s);
-                if (lane >= (1 << s)) y = fma_t<T>(PfL[s], up, y);
-            }
+            for (int s = 0; s < 5; ++s) y = fma_t<T>(PfL[s], __shfl_up_sync(kFull, y, 1 << s), y);
             T carry = __shfl_up_sync(kFull, y, 1);
             if (lane == 0) carry = (T)0;
             if (W > 1) {
-                if (lane == 31) Ef[warp] = y;
+                if (lane == 31) s_pair[0][warp][1] = y;
                 __syncthreads();
                 T c = (T)0;
-                for (int v = 0; v < warp; ++v) c = fma_t<T>(Tf[v], c, Ef[v]);
+#pragma unroll
+                for (int v = 0; v < W - 1; ++v)
+                    if (v < warp) c = fma_t<T>(s_pair[0][v][0], c, s_pair[0][v][1]);
                 carry = fma_t<T>(PfEx, c, carry);
             }
             y = carry;
@@ -211,22 +247,21 @@ __global__ void __launch_bounds__(kMaxThreads, 1) run_onchip_kernel(const RunArg
                 y = fma_t<T>(-l[j], y, x[j]);
                 x[j] = r[j] * y;  // t_j = r_j y_j
             }
-            // ---- backward sweep ----
+            // ---- backward sweep: x_i = t_i - g_i x_{i+1} ----
             T z = (T)0;
 #pragma unroll
             for (int j = CPT - 1; j >= 0; --j) z = fma_t<T>(-g[j], z, x[j]);
 #pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                const T dn = __shfl_down_sync(kFull, z, 1 << s);
-                if (lane + (1 << s) < 32) z = fma_t<T>(PbL[s], dn, z);
-            }
+            for (int s = 0; s < 5; ++s) z = fma_t<T>(PbL[s], __shfl_down_sync(kFull, z, 1 << s), z);
             carry = __shfl_down_sync(kFull, z, 1);
             if (lane == 31) carry = (T)0;
             if (W > 1) {
-                if (lane == 0) Eb[warp] = z;
+                if (lane == 0) s_pair[1][warp][1] = z;
                 __syncthreads();
                 T c = (T)0;
-                for (int v = W - 1; v > warp; --v) c = fma_t<T>(Tb[v], c, Eb[v]);
+#pragma unroll
+                for (int v = W - 1; v > 0; --v)
+                    if (v > warp) c = fma_t<T>(s_pair[1][v][0], c, s_pair[1][v][1]);
                 carry = fma_t<T>(PbEx, c, carry);
             }
             z = carry;
@@ -236,27 +271,32 @@ __global__ void __launch_bounds__(kMaxThreads, 1) run_onchip_kernel(const RunArg
                 x[j] = z;
             }
             // ---- fused objective ----
-            if (has_ob) {
-#pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    const unsigned slot = (unsigned)(ob >> (8 * j)) & 0xFF;
-                    if (slot != kSlotNone) {
-                        const double res = (double)x[j] - row[a.n_src + slot];
-                        acc = fma(wobs[slot] * res, res, acc);
+            if (ob_mode != kNone) {
+                if (ob_mode != kSlow) {  // one observed cell: its weight is applied once, after the loop
+                    const double res = (double)get_at<T, CPT>(x, ob_j) - ob_val;
+                    acc = fma(res, res, acc);
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < a.n_obs; ++k) {
+                        const int64_t jj = a.obs_idx[k] - cell0;
+                        if (jj >= 0 && jj < CPT) {
+                            const double res = (double)get_at<T, CPT>(x, (int)jj) - __ldg(a.obs + (n + 1) * a.n_obs + k);
+                            acc = fma((a.obs_w ? a.obs_w[k] : 1.0) * res, res, acc);
+                        }
                     }
                 }
             }
             // ---- sampled snapshot ----
-            if (snap_slot >= 0 && --snap_countdown == 0) {
-                snap_countdown = a.snapshot_every;
-                T *dst = reinterpret_cast<T *>(a.snap) + (snap_row * a.n_snap_models + snap_slot) * nx + cell0;
-                ++snap_row;
+            if (snap_dst && --snap_countdown == 0) {
+                snap_countdown = snap_every;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j)
-                    if (cell0 + j < nx) dst[j] = x[j];
+                    if (cell0 + j < nx) snap_dst[j] = x[j];
+                snap_dst += snap_stride;
             }
+            ov_val = ov_next;
+            ob_val = ob_next;
         }
-        __pipeline_wait_prior(0);
 
         // ---------------- per-model epilogue ----------------
         if (a.p_final) {
@@ -266,35 +306,42 @@ __global__ void __launch_bounds__(kMaxThreads, 1) run_onchip_kernel(const RunArg
                 if (cell0 + j < nx) dst[j] = x[j];
         }
         if (a.misfit) {
+            if (ob_mode == kFast && a.obs_w) acc *= a.obs_w[(obp - a.obs) % a.n_obs];
             for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
-            if (lane == 0) red[warp] = acc;
+            if (lane == 0) s_red[warp] = acc;
             __syncthreads();
             if (tid == 0) {
                 double tot = 0.0;
-                for (int w = 0; w < W; ++w) tot += red[w];
+                for (int w = 0; w < W; ++w) tot += s_red[w];
                 a.misfit[m] = tot;
             }
         }
-        __syncthreads();  // smem (tiles, red, snap slot) is reused by the next model
+        __syncthreads();  // shared scratch is reused by the next model
     }
 }
 
-template <typename T, int CPT>
-static int launch_onchip(const RunArgs &a, int threads, cudaStream_t stream) {
+template <typename T, int CPT, int W>
+static int launch_onchip(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
-    const int W = threads / 32;
-    size_t smem = ((4 * W * sizeof(T) + 15) / 16) * 16 + W * sizeof(double) + 2 * sizeof(long long) +
-                  2 * (size_t)kTileSteps * (a.n_src + a.n_obs) * sizeof(double) + (size_t)a.n_obs * sizeof(double);
-    auto kern = run_onchip_kernel<T, CPT>;
-    if (smem > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = run_onchip_kernel<T, CPT, W>;
     int occ = 0;
-    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, 0));
+    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d)", 32 * W);
     int64_t grid = (int64_t)occ * f.sm_count;
     if (grid > a.M) grid = a.M;
-    kern<<<(unsigned)grid, threads, smem, stream>>>(a);
+    kern<<<(unsigned)grid, 32 * W, 0, stream>>>(a);
     return check_launch("fbr_run (on-chip)");
+}
+
+template <typename T, int CPT>
+static int launch_cpt(const RunArgs &a, cudaStream_t stream) {
+    const int64_t threads = (a.nx + CPT - 1) / CPT;
+    if (threads <= 32) return launch_onchip<T, CPT, 1>(a, stream);
+    if (threads <= 64) return launch_onchip<T, CPT, 2>(a, stream);
+    if (threads <= 128) return launch_onchip<T, CPT, 4>(a, stream);
+    if (threads <= 256) return launch_onchip<T, CPT, 8>(a, stream);
+    return launch_onchip<T, CPT, 16>(a, stream);
 }
 
 template <typename T>
@@ -315,14 +362,13 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     int cpt = a.nx >= 256 ? 8 : a.nx >= 128 ? 4 : a.nx >= 64 ? 2 : 1;
     if (const char *e = getenv("FBR_CPT")) {  // tuning aid
         const int v = atoi(e);
-        if ((v == 1 || v == 2 || v == 4 || v == 8) && (a.nx + v - 1) / v <= kMaxThreads) cpt = v;
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && (a.nx + v - 1) / v <= 32 * kMaxWarps) cpt = v;
     }
-    const int threads = (int)(((a.nx + cpt - 1) / cpt + 31) / 32) * 32;
     switch (cpt) {
-        case 1: return launch_onchip<T, 1>(a, threads, stream);
-        case 2: return launch_onchip<T, 2>(a, threads, stream);
-        case 4: return launch_onchip<T, 4>(a, threads, stream);
-        default: return launch_onchip<T, 8>(a, threads, stream);
+        case 1: return launch_cpt<T, 1>(a, stream);
+        case 2: return launch_cpt<T, 2>(a, stream);
+        case 4: return launch_cpt<T, 4>(a, stream);
+        default: return launch_cpt<T, 8>(a, stream);
     }
 }
 
@@ -330,7 +376,7 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
 
 using namespace fbr;
 
-extern "C" int64_t fbr_run_max_nx(void) { return 8 * (int64_t)kMaxThreads; }
+extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
 
 #define FBR_FILL_ARGS()                                                                                   \
     RunArgs a;                                                                                            \

@@ -208,8 +208,13 @@ def _src_table(sources, taxis, t0):
 
 
 def solve_fixed(mesh, diffusivity, initial, lbc, rbc, sourceidx, sources, t0, dt, t_total,
-                mode="implicit", dense=False, pml_thickness=0.0, sigma_max=2):
-    """pds.py:243-310 for optimizer=False.  Returns (snapshot (nt+1,nx), taxis (nt+1,))."""
+                mode="implicit", dense=False, pml_thickness=0.0, sigma_max=2, rebuild_every_step=False):
+    """pds.py:243-310 for optimizer=False.  Returns (snapshot (nt+1,nx), taxis (nt+1,)).
+
+    ``dense=True`` solves the dense (nx, nx) system with ``scipy.linalg.solve`` as the reference
+    does; with ``rebuild_every_step=True`` the dense matrix is also re-assembled before every solve
+    (pds.py:294), which is the reference's cost profile minus its Python ``for`` loops — the mode
+    ``bench.py --impl reference`` times."""
     taxis = time_axis(t0, dt, t_total)
     sidx = np.atleast_1d(np.asarray(sourceidx)).astype(np.int64)
     S = _src_table(sources, taxis, t0)
@@ -224,6 +229,9 @@ def solve_fixed(mesh, diffusivity, initial, lbc, rbc, sourceidx, sources, t0, dt
         if mode != "implicit":
             snap[n + 1] = jacobi(dl, d, du, b)
         elif dense:
+            if rebuild_every_step:
+                A = dense_from_tridiag(*assemble_tridiag(mesh, diffusivity, dt, lbc, rbc, sidx, pml_thickness,
+                                                         sigma_max))
             snap[n + 1] = _dense_solve(A, b)
         else:
             snap[n + 1] = fac.solve(b)
