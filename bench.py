@@ -265,11 +265,10 @@ def run_gpu_arm(args):
     # observations = member 0's pressure at the observation cells (untimed set-up run on the device)
     f0 = E.factorize(*E.assemble_zonal(mesh_d, zv0_d, zone_d, 1, nx, dt, "Neumann", "Neumann", sidx_d, n_src))
     snap0, _, _ = E.run(f0, p0_d, 1, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1)
-    obs_d = torch.zeros((n_steps + 1, n_obs), dtype=torch.float64, device=mesh_d.device)
-    obs_d[1:] = snap0[:, 0, :][:, obs_idx_d]
+    obs_d = snap0[0][:, obs_idx_d].contiguous()  # (n_steps + 1, n_obs); row 0 (initial state) is unused
     obs_host = obs_d.cpu().numpy()
     del snap0, f0
-    snap_d = torch.empty((n_steps, n_audit, nx), dtype=torch.float64, device=mesh_d.device)
+    snap_d = torch.empty((n_audit, n_steps + 1, nx), dtype=torch.float64, device=mesh_d.device)
     misfit_d = torch.empty(M, dtype=torch.float64, device=mesh_d.device)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=mesh_d.device)  # > 126 MB L2
 

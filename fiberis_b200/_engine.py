@@ -101,20 +101,33 @@ def factorize(dl, d, du, check_singular=True):
 
 def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, snap_models=None,
         n_snap_models=None, want_final=False, obs_idx=None, n_obs=0, obs=None, obs_w=None, dtype="float64",
-        snap_out=None, misfit_out=None):
-    """K3: persistent on-chip integration.  Returns (snap | None, p_final | None, misfit | None)."""
+        with_initial_row=True, misfit_out=None, snap_out=None):
+    """K3: persistent on-chip integration.
+
+    Returns (snap | None, p_final | None, misfit | None).  ``snap`` has shape
+    (n_recorded_models, rows, nx) — the layout the result objects want, written directly by the
+    kernel — where rows = n_steps // snapshot_every (+ 1 leading row holding the initial state when
+    ``with_initial_row``).  ``snapshot_every=0`` disables snapshots.
+    """
     torch = _torch()
     lib = _cabi.load()
     fl, fr, fg = factors
     dev = fl.device
     tdt = torch.float64 if dtype == "float64" else torch.float32
     fn = lib.fbr_run_f64 if dtype == "float64" else lib.fbr_run_f32
-    snap = snap_out
     n_rows = n_steps // snapshot_every if snapshot_every else 0
-    if snap is None and snapshot_every and n_rows > 0:
+    snap = snap_ptr = None
+    row_stride = model_stride = 0
+    if n_rows > 0:
         ns = M if snap_models is None else n_snap_models
-        snap = torch.empty((n_rows, ns, nx), dtype=tdt, device=dev)
-        n_snap_models = ns
+        lead = 1 if with_initial_row else 0
+        snap = snap_out if snap_out is not None else torch.empty((ns, n_rows + lead, nx), dtype=tdt, device=dev)
+        assert snap.shape == (ns, n_rows + lead, nx) and snap.dtype == tdt
+        if lead:
+            first = p0 if p0.dim() == 1 else (p0 if snap_models is None else p0[snap_models])
+            snap[:, 0, :] = first.to(tdt)
+        row_stride, model_stride, n_snap_models = nx, (n_rows + lead) * nx, ns
+        snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * snap.element_size())
     p_final = torch.empty((M, nx), dtype=tdt, device=dev) if want_final else None
     misfit = misfit_out
     if misfit is None and obs_idx is not None:
@@ -122,9 +135,50 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     p0_stride = 0 if p0.dim() == 1 else nx
     check(fn(ptr(fl), ptr(fr), ptr(fg), ptr(p0), p0_stride, M, nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
              ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), ptr(snap_models),
-             int(n_snap_models or 0), ptr(snap), ptr(p_final), ptr(obs_idx), int(n_obs), ptr(obs), ptr(obs_w),
-             ptr(misfit), current_stream()))
+             int(n_snap_models or 0), row_stride, model_stride, snap_ptr, ptr(p_final), ptr(obs_idx), int(n_obs),
+             ptr(obs), ptr(obs_w), ptr(misfit), current_stream()))
     return snap, p_final, misfit
+
+
+class _PinnedPool:
+    """Page-locked host buffers for device->host result copies.  cudaHostAlloc costs ~0.6 ms/MB, so
+    buffers are kept and handed out again once the NumPy array that aliased them has been
+    garbage-collected (tracked with a weak reference); a live result is never overwritten."""
+
+    def __init__(self):
+        self.entries = []  # [pinned uint8 tensor, weakref to the last ndarray handed out]
+
+    def take(self, nbytes):
+        torch = _torch()
+        free = [e for e in self.entries if e[1]() is None]
+        fits = [e for e in free if nbytes <= e[0].numel() <= 2 * nbytes + 4096]
+        if fits:
+            return min(fits, key=lambda e: e[0].numel())
+        for e in free[: max(0, len(self.entries) - 7)]:  # bound the pool: drop unused buffers first
+            self.entries.remove(e)
+        entry = [torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True), lambda: None]
+        self.entries.append(entry)
+        return entry
+
+
+_pool = _PinnedPool()
+
+
+def to_host(t):
+    """Device tensor -> NumPy array through pooled pinned memory (one DMA, no extra host copy)."""
+    torch = _torch()
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (1 << 20):
+        return t.cpu().numpy()
+    import weakref
+    entry = _pool.take(nbytes)
+    host = entry[0][:nbytes].view(t.dtype).view(t.shape)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    arr = host.numpy()
+    entry[1] = weakref.ref(arr)
+    return arr
 
 
 def run_max_nx() -> int:

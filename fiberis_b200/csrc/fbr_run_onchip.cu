@@ -41,7 +41,8 @@ struct RunArgs {
     int64_t snapshot_every;
     const int64_t *snap_models;
     int64_t n_snap_models;
-    void *snap;     // ((n_steps / snapshot_every), n_snap_models, nx) of T
+    int64_t snap_row_stride, snap_model_stride;  // in elements
+    void *snap;     // element (row, slot, i) at row * snap_row_stride + slot * snap_model_stride + i
     void *p_final;  // (M, nx) of T
     const int64_t *obs_idx;
     int n_obs;
@@ -54,32 +55,38 @@ template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 
-// x[j] = v / v = x[j] for a run-time j without dynamic register indexing (a short branch tree)
-template <typename T, int CPT>
-__device__ __forceinline__ void set_at(T (&x)[CPT], int j, T v) {
-    switch (j) {
-        case 0: x[0] = v; break;
-        case 1: if (CPT > 1) x[CPT > 1 ? 1 : 0] = v; break;
-        case 2: if (CPT > 2) x[CPT > 2 ? 2 : 0] = v; break;
-        case 3: if (CPT > 3) x[CPT > 3 ? 3 : 0] = v; break;
-        case 4: if (CPT > 4) x[CPT > 4 ? 4 : 0] = v; break;
-        case 5: if (CPT > 5) x[CPT > 5 ? 5 : 0] = v; break;
-        case 6: if (CPT > 6) x[CPT > 6 ? 6 : 0] = v; break;
-        default: if (CPT > 7) x[CPT > 7 ? 7 : 0] = v; break;
-    }
+// x[j] = v for a run-time j, in place, without dynamic register indexing: one compare and one
+// predicated move per owned cell (inline PTX so that ptxas keeps x[] where it is).
+__device__ __forceinline__ void mov_if_eq(double &dst, double v, int j, int k) {
+    asm volatile("{ .reg .pred p; setp.eq.s32 p, %2, %3; @p mov.f64 %0, %1; }" : "+d"(dst) : "d"(v), "r"(j), "r"(k));
+}
+__device__ __forceinline__ void mov_if_eq(float &dst, float v, int j, int k) {
+    asm volatile("{ .reg .pred p; setp.eq.s32 p, %2, %3; @p mov.f32 %0, %1; }" : "+f"(dst) : "f"(v), "r"(j), "r"(k));
 }
 template <typename T, int CPT>
+__device__ __forceinline__ void set_at(T (&x)[CPT], int j, T v) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) mov_if_eq(x[k], v, j, k);
+}
+// v = x[j] for a run-time j: binary select tree on the bits of j
+template <typename T, int CPT>
 __device__ __forceinline__ T get_at(const T (&x)[CPT], int j) {
-    switch (j) {
-        case 0: return x[0];
-        case 1: return x[CPT > 1 ? 1 : 0];
-        case 2: return x[CPT > 2 ? 2 : 0];
-        case 3: return x[CPT > 3 ? 3 : 0];
-        case 4: return x[CPT > 4 ? 4 : 0];
-        case 5: return x[CPT > 5 ? 5 : 0];
-        case 6: return x[CPT > 6 ? 6 : 0];
-        default: return x[CPT > 7 ? 7 : 0];
-    }
+    if (CPT == 1) return x[0];
+    const bool b0 = j & 1, b1 = j & 2, b2 = j & 4;
+    T a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = (2 * k + 1 < CPT) ? (b0 ? x[(2 * k + 1) % CPT] : x[(2 * k) % CPT]) : x[(2 * k) % CPT];
+    if (CPT == 2) return a[0];
+    const T c0 = b1 ? a[1] : a[0], c1 = b1 ? a[3] : a[2];
+    if (CPT == 4) return c0;
+    return b2 ? c1 : c0;
+}
+// if (cond) c = fma(t, c, e): predicated FMA, no select
+__device__ __forceinline__ void fma_if(double &c, double t, double e, bool cond) {
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p fma.rn.f64 %0, %1, %0, %2; }" : "+d"(c) : "d"(t), "d"(e), "r"((int)cond));
+}
+__device__ __forceinline__ void fma_if(float &c, float t, float e, bool cond) {
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p fma.rn.f32 %0, %1, %0, %2; }" : "+f"(c) : "f"(t), "f"(e), "r"((int)cond));
 }
 
 // per-thread bookkeeping modes
@@ -195,8 +202,8 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
         double acc = 0.0;
         const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
         int snap_countdown = snap_every;
-        T *snap_dst = snap_slot >= 0 ? reinterpret_cast<T *>(a.snap) + snap_slot * nx + cell0 : nullptr;
-        const int64_t snap_stride = a.n_snap_models * nx;
+        T *snap_dst = snap_slot >= 0 ? reinterpret_cast<T *>(a.snap) + snap_slot * a.snap_model_stride + cell0 : nullptr;
+        const int64_t snap_stride = a.snap_row_stride;
         // per-step scalars are prefetched one step ahead straight from global memory by the (few)
         // threads that own an overridden / observed cell
         double ov_val = (ov_mode == kFast && a.n_steps > 0) ? __ldg(ovp) : 0.0;
@@ -237,8 +244,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 __syncthreads();
                 T c = (T)0;
 #pragma unroll
-                for (int v = 0; v < W - 1; ++v)
-                    if (v < warp) c = fma_t<T>(s_pair[0][v][0], c, s_pair[0][v][1]);
+                for (int v = 0; v < W - 1; ++v) fma_if(c, s_pair[0][v][0], s_pair[0][v][1], v < warp);
                 carry = fma_t<T>(PfEx, c, carry);
             }
             y = carry;
@@ -260,8 +266,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 __syncthreads();
                 T c = (T)0;
 #pragma unroll
-                for (int v = W - 1; v > 0; --v)
-                    if (v > warp) c = fma_t<T>(s_pair[1][v][0], c, s_pair[1][v][1]);
+                for (int v = W - 1; v > 0; --v) fma_if(c, s_pair[1][v][0], s_pair[1][v][1], v > warp);
                 carry = fma_t<T>(PbEx, c, carry);
             }
             z = carry;
@@ -356,6 +361,7 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     FBR_REQUIRE(a.n_obs == 0 || (a.obs_idx && a.obs && a.misfit), "observations given without obs / misfit");
     FBR_REQUIRE(!a.snap || (a.snapshot_every >= 1 && a.n_snap_models >= 1), "snapshot_every / n_snap_models must be >= 1");
     FBR_REQUIRE(!a.snap || a.snap_models || a.n_snap_models == a.M, "snap_models == NULL needs n_snap_models == M");
+    FBR_REQUIRE(!a.snap || (a.snap_row_stride >= a.nx && a.snap_model_stride >= a.nx), "snapshot strides must be >= nx");
     if (a.nx > fbr_run_max_nx())
         return fail(FBR_ERR_UNSUPPORTED, "nx=%lld exceeds the on-chip run kernel limit %lld", (long long)a.nx,
                     (long long)fbr_run_max_nx());
@@ -383,13 +389,15 @@ extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
     a.fl = fl; a.fr = fr; a.fg = fg; a.p0 = p0; a.p0_stride = p0_stride; a.M = M; a.nx = nx;              \
     a.n_steps = n_steps; a.lbc = lbc; a.rbc = rbc; a.src_idx = src_idx; a.n_src = n_src;                  \
     a.src_table = src_table; a.snapshot_every = snapshot_every; a.snap_models = snap_models;              \
-    a.n_snap_models = n_snap_models; a.snap = snap; a.p_final = p_final; a.obs_idx = obs_idx;             \
+    a.n_snap_models = n_snap_models; a.snap_row_stride = snap_row_stride;                                  \
+    a.snap_model_stride = snap_model_stride; a.snap = snap; a.p_final = p_final; a.obs_idx = obs_idx;             \
     a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit;
 
 extern "C" int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,
                            int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
                            const int64_t *src_idx, int n_src, const double *src_table, int64_t snapshot_every,
-                           const int64_t *snap_models, int64_t n_snap_models, double *snap, double *p_final,
+                           const int64_t *snap_models, int64_t n_snap_models, int64_t snap_row_stride,
+                           int64_t snap_model_stride, double *snap, double *p_final,
                            const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
                            double *misfit, void *stream) {
     FBR_FILL_ARGS();
@@ -399,7 +407,8 @@ extern "C" int fbr_run_f64(const double *fl, const double *fr, const double *fg,
 extern "C" int fbr_run_f32(const double *fl, const double *fr, const double *fg, const double *p0,
                            int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
                            const int64_t *src_idx, int n_src, const double *src_table, int64_t snapshot_every,
-                           const int64_t *snap_models, int64_t n_snap_models, float *snap, float *p_final,
+                           const int64_t *snap_models, int64_t n_snap_models, int64_t snap_row_stride,
+                           int64_t snap_model_stride, float *snap, float *p_final,
                            const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
                            double *misfit, void *stream) {
     FBR_FILL_ARGS();

@@ -189,10 +189,8 @@ class PDS1D_Ensemble:
 
         self.taxis = np.array(taxis)
         self.audit_models = audit
-        if n_audit and snap_d is not None:
-            rows = snap_d.permute(1, 0, 2).cpu().numpy().astype(np.float64, copy=False)
-            first = np.stack([(self.initial if self.initial.ndim == 1 else self.initial[a]) for a in audit])
-            self.snapshot = np.concatenate([first[:, None, :], rows], axis=1)
+        if n_audit and snap_d is not None:  # (n_audit, n_t, nx), row 0 = initial, straight from the kernel
+            self.snapshot = _engine.to_host(snap_d).astype(np.float64, copy=False)
         else:
             self.snapshot = None
         if misfit_d is not None:

@@ -281,10 +281,13 @@ class PDS1D_SingleSource:
             table_d = _engine.to_device(table)
             snap_d, _, _ = _engine.run(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                                        snapshot_every=every, dtype=dtype)
-            rows = snap_d[:, 0, :].cpu().numpy().astype(np.float64, copy=False)
+            if snap_d is None:  # snapshot_every > n_steps: only the initial state is kept
+                self.snapshot = initial[None, :].copy()
+            else:  # (1, rows + 1, nx) with row 0 = initial, written in place by the kernel
+                self.snapshot = _engine.to_host(snap_d[0]).astype(np.float64, copy=False)
         else:
             rows = self._jacobi_loop(dl, d, du, p0_d, sidx_d, n_src, table, n_steps, every)
-        self.snapshot = np.concatenate([initial[None, :], rows], axis=0)
+            self.snapshot = np.concatenate([initial[None, :], rows], axis=0)
         kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
         self.taxis = np.array(taxis)[kept] if every > 1 else np.array(taxis)
         self.record_log(f"{n_steps} full steps solved on device (dt={dt}, mode={mode}, dtype={dtype}). "

@@ -107,9 +107,12 @@ int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64
  * (src/fiberis/simulator/solver/matbuilder.py:45-76).
  *   p0          : (M, nx) with stride nx or shared (nx) with p0_stride 0
  *   src_table   : (n_steps, n_src) value of source k at the START of step n (host: np.interp)
- *   snap        : NULL, or ((n_steps / snapshot_every), n_snap_models, nx): state after steps
- *                 snapshot_every, 2*snapshot_every, ... of the models listed in snap_models
- *                 (int64 (n_snap_models); NULL = all M models, n_snap_models must then be M)
+ *   snap        : NULL, or the buffer that receives the state after steps snapshot_every,
+ *                 2*snapshot_every, ... of the models listed in snap_models (int64 (n_snap_models);
+ *                 NULL = all M models, n_snap_models must then be M).  Sample r of recorded model
+ *                 q, cell i goes to snap[r * snap_row_stride + q * snap_model_stride + i] (strides
+ *                 in elements), so the caller chooses (time, model, cell) or (model, time, cell)
+ *                 order and can reserve a leading row for the initial state by offsetting snap.
  *   p_final     : NULL or (M, nx): state after the last step
  *   obs_idx/obs/obs_w/misfit : fused objective (NULL obs_idx disables it):
  *                 misfit[m] = sum_{n=1..n_steps} sum_k obs_w[k] (p^n[m, obs_idx[k]] - obs[n, k])^2
@@ -121,14 +124,14 @@ int fbr_run_f64(const double *fl, const double *fr, const double *fg, const doub
                 int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
                 const int64_t *src_idx, int n_src, const double *src_table,
                 int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
-                double *snap, double *p_final, const int64_t *obs_idx, int n_obs,
+                int64_t snap_row_stride, int64_t snap_model_stride, double *snap, double *p_final, const int64_t *obs_idx, int n_obs,
                 const double *obs, const double *obs_w, double *misfit, void *stream);
 
 int fbr_run_f32(const double *fl, const double *fr, const double *fg, const double *p0,
                 int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
                 const int64_t *src_idx, int n_src, const double *src_table,
                 int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
-                float *snap, float *p_final, const int64_t *obs_idx, int n_obs,
+                int64_t snap_row_stride, int64_t snap_model_stride, float *snap, float *p_final, const int64_t *obs_idx, int n_obs,
                 const double *obs, const double *obs_w, double *misfit, void *stream);
 
 int64_t fbr_run_max_nx(void);
