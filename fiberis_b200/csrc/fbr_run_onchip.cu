@@ -89,16 +89,18 @@ __device__ __forceinline__ void fma_if(float &c, float t, float e, bool cond) {
     asm volatile("{ .reg .pred p; setp.ne.s32 p, %3, 0; @p fma.rn.f32 %0, %1, %0, %2; }" : "+f"(c) : "f"(t), "f"(e), "r"((int)cond));
 }
 
-// per-thread bookkeeping modes
-enum { kNone = 0, kFastZero = 1, kFast = 2, kSlow = 3 };
+__device__ const double kZero = 0.0;
 constexpr unsigned kSlotNone = 0xFF, kSlotZero = 0xFE;
 
 template <typename T, int CPT, int W>
 __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchip_kernel(const RunArgs a) {
     static_assert(CPT <= 8, "slot bytes are packed into one 64-bit word");
-    // [0] forward {T_w, E_w} pairs, [1] backward pairs; T = warp-total multiplier (time-invariant),
-    // E = this step's zero-carry warp-end value
-    __shared__ T s_pair[2][W][2];
+    // cross-warp carry: C_w = sum_v K[dir][w][v] * E[dir][v], K = products of the warp-total
+    // multipliers between warp v and warp w (time-invariant, zero where warp v does not feed warp w),
+    // E = this step's zero-carry warp-end values
+    __shared__ __align__(16) T s_K[2][W][W];
+    __shared__ __align__(16) T s_E[2][W];
+    __shared__ T s_T[2][W];
     __shared__ double s_red[W];
     __shared__ long long s_snap_slot;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -121,10 +123,12 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
             }
         }
         // Which of my cells are overridden in the right-hand side / observed?  The common case — at
-        // most one of each per thread — is handled with one register index (ov_j / ob_j); threads
-        // owning several (adjacent sources, a source next to a boundary) take a slow generic path.
-        int ov_mode = kNone, ov_j = 0, ob_mode = kNone, ob_j = 0;
-        const double *ovp = a.src_table, *obp = a.obs;
+        // most one of each per thread — is a register index (ov_j / ob_j, -1 = none) plus a pointer
+        // that walks down a column of src_table / obs; a boundary row reads a constant zero with
+        // stride 0.  Threads owning several such cells take a slow generic path.
+        int ov_j = -1, ob_j = -1, ov_stride = 0, ob_stride = 0;
+        bool ov_slow = false, ob_slow = false;
+        const double *ovp = &kZero, *obp = &kZero;
         if (cell0 < nx) {
             uint64_t ov = ~0ull;  // one slot byte per owned cell
             if (cell0 == 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~0xFFull) | kSlotZero;
@@ -142,21 +146,22 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
                 if (so != kSlotNone) {
                     ++n_ov; ov_j = j;
-                    ov_mode = so == kSlotZero ? kFastZero : kFast;
-                    if (so != kSlotZero) ovp = a.src_table + so;
+                    if (so != kSlotZero) { ovp = a.src_table + so; ov_stride = a.n_src; }
+                    else { ovp = &kZero; ov_stride = 0; }
                 }
             }
 #pragma unroll 1
             for (int k = 0; k < a.n_obs; ++k) {
                 const int64_t jj = a.obs_idx[k] - cell0;
                 if (jj >= 0 && jj < CPT && a.obs_idx[k] < nx) {
-                    ++n_ob; ob_j = (int)jj; ob_mode = kFast;
+                    ++n_ob; ob_j = (int)jj; ob_stride = a.n_obs;
                     obp = a.obs + a.n_obs + k;  // row 1 = state after the first step
                 }
             }
-            if (n_ov > 1) ov_mode = kSlow;
-            if (n_ob > 1) ob_mode = kSlow;
+            if (n_ov > 1) { ov_slow = true; ov_j = -1; ovp = &kZero; ov_stride = 0; }
+            if (n_ob > 1) { ob_slow = true; ob_j = -1; obp = &kZero; ob_stride = 0; }
         }
+        const double ob_w = (ob_j >= 0 && a.obs_w) ? a.obs_w[(obp - a.obs) % a.n_obs] : 1.0;
 
         // scan multipliers (time-invariant): stage products of the chunk multipliers; lanes that a
         // stage does not touch get a zero multiplier so the time loop needs no predicates
@@ -182,8 +187,21 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
             if (lane == 31) PbEx = (T)1;
             if (W > 1) {
                 __syncthreads();  // previous model's readers are done with the shared scratch
-                if (lane == 31) s_pair[0][warp][0] = pf;
-                if (lane == 0) s_pair[1][warp][0] = pb;
+                if (lane == 31) s_T[0][warp] = pf;
+                if (lane == 0) s_T[1][warp] = pb;
+                __syncthreads();
+                if (tid < W) {  // row tid of both tables
+                    T k = (T)1;
+                    for (int v = W - 1; v >= 0; --v) {  // forward: warps v < tid feed warp tid
+                        if (v >= tid) s_K[0][tid][v] = (T)0;
+                        else { s_K[0][tid][v] = k; k *= s_T[0][v]; }
+                    }
+                    k = (T)1;
+                    for (int v = 0; v < W; ++v) {  // backward: warps v > tid feed warp tid
+                        if (v <= tid) s_K[1][tid][v] = (T)0;
+                        else { s_K[1][tid][v] = k; k *= s_T[1][v]; }
+                    }
+                }
             }
         }
         // snapshot slot of this model (-1: not recorded)
@@ -201,34 +219,33 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
         const long long snap_slot = s_snap_slot;
         double acc = 0.0;
         const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
-        int snap_countdown = snap_every;
-        T *snap_dst = snap_slot >= 0 ? reinterpret_cast<T *>(a.snap) + snap_slot * a.snap_model_stride + cell0 : nullptr;
+        int snap_countdown = snap_slot >= 0 ? snap_every : 0x7fffffff;  // never reaches 0 when not recorded
+        T *snap_dst = reinterpret_cast<T *>(a.snap) + (snap_slot >= 0 ? snap_slot : 0) * a.snap_model_stride + cell0;
         const int64_t snap_stride = a.snap_row_stride;
-        // per-step scalars are prefetched one step ahead straight from global memory by the (few)
-        // threads that own an overridden / observed cell
-        double ov_val = (ov_mode == kFast && a.n_steps > 0) ? __ldg(ovp) : 0.0;
-        double ob_val = (ob_mode == kFast && a.n_steps > 0) ? __ldg(obp) : 0.0;
+        // per-step scalars are prefetched one step ahead straight from global memory (L2) by the
+        // threads that own an overridden / observed cell; everybody else re-reads a constant
+        double ov_val = a.n_steps > 0 ? __ldg(ovp) : 0.0;
+        double ob_val = a.n_steps > 0 ? __ldg(obp) : 0.0;
 
         // ---------------- time loop ----------------
-        for (int64_t n = 0; n < a.n_steps; ++n) {
-            const bool more = n + 1 < a.n_steps;
-            double ov_next = 0.0, ob_next = 0.0;
-            if (ov_mode == kFast && more) { ovp += a.n_src; ov_next = __ldg(ovp); }
-            if (ob_mode == kFast && more) { obp += a.n_obs; ob_next = __ldg(obp); }
+#pragma unroll 1
+        for (int left = (int)a.n_steps; left > 0; --left) {
+            if (left == 1) { ov_stride = 0; ob_stride = 0; }  // no row after the last one
+            ovp += ov_stride;
+            obp += ob_stride;
+            const double ov_next = __ldg(ovp), ob_next = __ldg(obp);
 
             // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
-            if (ov_mode != kNone) {
-                if (ov_mode != kSlow) {
-                    set_at<T, CPT>(x, ov_j, (T)ov_val);
-                } else {  // several overridden cells in this thread: re-derive them (rare, slow)
-                    if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (T)0;
-                    const int64_t jl = nx - 1 - cell0;
-                    if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) set_at<T, CPT>(x, (int)jl, (T)0);
+            if (ov_j >= 0) set_at<T, CPT>(x, ov_j, (T)ov_val);
+            if (ov_slow) {  // several overridden cells in this thread: re-derive them (rare, slow)
+                const int64_t n = a.n_steps - left;
+                if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (T)0;
+                const int64_t jl = nx - 1 - cell0;
+                if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) set_at<T, CPT>(x, (int)jl, (T)0);
 #pragma unroll 1
-                    for (int k = 0; k < a.n_src; ++k) {
-                        const int64_t jj = a.src_idx[k] - cell0;
-                        if (jj >= 0 && jj < CPT) set_at<T, CPT>(x, (int)jj, (T)__ldg(a.src_table + n * a.n_src + k));
-                    }
+                for (int k = 0; k < a.n_src; ++k) {
+                    const int64_t jj = a.src_idx[k] - cell0;
+                    if (jj >= 0 && jj < CPT) set_at<T, CPT>(x, (int)jj, (T)__ldg(a.src_table + n * a.n_src + k));
                 }
             }
             // ---- forward sweep: y_i = b_i - l_i y_{i-1} ----
@@ -240,11 +257,11 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
             T carry = __shfl_up_sync(kFull, y, 1);
             if (lane == 0) carry = (T)0;
             if (W > 1) {
-                if (lane == 31) s_pair[0][warp][1] = y;
+                if (lane == 31) s_E[0][warp] = y;
                 __syncthreads();
                 T c = (T)0;
 #pragma unroll
-                for (int v = 0; v < W - 1; ++v) fma_if(c, s_pair[0][v][0], s_pair[0][v][1], v < warp);
+                for (int v = 0; v < W - 1; ++v) c = fma_t<T>(s_K[0][warp][v], s_E[0][v], c);
                 carry = fma_t<T>(PfEx, c, carry);
             }
             y = carry;
@@ -262,11 +279,11 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
             carry = __shfl_down_sync(kFull, z, 1);
             if (lane == 31) carry = (T)0;
             if (W > 1) {
-                if (lane == 0) s_pair[1][warp][1] = z;
+                if (lane == 0) s_E[1][warp] = z;
                 __syncthreads();
                 T c = (T)0;
 #pragma unroll
-                for (int v = W - 1; v > 0; --v) fma_if(c, s_pair[1][v][0], s_pair[1][v][1], v > warp);
+                for (int v = 1; v < W; ++v) c = fma_t<T>(s_K[1][warp][v], s_E[1][v], c);
                 carry = fma_t<T>(PbEx, c, carry);
             }
             z = carry;
@@ -276,23 +293,23 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 x[j] = z;
             }
             // ---- fused objective ----
-            if (ob_mode != kNone) {
-                if (ob_mode != kSlow) {  // one observed cell: its weight is applied once, after the loop
-                    const double res = (double)get_at<T, CPT>(x, ob_j) - ob_val;
-                    acc = fma(res, res, acc);
-                } else {
+            if (ob_j >= 0) {  // one observed cell: its weight is applied once, after the loop
+                const double res = (double)get_at<T, CPT>(x, ob_j) - ob_val;
+                acc = fma(res, res, acc);
+            }
+            if (ob_slow) {
+                const int64_t n = a.n_steps - left;
 #pragma unroll 1
-                    for (int k = 0; k < a.n_obs; ++k) {
-                        const int64_t jj = a.obs_idx[k] - cell0;
-                        if (jj >= 0 && jj < CPT) {
-                            const double res = (double)get_at<T, CPT>(x, (int)jj) - __ldg(a.obs + (n + 1) * a.n_obs + k);
-                            acc = fma((a.obs_w ? a.obs_w[k] : 1.0) * res, res, acc);
-                        }
+                for (int k = 0; k < a.n_obs; ++k) {
+                    const int64_t jj = a.obs_idx[k] - cell0;
+                    if (jj >= 0 && jj < CPT) {
+                        const double res = (double)get_at<T, CPT>(x, (int)jj) - __ldg(a.obs + (n + 1) * a.n_obs + k);
+                        acc = fma((a.obs_w ? a.obs_w[k] : 1.0) * res, res, acc);
                     }
                 }
             }
             // ---- sampled snapshot ----
-            if (snap_dst && --snap_countdown == 0) {
+            if (--snap_countdown == 0) {
                 snap_countdown = snap_every;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j)
@@ -311,7 +328,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 if (cell0 + j < nx) dst[j] = x[j];
         }
         if (a.misfit) {
-            if (ob_mode == kFast && a.obs_w) acc *= a.obs_w[(obp - a.obs) % a.n_obs];
+            acc *= ob_w;  // 1 unless this thread took the single-observation fast path with weights
             for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
             if (lane == 0) s_red[warp] = acc;
             __syncthreads();
@@ -352,6 +369,7 @@ static int launch_cpt(const RunArgs &a, cudaStream_t stream) {
 template <typename T>
 static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     FBR_REQUIRE(a.M >= 1 && a.nx >= 1 && a.n_steps >= 0, "M, nx must be >= 1 and n_steps >= 0");
+    FBR_REQUIRE(a.n_steps <= 0x7fffffff, "n_steps per launch is limited to 2^31 - 1");
     FBR_REQUIRE(a.fl && a.fr && a.fg && a.p0, "NULL factor / initial-state pointer");
     FBR_REQUIRE(a.p0_stride == 0 || a.p0_stride >= a.nx, "bad p0_stride");
     FBR_REQUIRE(a.lbc >= 0 && a.lbc <= 2 && a.rbc >= 0 && a.rbc <= 2, "bad boundary code");
