@@ -273,14 +273,20 @@ class PDS1D_SingleSource:
         dl, d, du = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
         p0_d = _engine.to_device(initial[None, :])
         if mode == "implicit":
-            if nx > _engine.run_max_nx():
-                raise NotImplementedError(
-                    f"nx={nx}: meshes longer than {_engine.run_max_nx()} cells need the long-mesh kernel "
-                    "(not built yet in this round).")
             factors = _engine.factorize(dl, d, du)
             table_d = _engine.to_device(table)
-            snap_d, _, _ = _engine.run(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                       snapshot_every=every, dtype=dtype)
+            if nx <= _engine.run_max_nx():  # K3: one CTA keeps the whole model in registers
+                snap_d, _, _ = _engine.run(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                           snapshot_every=every, dtype=dtype)
+            elif nx <= _engine.run_long_max_nx():  # K3L: the mesh is tiled over one cooperative grid
+                if dtype != "float64":
+                    raise NotImplementedError("the long-mesh kernel is fp64 only")
+                snap_d, _ = _engine.run_long(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
+                                             table_d, snapshot_every=every)
+            else:
+                raise NotImplementedError(
+                    f"nx={nx}: meshes longer than {_engine.run_long_max_nx()} cells need the streaming long-mesh "
+                    "kernel (not built yet in this round).")
             if snap_d is None:  # snapshot_every > n_steps: only the initial state is kept
                 self.snapshot = initial[None, :].copy()
             else:  # (1, rows + 1, nx) with row 0 = initial, written in place by the kernel

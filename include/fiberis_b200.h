@@ -136,6 +136,23 @@ int fbr_run_f32(const double *fl, const double *fr, const double *fg, const doub
 
 int64_t fbr_run_max_nx(void);
 
+/* ------------------------------------------------------------------------------------------
+ * K3L the same persistent integration for LONG meshes (fbr_run_max_nx() < nx <=
+ * fbr_run_long_max_nx(), about 6e5 cells on a B200): the mesh is tiled over co-resident CTAs of
+ * one cooperative launch, every cell's pressure and factors stay in registers for all steps, tiles
+ * exchange carries through L2 with one grid barrier per sweep.  Models (M, usually 1) are run one
+ * after the other.  p0: (M, nx).  snap: sample r of model m, cell i at
+ * snap[r * snap_row_stride + m * snap_model_stride + i].  work: fbr_run_long_work_bytes(nx) bytes.
+ * No fused misfit on this path.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fbr_run_long_max_nx(void);
+int64_t fbr_run_long_work_bytes(int64_t nx);
+int fbr_run_long_f64(const double *fl, const double *fr, const double *fg, const double *p0,
+                     int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
+                     const int64_t *src_idx, int n_src, const double *src_table,
+                     int64_t snapshot_every, int64_t snap_row_stride, int64_t snap_model_stride,
+                     double *snap, double *p_final, double *work, void *stream);
+
 /* Running count of kernels this thread has launched through the library (bench.py's
  * gpu_launches is a difference of two readings). */
 int fbr_last_launch_count(void);
