@@ -34,11 +34,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+SINGLE = {
+    # name: (cells, steps, dt, n_src, snapshot_every, seed, description)  -- SURVEY.md 8(d) recipes
+    "c1": (200, 1000, 1.0, 1, 1, 101, "C1: single source, 200 uniform cells x 1000 steps (BASELINE.json configs[0])"),
+    "c2": (100_000, 10_000, 0.5, 8, 100, 202, "C2: 8 sources, variable D, non-uniform mesh, 1e5 cells x 1e4 steps (configs[1])"),
+    "c5": (10_000_000, 1000, 0.5, 16, 100, 505, "C5: long mesh 1e7 cells x 1000 steps, snapshots every 100 (configs[4])"),
+}
 WORKLOADS = {
     # name: (models per GPU, cells, steps, description)
     "c3": (4096, 1024, 5000, "C3: 4096 models x 1024 cells x 5000 steps per GPU (BASELINE.json configs[2])"),
     "c4": (125000, 512, 2000, "C4 shard: 125000 models x 512 cells x 2000 steps per GPU (configs[3] at 8 GPUs)"),
-    "c1": (1, 200, 1000, "C1: single model, 200 cells x 1000 steps (configs[0])"),
 }
 B_ALG = 16.0  # bytes per cell-update, fp64: read p^n + write p^{n+1}
 
@@ -50,14 +55,8 @@ def make_workload(name, world=1):
     M, nx, n_steps, desc = WORKLOADS[name]
     M_per_gpu = M
     M = M * world
-    seed = {"c3": 303, "c4": 404, "c1": 101}[name]
+    seed = {"c3": 303, "c4": 404}[name]
     rng = np.random.default_rng(seed)
-    if name == "c1":
-        mesh = np.linspace(0, 199, 200)
-        return dict(name=name, desc=desc, M=world, M_per_gpu=1, nx=nx, n_steps=n_steps, dt=1.0, mesh=mesh, zones=1,
-                    zone=np.zeros(nx, np.int32), zv=np.ones((world, 1)), sidx=np.array([100]),
-                    srcs=[(np.array([0.0, 500.0, 1000.0]), np.array([0.0, 10.0, 10.0]))],
-                    obs_idx=np.array([50, 150]), audit=[0], seed=seed)
     mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
     T = float(n_steps)
     srcs = [(np.linspace(0, T, 64), rng.uniform(1.0, 10.0, 64)) for _ in range(2)]
@@ -228,7 +227,162 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def run_single_reference_arm(args):
+    """--impl reference for single-model workloads: C1 goes through the reference's dense algorithm; at 1e5 /
+    1e7 cells the reference cannot run at all (dense nx*nx matrix = 80 GB / 800 TB, matbuilder.py:33), so the
+    banded NumPy oracle is timed instead and the line says so."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import pds_oracle as O
+    w = make_single(args.workload)
+    dense = w["nx"] <= 4096
+    ss = w["n_steps"] if dense else max(5, int(2e8 // w["nx"]))
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.solve_fixed(w["mesh"], w["D"], w["initial"], w["lbc"], w["rbc"], w["sidx"], w["srcs"], 0.0, w["dt"],
+                      ss * w["dt"], dense=dense, rebuild_every_step=dense)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    value = w["nx"] * ss / float(np.mean(times))
+    sample = (f"{w['nx']} cells x {ss} steps; " + ("reference algorithm (dense A rebuilt every step + scipy.linalg.solve)"
+              if dense else "reference cannot run at this size (dense nx^2 matrix); banded NumPy oracle (dgttrs per step) timed instead"))
+    print(json.dumps({"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": w["desc"], "seed": w["seed"], "sample": sample},
+                      "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
 # ------------------------------------------------------------------------------------------------
+def make_single(name):
+    nx, n_steps, dt, n_src, every, seed, desc = SINGLE[name]
+    rng = np.random.default_rng(seed)
+    T = n_steps * dt
+    if name == "c1":
+        return dict(name=name, desc=desc, nx=nx, n_steps=n_steps, dt=dt, every=every, seed=seed, T=T,
+                    mesh=np.linspace(0, 199, 200), D=np.ones(nx), initial=np.zeros(nx), lbc="Neumann", rbc="Neumann",
+                    sidx=[100], srcs=[(np.array([0.0, 500.0, 1000.0]), np.array([0.0, 10.0, 10.0]))])
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    D = 10 ** rng.uniform(-1, 1, nx)
+    initial = rng.uniform(0, 1, nx)
+    sidx = [int(round(f * nx)) for f in np.linspace(0.1, 0.9, n_src)]
+    srcs = [(np.linspace(0, T, 64), rng.uniform(-10, 10, 64)) for _ in range(n_src)]
+    return dict(name=name, desc=desc, nx=nx, n_steps=n_steps, dt=dt, every=every, seed=seed, T=T, mesh=mesh, D=D,
+                initial=initial, lbc="Neumann", rbc="Dirichlet", sidx=sidx, srcs=srcs)
+
+
+def build_single(w):
+    from fiberis_b200.analyzer.Data1D.core1D import Data1D
+    from fiberis_b200.simulator.core import pds
+    p = pds.PDS1D_MultiSource()
+    p.set_mesh(w["mesh"])
+    p.set_source([Data1D(data=d, taxis=t) for t, d in w["srcs"]])
+    p.set_bcs(w["lbc"], w["rbc"])
+    p.set_initial(w["initial"])
+    p.set_diffusivity(w["D"])
+    p.set_sourceidx(list(w["sidx"]))
+    p.set_t0(0.0)
+    return p
+
+
+def run_single_gpu_arm(args):
+    """Single-model workloads (C1 / C2 / C5): latency-bound, replicas only (no multi-GPU leg)."""
+    import contextlib
+    import io
+
+    import torch
+
+    from fiberis_b200 import _cabi, _engine as E
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    _cabi.require_cuda()
+    w = make_single(args.workload)
+    nx, n_steps, dt, every = w["nx"], w["n_steps"], w["dt"], w["every"]
+    work = float(nx) * n_steps
+    t_axis = np.arange(n_steps, dtype=np.float64) * dt
+    table = np.ascontiguousarray(np.stack([np.interp(t_axis, st, sd) for st, sd in w["srcs"]], axis=1))
+    mesh_d, D_d, p0_d = E.to_device(w["mesh"]), E.to_device(w["D"]), E.to_device(w["initial"][None, :])
+    sidx_d, n_src = E.index_tensor(np.asarray(w["sidx"]))
+    table_d = E.to_device(table)
+    long_mesh = nx > E.run_max_nx()
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=mesh_d.device)
+
+    def hot_path(ev=None):
+        fac = E.factorize(*E.assemble(mesh_d, D_d, 1, nx, dt, w["lbc"], w["rbc"], sidx_d, n_src), check_singular=False)
+        if ev:
+            ev[0].record()
+        if long_mesh:
+            out = E.run_long(fac, p0_d, 1, nx, n_steps, w["lbc"], w["rbc"], sidx_d, n_src, table_d, snapshot_every=every)[0]
+        else:
+            out = E.run(fac, p0_d, 1, nx, n_steps, w["lbc"], w["rbc"], sidx_d, n_src, table_d, snapshot_every=every)[0]
+        if ev:
+            ev[1].record()
+        return out
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        hot_path()
+    torch.cuda.synchronize()
+    step_ms, k_ms = [], []
+    launches0 = _cabi.launch_count()
+    with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clocks:
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            snap = hot_path((ev[2], ev[3]))
+            ev[1].record()
+            torch.cuda.synchronize()
+            step_ms.append(ev[0].elapsed_time(ev[1]))
+            k_ms.append(ev[2].elapsed_time(ev[3]))
+    launches = _cabi.launch_count() - launches0
+    resident = snap[0].cpu().numpy()
+    p = build_single(w)
+    e2e_s = []
+    for it in range(2 + args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            p.solve(dt=dt, t_total=w["T"], snapshot_every=every)
+        torch.cuda.synchronize()
+        if it >= 2:
+            e2e_s.append(time.perf_counter() - t0)
+    assert np.array_equal(p.snapshot, resident), "e2e and resident legs disagree"
+    peak, peak_src = measured_peak()
+    k_s = float(np.mean(k_ms)) / 1e3
+    achieved = work * B_ALG / k_s / 1e9
+    line = {
+        "metric": "cell-updates/sec (fp64)", "value": work / (float(np.mean(step_ms)) / 1e3), "unit": "cell-updates/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(step_ms)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["desc"], "seed": w["seed"], "cells": nx, "time_steps": n_steps, "snapshot_every": every,
+                   "us_per_time_step": k_s * 1e6 / n_steps, "l2": "flushed between timed iterations (512 MiB memset)",
+                   "timed_kernels": "K1 assemble + K1b factorize + " + ("K3L run_coop" if long_mesh else "K3 run_onchip")},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(args.workload), "kernel": "run_coop_kernel" if long_mesh else "run_onchip_kernel",
+                     "kernel_ms": k_s * 1e3, "peak_source": peak_src,
+                     "note": "single latency-bound system: the roofline fraction is quoted, not a target (SURVEY 8(d))"},
+        "e2e": {"value": work / float(np.mean(e2e_s)), "unit": "cell-updates/s",
+                "h2d_bytes_per_step": int(3 * 8 * nx + table.nbytes + 8 * n_src),
+                "d2h_bytes_per_step": int(p.snapshot.nbytes), "api": "PDS1D_MultiSource.solve(host arrays) -> snapshot ndarray"},
+        "gpu_launches": int(launches), "clocks": clocks.summary(),
+    }
+    if not args.no_cpu:
+        from oracle import c_oracle as CO
+        ss = n_steps if nx * n_steps <= 4e8 else max(10, int(4e8 // nx))
+        t0 = time.perf_counter()
+        CO.run(w["mesh"], w["D"], w["initial"], ss, dt, w["lbc"], w["rbc"], w["sidx"], table[:ss], every=0)
+        el = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nx * ss / el, "unit": "cell-updates/s", "cores": 1, "kind": "port",
+                                "sample": f"{nx} cells x {ss} steps of the same model, banded C oracle (one system is "
+                                          f"sequential: 1 thread), {el:.1f} s"}
+    print(json.dumps(line))
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -384,9 +538,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + sorted(SINGLE))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    if args.workload in SINGLE:
+        if args.impl == "reference":
+            run_single_reference_arm(args)
+        elif int(os.environ.get("RANK", "0")) == 0:
+            run_single_gpu_arm(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
         return

@@ -32,7 +32,8 @@ SIGNATURES = {
     "fbr_assemble_f64": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
     "fbr_assemble_zonal_f64": (_i32, [_p, _p, _i32, _p, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
     "fbr_pml_sigma_f64": (_i32, [_p, _i64, _f64, _f64, _p, _p]),
-    "fbr_factorize_f64": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
+    "fbr_factorize_work_bytes": (_i64, [_i64, _i64]),
+    "fbr_factorize_f64": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "fbr_run_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "fbr_run_f32": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "fbr_run_max_nx": (_i64, []),

@@ -92,8 +92,11 @@ def factorize(dl, d, du, check_singular=True):
     M, nx = d.shape
     out = torch.empty((3, M, nx), dtype=torch.float64, device=d.device)
     flags = torch.zeros(M, dtype=torch.int32, device=d.device)
+    work = None
+    if nx >= 512 and nx > 8 * M:  # long systems: cell-parallel factorisation needs scratch
+        work = torch.empty(int(lib.fbr_factorize_work_bytes(M, nx)) // 8, dtype=torch.float64, device=d.device)
     check(lib.fbr_factorize_f64(ptr(dl), ptr(d), ptr(du), M, nx, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(flags),
-                                current_stream()))
+                                ptr(work), current_stream()))
     if check_singular:
         raise_if_singular(flags, "model")
     return out[0], out[1], out[2]

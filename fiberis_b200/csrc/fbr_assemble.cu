@@ -1,4 +1,4 @@
-// K1 fused coefficient assembly, K1b time-invariant factorisation, right-hand side, K5 error norms.
+// K1 fused coefficient assembly, right-hand side, K5 error norms (K1b lives in fbr_factorize.cu).
 // All bandwidth-trivial one-off kernels (they run once per dt, the time loop is in fbr_run_onchip.cu).
 #include <stdarg.h>
 
@@ -112,30 +112,6 @@ __global__ void __launch_bounds__(256) assemble_kernel(const double *__restrict_
     }
 }
 
-// K1b: one thread per model, sequential elimination (run once per dt).
-__global__ void __launch_bounds__(128) factorize_kernel(const double *__restrict__ dl, const double *__restrict__ d,
-                                                        const double *__restrict__ du, int64_t M, int64_t nx,
-                                                        double *__restrict__ fl, double *__restrict__ fr,
-                                                        double *__restrict__ fg, int32_t *__restrict__ singular) {
-    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    const int64_t o = m * nx;
-    double u_prev = 1.0, c_prev = 0.0;
-    int32_t bad = 0;
-    for (int64_t i = 0; i < nx; ++i) {
-        const double a = dl[o + i], b = d[o + i], c = du[o + i];
-        const double l = (i == 0) ? 0.0 : a / u_prev;
-        const double u = b - l * c_prev;
-        if (!bad && (u == 0.0 || !isfinite(u))) bad = (int32_t)(i + 1);
-        fl[o + i] = l;
-        fr[o + i] = 1.0 / u;
-        fg[o + i] = c / u;
-        u_prev = u;
-        c_prev = c;
-    }
-    if (singular) singular[m] = bad;
-}
-
 __global__ void __launch_bounds__(256) rhs_kernel(const double *__restrict__ p, int64_t M, int64_t nx, int lbc,
                                                   int rbc, const int64_t *__restrict__ src_idx, int n_src,
                                                   const double *__restrict__ src_val, double *__restrict__ b) {
@@ -232,16 +208,6 @@ extern "C" int fbr_pml_sigma_f64(const double *mesh, int64_t nx, double pml_thic
     pml_sigma_kernel<<<grid_for(nx, 256, f.sm_count), 256, 0, as_stream(stream)>>>(mesh, nx, pml_thickness, sigma_max,
                                                                                  sigma);
     return check_launch("fbr_pml_sigma_f64");
-}
-
-extern "C" int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64_t M, int64_t nx,
-                                 double *fl, double *fr, double *fg, int32_t *singular, void *stream) {
-    FBR_REQUIRE(M >= 1 && nx >= 1, "M and nx must be >= 1");
-    FBR_REQUIRE(dl && d && du && fl && fr && fg, "NULL array argument");
-    const int block = M >= 128 * 148 ? 128 : 32;
-    factorize_kernel<<<(unsigned)((M + block - 1) / block), block, 0, as_stream(stream)>>>(dl, d, du, M, nx, fl, fr,
-                                                                                          fg, singular);
-    return check_launch("fbr_factorize_f64");
 }
 
 extern "C" int fbr_rhs_f64(const double *p, int64_t M, int64_t nx, int lbc, int rbc, const int64_t *src_idx,

@@ -91,12 +91,18 @@ int fbr_pml_sigma_f64(const double *mesh, int64_t nx, double pml_thickness, doub
  * src/fiberis/simulator/core/pds.py:287-310), so the elimination is done once:
  *   u_0 = d_0, l_i = dl_i / u_{i-1}, u_i = d_i - l_i du_{i-1}
  *   fl = l, fr = 1 / u, fg = du / u            (each (M, nx))
+ * work: NULL, or fbr_factorize_work_bytes(M, nx) bytes of scratch; with it, long systems
+ * (nx >= 512 and nx > 8 M) are factorised in parallel along the mesh (scan of 2x2 Moebius
+ * matrices for the pivot in front of every 8-cell chunk, then the plain recurrence inside the
+ * chunk); without it one thread walks each model.
  * singular[m] (int32, may be NULL) receives 1 + the first row with a zero/non-finite pivot, or 0.
  * The Python layer maps a non-zero flag to numpy.linalg.LinAlgError, the exception
  * scipy.linalg.solve raises in the reference (src/fiberis/simulator/solver/PDESolver_IMP.py:28).
  * ------------------------------------------------------------------------------------------ */
+int64_t fbr_factorize_work_bytes(int64_t M, int64_t nx);
 int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64_t M, int64_t nx,
-                      double *fl, double *fr, double *fg, int32_t *singular, void *stream);
+                      double *fl, double *fr, double *fg, int32_t *singular, double *work,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  persistent multi-step integration — replaces the time loop
