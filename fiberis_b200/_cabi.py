@@ -40,6 +40,8 @@ SIGNATURES = {
     "fbr_run_long_max_nx": (_i64, []),
     "fbr_run_long_work_bytes": (_i64, [_i64]),
     "fbr_run_long_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "fbr_run_stream_work_bytes": (_i64, [_i64]),
+    "fbr_run_stream_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _p, _p]),
     "fbr_solve_tridiag_work_bytes": (_i64, [_i64, _i64, _i32]),
     "fbr_solve_tridiag_f64": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p]),
     "fbr_rhs_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _i32, _p, _p, _p]),

@@ -173,6 +173,30 @@ def run_long(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, s
     return snap, p_final
 
 
+def run_stream(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, want_final=False,
+               with_initial_row=True):
+    """K3S: streaming integration of one very long mesh.  factors / p0: (1, nx).  Returns
+    (snap (1, rows, nx) | None, p_final | None)."""
+    torch = _torch()
+    lib = _cabi.load()
+    fl, fr, fg = factors
+    dev = fl.device
+    n_rows = n_steps // snapshot_every if snapshot_every else 0
+    snap = snap_ptr = None
+    lead = 1 if with_initial_row else 0
+    if n_rows > 0:
+        snap = torch.empty((1, n_rows + lead, nx), dtype=torch.float64, device=dev)
+        if lead:
+            snap[:, 0, :] = p0
+        snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * 8)
+    p_final = torch.empty((1, nx), dtype=torch.float64, device=dev) if want_final else None
+    work = torch.empty(int(lib.fbr_run_stream_work_bytes(nx)) // 8, dtype=torch.float64, device=dev)
+    check(lib.fbr_run_stream_f64(ptr(fl), ptr(fr), ptr(fg), ptr(p0), nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
+                                 ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), nx, snap_ptr,
+                                 ptr(p_final), ptr(work), current_stream()))
+    return snap, p_final
+
+
 class _PinnedPool:
     """Page-locked host buffers for device->host result copies.  cudaHostAlloc costs ~0.6 ms/MB, so
     buffers are kept and handed out again once the NumPy array that aliased them has been

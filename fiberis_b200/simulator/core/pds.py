@@ -278,15 +278,16 @@ class PDS1D_SingleSource:
             if nx <= _engine.run_max_nx():  # K3: one CTA keeps the whole model in registers
                 snap_d, _, _ = _engine.run(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                                            snapshot_every=every, dtype=dtype)
-            elif nx <= _engine.run_long_max_nx():  # K3L: the mesh is tiled over one cooperative grid
+            elif nx <= min(_engine.run_long_max_nx(), int(kwargs.get("_stream_above", 1 << 62))):  # K3L: tiled over one cooperative grid
                 if dtype != "float64":
                     raise NotImplementedError("the long-mesh kernel is fp64 only")
                 snap_d, _ = _engine.run_long(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
                                              table_d, snapshot_every=every)
-            else:
-                raise NotImplementedError(
-                    f"nx={nx}: meshes longer than {_engine.run_long_max_nx()} cells need the streaming long-mesh "
-                    "kernel (not built yet in this round).")
+            else:  # K3S: state and factors stream from HBM every step
+                if dtype != "float64":
+                    raise NotImplementedError("the long-mesh kernels are fp64 only")
+                snap_d, _ = _engine.run_stream(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                               snapshot_every=every)
             if snap_d is None:  # snapshot_every > n_steps: only the initial state is kept
                 self.snapshot = initial[None, :].copy()
             else:  # (1, rows + 1, nx) with row 0 = initial, written in place by the kernel

@@ -159,6 +159,21 @@ int fbr_run_long_f64(const double *fl, const double *fr, const double *fg, const
                      int64_t snapshot_every, int64_t snap_row_stride, int64_t snap_model_stride,
                      double *snap, double *p_final, double *work, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K3S the same integration for ONE model whose mesh does not fit on chip (nx >
+ * fbr_run_long_max_nx(); BASELINE.json configs[4], 1e7 cells).  State and factors stream from HBM
+ * every step through a hierarchy of chunked linear recurrences (thread per 32-cell chunk,
+ * chunk-interleaved layout, coalesced), see csrc/fbr_run_stream.cu.  Same argument meaning as
+ * fbr_run_long_f64 with M = 1; work: fbr_run_stream_work_bytes(nx) bytes.  Launches O(n_steps)
+ * kernels on `stream`.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fbr_run_stream_work_bytes(int64_t nx);
+int fbr_run_stream_f64(const double *fl, const double *fr, const double *fg, const double *p0,
+                       int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx,
+                       int n_src, const double *src_table, int64_t snapshot_every,
+                       int64_t snap_row_stride, double *snap, double *p_final, double *work,
+                       void *stream);
+
 /* Running count of kernels this thread has launched through the library (bench.py's
  * gpu_launches is a difference of two readings). */
 int fbr_last_launch_count(void);
