@@ -197,6 +197,32 @@ def run_stream(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, sn
     return snap, p_final
 
 
+def adaptive_max_nx() -> int:
+    return int(_cabi.load().fbr_run_adaptive_max_nx())
+
+
+def run_adaptive(mesh, diffusivity, state, ctrl, lbc, rbc, src_idx, n_src, src_taxis, src_data, src_len, t0, t_total,
+                 tol, adj_tol, safety, p_order, max_dt, min_dt, max_iters, capacity):
+    """One launch of the device-side adaptive loop for M models (state (M, nx), ctrl (M, 2) updated in
+    place).  Returns (snap (M, capacity, nx), taxis (M, capacity), counts (M, 4) int64) on the device."""
+    torch = _torch()
+    lib = _cabi.load()
+    M, nx = state.shape
+    dev = state.device
+    snap = torch.empty((M, capacity, nx), dtype=torch.float64, device=dev)
+    taxis = torch.empty((M, capacity), dtype=torch.float64, device=dev)
+    counts = torch.zeros((M, 4), dtype=torch.int64, device=dev)
+    ms = 0 if mesh.dim() == 1 else nx
+    ds = 0 if diffusivity.dim() == 1 else nx
+    width = int(src_taxis.shape[1]) if n_src else 0
+    check(lib.fbr_run_adaptive_f64(ptr(mesh), ms, ptr(diffusivity), ds, ptr(state), M, nx, BC_CODES[lbc], BC_CODES[rbc],
+                                   ptr(src_idx), n_src, ptr(src_taxis), ptr(src_data), ptr(src_len), width, float(t0),
+                                   float(t_total), ptr(ctrl), float(tol), float(adj_tol), float(safety), float(p_order),
+                                   float(max_dt), float(min_dt), int(max_iters), int(capacity), ptr(snap), ptr(taxis),
+                                   ptr(counts), current_stream()))
+    return snap, taxis, counts
+
+
 class _PinnedPool:
     """Page-locked host buffers for device->host result copies.  cudaHostAlloc costs ~0.6 ms/MB, so
     buffers are kept and handed out again once the NumPy array that aliased them has been

@@ -321,7 +321,67 @@ class PDS1D_SingleSource:
         return torch.stack(rows).cpu().numpy() if rows else np.zeros((0, dl.shape[1]))
 
     def _solve_adaptive(self, dt_init, t_total, kwargs):
-        """Step-doubling loop of reference pds.py:312-336 with device-resident states."""
+        """Step-doubling loop of reference pds.py:312-336.
+
+        Default: the whole loop runs in one persistent kernel per chunk of accepted steps
+        (``fbr_run_adaptive_f64``); only the accepted states come back.  Meshes above its size
+        limit, PML runs, ``print_progress`` and duck-typed sources use the host-driven loop below,
+        which keeps the states on the device and moves one 8-byte error per iteration."""
+        nx = len(self.mesh)
+        device_loop = (nx <= _engine.adaptive_max_nx() and not kwargs.get("print_progress")
+                       and float(kwargs.get("pml_thickness", 0.0)) == 0.0
+                       and all(_uses_stock_interp(s) for s in self._sources())
+                       and kwargs.get("adaptive_on_device", True))
+        if device_loop:
+            return self._solve_adaptive_device(dt_init, t_total, kwargs)
+        return self._solve_adaptive_host(dt_init, t_total, kwargs)
+
+    def _solve_adaptive_device(self, dt_init, t_total, kwargs):
+        import torch
+        nx, mesh_d, diff_d, sidx_d, n_src, _, _ = self._device_model(kwargs)
+        srcs = self._sources()
+        width = max(len(s.taxis) for s in srcs)
+        st = np.zeros((len(srcs), width))
+        sd = np.zeros((len(srcs), width))
+        for k, s in enumerate(srcs):
+            st[k, :len(s.taxis)] = np.asarray(s.taxis, dtype=np.float64)
+            sd[k, :len(s.data)] = np.asarray(s.data, dtype=np.float64)
+        st_d, sd_d = _engine.to_device(st), _engine.to_device(sd)
+        len_d = _engine.to_device(np.array([len(s.taxis) for s in srcs], dtype=np.int32), np.int32)
+        initial = np.asarray(self.initial, dtype=np.float64)
+        state = _engine.to_device(initial[None, :])
+        ctrl = _engine.to_device(np.array([[float(self.t0), float(dt_init)]]))
+        tol = kwargs.get("tol", 1e-3)
+        adj = dict(safety=kwargs.get("safety_factor", 0.9), p_order=kwargs.get("p", 2), max_dt=kwargs.get("max_dt", 40),
+                   min_dt=kwargs.get("min_dt", 1e-4))
+        budget = kwargs.get("max_iterations")
+        capacity = int(max(16, min(4096, (64 << 20) // (8 * nx))))
+        self.record_log("Start to solve the problem.")
+        rows, times, used, accepted = [initial[None, :]], [np.array([float(self.t0)])], 0, 0
+        while True:
+            per_launch = 200000 if budget is None else max(0, min(200000, budget - used))
+            snap, tax, counts = _engine.run_adaptive(mesh_d, diff_d, state, ctrl, self.lbc, self.rbc, sidx_d, n_src,
+                                                     st_d, sd_d, len_d, self.t0, t_total, tol, 1e-3, adj["safety"],
+                                                     adj["p_order"], adj["max_dt"], adj["min_dt"], per_launch, capacity)
+            n_rows, n_it, done, bad = (int(v) for v in counts[0].tolist())
+            if bad:
+                raise np.linalg.LinAlgError(f"Matrix is singular (zero pivot at row {bad - 1}).")
+            if n_rows:
+                rows.append(snap[0, :n_rows].cpu().numpy())
+                times.append(tax[0, :n_rows].cpu().numpy())
+            used += n_it
+            accepted += n_rows
+            if done or (budget is not None and used >= budget):
+                break
+            if n_rows == 0 and n_it >= per_launch:
+                raise RuntimeError("Adaptive time stepping made no progress in 200000 iterations (the step-doubling "
+                                   "error is NaN or above tol at min_dt); the reference loops forever in this case.")
+        self.snapshot = np.concatenate(rows, axis=0)
+        self.taxis = np.concatenate(times)
+        self.record_log(f"Dynamic time sampling on device: {accepted} steps accepted, {used - accepted} rejected, "
+                        f"final dt = {float(ctrl[0, 1])}")
+
+    def _solve_adaptive_host(self, dt_init, t_total, kwargs):
         import torch
         nx, mesh_d, diff_d, sidx_d, n_src, pml, smax = self._device_model(kwargs)
         self.snapshot = [self.initial]

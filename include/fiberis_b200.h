@@ -191,6 +191,30 @@ int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, c
                           double *x, int64_t M, int64_t nx, int variant, double *work,
                           int32_t *singular, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-side adaptive time stepping: the step-doubling loop of PDS1D_*.solve(optimizer=True)
+ * (src/fiberis/simulator/core/pds.py:312-336) with the controller of
+ * src/fiberis/simulator/optimizer/tso.py:4-50, one CTA per model, no host round trip per
+ * iteration.  Sources are sampled on the device with np.interp semantics from their own series:
+ * src_taxis / src_data: (n_src, src_width) rows padded to src_width, src_len: (n_src) int32.
+ *   state : (M, nx) in/out current pressure;  ctrl: (M, 2) in/out = (t, dt)
+ *   tol   : accept threshold; adj_tol: the tol adjust_dt uses (the reference never forwards the
+ *           user's tol to adjust_dt, so callers pass 1e-3); safety, p_order, max_dt, min_dt as in tso
+ *   snap  : (M, capacity, nx) accepted states in order; taxis_out: (M, capacity) their times
+ *   counts: (M, 4) int64 out = accepted rows, iterations used, done (t >= t_total), 1 + zero-pivot row
+ * The kernel returns when `capacity` rows are filled, t >= t_total or max_iters iterations ran;
+ * call again with the same state / ctrl to continue.  nx <= fbr_run_adaptive_max_nx(); no PML.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fbr_run_adaptive_max_nx(void);
+int fbr_run_adaptive_f64(const double *mesh, int64_t mesh_stride, const double *diffusivity,
+                         int64_t diff_stride, double *state, int64_t M, int64_t nx, int lbc, int rbc,
+                         const int64_t *src_idx, int n_src, const double *src_taxis,
+                         const double *src_data, const int32_t *src_len, int src_width, double t0,
+                         double t_total, double *ctrl, double tol, double adj_tol, double safety,
+                         double p_order, double max_dt, double min_dt, int64_t max_iters,
+                         int64_t capacity, double *snap, double *taxis_out, int64_t *counts,
+                         void *stream);
+
 /* Right-hand side of one step, b = p with boundary / source overrides
  * (src/fiberis/simulator/solver/matbuilder.py:45-76).  src_val: (n_src) DEVICE values shared by
  * all models.  b may alias p. */
