@@ -22,6 +22,26 @@ constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kCoopCPT = 8;
 constexpr int kCoopW = 4;
 constexpr int kCoopTile = 32 * kCoopW * kCoopCPT;  // cells per CTA
+constexpr int kRing = 16;      // published tile-end values are kept for this many steps
+constexpr int kMaxP2P = 12;    // widest carry horizon served by point-to-point flags (else grid barrier)
+
+// Flagged 16-byte message (the "LL" idea of collective libraries): a double travels as two 8-byte
+// words, each carrying half of the value and the 32-bit step number.  8-byte stores are atomic, so a
+// reader that sees the expected step in BOTH words has the whole value — no fences on either side.
+__device__ __forceinline__ void ll_publish(ulonglong2 *slot, double v, unsigned step) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    ulonglong2 m;
+    m.x = (bits & 0xffffffffull) | ((unsigned long long)step << 32);
+    m.y = (bits >> 32) | ((unsigned long long)step << 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(m.x), "l"(m.y) : "memory");
+}
+__device__ __forceinline__ double ll_wait(const ulonglong2 *slot, unsigned step) {
+    unsigned long long a, b;
+    do {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(slot) : "memory");
+    } while ((unsigned)(a >> 32) != step || (unsigned)(b >> 32) != step);
+    return __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+}
 
 struct CoopArgs {
     const double *fl, *fr, *fg;  // (nx) factors of this model
@@ -35,7 +55,7 @@ struct CoopArgs {
     double *snap;  // (n_steps / snapshot_every, nx) rows of this model, or NULL
     int64_t snap_row_stride;
     double *p_final;  // (nx) or NULL
-    double *work;     // 4 * n_tiles doubles: E[2][n_tiles], Ttile[2][n_tiles]
+    double *work;     // Ttile[2][n_tiles], E[2][n_tiles], message ring[2][kRing][n_tiles] (16 B each), max horizon
     int n_tiles;
 };
 
@@ -60,8 +80,10 @@ __global__ void __launch_bounds__(32 * kCoopW, 4) run_coop_kernel(const CoopArgs
     const int tile = blockIdx.x, n_tiles = a.n_tiles;
     const int64_t nx = a.nx;
     const int64_t cell0 = ((int64_t)tile * (32 * W) + tid) * CPT;
-    double *Eg = a.work;                  // [2][n_tiles]
-    double *Tg = a.work + 2 * n_tiles;    // [2][n_tiles]
+    double *Tg = a.work;                                    // [2][n_tiles]
+    double *Eg = a.work + 2 * n_tiles;                      // [2][n_tiles]  (grid-barrier mode)
+    ulonglong2 *ring = reinterpret_cast<ulonglong2 *>(Eg + 2 * n_tiles);  // [2][kRing][n_tiles] flagged messages
+    long long *max_hor = reinterpret_cast<long long *>(ring + 2 * kRing * n_tiles);
     double *Kf = s_row, *Kb = s_row + n_tiles;
 
     // ---------------- setup ----------------
@@ -148,6 +170,8 @@ __global__ void __launch_bounds__(32 * kCoopW, 4) run_coop_kernel(const CoopArgs
             for (int v = 0; v < W; ++v) { tf *= s_T[0][v]; tb *= s_T[1][v]; }
             Tg[tile] = tf;
             Tg[n_tiles + tile] = tb;
+            for (int q = 0; q < 2 * kRing; ++q) ring[q * n_tiles + tile] = make_ulonglong2(0ull, 0ull);
+            if (tile == 0) *max_hor = 0;
         }
     }
     __threadfence();
@@ -174,7 +198,14 @@ __global__ void __launch_bounds__(32 * kCoopW, 4) run_coop_kernel(const CoopArgs
         s_hor[1] = hor;
     }
     __syncthreads();
+    if (tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(max_hor), (unsigned long long)max(s_hor[0], s_hor[1]));
+    __threadfence();
+    grid.sync();
+    // short horizons (the normal case): tiles synchronise point to point through per-tile flags;
+    // otherwise every sweep ends in a grid-wide barrier
+    const bool p2p = *reinterpret_cast<volatile long long *>(max_hor) <= kMaxP2P;
     const int hor_f = s_hor[0], hor_b = s_hor[1];
+    unsigned step = 0;
     const double pre_f = s_pre[0][warp], pre_b = s_pre[1][warp];
 
     const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
@@ -223,14 +254,18 @@ __global__ void __launch_bounds__(32 * kCoopW, 4) run_coop_kernel(const CoopArgs
         double c = 0.0;
 #pragma unroll
         for (int v = 0; v < W - 1; ++v) c = fma(s_K[0][warp][v], s_E[0][v], c);
+        ++step;
+        ulonglong2 *rf = ring + (step % kRing) * n_tiles, *rb = ring + (kRing + step % kRing) * n_tiles;
         if (tid == 32 * W - 1) {  // zero-carry end value of the whole tile
-            Eg[tile] = fma(s_T[0][W - 1], c, y);
-            __threadfence();
+            const double e = fma(s_T[0][W - 1], c, y);
+            if (p2p) ll_publish(rf + tile, e, step);
+            else { Eg[tile] = e; __threadfence(); }
         }
-        grid.sync();
+        if (!p2p) grid.sync();
         if (warp == 0) {  // tile-level carry: dot product over the non-zero horizon of the K row
             double ck = 0.0;
-            for (int d = 1 + lane; d <= hor_f; d += 32) ck = fma(Kf[tile - d], __ldcg(Eg + tile - d), ck);
+            for (int d = 1 + lane; d <= hor_f; d += 32)
+                ck = fma(Kf[tile - d], p2p ? ll_wait(rf + tile - d, step) : __ldcg(Eg + tile - d), ck);
             for (int s = 16; s > 0; s >>= 1) ck += __shfl_xor_sync(kFullMask, ck, s);
             if (lane == 0) s_carry[0] = ck;
         }
@@ -256,13 +291,15 @@ __global__ void __launch_bounds__(32 * kCoopW, 4) run_coop_kernel(const CoopArgs
 #pragma unroll
         for (int v = 1; v < W; ++v) c = fma(s_K[1][warp][v], s_E[1][v], c);
         if (tid == 0) {
-            Eg[n_tiles + tile] = fma(s_T[1][0], c, z);
-            __threadfence();
+            const double e = fma(s_T[1][0], c, z);
+            if (p2p) ll_publish(rb + tile, e, step);
+            else { Eg[n_tiles + tile] = e; __threadfence(); }
         }
-        grid.sync();
+        if (!p2p) grid.sync();
         if (warp == 0) {
             double ck = 0.0;
-            for (int d = 1 + lane; d <= hor_b; d += 32) ck = fma(Kb[tile + d], __ldcg(Eg + n_tiles + tile + d), ck);
+            for (int d = 1 + lane; d <= hor_b; d += 32)
+                ck = fma(Kb[tile + d], p2p ? ll_wait(rb + tile + d, step) : __ldcg(Eg + n_tiles + tile + d), ck);
             for (int s = 16; s > 0; s >>= 1) ck += __shfl_xor_sync(kFullMask, ck, s);
             if (lane == 0) s_carry[1] = ck;
         }
@@ -312,7 +349,7 @@ extern "C" int64_t fbr_run_long_max_nx(void) {
 
 extern "C" int64_t fbr_run_long_work_bytes(int64_t nx) {
     const int64_t tiles = (nx + kCoopTile - 1) / kCoopTile;
-    return 4 * tiles * (int64_t)sizeof(double);
+    return ((4 + 4 * kRing) * tiles + 2) * (int64_t)sizeof(double);
 }
 
 extern "C" int fbr_run_long_f64(const double *fl, const double *fr, const double *fg, const double *p0, int64_t M,
