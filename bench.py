@@ -309,12 +309,22 @@ def run_single_gpu_arm(args):
     long_mesh = nx > E.run_max_nx()
     streaming = nx > E.run_long_max_nx()
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=mesh_d.device)
+    win = {}
 
     def hot_path(ev=None):
         fac = E.factorize(*E.assemble(mesh_d, D_d, 1, nx, dt, w["lbc"], w["rbc"], sidx_d, n_src), check_singular=False)
         if ev:
             ev[0].record()
-        if streaming:
+        plan = None
+        if long_mesh and args.long_mesh != "exact":  # same decision PDS1D_*.solve takes (16-byte D2H inside)
+            horizon = E.decay_horizon(fac)
+            plan = E.window_plan(nx, horizon, every)
+            if plan:
+                win.update(plan, horizon=list(horizon))
+        if plan:
+            out = E.run_window(fac, p0_d, nx, n_steps, w["lbc"], w["rbc"], sidx_d, n_src, table_d, horizon,
+                               snapshot_every=every)[0]
+        elif streaming:
             out = E.run_stream(fac, p0_d, nx, n_steps, w["lbc"], w["rbc"], sidx_d, n_src, table_d, snapshot_every=every)[0]
         elif long_mesh:
             out = E.run_long(fac, p0_d, 1, nx, n_steps, w["lbc"], w["rbc"], sidx_d, n_src, table_d, snapshot_every=every)[0]
@@ -350,7 +360,7 @@ def run_single_gpu_arm(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
-            p.solve(dt=dt, t_total=w["T"], snapshot_every=every)
+            p.solve(dt=dt, t_total=w["T"], snapshot_every=every, long_mesh=args.long_mesh)
         torch.cuda.synchronize()
         if it >= 2:
             e2e_s.append(time.perf_counter() - t0)
@@ -358,16 +368,18 @@ def run_single_gpu_arm(args):
     peak, peak_src = measured_peak()
     k_s = float(np.mean(k_ms)) / 1e3
     achieved = work * B_ALG / k_s / 1e9
+    kname = ("K3W run_window (time-tiled overlapping windows)" if win else "K3S streaming levels" if streaming
+             else "K3L run_coop" if long_mesh else "K3 run_onchip")
     line = {
         "metric": "cell-updates/sec (fp64)", "value": work / (float(np.mean(step_ms)) / 1e3), "unit": "cell-updates/s",
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(step_ms)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["desc"], "seed": w["seed"], "cells": nx, "time_steps": n_steps, "snapshot_every": every,
                    "us_per_time_step": k_s * 1e6 / n_steps, "l2": "flushed between timed iterations (512 MiB memset)",
-                   "timed_kernels": "K1 assemble + K1b factorize + " + ("K3S streaming levels" if streaming else "K3L run_coop" if long_mesh else "K3 run_onchip")},
+                   "timed_kernels": "K1 assemble + K1b factorize + " + kname, "window_plan": win or None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.workload), "kernel": "K3S level kernels (all)" if streaming else "run_coop_kernel" if long_mesh else "run_onchip_kernel",
-                     "achieved_88B": work * 88.0 / k_s / 1e9 if streaming else None,
+                     "traffic": ncu_traffic(args.workload), "kernel": kname,
+                     "achieved_88B": work * 88.0 / k_s / 1e9 if (streaming and not win) else None,
                      "kernel_ms": k_s * 1e3, "peak_source": peak_src,
                      "note": "single latency-bound system: the roofline fraction is quoted, not a target (SURVEY 8(d))"},
         "e2e": {"value": work / float(np.mean(e2e_s)), "unit": "cell-updates/s",
@@ -543,6 +555,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS) + sorted(SINGLE))
+    ap.add_argument("--long-mesh", default="auto", choices=["auto", "windowed", "exact"],
+                    help="long-mesh kernel family for c2 / c5 (PDS1D_*.solve's long_mesh kwarg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.workload in SINGLE:

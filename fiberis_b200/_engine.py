@@ -197,6 +197,57 @@ def run_stream(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, sn
     return snap, p_final
 
 
+def decay_horizon(factors, log2_eps=-80.0, cap=2048):
+    """(forward, backward) decay horizons of a factorisation (one model): how many consecutive
+    multipliers it takes for their product to fall below 2**log2_eps.  One 16-byte D2H read."""
+    torch = _torch()
+    lib = _cabi.load()
+    fl, _, fg = factors
+    nx = fl.shape[-1]
+    hor = torch.zeros(2, dtype=torch.int64, device=fl.device)
+    work = torch.zeros(4, dtype=torch.float64, device=fl.device)
+    check(lib.fbr_decay_horizon_f64(ptr(fl), ptr(fg), nx, float(log2_eps), int(cap), ptr(hor), ptr(work),
+                                    current_stream()))
+    hf, hb = (int(v) for v in hor.tolist())
+    return hf, hb
+
+
+def window_plan(nx, horizon, snapshot_every=0):
+    """What K3W would use for this mesh: dict(warps, steps_per_block, owned, windows), or None when
+    the horizons are too long for windows to pay."""
+    lib = _cabi.load()
+    out = (_cabi.C.c_int64 * 4)()
+    rc = lib.fbr_run_window_plan(int(nx), int(horizon[0]), int(horizon[1]), int(snapshot_every), out)
+    if rc == _cabi.FBR_ERR_UNSUPPORTED:
+        return None
+    check(rc)
+    return dict(warps=int(out[0]), steps_per_block=int(out[1]), owned=int(out[2]), windows=int(out[3]))
+
+
+def run_window(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, horizon, snapshot_every=1,
+               want_final=False, with_initial_row=True):
+    """K3W: time-tiled overlapping windows for one long mesh.  factors / p0: (1, nx).  Returns
+    (snap (1, rows, nx) | None, p_final | None)."""
+    torch = _torch()
+    lib = _cabi.load()
+    fl, fr, fg = factors
+    dev = fl.device
+    n_rows = n_steps // snapshot_every if snapshot_every else 0
+    snap = snap_ptr = None
+    lead = 1 if with_initial_row else 0
+    if n_rows > 0:
+        snap = torch.empty((1, n_rows + lead, nx), dtype=torch.float64, device=dev)
+        if lead:
+            snap[:, 0, :] = p0
+        snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * 8)
+    p_final = torch.empty((1, nx), dtype=torch.float64, device=dev) if want_final else None
+    work = torch.empty(int(lib.fbr_run_window_work_bytes(nx)) // 8, dtype=torch.float64, device=dev)
+    check(lib.fbr_run_window_f64(ptr(fl), ptr(fr), ptr(fg), ptr(p0), nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
+                                 ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), nx, snap_ptr,
+                                 ptr(p_final), int(horizon[0]), int(horizon[1]), ptr(work), current_stream()))
+    return snap, p_final
+
+
 def adaptive_max_nx() -> int:
     return int(_cabi.load().fbr_run_adaptive_max_nx())
 

@@ -278,16 +278,10 @@ class PDS1D_SingleSource:
             if nx <= _engine.run_max_nx():  # K3: one CTA keeps the whole model in registers
                 snap_d, _, _ = _engine.run(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                                            snapshot_every=every, dtype=dtype)
-            elif nx <= min(_engine.run_long_max_nx(), int(kwargs.get("_stream_above", 1 << 62))):  # K3L: tiled over one cooperative grid
-                if dtype != "float64":
-                    raise NotImplementedError("the long-mesh kernel is fp64 only")
-                snap_d, _ = _engine.run_long(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
-                                             table_d, snapshot_every=every)
-            else:  # K3S: state and factors stream from HBM every step
+            else:
                 if dtype != "float64":
                     raise NotImplementedError("the long-mesh kernels are fp64 only")
-                snap_d, _ = _engine.run_stream(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                               snapshot_every=every)
+                snap_d = self._run_long_mesh(factors, p0_d, nx, n_steps, sidx_d, n_src, table_d, every, kwargs)
             if snap_d is None:  # snapshot_every > n_steps: only the initial state is kept
                 self.snapshot = initial[None, :].copy()
             else:  # (1, rows + 1, nx) with row 0 = initial, written in place by the kernel
@@ -303,6 +297,36 @@ class PDS1D_SingleSource:
             for n in range(n_steps):
                 vals = table[n].tolist()
                 print("Time:", taxis[n + 1], "Source term:", vals if self._multi else vals[0])
+
+    def _run_long_mesh(self, factors, p0_d, nx, n_steps, sidx_d, n_src, table_d, every, kwargs):
+        """Meshes that do not fit one CTA.  ``long_mesh`` (additive kwarg): 'auto' (default) takes the
+        time-tiled window kernel K3W when the measured decay horizon of the factors makes it pay,
+        else the exact kernels; 'windowed' insists on K3W (NotImplementedError when the horizon is too
+        long); 'exact' uses only the exact kernels — K3L (cooperative, register-resident) up to its
+        capacity, K3S (streaming) beyond."""
+        which = kwargs.get("long_mesh", "auto")
+        if which not in ("auto", "windowed", "exact"):
+            raise ValueError("long_mesh must be 'auto', 'windowed' or 'exact'.")
+        self.long_mesh_path = None
+        if which != "exact":
+            horizon = _engine.decay_horizon(factors, log2_eps=float(kwargs.get("window_log2_eps", -80.0)))
+            plan = _engine.window_plan(nx, horizon, every)
+            if plan is None and which == "windowed":
+                raise NotImplementedError(f"decay horizon {horizon} is too long for the windowed path")
+            if plan is not None:
+                self.long_mesh_path = dict(kernel="K3W", horizon=horizon, **plan)
+                snap_d, _ = _engine.run_window(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
+                                               table_d, horizon, snapshot_every=every)
+                return snap_d
+        if nx <= min(_engine.run_long_max_nx(), int(kwargs.get("_stream_above", 1 << 62))):
+            self.long_mesh_path = dict(kernel="K3L")  # tiled over one cooperative grid
+            snap_d, _ = _engine.run_long(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
+                                         table_d, snapshot_every=every)
+        else:  # state and factors stream from HBM every step
+            self.long_mesh_path = dict(kernel="K3S")
+            snap_d, _ = _engine.run_stream(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                           snapshot_every=every)
+        return snap_d
 
     def _jacobi_loop(self, dl, d, du, p_d, sidx_d, n_src, table, n_steps, every):
         """mode != 'implicit': one Jacobi solve per step (reference pds.py:296-300)."""

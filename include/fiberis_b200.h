@@ -174,6 +174,36 @@ int fbr_run_stream_f64(const double *fl, const double *fr, const double *fg, con
                        int64_t snap_row_stride, double *snap, double *p_final, double *work,
                        void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K3W the same integration for ONE long mesh through overlapping on-chip WINDOWS with time blocking
+ * (csrc/fbr_run_window.cu).  The sweeps' multipliers decay geometrically, so a window of 2048 / 4096
+ * cells can be advanced s steps on chip and still be exact (to a 2^log2_eps truncation, default
+ * 2^-80, far below fp64 rounding) on all but s*horizon cells at each end; windows overlap by those
+ * halos.  HBM traffic per cell-update is (32 B * window/owned + 8 B) / s instead of 40 B.
+ *
+ * fbr_decay_horizon_f64 measures the horizons of a factorisation: horizon[0] (forward, from fl) and
+ * horizon[1] (backward, from fg) = the smallest H such that EVERY run of >= H consecutive
+ * multipliers has a product below 2^log2_eps (single multipliers may exceed one — the row after a
+ * source row, mesh-spacing jumps — which the kernel bounds rigorously); cap + 1 if that cannot be
+ * established within cap cells.  horizon: DEVICE int64[2]; work: DEVICE double[4].
+ * fbr_run_window_plan reports what the driver will use for a mesh (plan4 = warps per window CTA,
+ * steps per block, owned cells per window, windows) or FBR_ERR_UNSUPPORTED when the horizons are too
+ * long for windows to pay — callers then use the exact K3L / K3S paths.  HOST pointer plan4.
+ * fbr_run_window_f64: arguments as fbr_run_stream_f64 plus the horizons; work:
+ * fbr_run_window_work_bytes(nx) bytes (two state buffers).  Blocks never straddle a snapshot row;
+ * snapshot rows are written in place and serve as the next block's input.
+ * ------------------------------------------------------------------------------------------ */
+int fbr_decay_horizon_f64(const double *fl, const double *fg, int64_t nx, double log2_eps, int cap,
+                          int64_t *horizon, double *work, void *stream);
+int fbr_run_window_plan(int64_t nx, int64_t horizon_fwd, int64_t horizon_bwd,
+                        int64_t snapshot_every, int64_t *plan4);
+int64_t fbr_run_window_work_bytes(int64_t nx);
+int fbr_run_window_f64(const double *fl, const double *fr, const double *fg, const double *p0,
+                       int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx,
+                       int n_src, const double *src_table, int64_t snapshot_every,
+                       int64_t snap_row_stride, double *snap, double *p_final,
+                       int64_t horizon_fwd, int64_t horizon_bwd, double *work, void *stream);
+
 /* Running count of kernels this thread has launched through the library (bench.py's
  * gpu_launches is a difference of two readings). */
 int fbr_last_launch_count(void);
