@@ -19,11 +19,13 @@
 // Nothing is approximated beyond the 2^-80 truncation, and the path is only taken when the measured
 // horizon is short enough (fbr_run_window_plan); otherwise the exact long-mesh kernels (K3L / K3S) run.
 #include "fbr_common.cuh"
+#include "fbr_sweep.cuh"
 
 namespace fbr {
 
 constexpr unsigned kFullW = 0xffffffffu;
 constexpr int kWinCPT = 8;
+constexpr int kWinList = 64;  // sources per window kept in shared memory (more: global scan)
 
 struct WinArgs {
     const double *fl, *fr, *fg;  // (nx) factors
@@ -33,6 +35,8 @@ struct WinArgs {
     int64_t own, lead;  // owned cells per window; window k starts at cell k * own - lead
     int n_steps;        // steps in this block
     int nbf, nbb;       // number of preceding / following warps that can still reach a warp's carry
+    int64_t n_win;      // windows in the mesh
+    int aligned;        // all four per-cell arrays are 16-byte aligned (asynchronous staging allowed)
     int lbc, rbc;
     const int64_t *src_idx;
     int n_src;
@@ -66,24 +70,112 @@ __device__ __forceinline__ void load8(const double *__restrict__ base, int64_t c
     }
 }
 
-template <int W>
+// 16-byte asynchronous copy global -> shared (no register staging; completion via cp.async groups)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Staging layout of one per-cell array of a window in shared memory: thread t's 8 cells are the
+// 64-byte row t; inside a row the four 16-byte pieces are XOR-swizzled with (t >> 1) & 3, so that a
+// quarter-warp reading "piece j" of its eight rows touches eight different 16-byte bank groups
+// (rows are 64 B apart: unswizzled, LDS.128 would be 4-way bank conflicted).
+__device__ __forceinline__ int swz_piece(int row, int piece) { return row * 4 + (piece ^ ((row >> 1) & 3)); }
+
+// issue the copies of one array of window [win0, win0 + T*8): piece p (16 B) is fetched by thread
+// p % T — fully coalesced 512-byte warp requests — and lands in its consumer's swizzled row
+template <int T>
+__device__ __forceinline__ void stage_array(double *sm, const double *__restrict__ base, int64_t win0, int tid) {
+    const double2 *src = reinterpret_cast<const double2 *>(base + win0);
+    double2 *dst = reinterpret_cast<double2 *>(sm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int piece = i * T + tid;
+        cp_async16(dst + swz_piece(piece >> 2, piece & 3), src + piece);
+    }
+}
+__device__ __forceinline__ void unstage8(const double *sm, int tid, double (&v)[kWinCPT]) {
+    const double2 *src = reinterpret_cast<const double2 *>(sm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double2 t = src[swz_piece(tid, j)];
+        v[2 * j] = t.x;
+        v[2 * j + 1] = t.y;
+    }
+}
+
+// Persistent CTAs: CTA b integrates windows b, b + gridDim.x, ...; while it advances one window
+// through the time block, the next window's pressure and factors stream into shared memory
+// (cp.async), so HBM latency is hidden behind the sweeps.
+// NS = scan stages (5: exact; 3 / 4 when the horizon is <= 64 / 128 cells); NEAR: the horizon fits
+// one warp (256 cells), so a warp's carry comes from its immediate neighbour only.
+template <int W, int NS, bool NEAR>
 __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(const WinArgs a) {
     constexpr int CPT = kWinCPT;
+    constexpr int T = 32 * W;
+    constexpr int WC = T * CPT;  // cells per window
+    extern __shared__ __align__(128) double s_stage[];  // [4][WC]: l, r, g, p of the NEXT window
     __shared__ __align__(16) double s_K[2][W][W];
-    __shared__ __align__(16) double s_E[2][W];
+    __shared__ __align__(16) double s_Ef[W + 1];  // s_Ef[w + 1] = zero-carry end value of warp w; s_Ef[0] = 0
+    __shared__ __align__(16) double s_Eb[W + 1];  // s_Eb[w] = zero-carry first value of warp w; s_Eb[W] = 0
+    __shared__ double s_dummy;                    // where lanes that have nothing to publish store
     __shared__ double s_T[2][W];
+    __shared__ int s_list_n;
+    __shared__ int s_list_k[kWinList];    // sources that fall into this window: slot ...
+    __shared__ int s_list_off[kWinList];  // ... and offset from the window start
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nx = a.nx;
-    const int64_t own0 = (int64_t)blockIdx.x * a.own;
+    // a window can be staged asynchronously when it lies inside the mesh and everything is 16-byte aligned
+    auto stageable = [&](int64_t k) {
+        const int64_t w0 = k * a.own - a.lead;
+        return a.aligned && w0 >= 0 && w0 + WC <= nx;
+    };
+    int64_t k = blockIdx.x;
+    bool staged = k < a.n_win && stageable(k);
+    bool first = true;
+    if (staged) {  // time-invariant inputs of my first window: may run ahead of the previous time block
+        const int64_t w0 = k * a.own - a.lead;
+        stage_array<T>(s_stage, a.fl, w0, tid);
+        stage_array<T>(s_stage + WC, a.fr, w0, tid);
+        stage_array<T>(s_stage + 2 * WC, a.fg, w0, tid);
+        cp_async_commit();
+    }
+
+    for (; k < a.n_win; k += gridDim.x) {
+    const int64_t own0 = k * a.own;
     const int64_t own1 = own0 + a.own < nx ? own0 + a.own : nx;
-    const int64_t cell0 = own0 - a.lead + (int64_t)tid * CPT;
+    const int64_t win0 = own0 - a.lead;
+    const int64_t cell0 = win0 + (int64_t)tid * CPT;
 
     // ---------------- window setup ----------------
+    // Everything up to the grid-dependency wait reads only time-invariant inputs, so under
+    // programmatic dependent launch the first window's setup overlaps the previous time block.
+    if (tid == 0) s_list_n = 0;
     double l[CPT], r[CPT], g[CPT], x[CPT];
-    load8(a.fl, cell0, nx, 0.0, l);
-    load8(a.fr, cell0, nx, 1.0, r);
-    load8(a.fg, cell0, nx, 0.0, g);
-    load8(a.p_in, cell0, nx, 0.0, x);
+    if (staged) {
+        cp_async_wait_all();
+        __syncthreads();
+        unstage8(s_stage, tid, l);
+        unstage8(s_stage + WC, tid, r);
+        unstage8(s_stage + 2 * WC, tid, g);
+        if (!first) unstage8(s_stage + 3 * WC, tid, x);
+    } else {
+        load8(a.fl, cell0, nx, 0.0, l);
+        load8(a.fr, cell0, nx, 1.0, r);
+        load8(a.fg, cell0, nx, 0.0, g);
+    }
+    __syncthreads();
+    for (int q = tid; q < a.n_src; q += T) {  // one parallel pass over the source rows
+        const int64_t s = a.src_idx[q];
+        if (s >= 0 && s < nx && s >= win0 && s < win0 + WC) {
+            const int pos = atomicAdd(&s_list_n, 1);
+            if (pos < kWinList) { s_list_k[pos] = q; s_list_off[pos] = (int)(s - win0); }
+        }
+    }
+    __syncthreads();
+    const int list_n = s_list_n;
 
     // right-hand-side overrides owned by this thread (same scheme as fbr_run_onchip.cu), by GLOBAL cell
     int ov_j = -1, ov_stride = 0;
@@ -95,14 +187,24 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         if (cell0 <= 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~(0xFFull << (8 * (-cell0)))) | ((uint64_t)kZeroSlot << (8 * (-cell0)));
         const int64_t jl = nx - 1 - cell0;
         if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kZeroSlot << (8 * jl));
-        bool wide = false;
+        bool wide = list_n > kWinList;
+        // later duplicates win (matbuilder.py:156-161): the list is unordered, so keep the largest slot
+        auto claim = [&](int q, int jj) {
+            if (q >= 0xFE) wide = true;
+            const unsigned cur = (unsigned)(ov >> (8 * jj)) & 0xFF;
+            if (cur >= 0xFE || (unsigned)q > cur) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)(q & 0xFF) << (8 * jj));
+        };
+        if (list_n <= kWinList) {
+            for (int q = 0; q < list_n; ++q) {
+                const int jj = s_list_off[q] - tid * CPT;
+                if (jj >= 0 && jj < CPT) claim(s_list_k[q], jj);
+            }
+        } else {
 #pragma unroll 1
-        for (int k = 0; k < a.n_src; ++k) {
-            const int64_t s = a.src_idx[k];
-            const int64_t jj = s - cell0;
-            if (jj >= 0 && jj < CPT && s >= 0 && s < nx) {
-                if (k >= 0xFE) wide = true;
-                ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)(k & 0xFF) << (8 * jj));
+            for (int q = 0; q < a.n_src; ++q) {
+                const int64_t s = a.src_idx[q];
+                const int64_t jj = s - cell0;
+                if (jj >= 0 && jj < CPT && s >= 0 && s < nx) claim(q, (int)jj);
             }
         }
         int n_ov = 0;
@@ -119,124 +221,134 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     }
 
     // scan multipliers (time-invariant within the block)
-    double PfL[5], PbL[5], PfEx, PbEx;
-    {
-        double pf = 1.0, pb = 1.0;
+    const HalfProducts hf = half_products_fwd(l), hb = half_products_bwd(g);
+    const ScanMultipliers sm = scan_multipliers(hf.a * hf.b, hb.a * hb.b, lane);
+    double Pf[NS], Pb[NS];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) { pf *= -l[j]; pb *= -g[j]; }
-#pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            const bool fa = lane >= (1 << s), ba = lane + (1 << s) < 32;
-            PfL[s] = fa ? pf : 0.0;
-            PbL[s] = ba ? pb : 0.0;
-            const double upf = __shfl_up_sync(kFullW, pf, 1 << s);
-            const double dnb = __shfl_down_sync(kFullW, pb, 1 << s);
-            if (fa) pf *= upf;
-            if (ba) pb *= dnb;
-        }
-        PfEx = __shfl_up_sync(kFullW, pf, 1);
-        PbEx = __shfl_down_sync(kFullW, pb, 1);
-        if (lane == 0) PfEx = 1.0;
-        if (lane == 31) PbEx = 1.0;
-        if (lane == 31) s_T[0][warp] = pf;
-        if (lane == 0) s_T[1][warp] = pb;
+    for (int s = 0; s < NS; ++s) { Pf[s] = sm.f[s]; Pb[s] = sm.b[s]; }
+    if (!NEAR) {
+        if (lane == 31) s_T[0][warp] = sm.tot_f;
+        if (lane == 0) s_T[1][warp] = sm.tot_b;
         __syncthreads();
         if (tid < W) {
-            double k = 1.0;
+            double kk = 1.0;
             for (int v = W - 1; v >= 0; --v) {
                 if (v >= tid) s_K[0][tid][v] = 0.0;
-                else { s_K[0][tid][v] = k; k *= s_T[0][v]; }
+                else { s_K[0][tid][v] = kk; kk *= s_T[0][v]; }
             }
-            k = 1.0;
+            kk = 1.0;
             for (int v = 0; v < W; ++v) {
                 if (v <= tid) s_K[1][tid][v] = 0.0;
-                else { s_K[1][tid][v] = k; k *= s_T[1][v]; }
+                else { s_K[1][tid][v] = kk; kk *= s_T[1][v]; }
             }
         }
-        __syncthreads();
+    }
+    if (tid == 0) { s_Ef[0] = 0.0; s_Eb[W] = 0.0; }
+    const bool any_slow = __syncthreads_or(ov_slow);
+    if (first) {  // ---- the previous time block's output is needed from here on ----
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+    }
+    if (!staged || first) load8(a.p_in, cell0, nx, 0.0, x);
+    first = false;
+    __syncthreads();  // everybody has emptied the staging buffer: stream the next window in
+    {
+        const int64_t kn = k + gridDim.x;
+        staged = kn < a.n_win && stageable(kn);
+        if (staged) {
+            const int64_t w0 = kn * a.own - a.lead;
+            stage_array<T>(s_stage, a.fl, w0, tid);
+            stage_array<T>(s_stage + WC, a.fr, w0, tid);
+            stage_array<T>(s_stage + 2 * WC, a.fg, w0, tid);
+            stage_array<T>(s_stage + 3 * WC, a.p_in, w0, tid);
+            cp_async_commit();
+        }
     }
     const int vf0 = warp - a.nbf > 0 ? warp - a.nbf : 0;          // forward carry: warps vf0 .. warp-1
     const int vb1 = warp + a.nbb < W - 1 ? warp + a.nbb : W - 1;  // backward carry: warps warp+1 .. vb1
-    const bool near_f = a.nbf == 1, near_b = a.nbb == 1;
+    const unsigned st_f = smem_addr(lane == 31 ? &s_Ef[warp + 1] : &s_dummy), ld_f = smem_addr(&s_Ef[warp]);
+    const unsigned st_b = smem_addr(lane == 0 ? &s_Eb[warp] : &s_dummy), ld_b = smem_addr(&s_Eb[warp + 1]);
+    const int keep_f = lane == 0 ? 0 : -1, keep_b = lane == 31 ? 0 : -1;
     double ov_val = a.n_steps > 0 ? __ldg(ovp) : 0.0;
 
     // ---------------- time loop ----------------
 #pragma unroll 1
     for (int left = a.n_steps; left > 0; --left) {
-        if (left == 1) ov_stride = 0;
-        ovp += ov_stride;
-        const double ov_next = __ldg(ovp);
-        if (ov_j >= 0) {
-#pragma unroll
-            for (int k = 0; k < CPT; ++k) mov_if_eq_w(x[k], ov_val, ov_j, k);
+        if (ov_j >= 0) {  // only the threads that own an overridden cell come here
+            switch (ov_j) {
+                case 0: x[0] = ov_val; break;
+                case 1: x[1] = ov_val; break;
+                case 2: x[2] = ov_val; break;
+                case 3: x[3] = ov_val; break;
+                case 4: x[4] = ov_val; break;
+                case 5: x[5] = ov_val; break;
+                case 6: x[6] = ov_val; break;
+                default: x[7] = ov_val; break;
+            }
+            if (left == 1) ov_stride = 0;
+            ovp += ov_stride;
+            ov_val = __ldg(ovp);  // value for the next step
         }
-        if (ov_slow) {
-            const int64_t n = a.n_steps - left;
-            if (cell0 <= 0 && cell0 + CPT > 0 && a.lbc != FBR_BC_NONE) {
+        if (any_slow) {
+            if (ov_slow) {
+                const int64_t n = a.n_steps - left;
+                if (cell0 <= 0 && cell0 + CPT > 0 && a.lbc != FBR_BC_NONE) {
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) mov_if_eq_w(x[k], 0.0, (int)(-cell0), k);
-            }
-            const int64_t jl = nx - 1 - cell0;
-            if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) {
+                    for (int q = 0; q < CPT; ++q) mov_if_eq_w(x[q], 0.0, (int)(-cell0), q);
+                }
+                const int64_t jl = nx - 1 - cell0;
+                if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) {
 #pragma unroll
-                for (int k = 0; k < CPT; ++k) mov_if_eq_w(x[k], 0.0, (int)jl, k);
-            }
+                    for (int q = 0; q < CPT; ++q) mov_if_eq_w(x[q], 0.0, (int)jl, q);
+                }
 #pragma unroll 1
-            for (int q = 0; q < a.n_src; ++q) {
-                const int64_t s = a.src_idx[q];
-                const int64_t jj = s - cell0;
-                if (jj >= 0 && jj < CPT && s >= 0 && s < nx) {
-                    const double v = __ldg(a.src_table + n * a.n_src + q);
+                for (int q = 0; q < a.n_src; ++q) {
+                    const int64_t s = a.src_idx[q];
+                    const int64_t jj = s - cell0;
+                    if (jj >= 0 && jj < CPT && s >= 0 && s < nx) {
+                        const double v = __ldg(a.src_table + n * a.n_src + q);
 #pragma unroll
-                    for (int k = 0; k < CPT; ++k) mov_if_eq_w(x[k], v, (int)jj, k);
+                        for (int u = 0; u < CPT; ++u) mov_if_eq_w(x[u], v, (int)jj, u);
+                    }
                 }
             }
         }
-        // ---- forward sweep ----
-        double y = 0.0;
+        // ---- forward sweep: y_i = b_i - l_i y_{i-1}, then t_i = r_i y_i ----
+        {
+            double ya;
+            double y = chunk_end_fwd(x, l, hf.b, ya);
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) y = fma(-l[j], y, x[j]);
-#pragma unroll
-        for (int s = 0; s < 5; ++s) y = fma(PfL[s], __shfl_up_sync(kFullW, y, 1 << s), y);
-        double carry = __shfl_up_sync(kFullW, y, 1);
-        if (lane == 0) carry = 0.0;
-        if (lane == 31) s_E[0][warp] = y;
-        __syncthreads();
-        double c = 0.0;
-        if (near_f) {
-            if (warp > 0) c = s_E[0][warp - 1];
-        } else {
-            for (int v = vf0; v < warp; ++v) c = fma(s_K[0][warp][v], s_E[0][v], c);
+            for (int s = 0; s < NS; ++s) y = fma(Pf[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+            const double carry = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
+            sts_f64(st_f, y);
+            __syncthreads();
+            double c;
+            if (NEAR) {
+                c = lds_f64(ld_f);
+            } else {
+                c = 0.0;
+                for (int v = vf0; v < warp; ++v) c = fma(s_K[0][warp][v], s_Ef[v + 1], c);
+            }
+            chunk_apply_fwd(x, l, r, hf.a, ya, fma(sm.ex_f, c, carry));
         }
-        y = fma(PfEx, c, carry);
+        // ---- backward sweep: x_i = t_i - g_i x_{i+1} ----
+        {
+            double za;
+            double z = chunk_end_bwd(x, g, hb.b, za);
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            y = fma(-l[j], y, x[j]);
-            x[j] = r[j] * y;
+            for (int s = 0; s < NS; ++s) z = fma(Pb[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+            const double carry = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+            sts_f64(st_b, z);
+            __syncthreads();
+            double c;
+            if (NEAR) {
+                c = lds_f64(ld_b);
+            } else {
+                c = 0.0;
+                for (int v = vb1; v > warp; --v) c = fma(s_K[1][warp][v], s_Eb[v], c);
+            }
+            chunk_apply_bwd(x, g, hb.a, za, fma(sm.ex_b, c, carry));
         }
-        // ---- backward sweep ----
-        double z = 0.0;
-#pragma unroll
-        for (int j = CPT - 1; j >= 0; --j) z = fma(-g[j], z, x[j]);
-#pragma unroll
-        for (int s = 0; s < 5; ++s) z = fma(PbL[s], __shfl_down_sync(kFullW, z, 1 << s), z);
-        carry = __shfl_down_sync(kFullW, z, 1);
-        if (lane == 31) carry = 0.0;
-        if (lane == 0) s_E[1][warp] = z;
-        __syncthreads();
-        c = 0.0;
-        if (near_b) {
-            if (warp < W - 1) c = s_E[1][warp + 1];
-        } else {
-            for (int v = vb1; v > warp; --v) c = fma(s_K[1][warp][v], s_E[1][v], c);
-        }
-        z = fma(PbEx, c, carry);
-#pragma unroll
-        for (int j = CPT - 1; j >= 0; --j) {
-            z = fma(-g[j], z, x[j]);
-            x[j] = z;
-        }
-        ov_val = ov_next;
     }
 
     // ---------------- write back the owned cells ----------------
@@ -252,6 +364,7 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
             if (i >= own0 && i < own1) dst[j] = x[j];
         }
     }
+    }  // windows of this CTA
 }
 
 // ---- decay horizon of the factors ----------------------------------------------------------------
@@ -368,7 +481,9 @@ static bool plan_window(int64_t nx, int64_t Hf, int64_t Hb, int64_t max_s, int s
         if (force_w && W != force_w) continue;
         const int64_t wc = 32 * (int64_t)W * kWinCPT;
         const int resident = (W >= 16 ? 1 : 2) * sm_count;
-        const double t_step = W >= 16 ? 1.0 : 0.55, t_fixed = W >= 16 ? 4.0 : 3.0, t_launch = 2.5;
+        // us per window: fixed (load / setup / store) + per time step; measured on B200 (C2 / C5 sweeps,
+        // profiles/r01_k3w_sweep.txt).  Dependent launches hide the launch gap.
+        const double t_step = W >= 16 ? 0.58 : 0.46, t_fixed = W >= 16 ? 3.6 : 3.0, t_launch = 0.3;
         for (int64_t s = 1; s <= max_s; ++s) {
             if (force_s && s != force_s) continue;
             const int64_t own = wc - s * (hf + hb);
@@ -451,6 +566,20 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
     a.src_idx = src_idx; a.n_src = n_src;
     a.nbf = (int)((horizon_fwd + warp_span - 1) / warp_span); if (a.nbf < 1) a.nbf = 1;
     a.nbb = (int)((horizon_bwd + warp_span - 1) / warp_span); if (a.nbb < 1) a.nbb = 1;
+    const bool no_pdl = getenv("FBR_WIN_NO_PDL") != nullptr;  // tuning aid
+    a.n_win = pl.n_win;
+    const size_t smem = 4 * (size_t)(32 * pl.W * kWinCPT) * sizeof(double);  // staging: l, r, g, p of one window
+    // kernel variant: how many scan stages the horizon needs, and whether carries stop at the neighbouring warp
+    const int64_t hmax = horizon_fwd > horizon_bwd ? horizon_fwd : horizon_bwd;
+    const bool near = a.nbf == 1 && a.nbb == 1 && !getenv("FBR_WIN_GENERAL");
+    const int ns = !near ? 5 : hmax <= 64 ? 3 : hmax <= 128 ? 4 : 5;
+    void (*kern)(const WinArgs) = nullptr;
+    if (pl.W >= 16) kern = !near ? run_window_kernel<16, 5, false> : ns == 3 ? run_window_kernel<16, 3, true>
+                           : ns == 4 ? run_window_kernel<16, 4, true> : run_window_kernel<16, 5, true>;
+    else kern = !near ? run_window_kernel<8, 5, false> : ns == 3 ? run_window_kernel<8, 3, true>
+                : ns == 4 ? run_window_kernel<8, 4, true> : run_window_kernel<8, 5, true>;
+    FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t resident = (int64_t)(pl.W >= 16 ? 1 : 2) * f.sm_count;  // persistent CTAs, one wave
     double *buf[2] = {work, work + nx};
     const double *cur = p0;
     int64_t n = 0, snap_row = 0;
@@ -470,8 +599,22 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
         else { out = buf[which]; which ^= 1; }
         a.p_in = cur; a.p_out = out; a.n_steps = (int)len;
         a.src_table = src_table ? src_table + n * n_src : nullptr;
-        if (pl.W >= 16) run_window_kernel<16><<<(unsigned)pl.n_win, 512, 0, st>>>(a);
-        else run_window_kernel<8><<<(unsigned)pl.n_win, 256, 0, st>>>(a);
+        // every block but the first is a programmatic dependent launch: its factor loads and setup
+        // overlap the previous block's tail (the first one must see the caller's earlier work whole)
+        auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+        // asynchronous staging pays when a CTA walks several windows; a lone window loads directly
+        a.aligned = pl.n_win > resident && al16(fl) && al16(fr) && al16(fg) && al16(cur);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(pl.n_win < resident ? pl.n_win : resident));
+        cfg.blockDim = dim3(pl.W >= 16 ? 512 : 256);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (n > 0 && !no_pdl) ? 1 : 0;
+        FBR_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
         if (int rc = check_launch("fbr_run_window_f64")) return rc;
         if (at_snap) ++snap_row;
         if (at_end && at_snap && p_final)
