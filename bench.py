@@ -433,7 +433,8 @@ def run_gpu_arm(args):
     obs_idx_d, n_obs = E.index_tensor(w["obs_idx"])
     audit_d, n_audit = E.index_tensor(np.asarray(my_audit, dtype=np.int64))
     # observations = member 0's pressure at the observation cells (untimed set-up run on the device)
-    f0 = E.factorize(*E.assemble_zonal(mesh_d, zv0_d, zone_d, 1, nx, dt, "Neumann", "Neumann", sidx_d, n_src))
+    f0 = E.factorize(*E.assemble_zonal(mesh_d, zv0_d, zone_d, 1, nx, dt, "Neumann", "Neumann", sidx_d, n_src),
+                     parallel=False)  # the same per-model recurrence the batched run uses: bit-identical factors
     snap0, _, _ = E.run(f0, p0_d, 1, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1)
     obs_d = snap0[0][:, obs_idx_d].contiguous()  # (n_steps + 1, n_obs); row 0 (initial state) is unused
     obs_host = obs_d.cpu().numpy()

@@ -85,15 +85,19 @@ def pml_sigma(mesh, pml_thickness, sigma_max):
     return out
 
 
-def factorize(dl, d, du, check_singular=True):
-    """K1b: time-invariant factors (fl, fr, fg); raises LinAlgError on a zero pivot."""
+def factorize(dl, d, du, check_singular=True, parallel=None):
+    """K1b: time-invariant factors (fl, fr, fg); raises LinAlgError on a zero pivot.
+    ``parallel``: None = pick by shape; False = always the sequential per-model recurrence (bit-stable
+    across batch sizes); True = the cell-parallel variant (needs nx >= 512)."""
     torch = _torch()
     lib = _cabi.load()
     M, nx = d.shape
     out = torch.empty((3, M, nx), dtype=torch.float64, device=d.device)
     flags = torch.zeros(M, dtype=torch.int32, device=d.device)
     work = None
-    if nx >= 512 and nx > 8 * M:  # long systems: cell-parallel factorisation needs scratch
+    if parallel is None:
+        parallel = nx >= 512 and nx > 8 * M
+    if parallel and nx >= 512:  # long systems: cell-parallel factorisation needs scratch
         work = torch.empty(int(lib.fbr_factorize_work_bytes(M, nx)) // 8, dtype=torch.float64, device=d.device)
     check(lib.fbr_factorize_f64(ptr(dl), ptr(d), ptr(du), M, nx, ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(flags),
                                 ptr(work), current_stream()))

@@ -21,6 +21,9 @@
 // Source values and observations are read by the one thread that owns the cell, prefetched one
 // step ahead straight from global memory (L2), so the time loop has no staging code at all.
 #include "fbr_common.cuh"
+#include "fbr_sweep.cuh"
+
+#include <type_traits>
 
 namespace fbr {
 
@@ -49,6 +52,7 @@ struct RunArgs {
     const double *obs;    // (n_steps + 1, n_obs)
     const double *obs_w;  // (n_obs) or NULL
     double *misfit;       // (M)
+    int blk_steps;        // fp64 x8 kernel: time steps per staged block of per-step scalars
 };
 
 template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
@@ -90,7 +94,72 @@ __device__ __forceinline__ void fma_if(float &c, float t, float e, bool cond) {
 }
 
 __device__ const double kZero = 0.0;
+
 constexpr unsigned kSlotNone = 0xFF, kSlotZero = 0xFE;
+
+// Order in which a CTA walks the models.  A recorded model (snapshots every few steps) takes about
+// twice as long as the others, so a recorded model picked up in the last round would be the tail of
+// the whole launch (C3: +3.5 ms of 27).  With A recorded models (short lists only) and G CTAs:
+//   round 0 : the A CTAs at the END of the grid integrate one recorded model each, the other G - A
+//             CTAs take the first G - A unrecorded models;
+//   later   : unrecorded models are dealt G at a time, the A "recorded" CTAs LAST in every deal, so
+//             they are the ones that go without when the final deal is short.
+// preset: snapshot slot of the model (-1 none), or -2 = look it up (long lists, no reordering).
+struct ModelCursor {
+    int64_t n_rec, j_rec, k, p, n_plain;
+    bool round0;
+};
+__device__ __forceinline__ bool recorded_before(const RunArgs &a, int64_t q) {  // duplicate of an earlier entry?
+    for (int64_t e = 0; e < q; ++e)
+        if (a.snap_models[e] == a.snap_models[q]) return true;
+    return false;
+}
+__device__ __forceinline__ ModelCursor model_cursor(const RunArgs &a) {
+    ModelCursor c;
+    const int64_t G = gridDim.x, cp = G - 1 - blockIdx.x;
+    c.n_rec = (a.snap && a.snap_models && a.n_snap_models <= 16 && a.n_snap_models < G) ? a.n_snap_models : 0;
+    if (c.n_rec == 0) {
+        c.j_rec = 0; c.k = blockIdx.x; c.p = 0; c.round0 = false; c.n_plain = a.M;
+        return c;
+    }
+    int64_t distinct = 0;
+    for (int64_t q = 0; q < c.n_rec; ++q) distinct += !recorded_before(a, q);
+    c.n_plain = a.M - distinct;
+    c.j_rec = cp < c.n_rec ? cp : c.n_rec;
+    c.round0 = cp >= c.n_rec;
+    c.p = c.round0 ? cp - c.n_rec : G - c.n_rec + cp;
+    c.k = c.round0 ? c.p : (G - c.n_rec) + c.p;
+    return c;
+}
+__device__ __forceinline__ bool next_model(const RunArgs &a, ModelCursor &c, int64_t &m, long long &preset) {
+    const int64_t G = gridDim.x;
+    if (c.n_rec == 0) {
+        if (c.k >= a.M) return false;
+        m = c.k;
+        c.k += G;
+        preset = !a.snap ? -1 : !a.snap_models ? (long long)m : -2;
+        return true;
+    }
+    if (c.j_rec < c.n_rec) {
+        m = a.snap_models[c.j_rec];
+        preset = c.j_rec;
+        c.j_rec = c.n_rec;
+        return true;
+    }
+    if (c.k >= c.n_plain) return false;
+    // the k-th model that is not recorded
+    m = c.k;
+    for (;;) {
+        int64_t below = 0;
+        for (int64_t q = 0; q < c.n_rec; ++q) below += (a.snap_models[q] <= m) && !recorded_before(a, q);
+        if (c.k + below == m) break;
+        m = c.k + below;
+    }
+    c.k = c.round0 ? (G - c.n_rec) + c.p : c.k + G;
+    c.round0 = false;
+    preset = -1;
+    return true;
+}
 
 template <typename T, int CPT, int W>
 __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchip_kernel(const RunArgs a) {
@@ -107,7 +176,10 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
     const int64_t nx = a.nx;
     const int64_t cell0 = (int64_t)tid * CPT;
 
-    for (int64_t m = blockIdx.x; m < a.M; m += gridDim.x) {
+    ModelCursor cursor = model_cursor(a);
+    int64_t m;
+    long long preset;
+    while (next_model(a, cursor, m, preset)) {
         // ---------------- per-model setup ----------------
         T l[CPT], r[CPT], g[CPT], x[CPT];
 #pragma unroll
@@ -206,12 +278,11 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
         }
         // snapshot slot of this model (-1: not recorded)
         if (tid == 0) {
-            long long slot = -1;
-            if (a.snap) {
-                if (!a.snap_models) slot = m;
-                else
-                    for (int64_t q = 0; q < a.n_snap_models; ++q)
-                        if (a.snap_models[q] == m) slot = q;
+            long long slot = preset;
+            if (preset == -2) {
+                slot = -1;
+                for (int64_t q = 0; q < a.n_snap_models; ++q)
+                    if (a.snap_models[q] == m) slot = q;
             }
             s_snap_slot = slot;
         }
@@ -342,6 +413,368 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
     }
 }
 
+// ---- fp64, 8 cells per thread: the time loop built from the half-chain sweep blocks ---------------
+// Same algorithm and results as run_onchip_kernel<double, 8, W> (the cross-warp carry stays EXACT:
+// ensemble members are not required to have a short decay horizon), on a register diet so that the
+// loop holds almost nothing but the sweeps:
+//   * which of a thread's cells is overridden / observed, and by which column of src_table / obs, is
+//     one packed 32-bit descriptor; addresses are rebuilt from the step number inside the (divergent)
+//     branch only the owning threads enter;
+//   * snapshots are taken between runs of an inner loop that knows nothing about them;
+//   * threads that own several overridden or observed cells (adjacent sources ...) are served by a
+//     generic path guarded by one CTA-uniform flag.
+constexpr unsigned kDescNone = 0xF;  // "no cell" in a descriptor's cell field
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_k3() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_k3() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// descriptor: [3:0] overridden cell (0xF none)  [11:4] src column (0xFE: constant zero)
+//             [15:12] observed cell (0xF none)  [23:16] obs column
+__device__ __forceinline__ void put_cell(double (&x)[8], unsigned j, double v) {
+    switch (j) {
+        case 0: x[0] = v; break;
+        case 1: x[1] = v; break;
+        case 2: x[2] = v; break;
+        case 3: x[3] = v; break;
+        case 4: x[4] = v; break;
+        case 5: x[5] = v; break;
+        case 6: x[6] = v; break;
+        default: x[7] = v; break;
+    }
+}
+__device__ __forceinline__ double pick_cell(const double (&x)[8], unsigned j) {
+    switch (j) {
+        case 0: return x[0];
+        case 1: return x[1];
+        case 2: return x[2];
+        case 3: return x[3];
+        case 4: return x[4];
+        case 5: return x[5];
+        case 6: return x[6];
+        default: return x[7];
+    }
+}
+
+// One row of a warp's 256 cells to global memory with coalesced stores.  A thread holds 8 consecutive
+// cells; written directly, every store instruction would touch 32 half-filled sectors 64 bytes apart
+// (measured: 2.3 us per recorded row).  Instead the warp transposes through a private shared-memory
+// patch (rows padded to 72 bytes: conflict-free) and each instruction writes 256 contiguous bytes.
+__device__ __forceinline__ void store_row_coalesced(double *__restrict__ row, int64_t warp_cell0, int64_t nx,
+                                                    const double (&x)[8], double *patch, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) patch[lane * 9 + j] = x[j];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = 32 * i + lane;  // cell within the warp's 256
+        const double v = patch[(c >> 3) * 9 + (c & 7)];
+        if (warp_cell0 + c < nx) row[warp_cell0 + c] = v;
+    }
+}
+
+template <int W, int MINB>
+__global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs a) {
+    constexpr int CPT = 8;
+    __shared__ __align__(16) double s_K[2][W][W];
+    __shared__ __align__(16) double s_E[2][W];
+    __shared__ double s_dummy, s_zero;
+    __shared__ double s_T[2][W];
+    __shared__ double s_red[W];
+    __shared__ long long s_snap_slot;
+    extern __shared__ __align__(16) double s_dyn[];  // staged per-step scalars, see the time loop
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nx = a.nx;
+    const int64_t cell0 = (int64_t)tid * CPT;
+    if (tid == 0) s_zero = 0.0;
+    const unsigned st_f = smem_addr(lane == 31 ? &s_E[0][warp] : &s_dummy);
+    const unsigned st_b = smem_addr(lane == 0 ? &s_E[1][warp] : &s_dummy);
+    const int keep_f = lane == 0 ? 0 : -1, keep_b = lane == 31 ? 0 : -1;
+    const int n_steps = (int)a.n_steps;
+
+    ModelCursor cursor = model_cursor(a);
+    int64_t m;
+    long long preset;
+    while (next_model(a, cursor, m, preset)) {
+        // ---------------- per-model setup ----------------
+        double l[CPT], r[CPT], g[CPT], x[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int64_t i = cell0 + j;
+            if (i < nx) {
+                l[j] = __ldg(a.fl + m * nx + i);
+                r[j] = __ldg(a.fr + m * nx + i);
+                g[j] = __ldg(a.fg + m * nx + i);
+                x[j] = __ldg(a.p0 + m * a.p0_stride + i);
+            } else {  // padding cell: identity row, decoupled
+                l[j] = 0.0; r[j] = 1.0; g[j] = 0.0; x[j] = 0.0;
+            }
+        }
+        unsigned desc = kDescNone | (kDescNone << 12);
+        bool ov_slow = false, ob_slow = false;
+        if (cell0 < nx) {
+            uint64_t ov = ~0ull;  // one slot byte per owned cell
+            if (cell0 == 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~0xFFull) | kSlotZero;
+            const int64_t jl = nx - 1 - cell0;
+            if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE)
+                ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kSlotZero << (8 * jl));
+#pragma unroll 1
+            for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win (matbuilder.py:156-161)
+                const int64_t jj = a.src_idx[k] - cell0;
+                if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)k << (8 * jj));
+            }
+            int n_ov = 0, n_ob = 0;
+#pragma unroll 1
+            for (int j = 0; j < CPT; ++j) {
+                const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
+                if (so != kSlotNone) {
+                    ++n_ov;
+                    desc = (desc & ~0xFFFu) | (unsigned)j | (so << 4);
+                }
+            }
+#pragma unroll 1
+            for (int k = 0; k < a.n_obs; ++k) {
+                const int64_t jj = a.obs_idx[k] - cell0;
+                if (jj >= 0 && jj < CPT && a.obs_idx[k] < nx) {
+                    ++n_ob;
+                    desc = (desc & ~0xFFF000u) | ((unsigned)jj << 12) | ((unsigned)k << 16);
+                }
+            }
+            if (n_ov > 1) { ov_slow = true; desc |= kDescNone; }
+            if (n_ob > 1) { ob_slow = true; desc |= kDescNone << 12; }
+        }
+
+        const HalfProducts hf = half_products_fwd(l), hb = half_products_bwd(g);
+        const ScanMultipliers sm = scan_multipliers(hf.a * hf.b, hb.a * hb.b, lane);
+        if (W > 1) {
+            __syncthreads();  // previous model's readers are done with the shared scratch
+            if (lane == 31) s_T[0][warp] = sm.tot_f;
+            if (lane == 0) s_T[1][warp] = sm.tot_b;
+            __syncthreads();
+            if (tid < W) {  // row tid of both tables
+                double k = 1.0;
+                for (int v = W - 1; v >= 0; --v) {  // forward: warps v < tid feed warp tid
+                    if (v >= tid) s_K[0][tid][v] = 0.0;
+                    else { s_K[0][tid][v] = k; k *= s_T[0][v]; }
+                }
+                k = 1.0;
+                for (int v = 0; v < W; ++v) {  // backward: warps v > tid feed warp tid
+                    if (v <= tid) s_K[1][tid][v] = 0.0;
+                    else { s_K[1][tid][v] = k; k *= s_T[1][v]; }
+                }
+            }
+        }
+        if (tid == 0) {
+            long long slot = preset;
+            if (preset == -2) {
+                slot = -1;
+                for (int64_t q = 0; q < a.n_snap_models; ++q)
+                    if (a.snap_models[q] == m) slot = q;
+            }
+            s_snap_slot = slot;
+        }
+        const bool any_slow = __syncthreads_or(ov_slow || ob_slow);
+        const long long snap_slot = s_snap_slot;
+        double acc = 0.0;
+        // Per-step scalars never travel through a global load inside the sweeps: a load in flight across a
+        // sweep shares a scoreboard with its shuffles / shared-memory reads and stalls them (+25 % per
+        // step on B200, scratch/ubench_k3.cu), and a load consumed on the spot exposes L2 latency on
+        // an in-order warp.  Instead the time axis is cut into blocks of `blk` steps:
+        //   * the block's source values and observations stream into shared memory (cp.async) while
+        //     the previous block is integrated;
+        //   * observed pressures are only WRITTEN during the block (a store has no result latency)
+        //     into a trace, and the squared residuals of a whole block are summed cooperatively at
+        //     the next block boundary.
+        const bool has_ov = (desc & 0xF) != kDescNone, has_ob = ((desc >> 12) & 0xF) != kDescNone;
+        const bool ov_zero = ((desc >> 4) & 0xFF) == kSlotZero;
+        const int blk = a.blk_steps;
+        double *s_src = s_dyn;                                  // [2][blk][n_src]
+        double *s_obs = s_src + 2 * blk * a.n_src;              // [2][blk][n_obs]
+        double *s_tr = s_obs + 2 * blk * a.n_obs;               // [2][blk][n_obs]
+        double *s_patch = s_tr + 2 * blk * a.n_obs + warp * (32 * 9);  // [W][32 * 9] row-transposition patches
+        auto stage_block = [&](int b) {  // sources of steps [b blk, ..) and observations of the states after them
+            const int n0 = b * blk;
+            const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
+            if (rows <= 0) return;
+            const int buf = b & 1;
+            for (int e = tid; e < rows * a.n_src; e += 32 * W)
+                cp_async8(s_src + buf * blk * a.n_src + e, a.src_table + (int64_t)n0 * a.n_src + e);
+            for (int e = tid; e < rows * a.n_obs; e += 32 * W)
+                cp_async8(s_obs + buf * blk * a.n_obs + e, a.obs + (int64_t)(n0 + 1) * a.n_obs + e);
+        };
+        auto flush_block = [&](int b) {  // sum of weighted squared residuals of block b
+            const int n0 = b * blk;
+            const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
+            const int buf = b & 1;
+            for (int e = tid; e < rows * a.n_obs; e += 32 * W) {
+                const double res = s_tr[buf * blk * a.n_obs + e] - s_obs[buf * blk * a.n_obs + e];
+                const double wgt = a.obs_w ? __ldg(a.obs_w + e % a.n_obs) : 1.0;
+                acc = fma(wgt * res, res, acc);
+            }
+        };
+        stage_block(0);
+        cp_async_commit_k3();
+        unsigned src_addr = smem_addr(&s_zero), tr_addr = smem_addr(&s_dummy);
+        const unsigned src_inc = (has_ov && !ov_zero) ? 8u * a.n_src : 0u, tr_inc = has_ob ? 8u * a.n_obs : 0u;
+
+        // ---------------- time loop: runs of steps between block boundaries / snapshots ----------------
+        const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
+        int to_snap = snap_slot >= 0 ? snap_every : 0x7fffffff;  // never reaches 0 when not recorded
+        double *snap_row = reinterpret_cast<double *>(a.snap) + (snap_slot >= 0 ? snap_slot : 0) * a.snap_model_stride;
+        int done = 0;
+        while (done < n_steps) {
+            const int b = done / blk;
+            if (done % blk == 0) {  // entering block b (CTA-uniform)
+                cp_async_wait_all_k3();
+                __syncthreads();  // block b's inputs have landed; everybody is done with block b - 1
+                if (b > 0 && a.n_obs > 0) {
+                    flush_block(b - 1);
+                    __syncthreads();  // block b + 1 is staged into the observation buffer just read
+                }
+                stage_block(b + 1);
+                cp_async_commit_k3();
+                const int buf = b & 1;
+                if (has_ov && !ov_zero) src_addr = smem_addr(s_src + buf * blk * a.n_src + ((desc >> 4) & 0xFF));
+                if (has_ob) tr_addr = smem_addr(s_tr + buf * blk * a.n_obs + ((desc >> 16) & 0xFF));
+            }
+            int run = blk - done % blk;
+            if (run > n_steps - done) run = n_steps - done;
+            if (to_snap < run) run = to_snap;
+            // two copies of the step loop: the common one carries no code for threads that own several
+            // overridden / observed cells, which keeps its instruction footprint small
+            auto steps = [&](auto slow_tag, int n_begin, int n_end) {
+                constexpr bool SLOW = decltype(slow_tag)::value;
+#pragma unroll 1
+                for (int n = n_begin; n < n_end; ++n) {
+                    // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
+                    if (has_ov) {  // only the threads that own an overridden cell
+                        set_at<double, CPT>(x, (int)(desc & 0xF), lds_f64(src_addr));
+                        src_addr += src_inc;
+                    }
+                    if (SLOW && ov_slow) {  // several overridden cells in this thread: re-derive them (rare)
+                        if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = 0.0;
+                        const int64_t jl = nx - 1 - cell0;
+                        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) put_cell(x, (unsigned)jl, 0.0);
+#pragma unroll 1
+                        for (int k = 0; k < a.n_src; ++k) {
+                            const int64_t jj = a.src_idx[k] - cell0;
+                            if (jj >= 0 && jj < CPT) put_cell(x, (unsigned)jj, __ldg(a.src_table + (int64_t)n * a.n_src + k));
+                        }
+                    }
+                    // ---- forward sweep: y_i = b_i - l_i y_{i-1}, t_i = r_i y_i ----
+                    {
+                        double ya;
+                        double y = chunk_end_fwd(x, l, hf.b, ya);
+#pragma unroll
+                        for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+                        double c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
+                        if (W > 1) {
+                            sts_f64(st_f, y);
+                            __syncthreads();
+                            double cw = 0.0;
+#pragma unroll
+                            for (int v = 0; v < W - 1; ++v) cw = fma(s_K[0][warp][v], s_E[0][v], cw);
+                            c = fma(sm.ex_f, cw, c);
+                        }
+                        chunk_apply_fwd(x, l, r, hf.a, ya, c);
+                    }
+                    // ---- backward sweep: x_i = t_i - g_i x_{i+1} ----
+                    {
+                        double za;
+                        double z = chunk_end_bwd(x, g, hb.b, za);
+#pragma unroll
+                        for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+                        double c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+                        if (W > 1) {
+                            sts_f64(st_b, z);
+                            __syncthreads();
+                            double cw = 0.0;
+#pragma unroll
+                            for (int v = 1; v < W; ++v) cw = fma(s_K[1][warp][v], s_E[1][v], cw);
+                            c = fma(sm.ex_b, cw, c);
+                        }
+                        chunk_apply_bwd(x, g, hb.a, za, c);
+                    }
+                    // ---- fused objective: record the observed pressure (non-observers hit the dummy slot) ----
+                    sts_f64(tr_addr, get_at<double, CPT>(x, (int)((desc >> 12) & 0x7)));
+                    tr_addr += tr_inc;
+                    if (SLOW && ob_slow) {
+#pragma unroll 1
+                        for (int k = 0; k < a.n_obs; ++k) {
+                            const int64_t jj = a.obs_idx[k] - cell0;
+                            if (jj >= 0 && jj < CPT) {
+                                const double res = pick_cell(x, (unsigned)jj) - __ldg(a.obs + (int64_t)(n + 1) * a.n_obs + k);
+                                acc = fma((a.obs_w ? a.obs_w[k] : 1.0) * res, res, acc);
+                            }
+                        }
+                    }
+                }
+            };
+            if (any_slow) steps(std::true_type{}, done, done + run);
+            else steps(std::false_type{}, done, done + run);
+            done += run;
+            to_snap -= run;
+            // ---- sampled snapshot ----
+            if (to_snap == 0) {
+                to_snap = snap_every;
+                store_row_coalesced(snap_row, (int64_t)warp * 256, nx, x, s_patch, lane);
+                snap_row += a.snap_row_stride;
+            }
+        }
+        cp_async_wait_all_k3();
+        __syncthreads();
+        if (n_steps > 0 && a.n_obs > 0) flush_block((n_steps - 1) / blk);
+
+        // ---------------- per-model epilogue ----------------
+        if (a.p_final)
+            store_row_coalesced(reinterpret_cast<double *>(a.p_final) + m * nx, (int64_t)warp * 256, nx, x, s_patch, lane);
+        if (a.misfit) {
+            for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
+            if (lane == 0) s_red[warp] = acc;
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < W; ++w) tot += s_red[w];
+                a.misfit[m] = tot;
+            }
+        }
+        __syncthreads();  // shared scratch is reused by the next model
+    }
+}
+
+template <int W>
+static int launch_onchip8(const RunArgs &a, cudaStream_t stream) {
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    constexpr int kFull16 = (16 / W) > 0 ? (16 / W) : 1, kRoomy = (12 / W) > 0 ? (12 / W) : 1;
+    auto kern = getenv("FBR_K3_ROOMY") ? run_onchip8_kernel<W, kRoomy> : run_onchip8_kernel<W, kFull16>;
+    RunArgs b = a;
+    const int cols = a.n_src + 2 * a.n_obs;
+    b.blk_steps = cols <= 64 ? 32 : 8;  // keeps the staging area <= 32 KB per CTA
+    const size_t smem = (2 * (size_t)b.blk_steps * (cols > 0 ? cols : 1) + (size_t)W * 32 * 9) * sizeof(double);
+    if (smem > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
+    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d)", 32 * W);
+    int64_t grid = (int64_t)occ * f.sm_count;
+    if (grid > a.M) grid = a.M;
+    kern<<<(unsigned)grid, 32 * W, smem, stream>>>(b);
+    return check_launch("fbr_run (on-chip, fp64 x8)");
+}
+
+static int launch_f64x8(const RunArgs &a, cudaStream_t stream) {
+    const int64_t threads = (a.nx + 7) / 8;
+    if (threads <= 32) return launch_onchip8<1>(a, stream);
+    if (threads <= 64) return launch_onchip8<2>(a, stream);
+    if (threads <= 128) return launch_onchip8<4>(a, stream);
+    if (threads <= 256) return launch_onchip8<8>(a, stream);
+    return launch_onchip8<16>(a, stream);
+}
+
 template <typename T, int CPT, int W>
 static int launch_onchip(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
@@ -388,6 +821,7 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
         const int v = atoi(e);
         if ((v == 1 || v == 2 || v == 4 || v == 8) && (a.nx + v - 1) / v <= 32 * kMaxWarps) cpt = v;
     }
+    if (cpt == 8 && sizeof(T) == sizeof(double) && !getenv("FBR_K3_GENERIC")) return launch_f64x8(a, stream);
     switch (cpt) {
         case 1: return launch_cpt<T, 1>(a, stream);
         case 2: return launch_cpt<T, 2>(a, stream);
@@ -409,7 +843,7 @@ extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
     a.src_table = src_table; a.snapshot_every = snapshot_every; a.snap_models = snap_models;              \
     a.n_snap_models = n_snap_models; a.snap_row_stride = snap_row_stride;                                  \
     a.snap_model_stride = snap_model_stride; a.snap = snap; a.p_final = p_final; a.obs_idx = obs_idx;             \
-    a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit;
+    a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit; a.blk_steps = 0;
 
 extern "C" int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,
                            int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
