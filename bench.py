@@ -97,7 +97,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.first_seen = index, [], None, False
 
     def __enter__(self):
         try:
@@ -106,6 +106,13 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi's start-up (NVML initialisation) holds driver locks for tens of milliseconds and
+            # would stall kernel launches if it overlapped the timed region (seen on the launch-heavy
+            # single-model workloads): wait for its first sample, then count only what follows
+            t_end = time.perf_counter() + 3.0
+            while not self.first_seen and time.perf_counter() < t_end:
+                time.sleep(0.01)
+            self.rows.clear()
         except Exception:
             self.proc = None
         return self
@@ -113,6 +120,7 @@ class ClockSampler:
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+            self.first_seen = True
 
     def __exit__(self, *a):
         if self.proc:
@@ -531,7 +539,7 @@ def run_gpu_arm(args):
                        "timed_kernels": "K1 assemble_zonal + K1b factorize + K3 run_onchip"
                                         + (" + NCCL all-gather of misfits" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload), "kernel": "run_onchip_kernel<double,8>",
+                         "traffic": ncu_traffic(args.workload), "kernel": "run_onchip8_kernel<4> (K3, fp64 x8)",
                          "kernel_ms": k3_s * 1e3, "peak_source": peak_src,
                          "note": "algorithmic 16 B/cell-update; K3 keeps pressure+factors on chip for all time "
                                  "steps, so frac > 1 is expected - see traffic (ncu DRAM bytes per launch)"},

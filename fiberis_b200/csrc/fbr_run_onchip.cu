@@ -603,8 +603,12 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
             const int buf = b & 1;
             for (int e = tid; e < rows * a.n_src; e += 32 * W)
                 cp_async8(s_src + buf * blk * a.n_src + e, a.src_table + (int64_t)n0 * a.n_src + e);
-            for (int e = tid; e < rows * a.n_obs; e += 32 * W)
+            for (int e = tid; e < rows * a.n_obs; e += 32 * W) {
                 cp_async8(s_obs + buf * blk * a.n_obs + e, a.obs + (int64_t)(n0 + 1) * a.n_obs + e);
+                // the trace starts out equal to the observations: a column nobody owns (index outside
+                // the mesh) then contributes exactly nothing
+                cp_async8(s_tr + buf * blk * a.n_obs + e, a.obs + (int64_t)(n0 + 1) * a.n_obs + e);
+            }
         };
         auto flush_block = [&](int b) {  // sum of weighted squared residuals of block b
             const int n0 = b * blk;
@@ -702,14 +706,12 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
                     // ---- fused objective: record the observed pressure (non-observers hit the dummy slot) ----
                     sts_f64(tr_addr, get_at<double, CPT>(x, (int)((desc >> 12) & 0x7)));
                     tr_addr += tr_inc;
-                    if (SLOW && ob_slow) {
+                    if (SLOW && ob_slow) {  // several observed cells in this thread: record each of them
+                        double *row = s_tr + (((n / blk) & 1) * blk + n % blk) * a.n_obs;
 #pragma unroll 1
                         for (int k = 0; k < a.n_obs; ++k) {
                             const int64_t jj = a.obs_idx[k] - cell0;
-                            if (jj >= 0 && jj < CPT) {
-                                const double res = pick_cell(x, (unsigned)jj) - __ldg(a.obs + (int64_t)(n + 1) * a.n_obs + k);
-                                acc = fma((a.obs_w ? a.obs_w[k] : 1.0) * res, res, acc);
-                            }
+                            if (jj >= 0 && jj < CPT) row[k] = pick_cell(x, (unsigned)jj);
                         }
                     }
                 }

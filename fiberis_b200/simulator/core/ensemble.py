@@ -172,7 +172,9 @@ class PDS1D_Ensemble:
         table_d = _engine.to_device(table)
 
         audit = [int(a) for a in audit_models if lo <= int(a) < hi]
-        snap_models_d, n_audit = _engine.index_tensor(np.asarray(audit, dtype=np.int64) - lo) if audit else (None, 0)
+        # the kernel records every listed model once: repeated entries share one recorded slot
+        audit_unique, audit_slot = np.unique(np.asarray(audit, dtype=np.int64), return_inverse=True)
+        snap_models_d, n_audit = _engine.index_tensor(audit_unique - lo) if audit else (None, 0)
         obs_idx_d = obs_d = w_d = None
         n_obs = 0
         if self.obs_idx is not None:
@@ -191,6 +193,8 @@ class PDS1D_Ensemble:
         self.audit_models = audit
         if n_audit and snap_d is not None:  # (n_audit, n_t, nx), row 0 = initial, straight from the kernel
             self.snapshot = _engine.to_host(snap_d).astype(np.float64, copy=False)
+            if len(audit_unique) != len(audit) or np.any(audit_slot != np.arange(len(audit))):
+                self.snapshot = self.snapshot[audit_slot]  # back to the order (and repeats) the caller listed
         else:
             self.snapshot = None
         if misfit_d is not None:

@@ -114,8 +114,10 @@ int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64
  *   p0          : (M, nx) with stride nx or shared (nx) with p0_stride 0
  *   src_table   : (n_steps, n_src) value of source k at the START of step n (host: np.interp)
  *   snap        : NULL, or the buffer that receives the state after steps snapshot_every,
- *                 2*snapshot_every, ... of the models listed in snap_models (int64 (n_snap_models);
- *                 NULL = all M models, n_snap_models must then be M).  Sample r of recorded model
+ *                 2*snapshot_every, ... of the models listed in snap_models (int64 (n_snap_models),
+ *                 no repeated entries; NULL = all M models, n_snap_models must then be M).
+ *                 Recorded models cost about twice as much as the others; short lists (<= 16) are
+ *                 integrated first so that they never form the tail of the launch.  Sample r of recorded model
  *                 q, cell i goes to snap[r * snap_row_stride + q * snap_model_stride + i] (strides
  *                 in elements), so the caller chooses (time, model, cell) or (model, time, cell)
  *                 order and can reserve a leading row for the initial state by offsetting snap.

@@ -39,6 +39,6 @@ def main(name, n_steps, combos):
 if __name__ == "__main__":
     which = sys.argv[1]
     if which == "c2":
-        main("c2", 2000, [(W, s) for W in (8, 16) for s in (1, 2, 4, 5, 10, 20, 25, 50)])
+        main("c2", 2000, [(8, s) for s in (8, 10, 11, 12, 13, 14, 17, 20)] + [(16, s) for s in (20, 25, 30, 33)])
     else:
         main("c5", 200, [(W, s) for W in (8, 16) for s in (1, 2, 4, 5, 10, 20, 25)])

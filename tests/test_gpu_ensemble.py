@@ -113,3 +113,76 @@ def test_sharded_blocks_equal_full_run():
         lo, hi = shard_bounds(101, 4, r)
         parts.append(e.solve(dt=1.0, t_total=c["T"], models=(lo, hi)).copy())
     npt.assert_array_equal(np.concatenate(parts), full)
+
+
+# ---- the fp64 x8 run kernel: staged blocks of per-step scalars, observation trace, model schedule ----
+@pytest.mark.parametrize("n_steps", [1, 31, 32, 33, 64, 65, 100])
+@pytest.mark.parametrize("every", [1, 3, 40])
+def test_x8_block_boundaries_and_snapshot_rows(n_steps, every):
+    """Source values and observations are staged 32 steps at a time and residuals are summed at block
+    boundaries: every alignment of run length, block length and snapshot interval must agree with the
+    oracle, for snapshots and for the fused misfit."""
+    M, nx = 5, 1024
+    e, c = make_ensemble(900 + n_steps, M, nx, n_steps, n_obs=7)
+    rng = np.random.default_rng(n_steps)
+    obs = rng.uniform(-1, 1, (n_steps + 1, 7))
+    w = rng.uniform(0.5, 2.0, 7)
+    e.set_observations(c["obs_idx"], obs, w)
+    mis = e.solve(dt=c["dt"], t_total=c["T"], audit_models=[1, 4], snapshot_every=every)
+    for k, m in enumerate([1, 4]):
+        want, _ = O.solve_fixed(c["mesh"], c["zv"][m][c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                                c["srcs"], 0.0, c["dt"], c["T"])
+        rows = want[::every][: 1 + n_steps // every]
+        if n_steps >= every:  # (a run shorter than the interval records nothing: snapshot is None)
+            assert e.snapshot[k].shape == rows.shape
+            assert G.rel_max(e.snapshot[k], rows) <= 1e-10
+        else:
+            assert e.snapshot is None
+        assert mis[m] == pytest.approx(O.ensemble_misfit(want, c["obs_idx"], obs, w), rel=1e-9)
+
+
+def test_x8_recorded_models_schedule_with_duplicates_and_many_models():
+    """Recorded models are integrated first, by the CTAs at the end of the grid, and skipped in the
+    normal deal; duplicates in the list fill both slots; every other model is still integrated
+    exactly once (its misfit appears) whatever M is relative to the grid."""
+    nx, n_steps = 512, 40
+    for M, audit in [(700, [699, 0, 7, 7, 123]), (40, [39, 38, 0]), (3, [2, 2, 2, 1]), (1300, list(range(0, 1300, 100)))]:
+        e, c = make_ensemble(50 + M, M, nx, n_steps, n_obs=4)
+        obs = np.zeros((n_steps + 1, 4))
+        e.set_observations(c["obs_idx"], obs)
+        mis = e.solve(dt=c["dt"], t_total=c["T"], audit_models=audit).copy()
+        snap = e.snapshot.copy()
+        plain = e.solve(dt=c["dt"], t_total=c["T"])  # no recorded models: the plain deal
+        npt.assert_array_equal(mis, plain)
+        assert np.all(mis > 0)
+        for k, m in enumerate(audit):
+            want, _ = O.solve_fixed(c["mesh"], c["zv"][m][c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                                    c["srcs"], 0.0, c["dt"], c["T"])
+            assert G.rel_max(snap[k], want) <= 1e-10
+            assert mis[m] == pytest.approx(O.ensemble_misfit(want, c["obs_idx"], obs, None), rel=1e-9)
+
+
+def test_x8_several_overrides_and_observations_in_one_thread():
+    """Two sources / two observed cells inside one thread's 8-cell chunk (and a source next to a
+    boundary row) take the generic per-thread path of the x8 kernel."""
+    from fiberis_b200.simulator.core.ensemble import PDS1D_Ensemble
+    rng = np.random.default_rng(77)
+    M, nx, n_steps = 6, 600, 70
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    zone = (np.arange(nx) * 4) // nx
+    zv = 10 ** rng.uniform(-1, 1, (M, 4))
+    T = float(n_steps)
+    sidx = [1, 2, 300, 301, 303, 598]
+    srcs = [(np.linspace(0, T, 9), rng.uniform(-5, 5, 9)) for _ in sidx]
+    e = PDS1D_Ensemble()
+    e.set_mesh(mesh); e.set_source(Mo.sources_of(srcs)); e.set_sourceidx(sidx); e.set_bcs("Dirichlet", "Neumann")
+    e.set_initial(rng.uniform(0, 1, nx)); e.set_zonal_diffusivity(zv, zone)
+    obs_idx = np.array([8, 9, 15, 100, 302, 304, 599])
+    obs = rng.uniform(-1, 1, (n_steps + 1, len(obs_idx)))
+    w = rng.uniform(0.5, 2.0, len(obs_idx))
+    e.set_observations(obs_idx, obs, w)
+    mis = e.solve(dt=1.0, t_total=T, audit_models=[0, 5])
+    for k, m in enumerate([0, 5]):
+        want, _ = O.solve_fixed(mesh, zv[m][zone], e.initial, "Dirichlet", "Neumann", sidx, srcs, 0.0, 1.0, T)
+        assert G.rel_max(e.snapshot[k], want) <= 1e-10
+        assert mis[m] == pytest.approx(O.ensemble_misfit(want, obs_idx, obs, w), rel=1e-9)
