@@ -30,7 +30,9 @@ for i, name in enumerate(h):
 if band:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    h, data = rows[1], rows[2:]
+    hi = [i for i, r in enumerate(rows) if "Instructions Executed" in r][0]
+    h = rows[hi]
+    data = [r for r in rows[hi + 1:] if len(r) == len(h)]
     ie, ws, si = h.index("Instructions Executed"), h.index("Warp Stall Sampling (All Samples)"), h.index("Source")
 
     def f(x):
