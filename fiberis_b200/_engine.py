@@ -247,9 +247,62 @@ def run_window(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, ho
     p_final = torch.empty((1, nx), dtype=torch.float64, device=dev) if want_final else None
     work = torch.empty(int(lib.fbr_run_window_work_bytes(nx)) // 8, dtype=torch.float64, device=dev)
     check(lib.fbr_run_window_f64(ptr(fl), ptr(fr), ptr(fg), ptr(p0), nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
-                                 ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), nx, snap_ptr,
+                                 ptr(src_idx), n_src, ptr(src_table), int(snapshot_every) if snap is not None else 0, nx, snap_ptr,
                                  ptr(p_final), int(horizon[0]), int(horizon[1]), ptr(work), current_stream()))
     return snap, p_final
+
+
+def run_window_to_host(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, horizon, snapshot_every=1):
+    """K3W with the snapshot rows streamed to the host while later time blocks are still being
+    integrated: one library call per snapshot interval, an event after each, and the
+    row's device-to-host copy on a second stream into pooled pinned memory.  Returns the NumPy array
+    (rows + 1, nx), row 0 = initial state; None when no row is due."""
+    torch = _torch()
+    lib = _cabi.load()
+    fl, fr, fg = factors
+    dev = fl.device
+    n_rows = n_steps // snapshot_every if snapshot_every else 0
+    if n_rows == 0:
+        return None
+    import weakref
+    snap = torch.empty((n_rows + 1, nx), dtype=torch.float64, device=dev)
+    snap[0] = p0.reshape(-1)
+    entry = _pool.take(snap.numel() * 8)
+    host = entry[0][: snap.numel() * 8].view(torch.float64).view(snap.shape)
+    work = torch.empty(int(lib.fbr_run_window_work_bytes(nx)) // 8, dtype=torch.float64, device=dev)
+    main, side = torch.cuda.current_stream(), _copy_stream(dev)
+    ev = torch.cuda.Event()
+    ev.record(main)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        host[0].copy_(snap[0], non_blocking=True)
+    for r in range(n_rows):
+        check(lib.fbr_run_window_f64(ptr(fl), ptr(fr), ptr(fg), _cabi.C.c_void_p(snap[r].data_ptr()), nx, snapshot_every,
+                                     BC_CODES[lbc], BC_CODES[rbc], ptr(src_idx), n_src,
+                                     _cabi.C.c_void_p(src_table.data_ptr() + r * snapshot_every * n_src * 8) if n_src else None,
+                                     int(snapshot_every), nx, None, _cabi.C.c_void_p(snap[r + 1].data_ptr()), int(horizon[0]),
+                                     int(horizon[1]), ptr(work), current_stream()))
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            host[r + 1].copy_(snap[r + 1], non_blocking=True)
+    side.synchronize()
+    main.wait_stream(side)
+    arr = host.numpy()
+    entry[1] = weakref.ref(arr)
+    return arr
+
+
+_side_streams = {}
+
+
+def _copy_stream(dev):
+    torch = _torch()
+    key = (dev.type, dev.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=dev)
+    return _side_streams[key]
 
 
 def adaptive_max_nx() -> int:

@@ -544,19 +544,22 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
     FBR_REQUIRE(fl && fr && fg && p0 && work, "NULL factor / initial-state / work pointer");
     FBR_REQUIRE(lbc >= 0 && lbc <= 2 && rbc >= 0 && rbc <= 2, "bad boundary code");
     FBR_REQUIRE(n_src >= 0 && (n_src == 0 || (src_idx && src_table)), "sources given without src_idx / src_table");
-    FBR_REQUIRE(!snap || (snapshot_every >= 1 && snap_row_stride >= nx), "bad snapshot layout");
+    FBR_REQUIRE(snapshot_every >= 0 && (!snap || (snapshot_every >= 1 && snap_row_stride >= nx)), "bad snapshot layout");
     FBR_REQUIRE(horizon_fwd >= 0 && horizon_bwd >= 0, "bad decay horizon");
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
     cudaStream_t st = as_stream(stream);
     WinPlan pl;
-    const int64_t max_s = snap ? (snapshot_every < 4096 ? snapshot_every : 4096) : 4096;
+    // snapshot_every >= 1 caps the block length even without a snapshot buffer (a caller that streams
+    // rows out itself, one call per interval, then gets the same window geometry — the same bits — as
+    // the single-call path); 0 = no cap
+    const int64_t max_s = snapshot_every >= 1 ? (snapshot_every < 4096 ? snapshot_every : 4096) : 4096;
     if (!plan_window(nx, horizon_fwd, horizon_bwd, max_s, f.sm_count, &pl))
         return fail(FBR_ERR_UNSUPPORTED, "decay horizon (%lld, %lld) is too long for the windowed path",
                     (long long)horizon_fwd, (long long)horizon_bwd);
     // equalise the blocks inside one snapshot interval
     int64_t s_blk = pl.s;
-    if (snap) {
+    if (snapshot_every >= 1) {
         const int64_t nblk = (snapshot_every + s_blk - 1) / s_blk;
         s_blk = (snapshot_every + nblk - 1) / nblk;
     }
@@ -586,7 +589,7 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
     int which = 0;
     while (n < n_steps) {
         int64_t len = s_blk;
-        if (snap) {
+        if (snapshot_every >= 1) {
             const int64_t to_snap = snapshot_every - n % snapshot_every;
             if (len > to_snap) len = to_snap;
         }

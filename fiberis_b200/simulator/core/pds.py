@@ -31,6 +31,19 @@ from fiberis_b200.simulator.optimizer import tso
 _ALLOWED_BC = ["Dirichlet", "Neumann", "None"]
 
 
+def _in_mesh(idx, n) -> bool:
+    """``idx in np.arange(n)`` (the reference's membership test, pds.py:179-181, 478-490) without
+    materialising and scanning an n-element array per source: on a 1e7-cell mesh with 16 sources the
+    literal form costs 130 ms per solve.  Same truth value for every scalar (integral floats count,
+    NaN / negative / fractional do not); anything else falls back to the literal expression."""
+    if np.ndim(idx) == 0:
+        try:
+            return bool(0 <= idx < n and idx == int(idx))
+        except (TypeError, ValueError, OverflowError):
+            pass
+    return idx in np.arange(n)
+
+
 def _uses_stock_interp(src) -> bool:
     """True when ``src`` samples with plain np.interp on (taxis, data), so a whole step table can
     be produced by one vectorised np.interp call with identical results."""
@@ -159,7 +172,7 @@ class PDS1D_SingleSource:
     def _check_sourceidx(self):
         if self.sourceidx is None:
             return False, "Source index is not set."
-        if self.sourceidx not in np.arange(len(self.mesh)):
+        if not _in_mesh(self.sourceidx, len(self.mesh)):
             return False, "Source index is not in the mesh."
         return True, "Source index is properly set."
 
@@ -284,6 +297,8 @@ class PDS1D_SingleSource:
                 snap_d = self._run_long_mesh(factors, p0_d, nx, n_steps, sidx_d, n_src, table_d, every, kwargs)
             if snap_d is None:  # snapshot_every > n_steps: only the initial state is kept
                 self.snapshot = initial[None, :].copy()
+            elif isinstance(snap_d, np.ndarray):  # rows already streamed to the host
+                self.snapshot = snap_d
             else:  # (1, rows + 1, nx) with row 0 = initial, written in place by the kernel
                 self.snapshot = _engine.to_host(snap_d[0]).astype(np.float64, copy=False)
         else:
@@ -315,6 +330,11 @@ class PDS1D_SingleSource:
                 raise NotImplementedError(f"decay horizon {horizon} is too long for the windowed path")
             if plan is not None:
                 self.long_mesh_path = dict(kernel="K3W", horizon=horizon, **plan)
+                # rows of >= 8 MB: stream them to the host while later blocks are integrated
+                if nx * 8 >= (8 << 20) and kwargs.get("stream_rows", True):
+                    self.long_mesh_path["rows"] = "streamed to host"
+                    return _engine.run_window_to_host(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
+                                                      table_d, horizon, snapshot_every=every)
                 snap_d, _ = _engine.run_window(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
                                                table_d, horizon, snapshot_every=every)
                 return snap_d
@@ -540,9 +560,8 @@ class PDS1D_MultiSource(PDS1D_SingleSource):
         for idx in self.sourceidx:  # reference quirk: a raw list of Python ints is rejected; the setter
             if isinstance(idx, int):  # converts to an ndarray afterwards, whose entries are np.int64
                 return False, "Source index must be a list of integers."
-        nodes = np.arange(len(self.mesh))
         for idx in self.sourceidx:
-            if idx not in nodes:
+            if not _in_mesh(idx, len(self.mesh)):
                 return False, "Source index is not in the mesh."
         if self.source is not None and len(self.sourceidx) != len(self.source):
             return False, "Source index and source term length do not match."

@@ -193,7 +193,10 @@ int fbr_run_stream_f64(const double *fl, const double *fr, const double *fg, con
  * long for windows to pay — callers then use the exact K3L / K3S paths.  HOST pointer plan4.
  * fbr_run_window_f64: arguments as fbr_run_stream_f64 plus the horizons; work:
  * fbr_run_window_work_bytes(nx) bytes (two state buffers).  Blocks never straddle a snapshot row;
- * snapshot rows are written in place and serve as the next block's input.
+ * snapshot rows are written in place and serve as the next block's input.  snapshot_every >= 1 caps
+ * the block length (and fixes the window geometry) even when snap is NULL — a caller that streams
+ * rows out itself, one call per interval with p_final = the row, gets bit-identical results;
+ * snapshot_every = 0 (snap must be NULL) lifts the cap.
  * ------------------------------------------------------------------------------------------ */
 int fbr_decay_horizon_f64(const double *fl, const double *fg, int64_t nx, double log2_eps, int cap,
                           int64_t *horizon, double *work, void *stream);
