@@ -205,6 +205,92 @@ class PDS1D_Ensemble:
         return self.misfit
 
 
+    # -- adaptive time stepping, every member with its own dt ------------------------------------------
+    def solve_adaptive(self, dt_init, t_total=None, audit_models=(), models=None, max_iterations=None, **kwargs):
+        """Every member runs the reference's step-doubling loop (``solve(optimizer=True)``,
+        src/fiberis/simulator/core/pds.py:312-336 with src/fiberis/simulator/optimizer/tso.py:4-50)
+        on the device, each with its OWN time step, accept/reject history and time axis — SURVEY.md
+        8(f1).  One CTA per member (``fbr_run_adaptive_f64``), no host round trip per iteration.
+
+        Keyword arguments are the tso ones (``tol``, ``safety_factor``, ``p``, ``max_dt``, ``min_dt``; the
+        user's ``tol`` is not forwarded to ``adjust_dt``, as in the reference).  Returns, and keeps in
+        ``self.adaptive``, a dict: ``final_state (M, nx)``, ``final_time (M,)``, ``final_dt (M,)``, ``accepted (M,)``,
+        ``iterations (M,)``, and for the audited members the ragged ``taxis`` / ``snapshot`` lists (row 0 =
+        initial state).  ``max_iterations`` bounds every member's loop (the reference can spin forever
+        when the error estimate is NaN); a member that stalls without it raises ``RuntimeError``."""
+        import torch
+        M_all = self.n_models
+        if M_all == 0:
+            raise ValueError("No diffusivity set.")
+        nx = len(self.mesh)
+        if nx > _engine.adaptive_max_nx():
+            raise NotImplementedError(f"device-side adaptive stepping covers nx <= {_engine.adaptive_max_nx()}")
+        if t_total is None:
+            t_total = self.source[0].taxis[-1] + self.t0
+        lo, hi = (0, M_all) if models is None else models
+        M = hi - lo
+        mesh_d = _engine.to_device(self.mesh)
+        if self.diffusivity is not None:
+            diff_d = _engine.to_device(self.diffusivity[lo:hi])
+        else:  # zonal members: gather the (M, nx) diffusivity once on the device (buffer plumbing)
+            zone_d = _engine.to_device(self.zone_of_cell, np.int64)
+            diff_d = _engine.to_device(self.zone_value[lo:hi])[:, zone_d].contiguous()
+        sidx_d, n_src = _engine.index_tensor(self.sourceidx)
+        width = max(len(s.taxis) for s in self.source)
+        st, sd = np.zeros((len(self.source), width)), np.zeros((len(self.source), width))
+        for k, src in enumerate(self.source):
+            st[k, :len(src.taxis)] = np.asarray(src.taxis, dtype=np.float64)
+            sd[k, :len(src.data)] = np.asarray(src.data, dtype=np.float64)
+        st_d, sd_d = _engine.to_device(st), _engine.to_device(sd)
+        len_d = _engine.to_device(np.array([len(s.taxis) for s in self.source], dtype=np.int32), np.int32)
+        init = self.initial if self.initial.ndim == 2 else np.broadcast_to(self.initial, (M_all, nx))
+        state = _engine.to_device(np.ascontiguousarray(init[lo:hi]))
+        ctrl = _engine.to_device(np.tile(np.array([[float(self.t0), float(dt_init)]]), (M, 1)))
+        tol = kwargs.get("tol", 1e-3)
+        safety, p_order = kwargs.get("safety_factor", 0.9), kwargs.get("p", 2)
+        max_dt, min_dt = kwargs.get("max_dt", 40), kwargs.get("min_dt", 1e-4)
+        capacity = int(max(4, min(256, (256 << 20) // (8 * nx * M))))
+        audit = [int(a) - lo for a in audit_models if lo <= int(a) < hi]
+        rows = {a: [np.asarray(init[lo + a], dtype=np.float64)[None, :]] for a in audit}
+        times = {a: [np.array([float(self.t0)])] for a in audit}
+        accepted = np.zeros(M, dtype=np.int64)
+        used = np.zeros(M, dtype=np.int64)
+        done = np.zeros(M, dtype=bool)
+        per_launch_cap = 200000
+        while True:
+            left = per_launch_cap if max_iterations is None else int(min(per_launch_cap, max(0, max_iterations - used.min())))
+            snap, tax, counts = _engine.run_adaptive(mesh_d, diff_d, state, ctrl, self.lbc, self.rbc, sidx_d, n_src, st_d,
+                                                     sd_d, len_d, self.t0, t_total, tol, 1e-3, safety, p_order, max_dt,
+                                                     min_dt, left, capacity)
+            c = counts.cpu().numpy()
+            if np.any(c[:, 3]):
+                m = int(np.nonzero(c[:, 3])[0][0])
+                raise np.linalg.LinAlgError(f"Matrix is singular (model {lo + m}: zero pivot at row {int(c[m, 3]) - 1}).")
+            for a in audit:
+                n = int(c[a, 0])
+                if n:
+                    rows[a].append(snap[a, :n].cpu().numpy())
+                    times[a].append(tax[a, :n].cpu().numpy())
+            accepted += c[:, 0]
+            used += c[:, 1]
+            done = c[:, 2] != 0
+            if done.all() or (max_iterations is not None and used.min() >= max_iterations):
+                break
+            stalled = (~done) & (c[:, 0] == 0) & (c[:, 1] >= left)
+            if stalled.any():
+                raise RuntimeError(f"Adaptive time stepping made no progress in {left} iterations for member "
+                                   f"{lo + int(np.nonzero(stalled)[0][0])} (the step-doubling error is NaN or above tol "
+                                   "at min_dt); the reference loops forever in this case.")
+        ctrl_h = ctrl.cpu().numpy()
+        self.adaptive = dict(final_state=state.cpu().numpy(), final_time=ctrl_h[:, 0].copy(), final_dt=ctrl_h[:, 1].copy(),
+                             accepted=accepted, iterations=used, audit_models=[lo + a for a in audit],
+                             taxis=[np.concatenate(times[a]) for a in audit],
+                             snapshot=[np.concatenate(rows[a], axis=0) for a in audit])
+        self.history.append(f"{M} members x {nx} cells solved adaptively on device (dt_init={dt_init}, tol={tol}): "
+                            f"{int(accepted.sum())} accepted / {int(used.sum())} iterations.")
+        return self.adaptive
+
+
 def _dist(process_group):
     try:
         import torch.distributed as dist

@@ -186,3 +186,50 @@ def test_x8_several_overrides_and_observations_in_one_thread():
         want, _ = O.solve_fixed(mesh, zv[m][zone], e.initial, "Dirichlet", "Neumann", sidx, srcs, 0.0, 1.0, T)
         assert G.rel_max(e.snapshot[k], want) <= 1e-10
         assert mis[m] == pytest.approx(O.ensemble_misfit(want, obs_idx, obs, w), rel=1e-9)
+
+
+# ---- adaptive time stepping per ensemble member -------------------------------------
+def test_ensemble_adaptive_every_member_has_its_own_time_axis():
+    M, nx = 24, 300
+    e, c = make_ensemble(61, M, nx, 30)
+    out = e.solve_adaptive(dt_init=0.01, t_total=30.0, tol=2e-3, max_dt=2.0, audit_models=[0, 7, 23])
+    assert out["final_state"].shape == (M, nx) and np.all(out["final_time"] >= 30.0)
+    assert len(set(out["accepted"].tolist())) > 1  # members with different diffusivity take different paths
+    for k, m in enumerate([0, 7, 23]):
+        snap, taxis, n_it = O.solve_adaptive(c["mesh"], c["zv"][m][c["zone"]], np.zeros(nx), "Neumann", "Neumann",
+                                             c["sidx"], c["srcs"], 0.0, 0.01, 30.0, tol=2e-3, max_dt=2.0)
+        assert out["taxis"][k].shape == taxis.shape and out["iterations"][m] == n_it
+        npt.assert_allclose(out["taxis"][k], taxis, rtol=1e-9, atol=0)
+        assert G.rel_max(out["snapshot"][k], snap) <= 1e-9
+        npt.assert_array_equal(out["final_state"][m], out["snapshot"][k][-1])
+        assert out["accepted"][m] == len(taxis) - 1
+    # a member equals the single-model API run of the same member
+    p = e.member(7)
+    p.solve(optimizer=True, dt_init=0.01, t_total=30.0, tol=2e-3, max_dt=2.0)
+    npt.assert_array_equal(out["snapshot"][1], p.snapshot)
+    npt.assert_array_equal(out["taxis"][1], p.taxis)
+
+
+# ---- sweep driver ---------------------------------------------------------------
+def test_sweep_finds_the_generating_candidate_and_refines():
+    from fiberis_b200.simulator.optimizer import sweep
+    M, nx, n_steps = 64, 256, 60
+    e, c = make_ensemble(71, M, nx, n_steps, zones=3, n_obs=6)
+    truth = np.array([0.3, -0.4, 0.1])
+    want, _ = O.solve_fixed(c["mesh"], (10.0 ** truth)[c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                            c["srcs"], 0.0, c["dt"], c["T"])
+    theta = sweep.random_candidates(M, [-1, -1, -1], [1, 1, 1], seed=5)
+    theta[17] = truth
+    e.set_zonal_diffusivity(10.0 ** theta, c["zone"])  # observations = what candidate 17 produces on the device
+    e.solve(dt=c["dt"], t_total=c["T"], audit_models=[17])
+    assert G.rel_max(e.snapshot[0], want) <= 1e-10
+    e.set_observations(c["obs_idx"], e.snapshot[0][:, c["obs_idx"]].copy())
+    out = sweep.run_sweep(e, theta, c["zone"], c["dt"], c["T"])
+    assert out["best"] == 17 and out["best_misfit"] == 0.0
+    npt.assert_array_equal(out["best_theta"], truth)
+    assert np.all(np.diff(out["misfit"][out["order"]]) >= 0)
+    ref = sweep.refine_sweep(e, c["zone"], [-1, -1, -1], [1, 1, 1], c["dt"], c["T"], n_models=256, rounds=5, seed=9)
+    best = [h[0] for h in ref["history"]]
+    assert all(b1 <= b0 for b0, b1 in zip(best, best[1:])) and best[-1] < 0.05 * best[0]
+    # the zones that hold the sources are well determined by the data (the one between them is not)
+    assert np.max(np.abs(ref["best_theta"] - truth)[[0, 2]]) < 0.05

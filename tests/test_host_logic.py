@@ -287,3 +287,16 @@ def test_ensemble_validation():
         e.set_source("not a list")
     e.set_zonal_diffusivity(np.ones((3, 2)), np.arange(10) // 5)
     assert e.n_models == 3
+
+
+# ---- sweep driver: candidate generators (host only) ---------------------------------------------
+def test_sweep_candidate_generators():
+    from fiberis_b200.simulator.optimizer import sweep
+    g = sweep.grid_candidates([(-1, 1, 3), (0, 2, 2)])
+    assert g.shape == (6, 2)
+    np.testing.assert_array_equal(g[:, 0], [-1, -1, 0, 0, 1, 1])
+    np.testing.assert_array_equal(g[:, 1], [0, 2, 0, 2, 0, 2])
+    r = sweep.random_candidates(100, [-1, 0, 2], [1, 0.5, 3], seed=3)
+    assert r.shape == (100, 3) and np.all(r >= [-1, 0, 2]) and np.all(r <= [1, 0.5, 3])
+    np.testing.assert_array_equal(r, sweep.random_candidates(100, [-1, 0, 2], [1, 0.5, 3], seed=3))
+    assert not np.array_equal(r, sweep.random_candidates(100, [-1, 0, 2], [1, 0.5, 3], seed=4))
