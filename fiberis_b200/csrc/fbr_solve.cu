@@ -156,7 +156,9 @@ extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const do
     FBR_REQUIRE(M >= 1 && nx >= 1 && dl && d && du && b && x, "bad argument");
     FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_PCR, "unknown solver variant %d", variant);
     if (variant == FBR_SOLVER_AUTO)
-        variant = (nx <= kPcrMaxNx && nx >= 32 && (M < 16384 || !work)) ? FBR_SOLVER_PCR : FBR_SOLVER_THOMAS;
+        // measured on B200 (scratch/k2_bench.py, 40 B per unknown): PCR 0.3 - 1.5 TB/s over nx = 64 .. 4096
+        // at any batch size, thread-per-system Thomas on the model-major layout 0.01 - 0.27 TB/s
+        variant = (nx <= kPcrMaxNx && nx >= 32) ? FBR_SOLVER_PCR : FBR_SOLVER_THOMAS;
     if (variant == FBR_SOLVER_PCR) {
         if (nx > kPcrMaxNx)
             return fail(FBR_ERR_UNSUPPORTED, "PCR variant covers nx <= %d (got %lld)", kPcrMaxNx, (long long)nx);
