@@ -496,57 +496,70 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
     const int keep_f = lane == 0 ? 0 : -1, keep_b = lane == 31 ? 0 : -1;
     const int n_steps = (int)a.n_steps;
 
+    // Which of this thread's cells are overridden / observed depends only on the mesh length, the
+    // source / observation indices and the boundary codes — not on the member: work it out once.
+    unsigned desc = kDescNone | (kDescNone << 12);
+    bool ov_slow = false, ob_slow = false;
+    if (cell0 < nx) {
+        uint64_t ov = ~0ull;  // one slot byte per owned cell
+        if (cell0 == 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~0xFFull) | kSlotZero;
+        const int64_t jl = nx - 1 - cell0;
+        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE)
+            ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kSlotZero << (8 * jl));
+#pragma unroll 1
+        for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win (matbuilder.py:156-161)
+            const int64_t jj = a.src_idx[k] - cell0;
+            if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)k << (8 * jj));
+        }
+        int n_ov = 0, n_ob = 0;
+#pragma unroll 1
+        for (int j = 0; j < CPT; ++j) {
+            const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
+            if (so != kSlotNone) {
+                ++n_ov;
+                desc = (desc & ~0xFFFu) | (unsigned)j | (so << 4);
+            }
+        }
+#pragma unroll 1
+        for (int k = 0; k < a.n_obs; ++k) {
+            const int64_t jj = a.obs_idx[k] - cell0;
+            if (jj >= 0 && jj < CPT && a.obs_idx[k] < nx) {
+                ++n_ob;
+                desc = (desc & ~0xFFF000u) | ((unsigned)jj << 12) | ((unsigned)k << 16);
+            }
+        }
+        if (n_ov > 1) { ov_slow = true; desc |= kDescNone; }
+        if (n_ob > 1) { ob_slow = true; desc |= kDescNone << 12; }
+    }
+    const bool any_slow = __syncthreads_or(ov_slow || ob_slow);
+    // 16-byte loads of a thread's 8 cells when the rows allow it (nx even keeps every member's row aligned)
+    const bool vec_ok = (nx % 2 == 0) && cell0 + CPT <= nx && ((reinterpret_cast<uintptr_t>(a.fl) | reinterpret_cast<uintptr_t>(a.fr) |
+                         reinterpret_cast<uintptr_t>(a.fg) | reinterpret_cast<uintptr_t>(a.p0)) & 15) == 0 && a.p0_stride % 2 == 0;
+    auto load_row = [&](const double *row, double pad, double (&v)[CPT]) {
+        if (vec_ok) {
+            const double2 *q = reinterpret_cast<const double2 *>(row + cell0);
+#pragma unroll
+            for (int j = 0; j < CPT / 2; ++j) {
+                const double2 t = __ldg(q + j);
+                v[2 * j] = t.x;
+                v[2 * j + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) v[j] = cell0 + j < nx ? __ldg(row + cell0 + j) : pad;  // padding cell: identity row
+        }
+    };
+
     ModelCursor cursor = model_cursor(a);
     int64_t m;
     long long preset;
     while (next_model(a, cursor, m, preset)) {
         // ---------------- per-model setup ----------------
         double l[CPT], r[CPT], g[CPT], x[CPT];
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            const int64_t i = cell0 + j;
-            if (i < nx) {
-                l[j] = __ldg(a.fl + m * nx + i);
-                r[j] = __ldg(a.fr + m * nx + i);
-                g[j] = __ldg(a.fg + m * nx + i);
-                x[j] = __ldg(a.p0 + m * a.p0_stride + i);
-            } else {  // padding cell: identity row, decoupled
-                l[j] = 0.0; r[j] = 1.0; g[j] = 0.0; x[j] = 0.0;
-            }
-        }
-        unsigned desc = kDescNone | (kDescNone << 12);
-        bool ov_slow = false, ob_slow = false;
-        if (cell0 < nx) {
-            uint64_t ov = ~0ull;  // one slot byte per owned cell
-            if (cell0 == 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~0xFFull) | kSlotZero;
-            const int64_t jl = nx - 1 - cell0;
-            if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE)
-                ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kSlotZero << (8 * jl));
-#pragma unroll 1
-            for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win (matbuilder.py:156-161)
-                const int64_t jj = a.src_idx[k] - cell0;
-                if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)k << (8 * jj));
-            }
-            int n_ov = 0, n_ob = 0;
-#pragma unroll 1
-            for (int j = 0; j < CPT; ++j) {
-                const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
-                if (so != kSlotNone) {
-                    ++n_ov;
-                    desc = (desc & ~0xFFFu) | (unsigned)j | (so << 4);
-                }
-            }
-#pragma unroll 1
-            for (int k = 0; k < a.n_obs; ++k) {
-                const int64_t jj = a.obs_idx[k] - cell0;
-                if (jj >= 0 && jj < CPT && a.obs_idx[k] < nx) {
-                    ++n_ob;
-                    desc = (desc & ~0xFFF000u) | ((unsigned)jj << 12) | ((unsigned)k << 16);
-                }
-            }
-            if (n_ov > 1) { ov_slow = true; desc |= kDescNone; }
-            if (n_ob > 1) { ob_slow = true; desc |= kDescNone << 12; }
-        }
+        load_row(a.fl + m * nx, 0.0, l);
+        load_row(a.fr + m * nx, 1.0, r);
+        load_row(a.fg + m * nx, 0.0, g);
+        load_row(a.p0 + m * a.p0_stride, 0.0, x);
 
         const HalfProducts hf = half_products_fwd(l), hb = half_products_bwd(g);
         const ScanMultipliers sm = scan_multipliers(hf.a * hf.b, hb.a * hb.b, lane);
@@ -577,7 +590,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
             }
             s_snap_slot = slot;
         }
-        const bool any_slow = __syncthreads_or(ov_slow || ob_slow);
+        __syncthreads();
         const long long snap_slot = s_snap_slot;
         double acc = 0.0;
         // Per-step scalars never travel through a global load inside the sweeps: a load in flight across a
