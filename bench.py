@@ -328,7 +328,7 @@ def build_single(w):
     return p
 
 
-def run_single_gpu_arm(args):
+def run_single_gpu_arm(args, emit=True, sampler=True):
     """Single-model workloads (C1 / C2 / C5): latency-bound, replicas only (no multi-GPU leg)."""
     import contextlib
     import io
@@ -380,7 +380,7 @@ def run_single_gpu_arm(args):
     torch.cuda.synchronize()
     step_ms, k_ms = [], []
     launches0 = _cabi.launch_count()
-    with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clocks:
+    with (ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) if sampler else contextlib.nullcontext()) as clocks:
         for _ in range(args.steps):
             flush.zero_()
             torch.cuda.synchronize()
@@ -425,7 +425,7 @@ def run_single_gpu_arm(args):
         "e2e": {"value": work / float(np.mean(e2e_s)), "unit": "cell-updates/s",
                 "h2d_bytes_per_step": int(3 * 8 * nx + table.nbytes + 8 * n_src),
                 "d2h_bytes_per_step": int(p.snapshot.nbytes), "api": "PDS1D_MultiSource.solve(host arrays) -> snapshot ndarray"},
-        "gpu_launches": int(launches), "clocks": clocks.summary(),
+        "gpu_launches": int(launches), "clocks": clocks.summary() if sampler else None,
     }
     if not args.no_cpu:
         from oracle import c_oracle as CO
@@ -436,7 +436,9 @@ def run_single_gpu_arm(args):
         line["cpu_baseline"] = {"value": nx * ss / el, "unit": "cell-updates/s", "cores": 1, "kind": "port",
                                 "sample": f"{nx} cells x {ss} steps of the same model, banded C oracle (one system is "
                                           f"sequential: 1 thread), {el:.1f} s"}
-    print(json.dumps(line))
+    if emit:
+        print(json.dumps(line))
+    return line
 
 
 def run_gpu_arm(args):
@@ -586,6 +588,18 @@ def run_gpu_arm(args):
         }
         if world == 1 and not f32:
             line["single_step"] = single_step_probe(E, torch, peak)
+        if world == 1 and not f32 and not args.no_extra:
+            # the single-model configurations of BASELINE.json next to the headline (short runs, same code path
+            # as `--workload c2|c5`; full records under profiles/)
+            torch.cuda.empty_cache()
+            line["other_workloads"] = {}
+            for name in ("c2", "c5"):
+                sub = argparse.Namespace(**{**vars(args), "workload": name, "steps": 2, "no_cpu": True})
+                r = run_single_gpu_arm(sub, emit=False, sampler=False)
+                line["other_workloads"][name] = {
+                    "workload": r["config"]["workload"], "value": r["value"], "unit": r["unit"], "ms": r["ms_per_step"],
+                    "us_per_time_step": r["config"]["us_per_time_step"], "kernel": r["roofline"]["kernel"],
+                    "roofline_frac_16B": r["roofline"]["frac"], "e2e": r["e2e"]["value"], "window_plan": r["config"]["window_plan"]}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(line))
@@ -606,6 +620,7 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                     help="ensemble workloads: f32 = the separate fp32 mode (state and factors in float, gate 1e-5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C5 runs appended to the C3 line")
     args = ap.parse_args()
     if args.workload in SINGLE:
         if args.impl == "reference":
