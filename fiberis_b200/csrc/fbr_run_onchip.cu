@@ -684,8 +684,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
                     }
                     // ---- forward sweep: y_i = b_i - l_i y_{i-1}, t_i = r_i y_i ----
                     {
-                        double ya;
-                        double y = chunk_end_fwd(x, l, hf.b, ya);
+                        double y = chunk_end_fwd_plain(x, l);
 #pragma unroll
                         for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
                         double c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
@@ -697,12 +696,11 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
                             for (int v = 0; v < W - 1; ++v) cw = fma(s_K[0][warp][v], s_E[0][v], cw);
                             c = fma(sm.ex_f, cw, c);
                         }
-                        chunk_apply_fwd(x, l, r, hf.a, ya, c);
+                        chunk_apply_fwd_plain(x, l, r, c);
                     }
                     // ---- backward sweep: x_i = t_i - g_i x_{i+1} ----
                     {
-                        double za;
-                        double z = chunk_end_bwd(x, g, hb.b, za);
+                        double z = chunk_end_bwd_plain(x, g);
 #pragma unroll
                         for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
                         double c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
@@ -714,7 +712,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
                             for (int v = 1; v < W; ++v) cw = fma(s_K[1][warp][v], s_E[1][v], cw);
                             c = fma(sm.ex_b, cw, c);
                         }
-                        chunk_apply_bwd(x, g, hb.a, za, c);
+                        chunk_apply_bwd_plain(x, g, c);
                     }
                     // ---- fused objective: record the observed pressure (non-observers hit the dummy slot) ----
                     sts_f64(tr_addr, get_at<double, CPT>(x, (int)((desc >> 12) & 0x7)));
