@@ -355,6 +355,13 @@ class _PinnedPool:
 _pool = _PinnedPool()
 
 
+def as_f64(t):
+    """Results are handed out as float64 arrays (reference convention); fp32-mode buffers are widened on
+    the device — a host-side ``astype`` of a few hundred MB costs more than the run."""
+    torch = _torch()
+    return t if t.dtype == torch.float64 else t.to(torch.float64)
+
+
 def to_host(t):
     """Device tensor -> NumPy array through pooled pinned memory (one DMA, no extra host copy)."""
     torch = _torch()

@@ -423,7 +423,10 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
 //   * snapshots are taken between runs of an inner loop that knows nothing about them;
 //   * threads that own several overridden or observed cells (adjacent sources ...) are served by a
 //     generic path guarded by one CTA-uniform flag.
-constexpr unsigned kDescNone = 0xF;  // "no cell" in a descriptor's cell field
+// descriptor: [4:0] overridden cell (31 none)  [12:5] src column (0xFE: constant zero)
+//             [17:13] observed cell (31 none)  [25:18] obs column
+constexpr unsigned kDescNone = 0x1F;  // "no cell" in a descriptor's cell field
+constexpr unsigned kDescObShift = 13, kDescSrcColShift = 5, kDescObColShift = 18;
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -432,58 +435,44 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit_k3() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all_k3() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// descriptor: [3:0] overridden cell (0xF none)  [11:4] src column (0xFE: constant zero)
-//             [15:12] observed cell (0xF none)  [23:16] obs column
-__device__ __forceinline__ void put_cell(double (&x)[8], unsigned j, double v) {
-    switch (j) {
-        case 0: x[0] = v; break;
-        case 1: x[1] = v; break;
-        case 2: x[2] = v; break;
-        case 3: x[3] = v; break;
-        case 4: x[4] = v; break;
-        case 5: x[5] = v; break;
-        case 6: x[6] = v; break;
-        default: x[7] = v; break;
-    }
-}
-__device__ __forceinline__ double pick_cell(const double (&x)[8], unsigned j) {
-    switch (j) {
-        case 0: return x[0];
-        case 1: return x[1];
-        case 2: return x[2];
-        case 3: return x[3];
-        case 4: return x[4];
-        case 5: return x[5];
-        case 6: return x[6];
-        default: return x[7];
-    }
+// v = x[j] for a run-time j (any CPT): a chain of selects, no dynamic register indexing
+template <typename T, int CPT>
+__device__ __forceinline__ T pick_at(const T (&x)[CPT], int j) {
+    if (CPT <= 8) return get_at<T, CPT>(x, j);
+    T v = x[0];
+#pragma unroll
+    for (int k = 1; k < CPT; ++k) v = (j == k) ? x[k] : v;
+    return v;
 }
 
-// One row of a warp's 256 cells to global memory with coalesced stores.  A thread holds 8 consecutive
-// cells; written directly, every store instruction would touch 32 half-filled sectors 64 bytes apart
-// (measured: 2.3 us per recorded row).  Instead the warp transposes through a private shared-memory
-// patch (rows padded to 72 bytes: conflict-free) and each instruction writes 256 contiguous bytes.
-__device__ __forceinline__ void store_row_coalesced(double *__restrict__ row, int64_t warp_cell0, int64_t nx,
-                                                    const double (&x)[8], double *patch, int lane) {
+// One row of a warp's 32 * CPT cells to global memory with coalesced stores.  A thread holds CPT
+// consecutive cells (64 bytes); written directly, every store instruction would touch 32 half-filled
+// sectors 64 bytes apart (measured: 2.3 us per recorded row).  Instead the warp transposes through a
+// private shared-memory patch (rows padded by one element: conflict-free) and each instruction
+// writes 32 consecutive elements.
+template <typename T, int CPT>
+__device__ __forceinline__ void store_row_coalesced(T *__restrict__ row, int64_t warp_cell0, int64_t nx, const T (&x)[CPT],
+                                                    T *patch, int lane) {
     __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) patch[lane * 9 + j] = x[j];
+    for (int j = 0; j < CPT; ++j) patch[lane * (CPT + 1) + j] = x[j];
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = 32 * i + lane;  // cell within the warp's 256
-        const double v = patch[(c >> 3) * 9 + (c & 7)];
+    for (int i = 0; i < CPT; ++i) {
+        const int c = 32 * i + lane;  // cell within the warp's 32 * CPT
+        const T v = patch[(c / CPT) * (CPT + 1) + (c % CPT)];
         if (warp_cell0 + c < nx) row[warp_cell0 + c] = v;
     }
 }
 
-template <int W, int MINB>
-__global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs a) {
-    constexpr int CPT = 8;
-    __shared__ __align__(16) double s_K[2][W][W];
-    __shared__ __align__(16) double s_E[2][W];
-    __shared__ double s_dummy, s_zero;
-    __shared__ double s_T[2][W];
+template <typename T, int CPT, int W, int MINB>
+__global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs a) {
+    static_assert(CPT * sizeof(T) == 64, "a thread owns 64 bytes of state: 8 doubles or 16 floats");
+    __shared__ __align__(16) T s_K[2][W][W];
+    __shared__ __align__(16) T s_E[2][W];
+    __shared__ T s_dummy;
+    __shared__ double s_zero, s_trash;  // constant zero source value; where non-observers "record"
+    __shared__ T s_T[2][W];
     __shared__ double s_red[W];
     __shared__ long long s_snap_slot;
     extern __shared__ __align__(16) double s_dyn[];  // staged per-step scalars, see the time loop
@@ -498,55 +487,53 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
 
     // Which of this thread's cells are overridden / observed depends only on the mesh length, the
     // source / observation indices and the boundary codes — not on the member: work it out once.
-    unsigned desc = kDescNone | (kDescNone << 12);
+    unsigned desc = kDescNone | (kDescNone << kDescObShift);
     bool ov_slow = false, ob_slow = false;
     if (cell0 < nx) {
-        uint64_t ov = ~0ull;  // one slot byte per owned cell
-        if (cell0 == 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~0xFFull) | kSlotZero;
+        // slot of every owned cell (none / constant zero / src column), a bit mask of the cells that have one
+        unsigned have = 0, slot_of_last = kSlotNone;
+        int last = -1, n_ov = 0, n_ob = 0;
+        auto claim = [&](int j, unsigned so) {  // later claims win (matbuilder.py:156-161: sources over boundary rows)
+            if (!((have >> j) & 1)) { have |= 1u << j; ++n_ov; }
+            if (n_ov == 1 || j == last) { last = j; slot_of_last = so; }
+            else last = -2;  // several cells: the generic path re-derives them every step
+        };
+        if (cell0 == 0 && a.lbc != FBR_BC_NONE) claim(0, kSlotZero);
         const int64_t jl = nx - 1 - cell0;
-        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE)
-            ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kSlotZero << (8 * jl));
+        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) claim((int)jl, kSlotZero);
 #pragma unroll 1
-        for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win (matbuilder.py:156-161)
+        for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win
             const int64_t jj = a.src_idx[k] - cell0;
-            if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)k << (8 * jj));
+            if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) claim((int)jj, (unsigned)k);
         }
-        int n_ov = 0, n_ob = 0;
-#pragma unroll 1
-        for (int j = 0; j < CPT; ++j) {
-            const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
-            if (so != kSlotNone) {
-                ++n_ov;
-                desc = (desc & ~0xFFFu) | (unsigned)j | (so << 4);
-            }
-        }
+        if (n_ov == 1) desc = (desc & ~0x1FFFu) | (unsigned)last | (slot_of_last << kDescSrcColShift);
 #pragma unroll 1
         for (int k = 0; k < a.n_obs; ++k) {
             const int64_t jj = a.obs_idx[k] - cell0;
             if (jj >= 0 && jj < CPT && a.obs_idx[k] < nx) {
                 ++n_ob;
-                desc = (desc & ~0xFFF000u) | ((unsigned)jj << 12) | ((unsigned)k << 16);
+                desc = (desc & ~(0x1FFFu << kDescObShift)) | ((unsigned)jj << kDescObShift) | ((unsigned)k << kDescObColShift);
             }
         }
         if (n_ov > 1) { ov_slow = true; desc |= kDescNone; }
-        if (n_ob > 1) { ob_slow = true; desc |= kDescNone << 12; }
+        if (n_ob > 1) { ob_slow = true; desc |= kDescNone << kDescObShift; }
     }
     const bool any_slow = __syncthreads_or(ov_slow || ob_slow);
     // 16-byte loads of a thread's 8 cells when the rows allow it (nx even keeps every member's row aligned)
     const bool vec_ok = (nx % 2 == 0) && cell0 + CPT <= nx && ((reinterpret_cast<uintptr_t>(a.fl) | reinterpret_cast<uintptr_t>(a.fr) |
                          reinterpret_cast<uintptr_t>(a.fg) | reinterpret_cast<uintptr_t>(a.p0)) & 15) == 0 && a.p0_stride % 2 == 0;
-    auto load_row = [&](const double *row, double pad, double (&v)[CPT]) {
+    auto load_row = [&](const double *row, double pad, T (&v)[CPT]) {
         if (vec_ok) {
             const double2 *q = reinterpret_cast<const double2 *>(row + cell0);
 #pragma unroll
             for (int j = 0; j < CPT / 2; ++j) {
                 const double2 t = __ldg(q + j);
-                v[2 * j] = t.x;
-                v[2 * j + 1] = t.y;
+                v[2 * j] = (T)t.x;
+                v[2 * j + 1] = (T)t.y;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) v[j] = cell0 + j < nx ? __ldg(row + cell0 + j) : pad;  // padding cell: identity row
+            for (int j = 0; j < CPT; ++j) v[j] = (T)(cell0 + j < nx ? __ldg(row + cell0 + j) : pad);  // padding cell: identity row
         }
     };
 
@@ -555,28 +542,27 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
     long long preset;
     while (next_model(a, cursor, m, preset)) {
         // ---------------- per-model setup ----------------
-        double l[CPT], r[CPT], g[CPT], x[CPT];
+        T l[CPT], r[CPT], g[CPT], x[CPT];
         load_row(a.fl + m * nx, 0.0, l);
         load_row(a.fr + m * nx, 1.0, r);
         load_row(a.fg + m * nx, 0.0, g);
         load_row(a.p0 + m * a.p0_stride, 0.0, x);
 
-        const HalfProducts hf = half_products_fwd(l), hb = half_products_bwd(g);
-        const ScanMultipliers sm = scan_multipliers(hf.a * hf.b, hb.a * hb.b, lane);
+        const ScanMultipliersT<T> sm = scan_multipliers<T>(chunk_product<T, CPT>(l), chunk_product<T, CPT>(g), lane);
         if (W > 1) {
             __syncthreads();  // previous model's readers are done with the shared scratch
             if (lane == 31) s_T[0][warp] = sm.tot_f;
             if (lane == 0) s_T[1][warp] = sm.tot_b;
             __syncthreads();
             if (tid < W) {  // row tid of both tables
-                double k = 1.0;
+                T k = (T)1;
                 for (int v = W - 1; v >= 0; --v) {  // forward: warps v < tid feed warp tid
-                    if (v >= tid) s_K[0][tid][v] = 0.0;
+                    if (v >= tid) s_K[0][tid][v] = (T)0;
                     else { s_K[0][tid][v] = k; k *= s_T[0][v]; }
                 }
-                k = 1.0;
+                k = (T)1;
                 for (int v = 0; v < W; ++v) {  // backward: warps v > tid feed warp tid
-                    if (v <= tid) s_K[1][tid][v] = 0.0;
+                    if (v <= tid) s_K[1][tid][v] = (T)0;
                     else { s_K[1][tid][v] = k; k *= s_T[1][v]; }
                 }
             }
@@ -602,13 +588,13 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
         //   * observed pressures are only WRITTEN during the block (a store has no result latency)
         //     into a trace, and the squared residuals of a whole block are summed cooperatively at
         //     the next block boundary.
-        const bool has_ov = (desc & 0xF) != kDescNone, has_ob = ((desc >> 12) & 0xF) != kDescNone;
-        const bool ov_zero = ((desc >> 4) & 0xFF) == kSlotZero;
+        const bool has_ov = (desc & 0x1F) != kDescNone, has_ob = ((desc >> kDescObShift) & 0x1F) != kDescNone;
+        const bool ov_zero = ((desc >> kDescSrcColShift) & 0xFF) == kSlotZero;
         const int blk = a.blk_steps;
         double *s_src = s_dyn;                                  // [2][blk][n_src]
         double *s_obs = s_src + 2 * blk * a.n_src;              // [2][blk][n_obs]
         double *s_tr = s_obs + 2 * blk * a.n_obs;               // [2][blk][n_obs]
-        double *s_patch = s_tr + 2 * blk * a.n_obs + warp * (32 * 9);  // [W][32 * 9] row-transposition patches
+        T *s_patch = reinterpret_cast<T *>(s_tr + 2 * blk * a.n_obs + warp * (32 * 9));  // [W] row-transposition patches (2304 B each)
         auto stage_block = [&](int b) {  // sources of steps [b blk, ..) and observations of the states after them
             const int n0 = b * blk;
             const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
@@ -635,13 +621,13 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
         };
         stage_block(0);
         cp_async_commit_k3();
-        unsigned src_addr = smem_addr(&s_zero), tr_addr = smem_addr(&s_dummy);
+        unsigned src_addr = smem_addr(&s_zero), tr_addr = smem_addr(&s_trash);
         const unsigned src_inc = (has_ov && !ov_zero) ? 8u * a.n_src : 0u, tr_inc = has_ob ? 8u * a.n_obs : 0u;
 
         // ---------------- time loop: runs of steps between block boundaries / snapshots ----------------
         const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
         int to_snap = snap_slot >= 0 ? snap_every : 0x7fffffff;  // never reaches 0 when not recorded
-        double *snap_row = reinterpret_cast<double *>(a.snap) + (snap_slot >= 0 ? snap_slot : 0) * a.snap_model_stride;
+        T *snap_row = reinterpret_cast<T *>(a.snap) + (snap_slot >= 0 ? snap_slot : 0) * a.snap_model_stride;
         int done = 0;
         while (done < n_steps) {
             const int b = done / blk;
@@ -655,8 +641,8 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
                 stage_block(b + 1);
                 cp_async_commit_k3();
                 const int buf = b & 1;
-                if (has_ov && !ov_zero) src_addr = smem_addr(s_src + buf * blk * a.n_src + ((desc >> 4) & 0xFF));
-                if (has_ob) tr_addr = smem_addr(s_tr + buf * blk * a.n_obs + ((desc >> 16) & 0xFF));
+                if (has_ov && !ov_zero) src_addr = smem_addr(s_src + buf * blk * a.n_src + ((desc >> kDescSrcColShift) & 0xFF));
+                if (has_ob) tr_addr = smem_addr(s_tr + buf * blk * a.n_obs + ((desc >> kDescObColShift) & 0xFF));
             }
             int run = blk - done % blk;
             if (run > n_steps - done) run = n_steps - done;
@@ -669,60 +655,60 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
                 for (int n = n_begin; n < n_end; ++n) {
                     // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
                     if (has_ov) {  // only the threads that own an overridden cell
-                        set_at<double, CPT>(x, (int)(desc & 0xF), lds_f64(src_addr));
+                        set_at<T, CPT>(x, (int)(desc & 0x1F), (T)lds_f64(src_addr));
                         src_addr += src_inc;
                     }
                     if (SLOW && ov_slow) {  // several overridden cells in this thread: re-derive them (rare)
-                        if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = 0.0;
+                        if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (T)0;
                         const int64_t jl = nx - 1 - cell0;
-                        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) put_cell(x, (unsigned)jl, 0.0);
+                        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) set_at<T, CPT>(x, (int)jl, (T)0);
 #pragma unroll 1
                         for (int k = 0; k < a.n_src; ++k) {
                             const int64_t jj = a.src_idx[k] - cell0;
-                            if (jj >= 0 && jj < CPT) put_cell(x, (unsigned)jj, __ldg(a.src_table + (int64_t)n * a.n_src + k));
+                            if (jj >= 0 && jj < CPT) set_at<T, CPT>(x, (int)jj, (T)__ldg(a.src_table + (int64_t)n * a.n_src + k));
                         }
                     }
                     // ---- forward sweep: y_i = b_i - l_i y_{i-1}, t_i = r_i y_i ----
                     {
-                        double y = chunk_end_fwd_plain(x, l);
+                        T y = chunk_end_fwd_plain<T, CPT>(x, l);
 #pragma unroll
-                        for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
-                        double c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
+                        for (int s = 0; s < 5; ++s) y = fma_any<T>(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+                        T c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
                         if (W > 1) {
-                            sts_f64(st_f, y);
+                            sts_any(st_f, y);
                             __syncthreads();
-                            double cw = 0.0;
+                            T cw = (T)0;
 #pragma unroll
-                            for (int v = 0; v < W - 1; ++v) cw = fma(s_K[0][warp][v], s_E[0][v], cw);
-                            c = fma(sm.ex_f, cw, c);
+                            for (int v = 0; v < W - 1; ++v) cw = fma_any<T>(s_K[0][warp][v], s_E[0][v], cw);
+                            c = fma_any<T>(sm.ex_f, cw, c);
                         }
-                        chunk_apply_fwd_plain(x, l, r, c);
+                        chunk_apply_fwd_plain<T, CPT>(x, l, r, c);
                     }
                     // ---- backward sweep: x_i = t_i - g_i x_{i+1} ----
                     {
-                        double z = chunk_end_bwd_plain(x, g);
+                        T z = chunk_end_bwd_plain<T, CPT>(x, g);
 #pragma unroll
-                        for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
-                        double c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+                        for (int s = 0; s < 5; ++s) z = fma_any<T>(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+                        T c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
                         if (W > 1) {
-                            sts_f64(st_b, z);
+                            sts_any(st_b, z);
                             __syncthreads();
-                            double cw = 0.0;
+                            T cw = (T)0;
 #pragma unroll
-                            for (int v = 1; v < W; ++v) cw = fma(s_K[1][warp][v], s_E[1][v], cw);
-                            c = fma(sm.ex_b, cw, c);
+                            for (int v = 1; v < W; ++v) cw = fma_any<T>(s_K[1][warp][v], s_E[1][v], cw);
+                            c = fma_any<T>(sm.ex_b, cw, c);
                         }
-                        chunk_apply_bwd_plain(x, g, c);
+                        chunk_apply_bwd_plain<T, CPT>(x, g, c);
                     }
                     // ---- fused objective: record the observed pressure (non-observers hit the dummy slot) ----
-                    sts_f64(tr_addr, get_at<double, CPT>(x, (int)((desc >> 12) & 0x7)));
+                    sts_f64(tr_addr, (double)pick_at<T, CPT>(x, (int)((desc >> kDescObShift) & (CPT - 1))));
                     tr_addr += tr_inc;
                     if (SLOW && ob_slow) {  // several observed cells in this thread: record each of them
                         double *row = s_tr + (((n / blk) & 1) * blk + n % blk) * a.n_obs;
 #pragma unroll 1
                         for (int k = 0; k < a.n_obs; ++k) {
                             const int64_t jj = a.obs_idx[k] - cell0;
-                            if (jj >= 0 && jj < CPT) row[k] = pick_cell(x, (unsigned)jj);
+                            if (jj >= 0 && jj < CPT) row[k] = (double)pick_at<T, CPT>(x, (int)jj);
                         }
                     }
                 }
@@ -734,7 +720,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
             // ---- sampled snapshot ----
             if (to_snap == 0) {
                 to_snap = snap_every;
-                store_row_coalesced(snap_row, (int64_t)warp * 256, nx, x, s_patch, lane);
+                store_row_coalesced<T, CPT>(snap_row, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane);
                 snap_row += a.snap_row_stride;
             }
         }
@@ -744,7 +730,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
 
         // ---------------- per-model epilogue ----------------
         if (a.p_final)
-            store_row_coalesced(reinterpret_cast<double *>(a.p_final) + m * nx, (int64_t)warp * 256, nx, x, s_patch, lane);
+            store_row_coalesced<T, CPT>(reinterpret_cast<T *>(a.p_final) + m * nx, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane);
         if (a.misfit) {
             for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(kFull, acc, s);
             if (lane == 0) s_red[warp] = acc;
@@ -759,16 +745,16 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchip8_kernel(const RunArgs
     }
 }
 
-template <int W>
-static int launch_onchip8(const RunArgs &a, cudaStream_t stream) {
+template <typename T, int CPT, int W>
+static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
-    constexpr int kFull16 = (16 / W) > 0 ? (16 / W) : 1, kRoomy = (12 / W) > 0 ? (12 / W) : 1;
-    auto kern = getenv("FBR_K3_ROOMY") ? run_onchip8_kernel<W, kRoomy> : run_onchip8_kernel<W, kFull16>;
+    constexpr int kFull16 = (16 / W) > 0 ? (16 / W) : 1;
+    auto kern = run_onchipx_kernel<T, CPT, W, kFull16>;
     RunArgs b = a;
     const int cols = a.n_src + 2 * a.n_obs;
     b.blk_steps = cols <= 64 ? 32 : 8;  // keeps the staging area <= 32 KB per CTA
-    const size_t smem = (2 * (size_t)b.blk_steps * (cols > 0 ? cols : 1) + (size_t)W * 32 * 9) * sizeof(double);
+    const size_t smem = (2 * (size_t)b.blk_steps * (size_t)cols + (size_t)W * 32 * 9) * sizeof(double);
     if (smem > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
@@ -776,16 +762,19 @@ static int launch_onchip8(const RunArgs &a, cudaStream_t stream) {
     int64_t grid = (int64_t)occ * f.sm_count;
     if (grid > a.M) grid = a.M;
     kern<<<(unsigned)grid, 32 * W, smem, stream>>>(b);
-    return check_launch("fbr_run (on-chip, fp64 x8)");
+    return check_launch("fbr_run (on-chip, 64 B per thread)");
 }
 
-static int launch_f64x8(const RunArgs &a, cudaStream_t stream) {
-    const int64_t threads = (a.nx + 7) / 8;
-    if (threads <= 32) return launch_onchip8<1>(a, stream);
-    if (threads <= 64) return launch_onchip8<2>(a, stream);
-    if (threads <= 128) return launch_onchip8<4>(a, stream);
-    if (threads <= 256) return launch_onchip8<8>(a, stream);
-    return launch_onchip8<16>(a, stream);
+// 64 bytes of state per thread: 8 cells in fp64, 16 cells in the fp32 mode
+template <typename T>
+static int launch_x(const RunArgs &a, cudaStream_t stream) {
+    constexpr int CPT = 64 / sizeof(T);
+    const int64_t threads = (a.nx + CPT - 1) / CPT;
+    if (threads <= 32) return launch_onchipx<T, CPT, 1>(a, stream);
+    if (threads <= 64) return launch_onchipx<T, CPT, 2>(a, stream);
+    if (threads <= 128) return launch_onchipx<T, CPT, 4>(a, stream);
+    if (threads <= 256) return launch_onchipx<T, CPT, 8>(a, stream);
+    return launch_onchipx<T, CPT, 16>(a, stream);
 }
 
 template <typename T, int CPT, int W>
@@ -834,7 +823,8 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
         const int v = atoi(e);
         if ((v == 1 || v == 2 || v == 4 || v == 8) && (a.nx + v - 1) / v <= 32 * kMaxWarps) cpt = v;
     }
-    if (cpt == 8 && sizeof(T) == sizeof(double) && !getenv("FBR_K3_GENERIC")) return launch_f64x8(a, stream);
+    // 256 cells (fp64) / 512 cells (fp32 mode) and up: the 64-byte-per-thread kernel
+    if (a.nx >= 32 * (int64_t)(64 / sizeof(T)) && !getenv("FBR_K3_GENERIC")) return launch_x<T>(a, stream);
     switch (cpt) {
         case 1: return launch_cpt<T, 1>(a, stream);
         case 2: return launch_cpt<T, 2>(a, stream);

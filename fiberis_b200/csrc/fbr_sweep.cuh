@@ -101,61 +101,87 @@ __device__ __forceinline__ void chunk_apply_bwd(double (&x)[8], const double (&g
     x[0] = fma(-g[0], x[1], x[0]);
 }
 
-// Plain (single-chain) versions of the local passes: 16 instead of 22 fp64 operations per sweep, 8-deep
-// dependent chains.  Preferred where the SM is shared by many warps (ensembles: K3), where throughput
-// counts more than the depth of one warp's chain.
-__device__ __forceinline__ double chunk_end_fwd_plain(const double (&x)[8], const double (&l)[8]) {
-    double y = x[0];
+// Plain (single-chain) versions of the local passes: 16 instead of 22 operations per 8-cell sweep,
+// CPT-deep dependent chains.  Preferred where the SM is shared by many warps (ensembles: K3), where
+// throughput counts more than the depth of one warp's chain.  T = double (8 cells per thread) or
+// float (16 cells per thread: the fp32 mode has the same register footprint and half the shuffles).
+template <typename T> __device__ __forceinline__ T fma_any(T a, T b, T c);
+template <> __device__ __forceinline__ double fma_any<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> __device__ __forceinline__ float fma_any<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+template <typename T, int CPT>
+__device__ __forceinline__ T chunk_end_fwd_plain(const T (&x)[CPT], const T (&l)[CPT]) {
+    T y = x[0];
 #pragma unroll
-    for (int j = 1; j < 8; ++j) y = fma(-l[j], y, x[j]);
+    for (int j = 1; j < CPT; ++j) y = fma_any<T>(-l[j], y, x[j]);
     return y;
 }
-__device__ __forceinline__ void chunk_apply_fwd_plain(double (&x)[8], const double (&l)[8], const double (&r)[8], double c) {
-    double y = c;
+template <typename T, int CPT>
+__device__ __forceinline__ void chunk_apply_fwd_plain(T (&x)[CPT], const T (&l)[CPT], const T (&r)[CPT], T c) {
+    T y = c;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        y = fma(-l[j], y, x[j]);
+    for (int j = 0; j < CPT; ++j) {
+        y = fma_any<T>(-l[j], y, x[j]);
         x[j] = r[j] * y;
     }
 }
-__device__ __forceinline__ double chunk_end_bwd_plain(const double (&x)[8], const double (&g)[8]) {
-    double z = x[7];
+template <typename T, int CPT>
+__device__ __forceinline__ T chunk_end_bwd_plain(const T (&x)[CPT], const T (&g)[CPT]) {
+    T z = x[CPT - 1];
 #pragma unroll
-    for (int j = 6; j >= 0; --j) z = fma(-g[j], z, x[j]);
+    for (int j = CPT - 2; j >= 0; --j) z = fma_any<T>(-g[j], z, x[j]);
     return z;
 }
-__device__ __forceinline__ void chunk_apply_bwd_plain(double (&x)[8], const double (&g)[8], double c) {
-    double z = c;
+template <typename T, int CPT>
+__device__ __forceinline__ void chunk_apply_bwd_plain(T (&x)[CPT], const T (&g)[CPT], T c) {
+    T z = c;
 #pragma unroll
-    for (int j = 7; j >= 0; --j) {
-        z = fma(-g[j], z, x[j]);
+    for (int j = CPT - 1; j >= 0; --j) {
+        z = fma_any<T>(-g[j], z, x[j]);
         x[j] = z;
     }
 }
+// product of an even number of multipliers (the sign flips of -m cancel)
+template <typename T, int CPT>
+__device__ __forceinline__ T chunk_product(const T (&m)[CPT]) {
+    static_assert(CPT % 2 == 0, "an even chunk keeps the product's sign");
+    T p = m[0];
+#pragma unroll
+    for (int j = 1; j < CPT; ++j) p *= m[j];
+    return p;
+}
+__device__ __forceinline__ void sts_any(unsigned addr, double v) { sts_f64(addr, v); }
+__device__ __forceinline__ void sts_any(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float and_mask(float v, int keep) { return __int_as_float(__float_as_int(v) & keep); }
 
 // Time-invariant stage multipliers of the warp scan: stage s adds P[s] * (value of lane -/+ 2^s);
 // lanes a stage does not reach get a zero multiplier, so the scan needs no predicates.
 // tot_f / tot_b = products over lanes 0..lane / lane..31; ex_f / ex_b = the exclusive versions.
-struct ScanMultipliers {
-    double f[5], b[5], ex_f, ex_b, tot_f, tot_b;
+template <typename T>
+struct ScanMultipliersT {
+    T f[5], b[5], ex_f, ex_b, tot_f, tot_b;
 };
-__device__ __forceinline__ ScanMultipliers scan_multipliers(double chunk_f, double chunk_b, int lane) {
-    ScanMultipliers m;
-    double pf = chunk_f, pb = chunk_b;
+using ScanMultipliers = ScanMultipliersT<double>;
+template <typename T>
+__device__ __forceinline__ ScanMultipliersT<T> scan_multipliers(T chunk_f, T chunk_b, int lane) {
+    ScanMultipliersT<T> m;
+    T pf = chunk_f, pb = chunk_b;
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
         const bool fa = lane >= (1 << s), ba = lane + (1 << s) < 32;
-        m.f[s] = fa ? pf : 0.0;
-        m.b[s] = ba ? pb : 0.0;
-        const double upf = __shfl_up_sync(kAllLanes, pf, 1 << s);
-        const double dnb = __shfl_down_sync(kAllLanes, pb, 1 << s);
+        m.f[s] = fa ? pf : (T)0;
+        m.b[s] = ba ? pb : (T)0;
+        const T upf = __shfl_up_sync(kAllLanes, pf, 1 << s);
+        const T dnb = __shfl_down_sync(kAllLanes, pb, 1 << s);
         if (fa) pf *= upf;
         if (ba) pb *= dnb;
     }
     m.ex_f = __shfl_up_sync(kAllLanes, pf, 1);
     m.ex_b = __shfl_down_sync(kAllLanes, pb, 1);
-    if (lane == 0) m.ex_f = 1.0;
-    if (lane == 31) m.ex_b = 1.0;
+    if (lane == 0) m.ex_f = (T)1;
+    if (lane == 31) m.ex_b = (T)1;
     m.tot_f = pf;
     m.tot_b = pb;
     return m;

@@ -192,7 +192,7 @@ class PDS1D_Ensemble:
         self.taxis = np.array(taxis)
         self.audit_models = audit
         if n_audit and snap_d is not None:  # (n_audit, n_t, nx), row 0 = initial, straight from the kernel
-            self.snapshot = _engine.to_host(snap_d).astype(np.float64, copy=False)
+            self.snapshot = _engine.to_host(_engine.as_f64(snap_d))  # fp32 mode: widened on the device, not on the host
             if len(audit_unique) != len(audit) or np.any(audit_slot != np.arange(len(audit))):
                 self.snapshot = self.snapshot[audit_slot]  # back to the order (and repeats) the caller listed
         else:

@@ -300,7 +300,7 @@ class PDS1D_SingleSource:
             elif isinstance(snap_d, np.ndarray):  # rows already streamed to the host
                 self.snapshot = snap_d
             else:  # (1, rows + 1, nx) with row 0 = initial, written in place by the kernel
-                self.snapshot = _engine.to_host(snap_d[0]).astype(np.float64, copy=False)
+                self.snapshot = _engine.to_host(_engine.as_f64(snap_d[0]))  # fp32 mode: widened on the device
         else:
             rows = self._jacobi_loop(dl, d, du, p0_d, sidx_d, n_src, table, n_steps, every)
             self.snapshot = np.concatenate([initial[None, :], rows], axis=0)
