@@ -37,6 +37,7 @@ SIGNATURES = {
     "fbr_run_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "fbr_run_f32": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "fbr_run_max_nx": (_i64, []),
+    "fbr_run_reserve_ctas": (_i32, [_i32]),
     "fbr_run_long_max_nx": (_i64, []),
     "fbr_run_long_work_bytes": (_i64, [_i64]),
     "fbr_run_long_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _i64, _p, _p, _p, _p]),

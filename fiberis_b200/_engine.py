@@ -147,6 +147,11 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     return snap, p_final, misfit
 
 
+def reserve_ctas(n):
+    """Ask the next ``run`` of this thread to leave ``n`` CTA slots free (see fbr_run_reserve_ctas)."""
+    check(_cabi.load().fbr_run_reserve_ctas(int(n)))
+
+
 def run_long_max_nx() -> int:
     return int(_cabi.load().fbr_run_long_max_nx())
 
@@ -362,18 +367,21 @@ def as_f64(t):
     return t if t.dtype == torch.float64 else t.to(torch.float64)
 
 
-def to_host(t):
-    """Device tensor -> NumPy array through pooled pinned memory (one DMA, no extra host copy)."""
+def to_host(t, sync=True):
+    """Device tensor -> NumPy array through pooled pinned memory (one DMA, no extra host copy).
+    ``sync=False`` only enqueues the copy on the current stream: the caller synchronises that stream
+    before touching the array."""
     torch = _torch()
     t = t.contiguous()
     nbytes = t.numel() * t.element_size()
-    if nbytes < (1 << 20):
+    if nbytes < (1 << 20) and sync:
         return t.cpu().numpy()
     import weakref
-    entry = _pool.take(nbytes)
+    entry = _pool.take(max(nbytes, 1))
     host = entry[0][:nbytes].view(t.dtype).view(t.shape)
     host.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    if sync:
+        torch.cuda.current_stream().synchronize()
     arr = host.numpy()
     entry[1] = weakref.ref(arr)
     return arr

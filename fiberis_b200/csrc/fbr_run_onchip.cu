@@ -745,6 +745,13 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     }
 }
 
+// CTA slots the next launch of this thread leaves free (fbr_run_reserve_ctas): lets a small launch
+// enqueued just before on another stream stay resident next to the persistent grid.
+static int &reserved_ctas() {
+    static thread_local int n = 0;
+    return n;
+}
+
 template <typename T, int CPT, int W>
 static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
@@ -759,7 +766,9 @@ static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     int occ = 0;
     FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d)", 32 * W);
-    int64_t grid = (int64_t)occ * f.sm_count;
+    int64_t grid = (int64_t)occ * f.sm_count - reserved_ctas();
+    reserved_ctas() = 0;
+    if (grid < 1) grid = 1;
     if (grid > a.M) grid = a.M;
     kern<<<(unsigned)grid, 32 * W, smem, stream>>>(b);
     return check_launch("fbr_run (on-chip, 64 B per thread)");
@@ -838,6 +847,12 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
 using namespace fbr;
 
 extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
+
+extern "C" int fbr_run_reserve_ctas(int n) {
+    FBR_REQUIRE(n >= 0, "cannot reserve a negative number of CTA slots");
+    reserved_ctas() = n;
+    return FBR_OK;
+}
 
 #define FBR_FILL_ARGS()                                                                                   \
     RunArgs a;                                                                                            \

@@ -128,7 +128,7 @@ class PDS1D_Ensemble:
 
     # -- solve ------------------------------------------------------------------------------------
     def solve(self, dt, t_total=None, audit_models=(), snapshot_every=1, dtype="float64", models=None,
-              process_group=None, gather=True):
+              process_group=None, gather=True, split_audit=True):
         """Integrate every member with a fixed ``dt``.
 
         ``models=(lo, hi)`` restricts the run to a contiguous block (multi-GPU sharding does this
@@ -184,15 +184,46 @@ class PDS1D_Ensemble:
             obs_d = _engine.to_device(self.obs)
             w_d = None if self.obs_weights is None else _engine.to_device(self.obs_weights)
 
-        snap_d, _, misfit_d = _engine.run(
-            factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-            snapshot_every=snapshot_every if n_audit else 0, snap_models=snap_models_d, n_snap_models=n_audit,
-            obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, obs_w=w_d, dtype=dtype)
+        run_kw = dict(obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, obs_w=w_d, dtype=dtype)
+        n_rows = n_steps // snapshot_every if n_audit else 0
+        host_snap = None
+        if n_rows and M >= 8 * n_audit and M >= 512 and split_audit:
+            # Large sweep, few audited members: integrate the audited ones as their own small launch on a
+            # side stream and bring their snapshots home WHILE the big launch is still running (the
+            # device-to-host copy of a few hundred MB otherwise trails the run); the big launch then
+            # records nothing.  The audited members' factor rows are gathered into a contiguous batch.
+            import torch
+            main, side = torch.cuda.current_stream(), _engine._copy_stream(mesh_d.device)
+            pick = snap_models_d
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fac_a = tuple(f.index_select(0, pick).contiguous() for f in factors)
+                p0_a = p0_d if p0_d.dim() == 1 else p0_d.index_select(0, pick).contiguous()
+                # same observation arguments as the sweep: equal shared-memory footprints let CTAs of the two
+                # launches share an SM (with different footprints the audited CTAs kept their SMs to
+                # themselves and the sweep finished 2.5 ms later); the misfits computed here are discarded
+                snap_a, _, _ = _engine.run(fac_a, p0_a, n_audit, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                           snapshot_every=snapshot_every, **run_kw)
+                host_snap = _engine.to_host(_engine.as_f64(snap_a), sync=False)
+            _engine.reserve_ctas(n_audit)  # the audited members' CTAs stay resident next to the sweep's grid
+            _, _, misfit_d = _engine.run(factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                         snapshot_every=0, **run_kw)
+            main.wait_stream(side)
+            snap_d = snap_a
+        else:
+            snap_d, _, misfit_d = _engine.run(
+                factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                snapshot_every=snapshot_every if n_audit else 0, snap_models=snap_models_d, n_snap_models=n_audit,
+                **run_kw)
 
         self.taxis = np.array(taxis)
         self.audit_models = audit
         if n_audit and snap_d is not None:  # (n_audit, n_t, nx), row 0 = initial, straight from the kernel
-            self.snapshot = _engine.to_host(_engine.as_f64(snap_d))  # fp32 mode: widened on the device, not on the host
+            if host_snap is not None:
+                side.synchronize()
+                self.snapshot = host_snap
+            else:
+                self.snapshot = _engine.to_host(_engine.as_f64(snap_d))  # fp32 mode: widened on the device, not on the host
             if len(audit_unique) != len(audit) or np.any(audit_slot != np.arange(len(audit))):
                 self.snapshot = self.snapshot[audit_slot]  # back to the order (and repeats) the caller listed
         else:

@@ -144,6 +144,13 @@ int fbr_run_f32(const double *fl, const double *fr, const double *fg, const doub
 
 int64_t fbr_run_max_nx(void);
 
+/* The persistent grid of fbr_run_* normally fills every CTA slot of the device.  A caller that has just
+ * enqueued a SMALL fbr_run_* launch on another stream (e.g. the few recorded members of a sweep, whose
+ * snapshots should travel to the host while the sweep is still running) asks the NEXT fbr_run_* call
+ * of this thread to leave n slots free, so that both launches are resident together instead of the
+ * small one delaying n persistent CTAs.  The reservation is consumed by that one call. */
+int fbr_run_reserve_ctas(int n);
+
 /* ------------------------------------------------------------------------------------------
  * K3L the same persistent integration for LONG meshes (fbr_run_max_nx() < nx <=
  * fbr_run_long_max_nx(), about 6e5 cells on a B200): the mesh is tiled over co-resident CTAs of
