@@ -1,4 +1,6 @@
-// K1b  time-invariant factorisation  u_0 = d_0, l_i = dl_i / u_{i-1}, u_i = d_i - l_i du_{i-1}.
+// K1b  time-invariant factorisation  u_0 = d_0, l_i = dl_i r_{i-1}, u_i = d_i - l_i du_{i-1}, r_i = 1 / u_i,
+//      g_i = du_i r_i.  One division per cell: fp64 division is a ~30-instruction sequence on the
+//      sequential chain (three of them cost ~1000 cycles per cell on B200, one ~250).
 //
 // Two variants:
 //   * sequential, one thread per model  -> ensembles of short systems (C3/C4: thousands of models);
@@ -27,20 +29,81 @@ __global__ void __launch_bounds__(128) factorize_kernel(const double *__restrict
     const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (m >= M) return;
     const int64_t o = m * nx;
-    double u_prev = 1.0, c_prev = 0.0;
+    double r_prev = 1.0, c_prev = 0.0;  // r = 1 / u: ONE division per cell (see the file header)
     int32_t bad = 0;
     for (int64_t i = 0; i < nx; ++i) {
         const double a = dl[o + i], b = d[o + i], c = du[o + i];
-        const double l = (i == 0) ? 0.0 : a / u_prev;
+        const double l = (i == 0) ? 0.0 : a * r_prev;
         const double u = b - l * c_prev;
         if (!bad && (u == 0.0 || !isfinite(u))) bad = (int32_t)(i + 1);
+        const double r = 1.0 / u;
         fl[o + i] = l;
-        fr[o + i] = 1.0 / u;
-        fg[o + i] = c / u;
-        u_prev = u;
+        fr[o + i] = r;
+        fg[o + i] = c * r;
+        r_prev = r;
         c_prev = c;
     }
     if (singular) singular[m] = bad;
+}
+
+// ---- sequential recurrence, coalesced through shared-memory tiles ----
+// Same arithmetic per model as factorize_kernel (bit-identical factors), but a warp owns 32 models
+// and walks the mesh in tiles of 32 cells: a tile of every array is read with coalesced 256-byte
+// requests (lane = cell) into shared memory, transposed by indexing (lane = model) for the
+// recurrence, and written back the same way.  The plain kernel reads 32 different cache lines per
+// request (0.5 - 1 TB/s on B200); this one streams (see profiles/).
+constexpr int kTileCells = 32, kTileWarps = 4;
+
+__global__ void __launch_bounds__(32 * kTileWarps) factorize_tiled_kernel(
+    const double *__restrict__ dl, const double *__restrict__ d, const double *__restrict__ du, int64_t M, int64_t nx,
+    double *__restrict__ fl, double *__restrict__ fr, double *__restrict__ fg, int32_t *__restrict__ singular) {
+    extern __shared__ double s_tile[];  // [warp][3][cell][33]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double(*sa)[33] = reinterpret_cast<double(*)[33]>(s_tile + (size_t)warp * 3 * kTileCells * 33);
+    double(*sb)[33] = sa + kTileCells;
+    double(*sc)[33] = sb + kTileCells;
+    const int64_t m0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    if (m0 >= M) return;
+    const int rows = M - m0 < 32 ? (int)(M - m0) : 32;  // models of this group
+    double r_prev = 1.0, c_prev = 0.0;
+    int32_t bad = 0;
+    for (int64_t c0 = 0; c0 < nx; c0 += kTileCells) {
+        const int cells = nx - c0 < kTileCells ? (int)(nx - c0) : kTileCells;
+        __syncwarp();
+        for (int r0 = 0; r0 < rows; r0 += 8) {  // lane = cell; 24 independent loads in flight per thread
+            double va[8], vb[8], vc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = r0 + k < rows && lane < cells;
+                const int64_t o = (m0 + (ok ? r0 + k : 0)) * nx + c0 + (ok ? lane : 0);
+                va[k] = __ldg(dl + o); vb[k] = __ldg(d + o); vc[k] = __ldg(du + o);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (r0 + k < rows && lane < cells) { sa[lane][r0 + k] = va[k]; sb[lane][r0 + k] = vb[k]; sc[lane][r0 + k] = vc[k]; }
+        }
+        __syncwarp();
+        if (lane < rows) {  // lane = model
+            for (int c = 0; c < cells; ++c) {
+                const double a = sa[c][lane], b = sb[c][lane], cc = sc[c][lane];
+                const double l = (c0 + c == 0) ? 0.0 : a * r_prev;
+                const double u = b - l * c_prev;
+                if (!bad && (u == 0.0 || !isfinite(u))) bad = (int32_t)(c0 + c + 1);
+                const double r = 1.0 / u;
+                sa[c][lane] = l;
+                sb[c][lane] = r;
+                sc[c][lane] = cc * r;
+                r_prev = r;
+                c_prev = cc;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; ++r) {
+            const int64_t o = (m0 + r) * nx + c0 + lane;
+            if (lane < cells) { fl[o] = sa[lane][r]; fr[o] = sb[lane][r]; fg[o] = sc[lane][r]; }
+        }
+    }
+    if (singular && lane < rows) singular[m0 + lane] = bad;
 }
 
 // ---- parallel variant ----
@@ -160,7 +223,7 @@ __global__ void __launch_bounds__(32 * kFacW) factor_apply_kernel(const double *
     if (cell0 >= nx) return;
     const double *v = tile_vec + ((int64_t)blockIdx.y * n_tiles + blockIdx.x) * 2;
     const double p = ex.a * v[0] + ex.b * v[1], q = ex.c * v[0] + ex.d * v[1];
-    double u_prev = p / q;  // pivot in front of my chunk (unused for the very first cell)
+    double r_prev = q / p;  // reciprocal of the pivot in front of my chunk (unused for the very first cell)
     double c_prev = cell0 > 0 ? du[o + cell0 - 1] : 0.0;
     int bad = 0;
 #pragma unroll
@@ -168,13 +231,14 @@ __global__ void __launch_bounds__(32 * kFacW) factor_apply_kernel(const double *
         const int64_t i = cell0 + j;
         if (i < nx) {
             const double a = dl[o + i], b = d[o + i], c = du[o + i];
-            const double l = (i == 0) ? 0.0 : a / u_prev;
+            const double l = (i == 0) ? 0.0 : a * r_prev;
             const double u = b - l * c_prev;
             if (!bad && (u == 0.0 || !isfinite(u))) bad = (int)(i + 1);
+            const double r = 1.0 / u;
             fl[o + i] = l;
-            fr[o + i] = 1.0 / u;
-            fg[o + i] = c / u;
-            u_prev = u;
+            fr[o + i] = r;
+            fg[o + i] = c * r;
+            r_prev = r;
             c_prev = c;
         }
     }
@@ -209,6 +273,16 @@ extern "C" int fbr_factorize_f64(const double *dl, const double *d, const double
     // the caller's work buffer
     const bool parallel = work && nx >= 512 && M * 8 < nx;
     if (!parallel) {
+        if (M >= 64 && !getenv("FBR_FACTORIZE_PLAIN")) {  // many models: stream through transposing tiles
+            const int64_t groups = (M + 31) / 32;
+            const int warps = groups >= 8 * 148 ? kTileWarps : 1;  // few groups: one warp per CTA spreads them over the SMs
+            const size_t smem = (size_t)warps * 3 * kTileCells * 33 * sizeof(double);
+            FBR_CUDA(cudaFuncSetAttribute(factorize_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)((size_t)kTileWarps * 3 * kTileCells * 33 * sizeof(double))));
+            factorize_tiled_kernel<<<(unsigned)((groups + warps - 1) / warps), 32 * warps, smem, st>>>(
+                dl, d, du, M, nx, fl, fr, fg, singular);
+            return check_launch("fbr_factorize_f64 (tiled)");
+        }
         const int block = M >= 128 * 148 ? 128 : 32;
         factorize_kernel<<<(unsigned)((M + block - 1) / block), block, 0, st>>>(dl, d, du, M, nx, fl, fr, fg, singular);
         return check_launch("fbr_factorize_f64");

@@ -89,8 +89,8 @@ int fbr_pml_sigma_f64(const double *mesh, int64_t nx, double pml_thickness, doub
 /* ------------------------------------------------------------------------------------------
  * K1b time-invariant factorisation.  A is constant for a fixed dt (only b changes,
  * src/fiberis/simulator/core/pds.py:287-310), so the elimination is done once:
- *   u_0 = d_0, l_i = dl_i / u_{i-1}, u_i = d_i - l_i du_{i-1}
- *   fl = l, fr = 1 / u, fg = du / u            (each (M, nx))
+ *   u_0 = d_0, r_i = 1 / u_i, l_i = dl_i r_{i-1}, u_i = d_i - l_i du_{i-1}
+ *   fl = l, fr = r, fg = du r                  (each (M, nx); one division per cell)
  * work: NULL, or fbr_factorize_work_bytes(M, nx) bytes of scratch; with it, long systems
  * (nx >= 512 and nx > 8 M) are factorised in parallel along the mesh (scan of 2x2 Moebius
  * matrices for the pivot in front of every 8-cell chunk, then the plain recurrence inside the

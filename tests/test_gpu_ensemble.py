@@ -233,3 +233,27 @@ def test_sweep_finds_the_generating_candidate_and_refines():
     assert all(b1 <= b0 for b0, b1 in zip(best, best[1:])) and best[-1] < 0.05 * best[0]
     # the zones that hold the sources are well determined by the data (the one between them is not)
     assert np.max(np.abs(ref["best_theta"] - truth)[[0, 2]]) < 0.05
+
+
+def test_tiled_factorisation_is_bit_identical_to_the_plain_recurrence(monkeypatch):
+    """K1b for many models streams through transposing shared-memory tiles; per model it performs the
+    same operations in the same order as the thread-per-model kernel."""
+    import torch
+    from fiberis_b200 import _engine as E
+    for M, nx in [(64, 33), (100, 512), (257, 1000), (1000, 31)]:
+        rng = np.random.default_rng(M + nx)
+        mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+        zone = (np.arange(nx) * 4) // nx
+        zv = 10.0 ** rng.uniform(-1, 1, (M, 4))
+        sidx_d, n_src = E.index_tensor(np.array([nx // 3]))
+        diag = E.assemble_zonal(E.to_device(mesh), E.to_device(zv), E.to_device(zone, np.int32), M, nx, 0.7, "Neumann",
+                                "Dirichlet", sidx_d, n_src)
+        tiled = torch.stack(E.factorize(*diag, parallel=False)).cpu().numpy()
+        monkeypatch.setenv("FBR_FACTORIZE_PLAIN", "1")
+        plain = torch.stack(E.factorize(*diag, parallel=False)).cpu().numpy()
+        monkeypatch.delenv("FBR_FACTORIZE_PLAIN")
+        npt.assert_array_equal(tiled, plain)
+    # zero pivots are still flagged per model
+    dl = np.zeros((70, 40)); d = np.ones((70, 40)); du = np.zeros((70, 40)); d[5, 17] = 0.0
+    with pytest.raises(np.linalg.LinAlgError):
+        E.factorize(E.to_device(dl), E.to_device(d), E.to_device(du))
