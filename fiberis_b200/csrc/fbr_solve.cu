@@ -35,6 +35,105 @@ __global__ void __launch_bounds__(128) thomas_kernel(const double *__restrict__ 
     if (singular) singular[m] = bad;
 }
 
+// ---- THOMAS through transposing tiles: the "interleaved layout" is made on the fly ----
+// A warp owns 32 systems and walks the mesh in tiles of 32 cells: tiles are read / written with
+// coalesced 256-byte requests (lane = cell) and processed with lane = system out of shared memory
+// ([cell][33] doubles: conflict-free both ways).  Forward sweep stores the modified super-diagonal in
+// `work` and the intermediate solution in x; the backward sweep walks the tiles in reverse.
+// 72 B of traffic per unknown (40 B in, 16 B scratch out and in again, 8 B + 8 B for x).
+constexpr int kThCells = 32, kThWarps = 2;
+
+template <int NARR>
+__device__ __forceinline__ void tile_load(double (*const (&dst)[NARR])[33], const double *const (&src)[NARR], int64_t m0,
+                                          int rows, int64_t nx, int64_t c0, int cells, int lane) {
+    for (int r0 = 0; r0 < rows; r0 += 8) {  // 8 * NARR independent loads in flight per thread
+        double v[NARR][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool ok = r0 + k < rows && lane < cells;
+            const int64_t o = (m0 + (ok ? r0 + k : 0)) * nx + c0 + (ok ? lane : 0);
+#pragma unroll
+            for (int q = 0; q < NARR; ++q) v[q][k] = src[q][o];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (r0 + k < rows && lane < cells) {
+#pragma unroll
+                for (int q = 0; q < NARR; ++q) dst[q][lane][r0 + k] = v[q][k];
+            }
+    }
+}
+
+__global__ void __launch_bounds__(32 * kThWarps) thomas_tiled_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                                     const double *__restrict__ du, const double *b, double *x,
+                                                                     int64_t M, int64_t nx, double *__restrict__ work,
+                                                                     int32_t *__restrict__ singular) {
+    extern __shared__ double s_tile[];  // [warp][4][cell][33]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double(*s0)[33] = reinterpret_cast<double(*)[33]>(s_tile + (size_t)warp * 4 * kThCells * 33);
+    double(*s1)[33] = s0 + kThCells;
+    double(*s2)[33] = s1 + kThCells;
+    double(*s3)[33] = s2 + kThCells;
+    const int64_t m0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+    if (m0 >= M) return;
+    const int rows = M - m0 < 32 ? (int)(M - m0) : 32;
+    double cp = 0.0, xp = 0.0;
+    int32_t bad = 0;
+    // ---- forward ----
+    for (int64_t c0 = 0; c0 < nx; c0 += kThCells) {
+        const int cells = nx - c0 < kThCells ? (int)(nx - c0) : kThCells;
+        __syncwarp();
+        {
+            double(*const dst[4])[33] = {s0, s1, s2, s3};
+            const double *const src[4] = {dl, d, du, b};
+            tile_load<4>(dst, src, m0, rows, nx, c0, cells, lane);
+        }
+        __syncwarp();
+        if (lane < rows) {
+            for (int c = 0; c < cells; ++c) {
+                const double a = s0[c][lane];
+                const double den = s1[c][lane] - a * cp;
+                if (!bad && (den == 0.0 || !isfinite(den))) bad = (int32_t)(c0 + c + 1);
+                const double r = 1.0 / den;
+                cp = s2[c][lane] * r;
+                xp = (s3[c][lane] - a * xp) * r;
+                s0[c][lane] = cp;
+                s1[c][lane] = xp;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; ++r) {
+            const int64_t o = (m0 + r) * nx + c0 + lane;
+            if (lane < cells) { work[o] = s0[lane][r]; x[o] = s1[lane][r]; }
+        }
+    }
+    // ---- backward ----
+    const int64_t last0 = (nx - 1) / kThCells * kThCells;
+    for (int64_t c0 = last0; c0 >= 0; c0 -= kThCells) {
+        const int cells = nx - c0 < kThCells ? (int)(nx - c0) : kThCells;
+        __syncwarp();
+        {
+            double(*const dst[2])[33] = {s0, s1};
+            const double *const src[2] = {work, x};
+            tile_load<2>(dst, src, m0, rows, nx, c0, cells, lane);
+        }
+        __syncwarp();
+        if (lane < rows) {
+            for (int c = cells - 1; c >= 0; --c) {
+                if (c0 + c < nx - 1) xp = s1[c][lane] - s0[c][lane] * xp;
+                else xp = s1[c][lane];
+                s1[c][lane] = xp;
+            }
+        }
+        __syncwarp();
+        for (int r = 0; r < rows; ++r) {
+            const int64_t o = (m0 + r) * nx + c0 + lane;
+            if (lane < cells) x[o] = s1[lane][r];
+        }
+    }
+    if (singular && lane < rows) singular[m0 + lane] = bad;
+}
+
 // ---- PCR: CTA per system; every level halves the coupling distance ----
 template <int CELLS>
 __global__ void __launch_bounds__(1024) pcr_kernel(const double *__restrict__ dl, const double *__restrict__ d,
@@ -156,9 +255,10 @@ extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const do
     FBR_REQUIRE(M >= 1 && nx >= 1 && dl && d && du && b && x, "bad argument");
     FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_PCR, "unknown solver variant %d", variant);
     if (variant == FBR_SOLVER_AUTO)
-        // measured on B200 (scratch/k2_bench.py, 40 B per unknown): PCR 0.3 - 1.5 TB/s over nx = 64 .. 4096
-        // at any batch size, thread-per-system Thomas on the model-major layout 0.01 - 0.27 TB/s
-        variant = (nx <= kPcrMaxNx && nx >= 32) ? FBR_SOLVER_PCR : FBR_SOLVER_THOMAS;
+        // measured on B200 (scratch/k2_bench.py, profiles/r01_k2_bare_solve.txt): from ~3e4 systems the
+        // tile-transposed Thomas wins (1M x 64: 1.56 vs 1.80 ms, 65536 x 512: 1.13 vs 1.29 ms), below that
+        // PCR; the plain thread-per-system walk on the model-major layout is 4 - 30x slower than either
+        variant = (nx <= kPcrMaxNx && nx >= 32 && !(M >= 32768 && work)) ? FBR_SOLVER_PCR : FBR_SOLVER_THOMAS;
     if (variant == FBR_SOLVER_PCR) {
         if (nx > kPcrMaxNx)
             return fail(FBR_ERR_UNSUPPORTED, "PCR variant covers nx <= %d (got %lld)", kPcrMaxNx, (long long)nx);
@@ -179,6 +279,16 @@ extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const do
         }
     }
     FBR_REQUIRE(work, "the THOMAS variant needs a work array of fbr_solve_tridiag_work_bytes()");
+    if (M >= 64 && !getenv("FBR_THOMAS_PLAIN")) {  // many systems: coalesced through transposing tiles
+        const int64_t groups = (M + 31) / 32;
+        const int warps = groups >= 4 * 148 ? kThWarps : 1;
+        const size_t smem = (size_t)warps * 4 * kThCells * 33 * sizeof(double);
+        FBR_CUDA(cudaFuncSetAttribute(thomas_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)kThWarps * 4 * kThCells * 33 * sizeof(double))));
+        thomas_tiled_kernel<<<(unsigned)((groups + warps - 1) / warps), 32 * warps, smem, as_stream(stream)>>>(
+            dl, d, du, b, x, M, nx, work, singular);
+        return check_launch("fbr_solve_tridiag_f64 (Thomas, tiled)");
+    }
     const int block = M >= 128 * 148 ? 128 : 32;
     thomas_kernel<<<(unsigned)((M + block - 1) / block), block, 0, as_stream(stream)>>>(dl, d, du, b, x, M, nx, work,
                                                                                        singular);

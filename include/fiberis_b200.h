@@ -45,7 +45,8 @@ enum { FBR_BC_NONE = 0, FBR_BC_DIRICHLET = 1, FBR_BC_NEUMANN = 2 };
 /* Solver variants for fbr_solve_tridiag_* (north_star: "variant chosen by mesh length"). */
 enum {
     FBR_SOLVER_AUTO = 0,
-    FBR_SOLVER_THOMAS = 1, /* one thread per system (many small systems)            */
+    FBR_SOLVER_THOMAS = 1, /* one thread per system, tiles transposed in shared memory so that
+                              global traffic is coalesced (many small systems)        */
     FBR_SOLVER_PCR = 2     /* one CTA per system, shared-memory parallel cyclic reduction */
 };
 
