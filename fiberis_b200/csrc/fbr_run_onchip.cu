@@ -445,6 +445,24 @@ __device__ __forceinline__ T pick_at(const T (&x)[CPT], int j) {
     return v;
 }
 
+// A thread's 64 bytes straight to global memory (16-byte stores when aligned).
+template <typename T, int CPT>
+__device__ __forceinline__ void store_row_direct(T *__restrict__ dst, int64_t cell0, int64_t nx, const T (&x)[CPT]) {
+    if (cell0 + CPT <= nx && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        constexpr int PER = 16 / sizeof(T);
+#pragma unroll
+        for (int q = 0; q < CPT / PER; ++q) {
+            if constexpr (sizeof(T) == 8) reinterpret_cast<double2 *>(dst)[q] = make_double2((double)x[2 * q], (double)x[2 * q + 1]);
+            else reinterpret_cast<float4 *>(dst)[q] = make_float4((float)x[(4 * q) % CPT], (float)x[(4 * q + 1) % CPT],
+                                                                   (float)x[(4 * q + 2) % CPT], (float)x[(4 * q + 3) % CPT]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (cell0 + j < nx) dst[j] = x[j];
+    }
+}
+
 // One row of a warp's 32 * CPT cells to global memory with coalesced stores.  A thread holds CPT
 // consecutive cells (64 bytes); written directly, every store instruction would touch 32 half-filled
 // sectors 64 bytes apart (measured: 2.3 us per recorded row).  Instead the warp transposes through a
@@ -628,6 +646,10 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
         const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
         int to_snap = snap_slot >= 0 ? snap_every : 0x7fffffff;  // never reaches 0 when not recorded
         T *snap_row = reinterpret_cast<T *>(a.snap) + (snap_slot >= 0 ? snap_slot : 0) * a.snap_model_stride;
+        // a handful of CTAs (single models): the row goes out with plain 16-byte stores straight from the
+        // registers — no latency on the step; a full grid of recording members is bandwidth-bound and
+        // takes the transposing, fully coalesced path
+        const bool direct_rows = gridDim.x <= 64;
         int done = 0;
         while (done < n_steps) {
             const int b = done / blk;
@@ -646,11 +668,10 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             }
             int run = blk - done % blk;
             if (run > n_steps - done) run = n_steps - done;
-            if (to_snap < run) run = to_snap;
             // two copies of the step loop: the common one carries no code for threads that own several
             // overridden / observed cells, which keeps its instruction footprint small
-            auto steps = [&](auto slow_tag, int n_begin, int n_end) {
-                constexpr bool SLOW = decltype(slow_tag)::value;
+            auto steps = [&](auto slow_tag, auto rec_tag, int n_begin, int n_end) {
+                constexpr bool SLOW = decltype(slow_tag)::value, REC = decltype(rec_tag)::value;
 #pragma unroll 1
                 for (int n = n_begin; n < n_end; ++n) {
                     // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
@@ -711,18 +732,23 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                             if (jj >= 0 && jj < CPT) row[k] = (double)pick_at<T, CPT>(x, (int)jj);
                         }
                     }
+                    // ---- sampled snapshot (CTA-uniform countdown; never fires for unrecorded members) ----
+                    if (REC && --to_snap == 0) {
+                        to_snap = snap_every;
+                        if (direct_rows) store_row_direct<T, CPT>(snap_row + cell0, cell0, nx, x);
+                        else store_row_coalesced<T, CPT>(snap_row, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane);
+                        snap_row += a.snap_row_stride;
+                    }
                 }
             };
-            if (any_slow) steps(std::true_type{}, done, done + run);
-            else steps(std::false_type{}, done, done + run);
-            done += run;
-            to_snap -= run;
-            // ---- sampled snapshot ----
-            if (to_snap == 0) {
-                to_snap = snap_every;
-                store_row_coalesced<T, CPT>(snap_row, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane);
-                snap_row += a.snap_row_stride;
+            if (snap_slot >= 0) {  // (the copy for unrecorded members carries no snapshot code)
+                if (any_slow) steps(std::true_type{}, std::true_type{}, done, done + run);
+                else steps(std::false_type{}, std::true_type{}, done, done + run);
+            } else {
+                if (any_slow) steps(std::true_type{}, std::false_type{}, done, done + run);
+                else steps(std::false_type{}, std::false_type{}, done, done + run);
             }
+            done += run;
         }
         cp_async_wait_all_k3();
         __syncthreads();
@@ -833,7 +859,9 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
         if ((v == 1 || v == 2 || v == 4 || v == 8) && (a.nx + v - 1) / v <= 32 * kMaxWarps) cpt = v;
     }
     // 256 cells (fp64) / 512 cells (fp32 mode) and up: the 64-byte-per-thread kernel
-    if (a.nx >= 32 * (int64_t)(64 / sizeof(T)) && !getenv("FBR_K3_GENERIC")) return launch_x<T>(a, stream);
+    const char *min_env = getenv("FBR_K3_X_MIN_NX");  // tuning aid
+    const int64_t x_min = min_env ? atoll(min_env) : 32 * (int64_t)(64 / sizeof(T));
+    if (a.nx >= x_min && !getenv("FBR_K3_GENERIC")) return launch_x<T>(a, stream);
     switch (cpt) {
         case 1: return launch_cpt<T, 1>(a, stream);
         case 2: return launch_cpt<T, 2>(a, stream);
