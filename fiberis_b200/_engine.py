@@ -315,16 +315,24 @@ def adaptive_max_nx() -> int:
 
 
 def run_adaptive(mesh, diffusivity, state, ctrl, lbc, rbc, src_idx, n_src, src_taxis, src_data, src_len, t0, t_total,
-                 tol, adj_tol, safety, p_order, max_dt, min_dt, max_iters, capacity):
+                 tol, adj_tol, safety, p_order, max_dt, min_dt, max_iters, capacity, snap_models=None, n_snap_models=None):
     """One launch of the device-side adaptive loop for M models (state (M, nx), ctrl (M, 2) updated in
-    place).  Returns (snap (M, capacity, nx), taxis (M, capacity), counts (M, 4) int64) on the device."""
+    place).  ``snap_models`` (device int64 list, None = all): the models whose accepted states are
+    recorded.  Returns (snap (recorded, capacity, nx), taxis (recorded, capacity), counts (M, 4) int64)
+    on the device."""
     torch = _torch()
     lib = _cabi.load()
     M, nx = state.shape
     dev = state.device
-    snap = torch.empty((M, capacity, nx), dtype=torch.float64, device=dev)
-    taxis = torch.empty((M, capacity), dtype=torch.float64, device=dev)
+    n_rec = M if snap_models is None else int(n_snap_models)
+    snap = torch.empty((max(n_rec, 1), capacity, nx), dtype=torch.float64, device=dev)
+    taxis = torch.empty((max(n_rec, 1), capacity), dtype=torch.float64, device=dev)
     counts = torch.zeros((M, 4), dtype=torch.int64, device=dev)
+    if snap_models is None and n_rec == 0:
+        raise ValueError("no models")
+    rec_ptr = ptr(snap_models) if (snap_models is not None and n_rec > 0) else None
+    if snap_models is not None and n_rec == 0:  # nothing recorded: an empty list needs a non-NULL pointer
+        rec_ptr = ptr(torch.zeros(1, dtype=torch.int64, device=dev))
     ms = 0 if mesh.dim() == 1 else nx
     ds = 0 if diffusivity.dim() == 1 else nx
     width = int(src_taxis.shape[1]) if n_src else 0
@@ -332,7 +340,7 @@ def run_adaptive(mesh, diffusivity, state, ctrl, lbc, rbc, src_idx, n_src, src_t
                                    ptr(src_idx), n_src, ptr(src_taxis), ptr(src_data), ptr(src_len), width, float(t0),
                                    float(t_total), ptr(ctrl), float(tol), float(adj_tol), float(safety), float(p_order),
                                    float(max_dt), float(min_dt), int(max_iters), int(capacity), ptr(snap), ptr(taxis),
-                                   ptr(counts), current_stream()))
+                                   rec_ptr, n_rec, ptr(counts), current_stream()))
     return snap, taxis, counts
 
 

@@ -13,13 +13,13 @@
 //     thread then runs the plain sequential recurrence, so all factors come out of the same
 //     formulas as in the sequential variant (the chunk start differs from it by a few ulps at most).
 #include "fbr_common.cuh"
+#include "fbr_moebius.cuh"
 
 namespace fbr {
 
 constexpr int kFacCPT = 8;
 constexpr int kFacW = 4;
 constexpr int kFacTile = 32 * kFacW * kFacCPT;
-constexpr unsigned kAll = 0xffffffffu;
 
 // ---- sequential variant ----
 __global__ void __launch_bounds__(128) factorize_kernel(const double *__restrict__ dl, const double *__restrict__ d,
@@ -107,34 +107,6 @@ __global__ void __launch_bounds__(32 * kTileWarps) factorize_tiled_kernel(
 }
 
 // ---- parallel variant ----
-struct Mat2 {  // [[a, b], [c, d]]
-    double a, b, c, d;
-};
-
-__device__ __forceinline__ Mat2 rescale(Mat2 m) {
-    const double big = fmax(fmax(fabs(m.a), fabs(m.b)), fmax(fabs(m.c), fabs(m.d)));
-    if (big > 0.0 && isfinite(big)) {
-        const int e = -ilogb(big);
-        m.a = scalbn(m.a, e); m.b = scalbn(m.b, e); m.c = scalbn(m.c, e); m.d = scalbn(m.d, e);
-    }
-    return m;
-}
-// later * earlier (apply `earlier` first)
-__device__ __forceinline__ Mat2 compose(const Mat2 &later, const Mat2 &earlier) {
-    Mat2 r;
-    r.a = later.a * earlier.a + later.b * earlier.c;
-    r.b = later.a * earlier.b + later.b * earlier.d;
-    r.c = later.c * earlier.a + later.d * earlier.c;
-    r.d = later.c * earlier.b + later.d * earlier.d;
-    return rescale(r);
-}
-__device__ __forceinline__ Mat2 shfl_up_mat(const Mat2 &m, int delta) {
-    Mat2 r;
-    r.a = __shfl_up_sync(kAll, m.a, delta); r.b = __shfl_up_sync(kAll, m.b, delta);
-    r.c = __shfl_up_sync(kAll, m.c, delta); r.d = __shfl_up_sync(kAll, m.d, delta);
-    return r;
-}
-
 // Composite of the thread's chunk, then inclusive scan over the tile.  Returns the EXCLUSIVE prefix of
 // this thread within the tile (identity for thread 0); *tile_total receives the whole-tile composite
 // (valid in every thread).

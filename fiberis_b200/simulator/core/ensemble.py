@@ -280,8 +280,12 @@ class PDS1D_Ensemble:
         tol = kwargs.get("tol", 1e-3)
         safety, p_order = kwargs.get("safety_factor", 0.9), kwargs.get("p", 2)
         max_dt, min_dt = kwargs.get("max_dt", 40), kwargs.get("min_dt", 1e-4)
-        capacity = int(max(4, min(256, (256 << 20) // (8 * nx * M))))
         audit = [int(a) - lo for a in audit_models if lo <= int(a) < hi]
+        audit_d, n_rec = _engine.index_tensor(np.asarray(sorted(set(audit)), dtype=np.int64)) if audit else (None, 0)
+        if audit_d is None:
+            audit_d = torch.zeros(1, dtype=torch.int64, device=mesh_d.device)  # empty list: nobody is recorded
+        rec_slot = {a: k for k, a in enumerate(sorted(set(audit)))}
+        capacity = int(max(4, min(4096, (256 << 20) // (8 * nx * max(n_rec, 1)))))
         rows = {a: [np.asarray(init[lo + a], dtype=np.float64)[None, :]] for a in audit}
         times = {a: [np.array([float(self.t0)])] for a in audit}
         accepted = np.zeros(M, dtype=np.int64)
@@ -292,16 +296,16 @@ class PDS1D_Ensemble:
             left = per_launch_cap if max_iterations is None else int(min(per_launch_cap, max(0, max_iterations - used.min())))
             snap, tax, counts = _engine.run_adaptive(mesh_d, diff_d, state, ctrl, self.lbc, self.rbc, sidx_d, n_src, st_d,
                                                      sd_d, len_d, self.t0, t_total, tol, 1e-3, safety, p_order, max_dt,
-                                                     min_dt, left, capacity)
+                                                     min_dt, left, capacity, snap_models=audit_d, n_snap_models=n_rec)
             c = counts.cpu().numpy()
             if np.any(c[:, 3]):
                 m = int(np.nonzero(c[:, 3])[0][0])
                 raise np.linalg.LinAlgError(f"Matrix is singular (model {lo + m}: zero pivot at row {int(c[m, 3]) - 1}).")
-            for a in audit:
+            for a in rec_slot:
                 n = int(c[a, 0])
                 if n:
-                    rows[a].append(snap[a, :n].cpu().numpy())
-                    times[a].append(tax[a, :n].cpu().numpy())
+                    rows[a].append(snap[rec_slot[a], :n].cpu().numpy())
+                    times[a].append(tax[rec_slot[a], :n].cpu().numpy())
             accepted += c[:, 0]
             used += c[:, 1]
             done = c[:, 2] != 0

@@ -243,10 +243,15 @@ int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, c
  *   state : (M, nx) in/out current pressure;  ctrl: (M, 2) in/out = (t, dt)
  *   tol   : accept threshold; adj_tol: the tol adjust_dt uses (the reference never forwards the
  *           user's tol to adjust_dt, so callers pass 1e-3); safety, p_order, max_dt, min_dt as in tso
- *   snap  : (M, capacity, nx) accepted states in order; taxis_out: (M, capacity) their times
- *   counts: (M, 4) int64 out = accepted rows, iterations used, done (t >= t_total), 1 + zero-pivot row
- * The kernel returns when `capacity` rows are filled, t >= t_total or max_iters iterations ran;
- * call again with the same state / ctrl to continue.  nx <= fbr_run_adaptive_max_nx(); no PML.
+ *   snap_models / n_snap_models : the models whose accepted states are RECORDED (int64 list; NULL = all M,
+ *           n_snap_models must then be M).  Sweeps record a few audited members only: the others then
+ *           write nothing per step and are not stopped by `capacity`.
+ *   snap  : (n_snap_models, capacity, nx) accepted states in order; taxis_out: (n_snap_models, capacity)
+ *   counts: (M, 4) int64 out = accepted steps, iterations used, done (t >= t_total), 1 + zero-pivot row
+ * A member returns when its `capacity` rows are filled (recorded members only), t >= t_total or max_iters
+ * iterations ran; call again with the same state / ctrl to continue.  nx <= fbr_run_adaptive_max_nx();
+ * no PML.  Implementation: a thread owns 8 cells; A(h) is factorised in registers (pivots from a warp
+ * scan of 2x2 Moebius matrices, one division per cell) and applied with the run kernels' scan sweeps.
  * ------------------------------------------------------------------------------------------ */
 int64_t fbr_run_adaptive_max_nx(void);
 int fbr_run_adaptive_f64(const double *mesh, int64_t mesh_stride, const double *diffusivity,
@@ -255,7 +260,8 @@ int fbr_run_adaptive_f64(const double *mesh, int64_t mesh_stride, const double *
                          const double *src_data, const int32_t *src_len, int src_width, double t0,
                          double t_total, double *ctrl, double tol, double adj_tol, double safety,
                          double p_order, double max_dt, double min_dt, int64_t max_iters,
-                         int64_t capacity, double *snap, double *taxis_out, int64_t *counts,
+                         int64_t capacity, double *snap, double *taxis_out,
+                         const int64_t *snap_models, int64_t n_snap_models, int64_t *counts,
                          void *stream);
 
 /* Right-hand side of one step, b = p with boundary / source overrides
