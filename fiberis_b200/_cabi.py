@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libf
 
 FBR_OK, FBR_ERR_BAD_ARG, FBR_ERR_UNSUPPORTED, FBR_ERR_CUDA = 0, -1, -2, -3
 BC_CODES = {"None": 0, "Dirichlet": 1, "Neumann": 2}
-SOLVER_AUTO, SOLVER_THOMAS, SOLVER_PCR = 0, 1, 2
+SOLVER_AUTO, SOLVER_THOMAS, SOLVER_PCR, SOLVER_REG = 0, 1, 2, 3
 
 _p = C.c_void_p
 _i64 = C.c_int64

@@ -417,7 +417,7 @@ def solve_tridiag(dl, d, du, b, variant=_cabi.SOLVER_AUTO, check_singular=True):
     x = torch.empty_like(b)
     flags = torch.zeros(M, dtype=torch.int32, device=d.device)
     work = None
-    if variant == _cabi.SOLVER_THOMAS or (variant == _cabi.SOLVER_AUTO and (nx < 32 or nx > 4096 or M >= 32768)):
+    if variant == _cabi.SOLVER_THOMAS or (variant == _cabi.SOLVER_AUTO and nx > 4096):
         work = torch.empty((M, nx), dtype=torch.float64, device=d.device)
     check(lib.fbr_solve_tridiag_f64(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(x), M, nx, int(variant), ptr(work),
                                     ptr(flags), current_stream()))

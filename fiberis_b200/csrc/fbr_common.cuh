@@ -51,6 +51,11 @@ struct DeviceFacts {
 };
 int device_facts(DeviceFacts *out);
 
+// K2 REG (fbr_solve_reg.cu): register-resident bare solve, 1 <= nx <= kSolveRegMaxNx
+constexpr int kSolveRegMaxNx = 4096;
+int solve_reg_dispatch(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
+                       int32_t *singular, cudaStream_t stream);
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace fbr

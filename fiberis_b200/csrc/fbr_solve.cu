@@ -1,7 +1,8 @@
 // K2  bare batched tridiagonal solves (matrix changes every call: adaptive time stepping) and the
 // Jacobi "explicit" mode.  Two variants, chosen by shape (north_star: "variant chosen by mesh length"):
-//   THOMAS  one thread per system, sequential elimination      -> many systems
-//   PCR     one CTA per system, shared-memory parallel cyclic reduction, log2(nx) levels -> few, longer systems
+//   THOMAS  one thread per system, sequential elimination      -> systems longer than 4096 cells
+//   PCR     one CTA per system, shared-memory parallel cyclic reduction, log2(nx) levels
+//   REG     register-resident Moebius-scan pivots + scan sweeps (fbr_solve_reg.cu) -> AUTO's choice up to 4096 cells
 #include "fbr_common.cuh"
 
 namespace fbr {
@@ -245,7 +246,8 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const double *__restrict__
 using namespace fbr;
 
 extern "C" int64_t fbr_solve_tridiag_work_bytes(int64_t M, int64_t nx, int variant) {
-    if (variant == FBR_SOLVER_PCR) return 0;
+    if (variant == FBR_SOLVER_PCR || variant == FBR_SOLVER_REG) return 0;
+    if (variant == FBR_SOLVER_AUTO && nx <= kSolveRegMaxNx) return 0;
     return M * nx * (int64_t)sizeof(double);
 }
 
@@ -253,12 +255,12 @@ extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const do
                                      double *x, int64_t M, int64_t nx, int variant, double *work,
                                      int32_t *singular, void *stream) {
     FBR_REQUIRE(M >= 1 && nx >= 1 && dl && d && du && b && x, "bad argument");
-    FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_PCR, "unknown solver variant %d", variant);
+    FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_REG, "unknown solver variant %d", variant);
     if (variant == FBR_SOLVER_AUTO)
-        // measured on B200 (scratch/k2_bench.py, profiles/r01_k2_bare_solve.txt): from ~3e4 systems the
-        // tile-transposed Thomas wins (1M x 64: 1.56 vs 1.80 ms, 65536 x 512: 1.13 vs 1.29 ms), below that
-        // PCR; the plain thread-per-system walk on the model-major layout is 4 - 30x slower than either
-        variant = (nx <= kPcrMaxNx && nx >= 32 && !(M >= 32768 && work)) ? FBR_SOLVER_PCR : FBR_SOLVER_THOMAS;
+        // measured on B200 (scratch/k2_bench.py, profiles/r01_k2_bare_solve.txt): the register-resident variant
+        // wins at every shape it covers; beyond 4096 cells the tile-transposed Thomas walk
+        variant = nx <= kSolveRegMaxNx ? FBR_SOLVER_REG : FBR_SOLVER_THOMAS;
+    if (variant == FBR_SOLVER_REG) return solve_reg_dispatch(dl, d, du, b, x, M, nx, singular, as_stream(stream));
     if (variant == FBR_SOLVER_PCR) {
         if (nx > kPcrMaxNx)
             return fail(FBR_ERR_UNSUPPORTED, "PCR variant covers nx <= %d (got %lld)", kPcrMaxNx, (long long)nx);

@@ -1,0 +1,262 @@
+// K2 REG  bare batched tridiagonal solve, register-resident: one pass over HBM (40 B per unknown:
+// dl, d, du, b in, x out), no scratch array, no shared-memory copy of the system.
+//
+// A thread owns CPT consecutive cells of one system (64 bytes per array, 16-byte loads), W warps own a
+// system.  The elimination is made parallel along the mesh the same way as in the adaptive loop
+// (fbr_adaptive.cu) and the run kernels (fbr_sweep.cuh):
+//   1. pivots: u_i = d_i - dl_i du_{i-1} / u_{i-1} is a Moebius map of u_{i-1}.  With u_i = p_i / p_{i-1}
+//      it is the linear recurrence p_i = d_i p_{i-1} + e_i p_{i-2}, e_i = -dl_i du_{i-1} (the p_i are the
+//      leading principal minors up to a power-of-two scale).  A thread composes the 2x2 matrix of its
+//      chunk, the warp scans the matrices (fbr_moebius.cuh), warps exchange their totals through shared
+//      memory; the thread then runs the two-term recurrence from the true (p, q) in front of its chunk —
+//      FMAs only on the dependent chain — and takes r_i = p_{i-1} / p_i with CPT INDEPENDENT divisions
+//      (the sequential algorithm has one division per cell ON the chain).
+//   2. Thomas in its normalised form: z_i = r_i b_i - (r_i dl_i) z_{i-1};  x_i = z_i - (r_i du_i) x_{i+1}:
+//      two first-order linear recurrences = two scan sweeps (local pass, Kogge-Stone over the warp with the
+//      multipliers' running products, carry over the warps, second local pass).
+// Rows beyond nx are padded with identity rows.  Zero / non-finite pivots are flagged per system
+// (1 + first such row among the rows a thread saw; 0 = fine), like the other K2 variants.
+#include "fbr_common.cuh"
+#include "fbr_moebius.cuh"
+#include "fbr_sweep.cuh"
+
+namespace fbr {
+
+// scale a 2x2 matrix / a pair by the power of two that brings its largest entry to [1, 2): integer
+// work on the exponent fields only (the library scalbn / ilogb pair costs ~10x as much)
+__device__ __forceinline__ double pow2_scale_for(int hi_max_exp_field) {
+    // hi_max_exp_field = (hi word & 0x7ff00000) of the largest magnitude;  2^(1023 - E) has hi word 0x7fe00000 - field
+    int s = max(0x7fe00000 - hi_max_exp_field, 0x00100000);  // never below the smallest normal
+    if (hi_max_exp_field >= 0x7ff00000) s = 0x3ff00000;      // inf / nan: leave alone
+    return __hiloint2double(s, 0);
+}
+__device__ __forceinline__ int exp_field(double v) { return __double2hiint(v) & 0x7ff00000; }
+__device__ __forceinline__ Mat2 rescale_fast(Mat2 m) {
+    const double s = pow2_scale_for(max(max(exp_field(m.a), exp_field(m.b)), max(exp_field(m.c), exp_field(m.d))));
+    m.a *= s; m.b *= s; m.c *= s; m.d *= s;
+    return m;
+}
+__device__ __forceinline__ Mat2 compose_raw(const Mat2 &later, const Mat2 &earlier) {
+    Mat2 r;
+    r.a = fma(later.a, earlier.a, later.b * earlier.c);
+    r.b = fma(later.a, earlier.b, later.b * earlier.d);
+    r.c = fma(later.c, earlier.a, later.d * earlier.c);
+    r.d = fma(later.c, earlier.b, later.d * earlier.d);
+    return r;
+}
+
+template <int CPT>
+__device__ __forceinline__ void load_chunk(const double *__restrict__ row, int64_t cell0, int64_t nx, bool vec, double pad,
+                                           double (&v)[CPT]) {
+    if (vec) {
+        const double2 *q = reinterpret_cast<const double2 *>(row + cell0);
+#pragma unroll
+        for (int j = 0; j < CPT / 2; ++j) {
+            const double2 t = __ldg(q + j);
+            v[2 * j] = t.x;
+            v[2 * j + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) v[j] = cell0 + j < nx ? __ldg(row + cell0 + j) : pad;
+    }
+}
+
+// W warps per system, S systems per CTA (S > 1 only with W == 1: no CTA barrier inside the loop then)
+template <int CPT, int W, int S>
+__global__ void __launch_bounds__(32 * W * S) solve_reg_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                               const double *__restrict__ du, const double *b, double *x,
+                                                               int64_t M, int64_t nx, int32_t *__restrict__ singular) {
+    static_assert(S == 1 || W == 1, "several systems per CTA only for single-warp systems");
+    static_assert(CPT % 2 == 0, "16-byte accesses and sign-free chunk products need an even chunk");
+    __shared__ Mat2 s_w[W];
+    __shared__ double s_E[2][W], s_T[2][W];
+    __shared__ unsigned s_first[W];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wl = W > 1 ? warp : 0, sys = W > 1 ? 0 : warp;
+    const int64_t cell0 = ((int64_t)wl * 32 + lane) * CPT;
+    const int keep_f = lane == 0 ? 0 : -1, keep_b = lane == 31 ? 0 : -1;
+    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(dl) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(du) |
+                          reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+
+    for (int64_t m = (int64_t)blockIdx.x * S + sys; m < M; m += (int64_t)gridDim.x * S) {
+        const int64_t o = m * nx;
+        const bool vec = ptr_ok && cell0 + CPT <= nx && ((o + cell0) & 1) == 0;
+        double l[CPT], dd[CPT], g[CPT], v[CPT];
+        load_chunk<CPT>(dl + o, cell0, nx, vec, 0.0, l);
+        load_chunk<CPT>(d + o, cell0, nx, vec, 1.0, dd);
+        load_chunk<CPT>(du + o, cell0, nx, vec, 0.0, g);
+        load_chunk<CPT>(b + o, cell0, nx, vec, 0.0, v);
+        // super-diagonal entry of the row in front of my chunk; the first sub- and the last super-diagonal entry are
+        // outside the matrix
+        double c_prev = __shfl_up_sync(kAll, g[CPT - 1], 1);
+        if (lane == 0) c_prev = (cell0 > 0 && cell0 <= nx) ? __ldg(du + o + cell0 - 1) : 0.0;
+        if (cell0 == 0) l[0] = 0.0;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (cell0 + j == nx - 1) g[j] = 0.0;
+        if (cell0 == nx) c_prev = 0.0;  // first padding row
+
+        // ---- 1. pivots ----
+        // e_j = -dl_j du_{j-1} replaces dl_j for now (dl_j itself is recovered as needed: kept in l, e in ee)
+        double ee[CPT];
+        {
+            double cp = c_prev;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                ee[j] = -l[j] * cp;
+                cp = g[j];
+            }
+        }
+        Mat2 G{dd[0], ee[0], 1.0, 0.0};
+#pragma unroll
+        for (int j = 1; j < CPT; ++j) {
+            const Mat2 nm{fma(dd[j], G.a, ee[j] * G.c), fma(dd[j], G.b, ee[j] * G.d), G.a, G.b};
+            G = (j == CPT / 2 - 1) ? rescale_fast(nm) : nm;
+        }
+        Mat2 inc = rescale_fast(G);
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const Mat2 up = shfl_up_mat(inc, s);
+            if (lane >= s) inc = compose_raw(inc, up);
+            if (s == 4) inc = rescale_fast(inc);
+        }
+        inc = rescale_fast(inc);
+        Mat2 ex = shfl_up_mat(inc, 1);
+        if (lane == 0) ex = Mat2{1.0, 0.0, 0.0, 1.0};
+        if (W > 1) {
+            if (lane == 31) s_w[warp] = inc;
+            __syncthreads();
+            Mat2 before{1.0, 0.0, 0.0, 1.0};
+            if (W <= 4) {
+                for (int q = 0; q < warp; ++q) before = rescale_fast(compose_raw(s_w[q], before));
+            } else {  // every warp scans the W warp totals itself (lane = warp index) and picks the prefix in front of it
+                Mat2 t = lane < W ? s_w[lane] : Mat2{1.0, 0.0, 0.0, 1.0};
+#pragma unroll
+                for (int s = 1; s < W; s <<= 1) {
+                    const Mat2 up = shfl_up_mat(t, s);
+                    if (lane >= s) t = rescale_fast(compose_raw(t, up));
+                }
+                const int srcl = warp > 0 ? warp - 1 : 0;
+                before.a = __shfl_sync(kAll, t.a, srcl); before.b = __shfl_sync(kAll, t.b, srcl);
+                before.c = __shfl_sync(kAll, t.c, srcl); before.d = __shfl_sync(kAll, t.d, srcl);
+                if (warp == 0) before = Mat2{1.0, 0.0, 0.0, 1.0};
+            }
+            ex = compose_raw(ex, before);
+        }
+        // (p, q) in front of my chunk: the map applied to any finite start (e_0 = 0 makes the start irrelevant)
+        double p1 = ex.a + ex.b, p2 = ex.c + ex.d;  // p_{i-1}, p_{i-2}
+        {
+            const double s = pow2_scale_for(max(exp_field(p1), exp_field(p2)));
+            p1 *= s; p2 *= s;
+        }
+        int bad = 0;
+        double r[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            double p0 = fma(dd[j], p1, ee[j] * p2);
+            if (!bad && cell0 + j < nx && (p0 == 0.0 || !isfinite(p0))) bad = (int)(cell0 + j) + 1;
+            r[j] = p1 / p0;  // off the chain: the recurrence continues with p0
+            p2 = p1; p1 = p0;
+            if (j == CPT / 2 - 1) {
+                const double s = pow2_scale_for(max(exp_field(p1), exp_field(p2)));
+                p1 *= s; p2 *= s;
+            }
+        }
+        // normalised rows: z_i = r_i b_i - (r_i dl_i) z_{i-1};  x_i = z_i - (r_i du_i) x_{i+1}
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            l[j] *= r[j];
+            g[j] *= r[j];
+            v[j] *= r[j];
+        }
+        const ScanMultipliers sm = scan_multipliers<double>(chunk_product<double, CPT>(l), chunk_product<double, CPT>(g), lane);
+
+        // ---- 2. the two sweeps ----
+        {
+            double y = chunk_end_fwd_plain<double, CPT>(v, l);
+#pragma unroll
+            for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAll, y, 1 << s), y);
+            double c = and_mask(__shfl_up_sync(kAll, y, 1), keep_f);
+            if (W > 1) {
+                const unsigned first = __reduce_min_sync(kAll, bad ? (unsigned)bad : 0xffffffffu);
+                if (lane == 31) { s_E[0][warp] = y; s_T[0][warp] = sm.tot_f; }
+                if (lane == 0) { s_T[1][warp] = sm.tot_b; s_first[warp] = first; }
+                __syncthreads();
+                if (singular && tid == 0) {  // first zero / non-finite pivot of the system (the flags ride on this barrier)
+                    unsigned f = 0xffffffffu;
+                    for (int q = 0; q < W; ++q) f = min(f, s_first[q]);
+                    singular[m] = f == 0xffffffffu ? 0 : (int32_t)f;
+                }
+                double cw = 0.0;
+                for (int q = 0; q < warp; ++q) cw = fma(s_T[0][q], cw, s_E[0][q]);
+                c = fma(sm.ex_f, cw, c);
+            }
+            double yy = c;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                yy = fma(-l[j], yy, v[j]);
+                v[j] = yy;
+            }
+        }
+        {
+            double z = chunk_end_bwd_plain<double, CPT>(v, g);
+#pragma unroll
+            for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAll, z, 1 << s), z);
+            double c = and_mask(__shfl_down_sync(kAll, z, 1), keep_b);
+            if (W > 1) {
+                if (lane == 0) s_E[1][warp] = z;
+                __syncthreads();
+                double cw = 0.0;
+                for (int q = W - 1; q > warp; --q) cw = fma(s_T[1][q], cw, s_E[1][q]);
+                c = fma(sm.ex_b, cw, c);
+            }
+            chunk_apply_bwd_plain<double, CPT>(v, g, c);
+        }
+        // ---- store ----
+        if (vec) {
+            double2 *q = reinterpret_cast<double2 *>(x + o + cell0);
+#pragma unroll
+            for (int j = 0; j < CPT / 2; ++j) q[j] = make_double2(v[2 * j], v[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
+                if (cell0 + j < nx) x[o + cell0 + j] = v[j];
+        }
+        if (singular && W == 1) {
+            const unsigned first = __reduce_min_sync(kAll, bad ? (unsigned)bad : 0xffffffffu);
+            if (lane == 0) singular[m] = first == 0xffffffffu ? 0 : (int32_t)first;
+        }
+    }
+}
+
+template <int CPT, int W, int S>
+static int launch_reg(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
+                      int32_t *singular, cudaStream_t stream) {
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    auto kern = solve_reg_kernel<CPT, W, S>;
+    int occ = 0;
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W * S, 0));
+    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "REG solve kernel does not fit on an SM (threads=%d)", 32 * W * S);
+    int64_t grid = (int64_t)occ * f.sm_count;
+    const int64_t groups = (M + S - 1) / S;
+    if (grid > groups) grid = groups;
+    kern<<<(unsigned)grid, 32 * W * S, 0, stream>>>(dl, d, du, b, x, M, nx, singular);
+    return check_launch("fbr_solve_tridiag_f64 (REG)");
+}
+
+int solve_reg_dispatch(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
+                       int32_t *singular, cudaStream_t stream) {
+    if (nx > kSolveRegMaxNx)
+        return fail(FBR_ERR_UNSUPPORTED, "REG variant covers nx <= %d (got %lld)", kSolveRegMaxNx, (long long)nx);
+    if (nx <= 64) return launch_reg<2, 1, 4>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 128) return launch_reg<4, 1, 4>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 256) return launch_reg<8, 1, 4>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 512) return launch_reg<8, 2, 1>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 1024) return launch_reg<8, 4, 1>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 2048) return launch_reg<8, 8, 1>(dl, d, du, b, x, M, nx, singular, stream);
+    return launch_reg<8, 16, 1>(dl, d, du, b, x, M, nx, singular, stream);
+}
+
+}  // namespace fbr

@@ -47,7 +47,10 @@ enum {
     FBR_SOLVER_AUTO = 0,
     FBR_SOLVER_THOMAS = 1, /* one thread per system, tiles transposed in shared memory so that
                               global traffic is coalesced (many small systems)        */
-    FBR_SOLVER_PCR = 2     /* one CTA per system, shared-memory parallel cyclic reduction */
+    FBR_SOLVER_PCR = 2,    /* one CTA per system, shared-memory parallel cyclic reduction */
+    FBR_SOLVER_REG = 3     /* register-resident: a thread owns 8 consecutive cells, pivots from a scan of
+                              2x2 Moebius matrices, the two sweeps as warp scans; one pass over HBM
+                              (40 B per unknown), no work array; 1 <= nx <= 4096 (AUTO's choice there) */
 };
 
 int fbr_version(void);
@@ -227,7 +230,8 @@ int fbr_last_launch_count(void);
  * (src/fiberis/simulator/solver/PDESolver_IMP.py:9-34) for tridiagonal A; used by the adaptive
  * time-step loop where A changes every iteration (src/fiberis/simulator/core/pds.py:312-336).
  * x may alias b.  singular as in fbr_factorize_f64.  work: (M, nx) scratch needed by the THOMAS
- * variant (fbr_solve_tridiag_work_bytes); may be NULL for PCR.  PCR covers 1 <= nx <= 4096.
+ * variant (fbr_solve_tridiag_work_bytes); may be NULL for PCR / REG.  PCR and REG cover 1 <= nx <= 4096;
+ * AUTO = REG up to 4096 cells, THOMAS beyond (work must then be given).
  * ------------------------------------------------------------------------------------------ */
 int64_t fbr_solve_tridiag_work_bytes(int64_t M, int64_t nx, int variant);
 int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, const double *b,

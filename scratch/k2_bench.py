@@ -19,7 +19,12 @@ def run(M, nx, variant, name):
     err = float((r - b).abs().max())
     ms = min(ts)
     print(f"{name:8s} M={M:7d} nx={nx:5d}  {ms:8.3f} ms  {M*nx*40/ms/1e6:8.1f} GB/s (40 B/unknown)  {M*nx/ms/1e6:7.2f} G unknowns/s  resid {err:.1e}")
-for M, nx in [(65536, 512), (4096, 1024), (1048576, 64), (256, 4096), (16384, 256)]:
-    for v, n in [(_cabi.SOLVER_THOMAS, "thomas"), (_cabi.SOLVER_PCR, "pcr"), (_cabi.SOLVER_AUTO, "auto")]:
+shapes = [(65536, 512), (4096, 1024), (32768, 1024), (1048576, 64), (524288, 128), (256, 4096), (8192, 4096), (16384, 256), (262144, 256), (16384, 2048), (65536, 500), (65536, 511)]
+variants = [(_cabi.SOLVER_THOMAS, "thomas"), (_cabi.SOLVER_PCR, "pcr"), (_cabi.SOLVER_REG, "reg")]
+if len(sys.argv) > 1:  # e.g. `k2_bench.py reg 65536x512 32768x1024`
+    variants = [v for v in variants if v[1] in sys.argv[1].split(",")]
+    if len(sys.argv) > 2: shapes = [tuple(int(q) for q in a.split("x")) for a in sys.argv[2:]]
+for M, nx in shapes:
+    for v, n in variants:
         try: run(M, nx, v, n)
         except Exception as ex: print(n, M, nx, "ERR", str(ex)[:80])
