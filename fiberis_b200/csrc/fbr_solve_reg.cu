@@ -1,5 +1,9 @@
 // K2 REG  bare batched tridiagonal solve, register-resident: one pass over HBM (40 B per unknown:
-// dl, d, du, b in, x out), no scratch array, no shared-memory copy of the system.
+// dl, d, du, b in, x out), no scratch array, no shared-memory copy of the system.  (Staging the next system
+// of a persistent CTA through shared memory with cp.async was measured and dropped: the kernel's shuffles
+// already load the MIO queue, the extra LDGSTS / LDS traffic cost more than the hidden latency gave back —
+// 65536 x 512: 0.40 ms staged against 0.31 ms with plain 16-byte loads.  16 cells per thread — half the
+// shuffles per cell, but 225 registers — was slower as well: 0.38 ms.)
 //
 // A thread owns CPT consecutive cells of one system (64 bytes per array, 16-byte loads), W warps own a
 // system.  The elimination is made parallel along the mesh the same way as in the adaptive loop
@@ -46,10 +50,9 @@ __device__ __forceinline__ Mat2 compose_raw(const Mat2 &later, const Mat2 &earli
 }
 
 template <int CPT>
-__device__ __forceinline__ void load_chunk(const double *__restrict__ row, int64_t cell0, int64_t nx, bool vec, double pad,
-                                           double (&v)[CPT]) {
+__device__ __forceinline__ void load_chunk(const double *__restrict__ row, int nvalid, bool vec, double pad, double (&v)[CPT]) {
     if (vec) {
-        const double2 *q = reinterpret_cast<const double2 *>(row + cell0);
+        const double2 *q = reinterpret_cast<const double2 *>(row);
 #pragma unroll
         for (int j = 0; j < CPT / 2; ++j) {
             const double2 t = __ldg(q + j);
@@ -58,48 +61,109 @@ __device__ __forceinline__ void load_chunk(const double *__restrict__ row, int64
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) v[j] = cell0 + j < nx ? __ldg(row + cell0 + j) : pad;
+        for (int j = 0; j < CPT; ++j) v[j] = j < nvalid ? __ldg(row + j) : pad;
     }
 }
+// num / den without the library's special-case path: den is a rescaled pivot numerator (normal range, or an
+// exact zero -> non-finite quotient, which the caller flags).  Hardware seed, two Newton steps, one correction.
+__device__ __forceinline__ double div_fast(double num, double den) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(den));
+    double e = fma(-den, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-den, x, 1.0);
+    x = fma(x, e, x);
+    const double q = num * x;
+    return fma(fma(-den, q, num), x, q);
+}
 
-// W warps per system, S systems per CTA (S > 1 only with W == 1: no CTA barrier inside the loop then)
-template <int CPT, int W, int S>
-__global__ void __launch_bounds__(32 * W * S) solve_reg_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+// the sweeps' stage multipliers for groups of L lanes (fbr_sweep.cuh's scan_multipliers is the L = 32 case)
+template <int L>
+struct GroupMultipliers {
+    static constexpr int NS = L == 32 ? 5 : L == 16 ? 4 : L == 8 ? 3 : L == 4 ? 2 : 1;
+    double f[NS], b[NS], ex_f, ex_b, tot_f, tot_b;
+};
+template <int L>
+__device__ __forceinline__ GroupMultipliers<L> group_multipliers(double chunk_f, double chunk_b, int sub) {
+    GroupMultipliers<L> m;
+    double pf = chunk_f, pb = chunk_b;
+#pragma unroll
+    for (int s = 0; s < GroupMultipliers<L>::NS; ++s) {
+        const bool fa = sub >= (1 << s), ba = sub + (1 << s) < L;
+        m.f[s] = fa ? pf : 0.0;
+        m.b[s] = ba ? pb : 0.0;
+        const double upf = __shfl_up_sync(kAll, pf, 1 << s, L);
+        const double dnb = __shfl_down_sync(kAll, pb, 1 << s, L);
+        if (fa) pf *= upf;
+        if (ba) pb *= dnb;
+    }
+    m.ex_f = __shfl_up_sync(kAll, pf, 1, L);
+    m.ex_b = __shfl_down_sync(kAll, pb, 1, L);
+    if (sub == 0) m.ex_f = 1.0;
+    if (sub == L - 1) m.ex_b = 1.0;
+    m.tot_f = pf;
+    m.tot_b = pb;
+    return m;
+}
+template <int L>
+__device__ __forceinline__ Mat2 shfl_up_mat_w(const Mat2 &m, int delta) {
+    Mat2 r;
+    r.a = __shfl_up_sync(kAll, m.a, delta, L); r.b = __shfl_up_sync(kAll, m.b, delta, L);
+    r.c = __shfl_up_sync(kAll, m.c, delta, L); r.d = __shfl_up_sync(kAll, m.d, delta, L);
+    return r;
+}
+
+// W warps per system, S warps of single-warp systems per CTA (S > 1 only with W == 1: no CTA barrier inside the loop
+// then), L lanes per system (L < 32 only with W == 1: 32 / L small systems share a warp, shuffles stay inside a group)
+template <int CPT, int W, int S, int L>
+__global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kernel(const double *__restrict__ dl, const double *__restrict__ d,
                                                                const double *__restrict__ du, const double *b, double *x,
                                                                int64_t M, int64_t nx, int32_t *__restrict__ singular) {
     static_assert(S == 1 || W == 1, "several systems per CTA only for single-warp systems");
     static_assert(CPT % 2 == 0, "16-byte accesses and sign-free chunk products need an even chunk");
+    static_assert(L == 32 || W == 1, "sub-warp groups only for single-warp systems");
+    constexpr int HP = CPT / 2, GPW = 32 / L;  // systems per warp
     __shared__ Mat2 s_w[W];
     __shared__ double s_E[2][W], s_T[2][W];
     __shared__ unsigned s_first[W];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wl = W > 1 ? warp : 0, sys = W > 1 ? 0 : warp;
-    const int64_t cell0 = ((int64_t)wl * 32 + lane) * CPT;
-    const int keep_f = lane == 0 ? 0 : -1, keep_b = lane == 31 ? 0 : -1;
+    const int sub = lane & (L - 1), grp = lane / L;
+    const int wl = W > 1 ? warp : 0, sys = W > 1 ? 0 : warp * GPW + grp;
+    const int nxi = (int)nx;
+    const int cell0 = (wl * 32 + sub) * CPT;
+    const int nvalid = min(max(nxi - cell0, 0), CPT);  // rows of the matrix in my chunk (the rest is identity padding)
+    const int jlast = nxi - 1 - cell0;                 // chunk position of the last row, when it is mine
+    const int keep_f = sub == 0 ? 0 : -1, keep_b = sub == L - 1 ? 0 : -1;
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(dl) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(du) |
                           reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+    const int64_t stride = (int64_t)gridDim.x * S * GPW;
 
-    for (int64_t m = (int64_t)blockIdx.x * S + sys; m < M; m += (int64_t)gridDim.x * S) {
+    // the loop bound is uniform over a warp (and over the CTA when W > 1); groups past the last system redo system
+    // M - 1 and skip the stores
+    for (int64_t m_raw = (int64_t)blockIdx.x * S * GPW + sys; m_raw - grp < M; m_raw += stride) {
+        const bool live = m_raw < M;
+        const int64_t m = live ? m_raw : M - 1;
         const int64_t o = m * nx;
-        const bool vec = ptr_ok && cell0 + CPT <= nx && ((o + cell0) & 1) == 0;
         double l[CPT], dd[CPT], g[CPT], v[CPT];
-        load_chunk<CPT>(dl + o, cell0, nx, vec, 0.0, l);
-        load_chunk<CPT>(d + o, cell0, nx, vec, 1.0, dd);
-        load_chunk<CPT>(du + o, cell0, nx, vec, 0.0, g);
-        load_chunk<CPT>(b + o, cell0, nx, vec, 0.0, v);
-        // super-diagonal entry of the row in front of my chunk; the first sub- and the last super-diagonal entry are
-        // outside the matrix
-        double c_prev = __shfl_up_sync(kAll, g[CPT - 1], 1);
-        if (lane == 0) c_prev = (cell0 > 0 && cell0 <= nx) ? __ldg(du + o + cell0 - 1) : 0.0;
-        if (cell0 == 0) l[0] = 0.0;
+        const bool vec = nvalid == CPT && ptr_ok && ((o + cell0) & 1) == 0;
+        load_chunk<CPT>(dl + o + cell0, nvalid, vec, 0.0, l);
+        load_chunk<CPT>(d + o + cell0, nvalid, vec, 1.0, dd);
+        load_chunk<CPT>(du + o + cell0, nvalid, vec, 0.0, g);
+        load_chunk<CPT>(b + o + cell0, nvalid, vec, 0.0, v);
+        // super-diagonal entry in front of a warp's first chunk (the first padding row has none)
+        double c_first = 0.0;
+        if (W > 1 && lane == 0 && cell0 > 0 && cell0 < nxi) c_first = __ldg(du + o + cell0 - 1);
+        if ((unsigned)jlast < (unsigned)CPT) {
 #pragma unroll
-        for (int j = 0; j < CPT; ++j)
-            if (cell0 + j == nx - 1) g[j] = 0.0;
-        if (cell0 == nx) c_prev = 0.0;  // first padding row
+            for (int j = 0; j < CPT; ++j)
+                if (j == jlast) g[j] = 0.0;
+        }
+        if (cell0 == 0) l[0] = 0.0;  // the first sub-diagonal entry is outside the matrix
+        double c_prev = __shfl_up_sync(kAll, g[CPT - 1], 1, L);
+        if (sub == 0) c_prev = c_first;
 
         // ---- 1. pivots ----
-        // e_j = -dl_j du_{j-1} replaces dl_j for now (dl_j itself is recovered as needed: kept in l, e in ee)
-        double ee[CPT];
+        double ee[CPT];  // e_j = -dl_j du_{j-1}
         {
             double cp = c_prev;
 #pragma unroll
@@ -116,14 +180,14 @@ __global__ void __launch_bounds__(32 * W * S) solve_reg_kernel(const double *__r
         }
         Mat2 inc = rescale_fast(G);
 #pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const Mat2 up = shfl_up_mat(inc, s);
-            if (lane >= s) inc = compose_raw(inc, up);
-            if (s == 4) inc = rescale_fast(inc);
+        for (int s = 1; s < L; s <<= 1) {
+            const Mat2 up = shfl_up_mat_w<L>(inc, s);
+            if (sub >= s) inc = compose_raw(inc, up);
+            if (s == 4 && L > 8) inc = rescale_fast(inc);
         }
         inc = rescale_fast(inc);
-        Mat2 ex = shfl_up_mat(inc, 1);
-        if (lane == 0) ex = Mat2{1.0, 0.0, 0.0, 1.0};
+        Mat2 ex = shfl_up_mat_w<L>(inc, 1);
+        if (sub == 0) ex = Mat2{1.0, 0.0, 0.0, 1.0};
         if (W > 1) {
             if (lane == 31) s_w[warp] = inc;
             __syncthreads();
@@ -144,24 +208,29 @@ __global__ void __launch_bounds__(32 * W * S) solve_reg_kernel(const double *__r
             }
             ex = compose_raw(ex, before);
         }
-        // (p, q) in front of my chunk: the map applied to any finite start (e_0 = 0 makes the start irrelevant)
-        double p1 = ex.a + ex.b, p2 = ex.c + ex.d;  // p_{i-1}, p_{i-2}
+        // (p_{i-1}, p_{i-2}) in front of my chunk: the map applied to any finite start (e_0 = 0 makes the start irrelevant)
+        double p1 = ex.a + ex.b, p2 = ex.c + ex.d;
         {
             const double s = pow2_scale_for(max(exp_field(p1), exp_field(p2)));
             p1 *= s; p2 *= s;
         }
-        int bad = 0;
-        double r[CPT];
+        double r[CPT], nanacc = 0.0;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-            double p0 = fma(dd[j], p1, ee[j] * p2);
-            if (!bad && cell0 + j < nx && (p0 == 0.0 || !isfinite(p0))) bad = (int)(cell0 + j) + 1;
-            r[j] = p1 / p0;  // off the chain: the recurrence continues with p0
+            const double p0 = fma(dd[j], p1, ee[j] * p2);
+            r[j] = div_fast(p1, p0);  // off the chain: the recurrence continues with p0
+            nanacc = fma(r[j], 0.0, nanacc);
             p2 = p1; p1 = p0;
             if (j == CPT / 2 - 1) {
                 const double s = pow2_scale_for(max(exp_field(p1), exp_field(p2)));
                 p1 *= s; p2 *= s;
             }
+        }
+        int bad = 0;
+        if (nanacc != nanacc) {  // a zero (or non-finite) pivot makes its quotient non-finite: find the first such row
+#pragma unroll
+            for (int j = CPT - 1; j >= 0; --j)
+                if (j < nvalid && !isfinite(r[j])) bad = cell0 + j + 1;
         }
         // normalised rows: z_i = r_i b_i - (r_i dl_i) z_{i-1};  x_i = z_i - (r_i du_i) x_{i+1}
 #pragma unroll
@@ -170,14 +239,15 @@ __global__ void __launch_bounds__(32 * W * S) solve_reg_kernel(const double *__r
             g[j] *= r[j];
             v[j] *= r[j];
         }
-        const ScanMultipliers sm = scan_multipliers<double>(chunk_product<double, CPT>(l), chunk_product<double, CPT>(g), lane);
+        const GroupMultipliers<L> sm = group_multipliers<L>(chunk_product<double, CPT>(l), chunk_product<double, CPT>(g), sub);
+        constexpr int NS = GroupMultipliers<L>::NS;
 
         // ---- 2. the two sweeps ----
         {
             double y = chunk_end_fwd_plain<double, CPT>(v, l);
 #pragma unroll
-            for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAll, y, 1 << s), y);
-            double c = and_mask(__shfl_up_sync(kAll, y, 1), keep_f);
+            for (int s = 0; s < NS; ++s) y = fma(sm.f[s], __shfl_up_sync(kAll, y, 1 << s, L), y);
+            double c = and_mask(__shfl_up_sync(kAll, y, 1, L), keep_f);
             if (W > 1) {
                 const unsigned first = __reduce_min_sync(kAll, bad ? (unsigned)bad : 0xffffffffu);
                 if (lane == 31) { s_E[0][warp] = y; s_T[0][warp] = sm.tot_f; }
@@ -202,8 +272,8 @@ __global__ void __launch_bounds__(32 * W * S) solve_reg_kernel(const double *__r
         {
             double z = chunk_end_bwd_plain<double, CPT>(v, g);
 #pragma unroll
-            for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAll, z, 1 << s), z);
-            double c = and_mask(__shfl_down_sync(kAll, z, 1), keep_b);
+            for (int s = 0; s < NS; ++s) z = fma(sm.b[s], __shfl_down_sync(kAll, z, 1 << s, L), z);
+            double c = and_mask(__shfl_down_sync(kAll, z, 1, L), keep_b);
             if (W > 1) {
                 if (lane == 0) s_E[1][warp] = z;
                 __syncthreads();
@@ -214,35 +284,46 @@ __global__ void __launch_bounds__(32 * W * S) solve_reg_kernel(const double *__r
             chunk_apply_bwd_plain<double, CPT>(v, g, c);
         }
         // ---- store ----
-        if (vec) {
-            double2 *q = reinterpret_cast<double2 *>(x + o + cell0);
+        if (live) {
+            if (vec) {
+                double2 *q = reinterpret_cast<double2 *>(x + o + cell0);
 #pragma unroll
-            for (int j = 0; j < CPT / 2; ++j) q[j] = make_double2(v[2 * j], v[2 * j + 1]);
-        } else {
+                for (int j = 0; j < HP; ++j) q[j] = make_double2(v[2 * j], v[2 * j + 1]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < CPT; ++j)
-                if (cell0 + j < nx) x[o + cell0 + j] = v[j];
+                for (int j = 0; j < CPT; ++j)
+                    if (j < nvalid) x[o + cell0 + j] = v[j];
+            }
         }
         if (singular && W == 1) {
-            const unsigned first = __reduce_min_sync(kAll, bad ? (unsigned)bad : 0xffffffffu);
-            if (lane == 0) singular[m] = first == 0xffffffffu ? 0 : (int32_t)first;
+            unsigned first = bad ? (unsigned)bad : 0xffffffffu;
+            if (L == 32) {
+                first = __reduce_min_sync(kAll, first);
+            } else {
+#pragma unroll
+                for (int s = 1; s < L; s <<= 1) first = min(first, __shfl_xor_sync(kAll, first, s, L));
+            }
+            if (sub == 0 && live) singular[m] = first == 0xffffffffu ? 0 : (int32_t)first;
         }
     }
 }
 
-template <int CPT, int W, int S>
+template <int CPT, int W, int S, int L>
 static int launch_reg(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
                       int32_t *singular, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
-    auto kern = solve_reg_kernel<CPT, W, S>;
+    auto kern = solve_reg_kernel<CPT, W, S, L>;
+    constexpr int NT = 32 * W * S;
+    const size_t smem = 0;
     int occ = 0;
-    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W * S, 0));
-    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "REG solve kernel does not fit on an SM (threads=%d)", 32 * W * S);
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "REG solve kernel does not fit on an SM (threads=%d)", NT);
     int64_t grid = (int64_t)occ * f.sm_count;
-    const int64_t groups = (M + S - 1) / S;
+    const int64_t per_cta = S * (32 / L);
+    const int64_t groups = (M + per_cta - 1) / per_cta;
     if (grid > groups) grid = groups;
-    kern<<<(unsigned)grid, 32 * W * S, 0, stream>>>(dl, d, du, b, x, M, nx, singular);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(dl, d, du, b, x, M, nx, singular);
     return check_launch("fbr_solve_tridiag_f64 (REG)");
 }
 
@@ -250,13 +331,15 @@ int solve_reg_dispatch(const double *dl, const double *d, const double *du, cons
                        int32_t *singular, cudaStream_t stream) {
     if (nx > kSolveRegMaxNx)
         return fail(FBR_ERR_UNSUPPORTED, "REG variant covers nx <= %d (got %lld)", kSolveRegMaxNx, (long long)nx);
-    if (nx <= 64) return launch_reg<2, 1, 4>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 128) return launch_reg<4, 1, 4>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 256) return launch_reg<8, 1, 4>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 512) return launch_reg<8, 2, 1>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 1024) return launch_reg<8, 4, 1>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 2048) return launch_reg<8, 8, 1>(dl, d, du, b, x, M, nx, singular, stream);
-    return launch_reg<8, 16, 1>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 16) return launch_reg<2, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 32) return launch_reg<4, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 64) return launch_reg<8, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 128) return launch_reg<8, 1, 4, 16>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 256) return launch_reg<8, 1, 4, 32>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 512) return launch_reg<8, 2, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 1024) return launch_reg<8, 4, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
+    if (nx <= 2048) return launch_reg<8, 8, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
+    return launch_reg<8, 16, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
 }
 
 }  // namespace fbr
