@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libf
 FBR_OK, FBR_ERR_BAD_ARG, FBR_ERR_UNSUPPORTED, FBR_ERR_CUDA = 0, -1, -2, -3
 BC_CODES = {"None": 0, "Dirichlet": 1, "Neumann": 2}
 SOLVER_AUTO, SOLVER_THOMAS, SOLVER_PCR, SOLVER_REG = 0, 1, 2, 3
+WS_FACTORIZE, WS_SOLVE, WS_SOLVE_THOMAS, WS_RUN, WS_RUN_LONG, WS_RUN_STREAM, WS_RUN_WINDOW = range(7)
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -52,6 +53,9 @@ SIGNATURES = {
                                     _p, _f64, _f64, _f64, _f64, _f64, _f64, _i64, _i64, _p, _p, _p, _i64, _p, _p]),
     "fbr_solve_tridiag_work_bytes": (_i64, [_i64, _i64, _i32]),
     "fbr_solve_tridiag_f64": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p]),
+    "fbr_step_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i32, _p, _p, _p]),
+    "fbr_misfit_f64": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i32, _p, _p, _i64, _p, _p]),
+    "fbr_workspace_bytes": (_i64, [_i32, _i64, _i64]),
     "fbr_rhs_f64": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _i32, _p, _p, _p]),
     "fbr_error_norms_f64": (_i32, [_p, _p, _i64, _i64, _p, _p]),
     "fbr_jacobi_f64": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _f64, _i32, _p, _p]),

@@ -426,6 +426,36 @@ def solve_tridiag(dl, d, du, b, variant=_cabi.SOLVER_AUTO, check_singular=True):
     return x
 
 
+def step(dl, d, du, p, lbc, rbc, src_idx, n_src, src_val, variant=_cabi.SOLVER_AUTO, out=None, check_singular=True):
+    """One implicit step of M models: p_next = A^-1 rhs(p) (fbr_step_f64; overrides fused into the
+    register-resident solve up to 4096 cells).  src_val: (n_src) shared or (M, n_src) per model."""
+    torch = _torch()
+    lib = _cabi.load()
+    M, nx = d.shape
+    x = torch.empty_like(p) if out is None else out
+    flags = torch.zeros(M, dtype=torch.int32, device=d.device)
+    work = None
+    if variant == _cabi.SOLVER_THOMAS or (variant == _cabi.SOLVER_AUTO and nx > 4096):
+        work = torch.empty((M, nx), dtype=torch.float64, device=d.device)
+    stride = 0 if (src_val is None or src_val.dim() == 1) else int(src_val.shape[1])
+    check(lib.fbr_step_f64(ptr(dl), ptr(d), ptr(du), ptr(p), M, nx, BC_CODES[lbc], BC_CODES[rbc], ptr(src_idx), n_src,
+                           ptr(src_val), stride, ptr(x), int(variant), ptr(work), ptr(flags), current_stream()))
+    if check_singular:
+        raise_if_singular(flags, "system")
+    return x
+
+
+def misfit_of_rows(snap, obs_idx, obs, obs_w=None, first_row=1):
+    """Misfit of stored rows (n_models, n_rows, nx) against obs (n_rows, n_obs): fbr_misfit_f64."""
+    torch = _torch()
+    lib = _cabi.load()
+    R, n_rows, nx = snap.shape
+    out = torch.empty(R, dtype=torch.float64, device=snap.device)
+    check(lib.fbr_misfit_f64(ptr(snap), R, n_rows, nx, snap.stride(1), snap.stride(0), ptr(obs_idx), int(obs.shape[1]),
+                             ptr(obs), ptr(obs_w), int(first_row), ptr(out), current_stream()))
+    return out
+
+
 def error_norms(u1, u2):
     torch = _torch()
     lib = _cabi.load()

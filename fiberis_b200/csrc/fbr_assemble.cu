@@ -228,6 +228,58 @@ extern "C" int fbr_error_norms_f64(const double *u1, const double *u2, int64_t M
     return check_launch("fbr_error_norms_f64");
 }
 
+// Misfit of stored rows against observations (the fused form lives in K3; this one serves every other run kernel):
+// misfit[r] = sum_{t >= first_row} sum_k w_k (snap[r, t, obs_idx[k]] - obs[t, k])^2, one CTA per model, fixed summation order.
+__global__ void __launch_bounds__(256) misfit_kernel(const double *__restrict__ snap, int64_t n_rows, int64_t row_stride,
+                                                     int64_t model_stride, const int64_t *__restrict__ obs_idx, int n_obs,
+                                                     const double *__restrict__ obs, const double *__restrict__ obs_w,
+                                                     int64_t first_row, double *__restrict__ misfit) {
+    __shared__ double s_part[8];
+    const double *base = snap + blockIdx.x * model_stride;
+    double acc = 0.0;
+    const int64_t total = (n_rows - first_row) * n_obs;
+    for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+        const int64_t t = first_row + e / n_obs;
+        const int k = (int)(e % n_obs);
+        const double r = base[t * row_stride + obs_idx[k]] - obs[t * n_obs + k];
+        acc = fma(obs_w ? obs_w[k] * r : r, r, acc);
+    }
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += s_part[w];
+        misfit[blockIdx.x] = v;
+    }
+}
+
+extern "C" int fbr_misfit_f64(const double *snap, int64_t n_models, int64_t n_rows, int64_t nx, int64_t snap_row_stride,
+                              int64_t snap_model_stride, const int64_t *obs_idx, int n_obs, const double *obs,
+                              const double *obs_w, int64_t first_row, double *misfit, void *stream) {
+    FBR_REQUIRE(snap && obs_idx && obs && misfit, "NULL array argument");
+    FBR_REQUIRE(n_models >= 1 && n_rows >= 1 && nx >= 1 && n_obs >= 1, "n_models, n_rows, nx and n_obs must be >= 1");
+    FBR_REQUIRE(first_row >= 0 && first_row <= n_rows, "first_row outside [0, n_rows]");
+    FBR_REQUIRE(snap_row_stride >= nx && snap_model_stride >= nx, "snapshot strides must be >= nx");
+    misfit_kernel<<<(unsigned)n_models, 256, 0, as_stream(stream)>>>(snap, n_rows, snap_row_stride, snap_model_stride, obs_idx,
+                                                                      n_obs, obs, obs_w, first_row, misfit);
+    return check_launch("fbr_misfit_f64");
+}
+
+// One front door for the scratch sizes ("library allocates nothing persistent").
+extern "C" int64_t fbr_workspace_bytes(int what, int64_t M, int64_t nx) {
+    switch (what) {
+        case FBR_WS_FACTORIZE: return fbr_factorize_work_bytes(M, nx);
+        case FBR_WS_SOLVE: return fbr_solve_tridiag_work_bytes(M, nx, FBR_SOLVER_AUTO);
+        case FBR_WS_SOLVE_THOMAS: return fbr_solve_tridiag_work_bytes(M, nx, FBR_SOLVER_THOMAS);
+        case FBR_WS_RUN: return 0;
+        case FBR_WS_RUN_LONG: return fbr_run_long_work_bytes(nx);
+        case FBR_WS_RUN_STREAM: return fbr_run_stream_work_bytes(nx);
+        case FBR_WS_RUN_WINDOW: return fbr_run_window_work_bytes(nx);
+        default: fail(FBR_ERR_BAD_ARG, "unknown workspace kind %d", what); return -1;
+    }
+}
+
 extern "C" int fbr_version(void) { return FBR_VERSION; }
 extern "C" const char *fbr_last_error(void) { return last_error_ref().c_str(); }
 extern "C" int fbr_last_launch_count(void) { return launch_count_ref(); }

@@ -56,6 +56,10 @@ constexpr int kSolveRegMaxNx = 4096;
 int solve_reg_dispatch(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
                        int32_t *singular, cudaStream_t stream);
 
+int step_reg_dispatch(const double *dl, const double *d, const double *du, const double *p, double *p_next, int64_t M, int64_t nx,
+                      int lbc, int rbc, const int64_t *src_idx, int n_src, const double *src_val, int64_t src_val_stride,
+                      int32_t *singular, cudaStream_t stream);
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace fbr

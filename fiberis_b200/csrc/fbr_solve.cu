@@ -297,6 +297,27 @@ extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const do
     return check_launch("fbr_solve_tridiag_f64 (Thomas)");
 }
 
+// One implicit step, batched: p_next = A^-1 rhs(p), rhs = p with boundary / source overrides
+// (matbuilder.py:45-76 + PDESolver_IMP.py:28).  Up to 4096 cells the overrides are applied to the registers of the
+// REG solve (one kernel, 40 B per cell-update); longer systems go through fbr_rhs_f64 + the chosen variant.
+extern "C" int fbr_step_f64(const double *dl, const double *d, const double *du, const double *p, int64_t M, int64_t nx,
+                            int lbc, int rbc, const int64_t *src_idx, int n_src, const double *src_val,
+                            int64_t src_val_stride, double *p_next, int variant, double *work, int32_t *singular,
+                            void *stream) {
+    FBR_REQUIRE(M >= 1 && nx >= 2 && dl && d && du && p && p_next, "bad argument");
+    FBR_REQUIRE(lbc >= 0 && lbc <= 2 && rbc >= 0 && rbc <= 2, "boundary codes must be 0 (None), 1 (Dirichlet) or 2 (Neumann)");
+    FBR_REQUIRE(n_src >= 0 && n_src < 0xFE && (n_src == 0 || (src_idx && src_val)), "bad source arguments (n_src=%d)", n_src);
+    FBR_REQUIRE(src_val_stride == 0 || src_val_stride >= n_src, "src_val_stride must be 0 (shared values) or >= n_src");
+    FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_REG, "unknown solver variant %d", variant);
+    if (variant == FBR_SOLVER_REG || (variant == FBR_SOLVER_AUTO && nx <= kSolveRegMaxNx))
+        return step_reg_dispatch(dl, d, du, p, p_next, M, nx, lbc, rbc, src_idx, n_src, src_val, src_val_stride, singular,
+                                 as_stream(stream));
+    if (src_val_stride != 0 && M > 1)
+        return fail(FBR_ERR_UNSUPPORTED, "per-model source values need the REG variant (nx <= %d)", kSolveRegMaxNx);
+    if (int rc = fbr_rhs_f64(p, M, nx, lbc, rbc, src_idx, n_src, src_val, p_next, stream)) return rc;
+    return fbr_solve_tridiag_f64(dl, d, du, p_next, p_next, M, nx, variant, work, singular, stream);
+}
+
 extern "C" int fbr_jacobi_f64(const double *dl, const double *d, const double *du, const double *b, double *x,
                               int64_t M, int64_t nx, double tol, int max_iter, int32_t *iters, void *stream) {
     FBR_REQUIRE(M >= 1 && nx >= 1 && dl && d && du && b && x && max_iter >= 0, "bad argument");

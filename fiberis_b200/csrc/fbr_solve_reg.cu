@@ -113,12 +113,22 @@ __device__ __forceinline__ Mat2 shfl_up_mat_w(const Mat2 &m, int delta) {
     return r;
 }
 
+// fbr_step_f64: the right-hand side is the current pressure with boundary / source overrides
+// (matbuilder.py:45-76) applied while it sits in registers; enabled == 0 for the bare solve.
+struct StepOverrides {
+    int enabled, lbc, rbc, n_src;
+    const int64_t *src_idx;
+    const double *src_val;   // (n_src), or (M, n_src) with src_val_stride = n_src
+    int64_t src_val_stride;
+};
+
 // W warps per system, S warps of single-warp systems per CTA (S > 1 only with W == 1: no CTA barrier inside the loop
 // then), L lanes per system (L < 32 only with W == 1: 32 / L small systems share a warp, shuffles stay inside a group)
 template <int CPT, int W, int S, int L>
 __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kernel(const double *__restrict__ dl, const double *__restrict__ d,
                                                                const double *__restrict__ du, const double *b, double *x,
-                                                               int64_t M, int64_t nx, int32_t *__restrict__ singular) {
+                                                               int64_t M, int64_t nx, int32_t *__restrict__ singular,
+                                                               const StepOverrides ov) {
     static_assert(S == 1 || W == 1, "several systems per CTA only for single-warp systems");
     static_assert(CPT % 2 == 0, "16-byte accesses and sign-free chunk products need an even chunk");
     static_assert(L == 32 || W == 1, "sub-warp groups only for single-warp systems");
@@ -137,6 +147,17 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(dl) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(du) |
                           reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
     const int64_t stride = (int64_t)gridDim.x * S * GPW;
+    // which of my rows get an overridden right-hand side: one byte per row (0xFF none, 0xFE zero, else source column);
+    // later claims win (sources over boundary rows, later duplicates over earlier ones)
+    uint64_t slots = ~0ull;
+    if (ov.enabled) {
+        if (cell0 == 0 && ov.lbc != FBR_BC_NONE) slots = (slots & ~0xFFull) | 0xFEull;
+        if ((unsigned)jlast < (unsigned)CPT && ov.rbc != FBR_BC_NONE) slots = (slots & ~(0xFFull << (8 * jlast))) | (0xFEull << (8 * jlast));
+        for (int k = 0; k < ov.n_src; ++k) {
+            const int64_t jj = ov.src_idx[k] - cell0;
+            if (jj >= 0 && jj < nvalid) slots = (slots & ~(0xFFull << (8 * jj))) | ((uint64_t)k << (8 * jj));
+        }
+    }
 
     // the loop bound is uniform over a warp (and over the CTA when W > 1); groups past the last system redo system
     // M - 1 and skip the stores
@@ -159,6 +180,14 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
                 if (j == jlast) g[j] = 0.0;
         }
         if (cell0 == 0) l[0] = 0.0;  // the first sub-diagonal entry is outside the matrix
+        if (slots != ~0ull) {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const unsigned so = (unsigned)(slots >> (8 * j)) & 0xFFu;
+                if (so == 0xFEu) v[j] = 0.0;
+                else if (so != 0xFFu) v[j] = __ldg(ov.src_val + m * ov.src_val_stride + so);
+            }
+        }
         double c_prev = __shfl_up_sync(kAll, g[CPT - 1], 1, L);
         if (sub == 0) c_prev = c_first;
 
@@ -310,7 +339,7 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
 
 template <int CPT, int W, int S, int L>
 static int launch_reg(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
-                      int32_t *singular, cudaStream_t stream) {
+                      int32_t *singular, const StepOverrides &ov, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
     auto kern = solve_reg_kernel<CPT, W, S, L>;
@@ -323,23 +352,36 @@ static int launch_reg(const double *dl, const double *d, const double *du, const
     const int64_t per_cta = S * (32 / L);
     const int64_t groups = (M + per_cta - 1) / per_cta;
     if (grid > groups) grid = groups;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(dl, d, du, b, x, M, nx, singular);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(dl, d, du, b, x, M, nx, singular, ov);
     return check_launch("fbr_solve_tridiag_f64 (REG)");
+}
+
+static int reg_dispatch(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
+                        int32_t *singular, const StepOverrides &ov, cudaStream_t stream) {
+    if (nx > kSolveRegMaxNx)
+        return fail(FBR_ERR_UNSUPPORTED, "REG variant covers nx <= %d (got %lld)", kSolveRegMaxNx, (long long)nx);
+    if (nx <= 16) return launch_reg<2, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    if (nx <= 32) return launch_reg<4, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    if (nx <= 64) return launch_reg<8, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    if (nx <= 128) return launch_reg<8, 1, 4, 16>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    if (nx <= 256) return launch_reg<8, 1, 4, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    if (nx <= 512) return launch_reg<8, 2, 1, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    if (nx <= 1024) return launch_reg<8, 4, 1, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    if (nx <= 2048) return launch_reg<8, 8, 1, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
+    return launch_reg<8, 16, 1, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
 }
 
 int solve_reg_dispatch(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
                        int32_t *singular, cudaStream_t stream) {
-    if (nx > kSolveRegMaxNx)
-        return fail(FBR_ERR_UNSUPPORTED, "REG variant covers nx <= %d (got %lld)", kSolveRegMaxNx, (long long)nx);
-    if (nx <= 16) return launch_reg<2, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 32) return launch_reg<4, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 64) return launch_reg<8, 1, 4, 8>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 128) return launch_reg<8, 1, 4, 16>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 256) return launch_reg<8, 1, 4, 32>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 512) return launch_reg<8, 2, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 1024) return launch_reg<8, 4, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
-    if (nx <= 2048) return launch_reg<8, 8, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
-    return launch_reg<8, 16, 1, 32>(dl, d, du, b, x, M, nx, singular, stream);
+    StepOverrides ov{};
+    return reg_dispatch(dl, d, du, b, x, M, nx, singular, ov, stream);
+}
+
+int step_reg_dispatch(const double *dl, const double *d, const double *du, const double *p, double *p_next, int64_t M, int64_t nx,
+                      int lbc, int rbc, const int64_t *src_idx, int n_src, const double *src_val, int64_t src_val_stride,
+                      int32_t *singular, cudaStream_t stream) {
+    StepOverrides ov{1, lbc, rbc, n_src, src_idx, src_val, src_val_stride};
+    return reg_dispatch(dl, d, du, p, p_next, M, nx, singular, ov, stream);
 }
 
 }  // namespace fbr

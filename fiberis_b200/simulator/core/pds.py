@@ -443,12 +443,12 @@ class PDS1D_SingleSource:
             vals = self._source_values_at(self.taxis[-1] - self.t0)
             self.record_log("Time:", self.taxis[-1], "Source term:", vals if self._multi else vals[0])
             vals_d = _engine.to_device(np.asarray(vals, dtype=np.float64))
-            b = _engine.rhs(p_d, self.lbc, self.rbc, sidx_d, n_src, vals_d)
-            full = _engine.solve_tridiag(
-                *_engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax), b)
+            bc = (self.lbc, self.rbc, sidx_d, n_src, vals_d)  # fbr_step_f64: rhs overrides fused into the solve
+            full = _engine.step(*_engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax),
+                                p_d, *bc)
             half_sys = _engine.assemble(mesh_d, diff_d, 1, nx, dt / 2, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
-            mid = _engine.solve_tridiag(*half_sys, b)
-            half = _engine.solve_tridiag(*half_sys, _engine.rhs(mid, self.lbc, self.rbc, sidx_d, n_src, vals_d))
+            mid = _engine.step(*half_sys, p_d, *bc)
+            half = _engine.step(*half_sys, mid, *bc)
             error = tso.step_error(full, half)
             n_before = len(self.taxis)
             marker = _DeviceRow(len(accepted))

@@ -238,6 +238,19 @@ int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, c
                           double *x, int64_t M, int64_t nx, int variant, double *work,
                           int32_t *singular, void *stream);
 
+/* One implicit step, batched (SURVEY 8(b) "fbr_step_*"): p_next = A^-1 rhs(p) with the diagonals of
+ * A(dt) from fbr_assemble_*; rhs = p with the boundary / source overrides of
+ * src/fiberis/simulator/solver/matbuilder.py:45-76, the solve of PDESolver_IMP.py:28.  Replaces the
+ * pair matbuilder.*(pds, dt) / solver_implicit(A, b) of src/fiberis/simulator/core/pds.py:294-303 for
+ * one step of M models.  src_val: DEVICE values of this step, (n_src) shared by all models
+ * (src_val_stride = 0) or (M, n_src) rows (src_val_stride >= n_src).  p_next may alias p.  variant /
+ * work / singular as in fbr_solve_tridiag_f64; up to 4096 cells the overrides are fused into the
+ * register-resident solve (one kernel, 40 B of HBM traffic per cell-update). */
+int fbr_step_f64(const double *dl, const double *d, const double *du, const double *p, int64_t M,
+                 int64_t nx, int lbc, int rbc, const int64_t *src_idx, int n_src, const double *src_val,
+                 int64_t src_val_stride, double *p_next, int variant, double *work, int32_t *singular,
+                 void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Device-side adaptive time stepping: the step-doubling loop of PDS1D_*.solve(optimizer=True)
  * (src/fiberis/simulator/core/pds.py:312-336) with the controller of
@@ -273,6 +286,24 @@ int fbr_run_adaptive_f64(const double *mesh, int64_t mesh_stride, const double *
  * all models.  b may alias p. */
 int fbr_rhs_f64(const double *p, int64_t M, int64_t nx, int lbc, int rbc, const int64_t *src_idx,
                 int n_src, const double *src_val, double *b, void *stream);
+
+/* Misfit of STORED rows against observations (SURVEY 8(b) "fbr_misfit_*"; the same quantity K3 sums
+ * on the fly through fbr_run_*'s obs arguments — parity unpinned, modelled on
+ * src/fiberis/moose/templates/baseline_model_generator.py:394-404):
+ *   misfit[r] = sum_{t = first_row}^{n_rows - 1} sum_k obs_w[k] (snap[r, t, obs_idx[k]] - obs[t, k])^2
+ * snap[r * snap_model_stride + t * snap_row_stride + i]; obs: (n_rows, n_obs); obs_w: (n_obs) or NULL. */
+int fbr_misfit_f64(const double *snap, int64_t n_models, int64_t n_rows, int64_t nx,
+                   int64_t snap_row_stride, int64_t snap_model_stride, const int64_t *obs_idx, int n_obs,
+                   const double *obs, const double *obs_w, int64_t first_row, double *misfit,
+                   void *stream);
+
+/* Scratch sizes through one entry point (the caller owns all device memory): bytes of `work` the call
+ * named by `what` needs for M models of nx cells (0 = none); < 0 on an unknown kind. */
+enum {
+    FBR_WS_FACTORIZE = 0, FBR_WS_SOLVE = 1, FBR_WS_SOLVE_THOMAS = 2, FBR_WS_RUN = 3, FBR_WS_RUN_LONG = 4,
+    FBR_WS_RUN_STREAM = 5, FBR_WS_RUN_WINDOW = 6
+};
+int64_t fbr_workspace_bytes(int what, int64_t M, int64_t nx);
 
 /* ------------------------------------------------------------------------------------------
  * K5  step-doubling error of the adaptive controller: err[m] = ||u1 - u2||_2 / ||u1||_2
