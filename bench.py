@@ -498,25 +498,38 @@ def run_gpu_arm(args):
     obs_idx_d, n_obs = E.index_tensor(w["obs_idx"])
     audit_d, n_audit = E.index_tensor(np.asarray(my_audit, dtype=np.int64))
     # observations = member 0's pressure at the observation cells (untimed set-up run on the device)
-    f0 = E.factorize(*E.assemble_zonal(mesh_d, zv0_d, zone_d, 1, nx, dt, "Neumann", "Neumann", sidx_d, n_src),
-                     parallel=False)  # the same per-model recurrence the batched run uses: bit-identical factors
-    snap0, _, _ = E.run(f0, p0_d, 1, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1)
+    f32 = args.dtype == "f32"  # fp32 MODE of north_star (state and factors in float; gate 1e-5), reported separately
+    # fp64: assembly + factorisation inside the run kernel (fbr_run_zonal_f64); --three-kernels / fp32: K1 + K1b + K3
+    on_chip = not f32 and not args.three_kernels
+    if on_chip:  # through the same code path as the timed run: the generating member's misfit is then exactly 0
+        snap0, _, _ = E.run(None, p0_d, 1, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1,
+                            zonal=(mesh_d, zv0_d, zone_d, dt, None))
+    else:
+        f0 = E.factorize(*E.assemble_zonal(mesh_d, zv0_d, zone_d, 1, nx, dt, "Neumann", "Neumann", sidx_d, n_src),
+                         parallel=False)  # the same per-model recurrence the batched run uses: bit-identical factors
+        snap0, _, _ = E.run(f0, p0_d, 1, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1)
+        del f0
     obs_d = snap0[0][:, obs_idx_d].contiguous()  # (n_steps + 1, n_obs); row 0 (initial state) is unused
     obs_host = obs_d.cpu().numpy()
-    del snap0, f0
-    f32 = args.dtype == "f32"  # fp32 MODE of north_star (state and factors in float; gate 1e-5), reported separately
+    del snap0
+    flags_d = E.zonal_flags(M, mesh_d.device)
     snap_d = torch.empty((n_audit, n_steps + 1, nx), dtype=torch.float32 if f32 else torch.float64, device=mesh_d.device)
     misfit_d = torch.empty(M, dtype=torch.float64, device=mesh_d.device)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=mesh_d.device)  # > 126 MB L2
 
     def hot_path(ev=None):
-        diag = E.assemble_zonal(mesh_d, zv_d, zone_d, M, nx, dt, "Neumann", "Neumann", sidx_d, n_src)
-        fac = E.factorize(*diag, check_singular=False)
+        if on_chip:  # assembly + factorisation inside the run kernel (fbr_run_zonal_f64)
+            fac, zonal = None, (mesh_d, zv_d, zone_d, dt, None)
+            flags_d.fill_(2**31 - 1)
+        else:
+            diag = E.assemble_zonal(mesh_d, zv_d, zone_d, M, nx, dt, "Neumann", "Neumann", sidx_d, n_src)
+            fac, zonal = E.factorize(*diag, check_singular=False), None
         if ev:
             ev[0].record()
         E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1,
               snap_models=audit_d, n_snap_models=n_audit, obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d,
-              snap_out=snap_d, misfit_out=misfit_d, dtype="float32" if f32 else "float64")
+              snap_out=snap_d, misfit_out=misfit_d, dtype="float32" if f32 else "float64", zonal=zonal,
+              singular_flags=flags_d if on_chip else None)
         if ev:
             ev[1].record()
         return gather_misfit(misfit_d, M * world) if world > 1 else misfit_d
@@ -567,7 +580,8 @@ def run_gpu_arm(args):
         flush.zero_()
         sync_all()
         t0 = time.perf_counter()
-        mis = ens.solve(dt=dt, t_total=n_steps * dt, audit_models=w["audit"], dtype="float32" if f32 else "float64")
+        mis = ens.solve(dt=dt, t_total=n_steps * dt, audit_models=w["audit"], dtype="float32" if f32 else "float64",
+                        on_chip_assembly=on_chip)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if it >= 2:
@@ -595,7 +609,8 @@ def run_gpu_arm(args):
                        "diffusivity": "zonal, 8 zones, 10**U(-1,1)", "sources": 2, "obs_cells": int(n_obs),
                        "audit_members_with_full_snapshots": n_audit, "bc": "Neumann/Neumann",
                        "l2": "flushed between timed iterations (512 MiB memset)",
-                       "timed_kernels": "K1 assemble_zonal + K1b factorize + K3 run_onchip"
+                       "timed_kernels": ("K3 run_onchip with on-chip assembly + factorisation (fbr_run_zonal_f64)" if on_chip
+                                         else "K1 assemble_zonal + K1b factorize + K3 run_onchip")
                                         + (" + NCCL all-gather of misfits" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if f32 else ncu_traffic(args.workload),
@@ -644,6 +659,8 @@ def main():
                     help="long-mesh kernel family for c2 / c5 (PDS1D_*.solve's long_mesh kwarg)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                     help="ensemble workloads: f32 = the separate fp32 mode (state and factors in float, gate 1e-5)")
+    ap.add_argument("--three-kernels", action="store_true",
+                    help="ensembles: K1 assemble + K1b factorize + K3 run as separate kernels instead of on-chip assembly")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C5 runs appended to the C3 line")
     args = ap.parse_args()

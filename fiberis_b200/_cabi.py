@@ -37,6 +37,8 @@ SIGNATURES = {
     "fbr_factorize_f64": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     "fbr_run_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "fbr_run_f32": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "fbr_run_zonal_f64": (_i32, [_p, _p, _i32, _p, _f64, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p,
+                                 _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
     "fbr_run_max_nx": (_i64, []),
     "fbr_run_reserve_ctas": (_i32, [_i32]),
     "fbr_run_long_max_nx": (_i64, []),

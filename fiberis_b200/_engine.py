@@ -108,8 +108,14 @@ def factorize(dl, d, du, check_singular=True, parallel=None):
 
 def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, snap_models=None,
         n_snap_models=None, want_final=False, obs_idx=None, n_obs=0, obs=None, obs_w=None, dtype="float64",
-        with_initial_row=True, misfit_out=None, snap_out=None):
+        with_initial_row=True, misfit_out=None, snap_out=None, zonal=None, singular_flags=None):
     """K3: persistent on-chip integration.
+
+    ``factors`` = (fl, fr, fg) from ``factorize``; or ``factors=None`` and ``zonal=(mesh, zone_value (M, n_zones),
+    zone_of_cell int32 (nx), dt, sigma | None)``: assembly and factorisation happen inside the kernel
+    (``fbr_run_zonal_f64``, fp64, 256 <= nx <= 4096).  Singular members raise ``LinAlgError`` here, unless the
+    caller passes ``singular_flags`` (from ``zonal_flags(M)``) and checks them later with
+    ``raise_if_singular_zonal`` — which keeps the launch asynchronous.
 
     Returns (snap | None, p_final | None, misfit | None).  ``snap`` has shape
     (n_recorded_models, rows, nx) — the layout the result objects want, written directly by the
@@ -118,8 +124,13 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     """
     torch = _torch()
     lib = _cabi.load()
-    fl, fr, fg = factors
-    dev = fl.device
+    if zonal is not None:
+        assert factors is None and dtype == "float64"
+        z_mesh, z_value, z_of_cell, z_dt, z_sigma = zonal
+        dev = z_mesh.device
+    else:
+        fl, fr, fg = factors
+        dev = fl.device
     tdt = torch.float64 if dtype == "float64" else torch.float32
     fn = lib.fbr_run_f64 if dtype == "float64" else lib.fbr_run_f32
     n_rows = n_steps // snapshot_every if snapshot_every else 0
@@ -140,11 +151,29 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     if misfit is None and obs_idx is not None:
         misfit = torch.empty(M, dtype=torch.float64, device=dev)
     p0_stride = 0 if p0.dim() == 1 else nx
-    check(fn(ptr(fl), ptr(fr), ptr(fg), ptr(p0), p0_stride, M, nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
-             ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), ptr(snap_models),
-             int(n_snap_models or 0), row_stride, model_stride, snap_ptr, ptr(p_final), ptr(obs_idx), int(n_obs),
-             ptr(obs), ptr(obs_w), ptr(misfit), current_stream()))
+    tail = (ptr(p0), p0_stride, M, nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
+            ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), ptr(snap_models),
+            int(n_snap_models or 0), row_stride, model_stride, snap_ptr, ptr(p_final), ptr(obs_idx), int(n_obs),
+            ptr(obs), ptr(obs_w), ptr(misfit), current_stream())
+    if zonal is not None:
+        flags = zonal_flags(M, dev) if singular_flags is None else singular_flags
+        check(lib.fbr_run_zonal_f64(ptr(z_mesh), ptr(z_value), int(z_value.shape[1]), ptr(z_of_cell), float(z_dt), ptr(z_sigma),
+                                    ptr(flags), *tail))
+        if singular_flags is None:
+            raise_if_singular_zonal(flags)
+    else:
+        check(fn(ptr(fl), ptr(fr), ptr(fg), *tail))
     return snap, p_final, misfit
+
+
+def zonal_flags(M, dev=None):
+    """Per-member flag array for fbr_run_zonal_f64 (the kernel takes the minimum with 1 + zero-pivot row)."""
+    return _torch().full((M,), 2**31 - 1, dtype=_torch().int32, device=device(dev))
+
+
+def raise_if_singular_zonal(flags):
+    """Flags of fbr_run_zonal_f64 (INT32_MAX = fine) -> the exception the reference's scipy.linalg.solve raises."""
+    raise_if_singular(flags * (flags != 2**31 - 1), "system")
 
 
 def reserve_ctas(n):

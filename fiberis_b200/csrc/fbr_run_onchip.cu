@@ -22,6 +22,7 @@
 // step ahead straight from global memory (L2), so the time loop has no staging code at all.
 #include "fbr_common.cuh"
 #include "fbr_sweep.cuh"
+#include "fbr_factor_reg.cuh"
 
 #include <type_traits>
 
@@ -53,7 +54,64 @@ struct RunArgs {
     const double *obs_w;  // (n_obs) or NULL
     double *misfit;       // (M)
     int blk_steps;        // fp64 x8 kernel: time steps per staged block of per-step scalars
+    // on-chip assembly mode (fbr_run_zonal_f64): no factor arrays, the members' matrices are assembled (K1 arithmetic)
+    // and factorised in registers from the shared mesh and n_zones diffusivities per member
+    const double *z_mesh;        // (nx)
+    const double *z_value;       // (M, z_n)
+    const int32_t *z_of_cell;    // (nx)
+    int z_n;
+    double z_dt;
+    const double *z_sigma;       // (nx) PML damping or NULL
+    int32_t *z_singular;         // (M) preset to INT32_MAX by the caller; atomicMin of 1 + zero-pivot row; may be NULL
 };
+
+// Rows of A(dt) for CPT consecutive cells of member m, exactly K1's arithmetic (fbr_assemble.cu, matbuilder.py:21-81).
+template <int CPT>
+__device__ __forceinline__ void assemble_zonal_chunk(const RunArgs &a, int64_t m, int cell0, unsigned src_mask, double (&dl)[CPT],
+                                                     double (&d)[CPT], double (&du)[CPT]) {
+    const int nx = (int)a.nx;
+    const double *zv = a.z_value + m * a.z_n;
+    double xs[CPT + 2], Ds[CPT + 2];
+#pragma unroll
+    for (int j = 0; j < CPT + 2; ++j) {
+        int i = cell0 - 1 + j;
+        i = i < 0 ? 0 : (i > nx - 1 ? nx - 1 : i);
+        xs[j] = __ldg(a.z_mesh + i);
+        Ds[j] = __ldg(zv + __ldg(a.z_of_cell + i));
+    }
+    double he[CPT + 1];  // harmonic means between neighbours: he[j] couples cells cell0 + j - 1 and cell0 + j
+#pragma unroll
+    for (int j = 0; j < CPT + 1; ++j)
+        he[j] = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, Ds[j]), Ds[j + 1]), __dadd_rn(Ds[j], Ds[j + 1]));
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) {
+        const int i = cell0 + j;
+        double aa = 0.0, bb = 0.0, cc = 0.0;
+        if (i > 0 && i < nx - 1) {
+            const double dxm = __dsub_rn(xs[j + 1], xs[j]), dxp = __dsub_rn(xs[j + 2], xs[j + 1]);
+            const double sum = __dadd_rn(dxm, dxp);
+            const double al = __ddiv_rn(__dmul_rn(he[j], a.z_dt), __dmul_rn(__dmul_rn(dxm, sum), 0.5));
+            const double ar = __ddiv_rn(__dmul_rn(he[j + 1], a.z_dt), __dmul_rn(__dmul_rn(dxp, sum), 0.5));
+            aa = -al;
+            bb = __dadd_rn(__dadd_rn(1.0, al), ar);
+            cc = -ar;
+        }
+        if (i == 0) {
+            if (a.lbc == FBR_BC_DIRICHLET) bb = 1.0;
+            else if (a.lbc == FBR_BC_NEUMANN) { bb = -1.0; cc = 1.0; }
+        }
+        if (i == nx - 1) {
+            if (a.rbc == FBR_BC_DIRICHLET) bb = 1.0;
+            else if (a.rbc == FBR_BC_NEUMANN) { bb = -1.0; aa = 1.0; }
+        }
+        if ((src_mask >> j) & 1) { aa = 0.0; bb = 1.0; cc = 0.0; }
+        if (a.z_sigma && i < nx) bb = __dadd_rn(bb, __dmul_rn(a.z_dt, __ldg(a.z_sigma + i)));
+        if (i == 0) aa = 0.0;
+        if (i >= nx - 1) cc = 0.0;
+        if (i >= nx) { aa = 0.0; bb = 1.0; }  // identity rows behind the mesh
+        dl[j] = aa; d[j] = bb; du[j] = cc;
+    }
+}
 
 template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
@@ -483,8 +541,10 @@ __device__ __forceinline__ void store_row_coalesced(T *__restrict__ row, int64_t
     }
 }
 
-template <typename T, int CPT, int W, int MINB>
+template <typename T, int CPT, int W, int MINB, bool ZONAL>
 __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs a) {
+    __shared__ Mat2 s_zw[ZONAL ? W : 1];
+    __shared__ double s_zc[ZONAL ? W : 1];
     static_assert(CPT * sizeof(T) == 64, "a thread owns 64 bytes of state: 8 doubles or 16 floats");
     __shared__ __align__(16) T s_K[2][W][W];
     __shared__ __align__(16) T s_E[2][W];
@@ -555,15 +615,35 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
         }
     };
 
+    unsigned src_rows = 0;  // which of my cells are source rows of the matrix (on-chip assembly mode)
+    if (ZONAL) {
+#pragma unroll 1
+        for (int k = 0; k < a.n_src; ++k) {
+            const int64_t jj = a.src_idx[k] - cell0;
+            if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) src_rows |= 1u << jj;
+        }
+    }
+
     ModelCursor cursor = model_cursor(a);
     int64_t m;
     long long preset;
     while (next_model(a, cursor, m, preset)) {
         // ---------------- per-model setup ----------------
         T l[CPT], r[CPT], g[CPT], x[CPT];
-        load_row(a.fl + m * nx, 0.0, l);
-        load_row(a.fr + m * nx, 1.0, r);
-        load_row(a.fg + m * nx, 0.0, g);
+        if constexpr (ZONAL) {
+            double zl[CPT], zr[CPT], zg[CPT];
+            assemble_zonal_chunk<CPT>(a, m, (int)cell0, src_rows, zl, zr, zg);
+            const int64_t left = nx - cell0;
+            const int bad = factor_rows_in_registers<CPT, W>(zl, zr, zg, (int)cell0, (int)(left < 0 ? 0 : left > CPT ? CPT : left),
+                                                             lane, warp, s_zw, s_zc);
+            if (bad && a.z_singular) atomicMin(a.z_singular + m, bad);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) { l[j] = (T)zl[j]; r[j] = (T)zr[j]; g[j] = (T)zg[j]; }
+        } else {
+            load_row(a.fl + m * nx, 0.0, l);
+            load_row(a.fr + m * nx, 1.0, r);
+            load_row(a.fg + m * nx, 0.0, g);
+        }
         load_row(a.p0 + m * a.p0_stride, 0.0, x);
 
         const ScanMultipliersT<T> sm = scan_multipliers<T>(chunk_product<T, CPT>(l), chunk_product<T, CPT>(g), lane);
@@ -778,12 +858,12 @@ static int &reserved_ctas() {
     return n;
 }
 
-template <typename T, int CPT, int W>
+template <typename T, int CPT, int W, bool ZONAL = false>
 static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
     constexpr int kFull16 = (16 / W) > 0 ? (16 / W) : 1;
-    auto kern = run_onchipx_kernel<T, CPT, W, kFull16>;
+    auto kern = run_onchipx_kernel<T, CPT, W, kFull16, ZONAL>;
     RunArgs b = a;
     const int cols = a.n_src + 2 * a.n_obs;
     b.blk_steps = cols <= 64 ? 32 : 8;  // keeps the staging area <= 32 KB per CTA
@@ -805,6 +885,15 @@ template <typename T>
 static int launch_x(const RunArgs &a, cudaStream_t stream) {
     constexpr int CPT = 64 / sizeof(T);
     const int64_t threads = (a.nx + CPT - 1) / CPT;
+    if constexpr (sizeof(T) == 8) {
+        if (a.z_mesh) {  // on-chip assembly + factorisation (fbr_run_zonal_f64)
+            if (threads <= 32) return launch_onchipx<T, CPT, 1, true>(a, stream);
+            if (threads <= 64) return launch_onchipx<T, CPT, 2, true>(a, stream);
+            if (threads <= 128) return launch_onchipx<T, CPT, 4, true>(a, stream);
+            if (threads <= 256) return launch_onchipx<T, CPT, 8, true>(a, stream);
+            return launch_onchipx<T, CPT, 16, true>(a, stream);
+        }
+    }
     if (threads <= 32) return launch_onchipx<T, CPT, 1>(a, stream);
     if (threads <= 64) return launch_onchipx<T, CPT, 2>(a, stream);
     if (threads <= 128) return launch_onchipx<T, CPT, 4>(a, stream);
@@ -840,7 +929,7 @@ template <typename T>
 static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     FBR_REQUIRE(a.M >= 1 && a.nx >= 1 && a.n_steps >= 0, "M, nx must be >= 1 and n_steps >= 0");
     FBR_REQUIRE(a.n_steps <= 0x7fffffff, "n_steps per launch is limited to 2^31 - 1");
-    FBR_REQUIRE(a.fl && a.fr && a.fg && a.p0, "NULL factor / initial-state pointer");
+    FBR_REQUIRE(((a.fl && a.fr && a.fg) || a.z_mesh) && a.p0, "NULL factor / initial-state pointer");
     FBR_REQUIRE(a.p0_stride == 0 || a.p0_stride >= a.nx, "bad p0_stride");
     FBR_REQUIRE(a.lbc >= 0 && a.lbc <= 2 && a.rbc >= 0 && a.rbc <= 2, "bad boundary code");
     FBR_REQUIRE(a.n_src >= 0 && a.n_src <= kMaxSrc, "n_src=%d outside [0, %d]", a.n_src, kMaxSrc);
@@ -889,7 +978,9 @@ extern "C" int fbr_run_reserve_ctas(int n) {
     a.src_table = src_table; a.snapshot_every = snapshot_every; a.snap_models = snap_models;              \
     a.n_snap_models = n_snap_models; a.snap_row_stride = snap_row_stride;                                  \
     a.snap_model_stride = snap_model_stride; a.snap = snap; a.p_final = p_final; a.obs_idx = obs_idx;             \
-    a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit; a.blk_steps = 0;
+    a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit; a.blk_steps = 0;     \
+    a.z_mesh = nullptr; a.z_value = nullptr; a.z_of_cell = nullptr; a.z_n = 0; a.z_dt = 0.0;              \
+    a.z_sigma = nullptr; a.z_singular = nullptr;
 
 extern "C" int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,
                            int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
@@ -911,4 +1002,21 @@ extern "C" int fbr_run_f32(const double *fl, const double *fr, const double *fg,
                            double *misfit, void *stream) {
     FBR_FILL_ARGS();
     return run_dispatch<float>(a, as_stream(stream));
+}
+
+extern "C" int fbr_run_zonal_f64(const double *mesh, const double *zone_value, int n_zones, const int32_t *zone_of_cell,
+                                 double dt, const double *sigma, int32_t *singular, const double *p0, int64_t p0_stride,
+                                 int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                                 const double *src_table, int64_t snapshot_every, const int64_t *snap_models,
+                                 int64_t n_snap_models, int64_t snap_row_stride, int64_t snap_model_stride, double *snap,
+                                 double *p_final, const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
+                                 double *misfit, void *stream) {
+    const double *fl = nullptr, *fr = nullptr, *fg = nullptr;
+    FBR_FILL_ARGS();
+    FBR_REQUIRE(mesh && zone_value && zone_of_cell && n_zones >= 1, "NULL mesh / zone arguments");
+    FBR_REQUIRE(nx >= 256 && nx <= fbr_run_max_nx(), "on-chip assembly covers 256 <= nx <= %lld (got %lld)",
+                (long long)fbr_run_max_nx(), (long long)nx);
+    a.z_mesh = mesh; a.z_value = zone_value; a.z_of_cell = zone_of_cell; a.z_n = n_zones; a.z_dt = dt; a.z_sigma = sigma;
+    a.z_singular = singular;
+    return run_dispatch<double>(a, as_stream(stream));
 }

@@ -22,32 +22,10 @@
 // (1 + first such row among the rows a thread saw; 0 = fine), like the other K2 variants.
 #include "fbr_common.cuh"
 #include "fbr_moebius.cuh"
+#include "fbr_factor_reg.cuh"
 #include "fbr_sweep.cuh"
 
 namespace fbr {
-
-// scale a 2x2 matrix / a pair by the power of two that brings its largest entry to [1, 2): integer
-// work on the exponent fields only (the library scalbn / ilogb pair costs ~10x as much)
-__device__ __forceinline__ double pow2_scale_for(int hi_max_exp_field) {
-    // hi_max_exp_field = (hi word & 0x7ff00000) of the largest magnitude;  2^(1023 - E) has hi word 0x7fe00000 - field
-    int s = max(0x7fe00000 - hi_max_exp_field, 0x00100000);  // never below the smallest normal
-    if (hi_max_exp_field >= 0x7ff00000) s = 0x3ff00000;      // inf / nan: leave alone
-    return __hiloint2double(s, 0);
-}
-__device__ __forceinline__ int exp_field(double v) { return __double2hiint(v) & 0x7ff00000; }
-__device__ __forceinline__ Mat2 rescale_fast(Mat2 m) {
-    const double s = pow2_scale_for(max(max(exp_field(m.a), exp_field(m.b)), max(exp_field(m.c), exp_field(m.d))));
-    m.a *= s; m.b *= s; m.c *= s; m.d *= s;
-    return m;
-}
-__device__ __forceinline__ Mat2 compose_raw(const Mat2 &later, const Mat2 &earlier) {
-    Mat2 r;
-    r.a = fma(later.a, earlier.a, later.b * earlier.c);
-    r.b = fma(later.a, earlier.b, later.b * earlier.d);
-    r.c = fma(later.c, earlier.a, later.d * earlier.c);
-    r.d = fma(later.c, earlier.b, later.d * earlier.d);
-    return r;
-}
 
 template <int CPT>
 __device__ __forceinline__ void load_chunk(const double *__restrict__ row, int nvalid, bool vec, double pad, double (&v)[CPT]) {
@@ -64,19 +42,6 @@ __device__ __forceinline__ void load_chunk(const double *__restrict__ row, int n
         for (int j = 0; j < CPT; ++j) v[j] = j < nvalid ? __ldg(row + j) : pad;
     }
 }
-// num / den without the library's special-case path: den is a rescaled pivot numerator (normal range, or an
-// exact zero -> non-finite quotient, which the caller flags).  Hardware seed, two Newton steps, one correction.
-__device__ __forceinline__ double div_fast(double num, double den) {
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(den));
-    double e = fma(-den, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-den, x, 1.0);
-    x = fma(x, e, x);
-    const double q = num * x;
-    return fma(fma(-den, q, num), x, q);
-}
-
 // the sweeps' stage multipliers for groups of L lanes (fbr_sweep.cuh's scan_multipliers is the L = 32 case)
 template <int L>
 struct GroupMultipliers {

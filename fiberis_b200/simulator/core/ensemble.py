@@ -128,8 +128,11 @@ class PDS1D_Ensemble:
 
     # -- solve ------------------------------------------------------------------------------------
     def solve(self, dt, t_total=None, audit_models=(), snapshot_every=1, dtype="float64", models=None,
-              process_group=None, gather=True, split_audit=True):
+              process_group=None, gather=True, split_audit=True, on_chip_assembly=True):
         """Integrate every member with a fixed ``dt``.
+
+        Zonal ensembles in fp64 with 256..4096 cells assemble and factorise their matrices inside the run
+        kernel (``fbr_run_zonal_f64``; ``on_chip_assembly=False`` selects the three-kernel path K1 + K1b + K3).
 
         ``models=(lo, hi)`` restricts the run to a contiguous block (multi-GPU sharding does this
         per rank when ``process_group`` / an initialised default group is given); ``misfit`` is then
@@ -158,15 +161,26 @@ class PDS1D_Ensemble:
 
         mesh_d = _engine.to_device(self.mesh)
         sidx_d, n_src = _engine.index_tensor(self.sourceidx)
-        if self.diffusivity is not None:
-            diag = _engine.assemble(mesh_d, _engine.to_device(self.diffusivity[lo:hi]), M, nx, dt, self.lbc, self.rbc,
-                                    sidx_d, n_src)
+        # Zonal members in fp64: the matrices are assembled and factorised inside the run kernel (fbr_run_zonal_f64),
+        # no (M, nx) coefficient array exists.  Dense diffusivities / the fp32 mode / short meshes: K1 + K1b + K3.
+        zonal = flags_d = None
+        on_chip = (self.diffusivity is None and dtype == "float64" and 256 <= nx <= _engine.run_max_nx()
+                   and on_chip_assembly)
+        if on_chip:
+            zonal = (mesh_d, _engine.to_device(self.zone_value[lo:hi]), _engine.to_device(self.zone_of_cell, np.int32),
+                     dt, None)
+            flags_d = _engine.zonal_flags(M, mesh_d.device)
+            factors = None
         else:
-            diag = _engine.assemble_zonal(mesh_d, _engine.to_device(self.zone_value[lo:hi]),
-                                          _engine.to_device(self.zone_of_cell, np.int32), M, nx, dt, self.lbc,
-                                          self.rbc, sidx_d, n_src)
-        factors = _engine.factorize(*diag)
-        del diag
+            if self.diffusivity is not None:
+                diag = _engine.assemble(mesh_d, _engine.to_device(self.diffusivity[lo:hi]), M, nx, dt, self.lbc, self.rbc,
+                                        sidx_d, n_src)
+            else:
+                diag = _engine.assemble_zonal(mesh_d, _engine.to_device(self.zone_value[lo:hi]),
+                                              _engine.to_device(self.zone_of_cell, np.int32), M, nx, dt, self.lbc,
+                                              self.rbc, sidx_d, n_src)
+            factors = _engine.factorize(*diag)
+            del diag
         init = self.initial if self.initial.ndim == 1 else self.initial[lo:hi]
         p0_d = _engine.to_device(init)
         table_d = _engine.to_device(table)
@@ -197,24 +211,30 @@ class PDS1D_Ensemble:
             pick = snap_models_d
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                fac_a = tuple(f.index_select(0, pick).contiguous() for f in factors)
+                if on_chip:
+                    fac_a, zon_a = None, (zonal[0], zonal[1].index_select(0, pick).contiguous(), zonal[2], dt, None)
+                    flags_a = _engine.zonal_flags(n_audit, mesh_d.device)  # duplicates of the sweep's flags: not checked
+                else:
+                    fac_a, zon_a, flags_a = tuple(f.index_select(0, pick).contiguous() for f in factors), None, None
                 p0_a = p0_d if p0_d.dim() == 1 else p0_d.index_select(0, pick).contiguous()
                 # same observation arguments as the sweep: equal shared-memory footprints let CTAs of the two
                 # launches share an SM (with different footprints the audited CTAs kept their SMs to
                 # themselves and the sweep finished 2.5 ms later); the misfits computed here are discarded
                 snap_a, _, _ = _engine.run(fac_a, p0_a, n_audit, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                           snapshot_every=snapshot_every, **run_kw)
+                                           snapshot_every=snapshot_every, zonal=zon_a, singular_flags=flags_a, **run_kw)
                 host_snap = _engine.to_host(_engine.as_f64(snap_a), sync=False)
             _engine.reserve_ctas(n_audit)  # the audited members' CTAs stay resident next to the sweep's grid
             _, _, misfit_d = _engine.run(factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                         snapshot_every=0, **run_kw)
+                                         snapshot_every=0, zonal=zonal, singular_flags=flags_d, **run_kw)
             main.wait_stream(side)
             snap_d = snap_a
         else:
             snap_d, _, misfit_d = _engine.run(
                 factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                 snapshot_every=snapshot_every if n_audit else 0, snap_models=snap_models_d, n_snap_models=n_audit,
-                **run_kw)
+                zonal=zonal, singular_flags=flags_d, **run_kw)
+        if flags_d is not None:
+            _engine.raise_if_singular_zonal(flags_d)
 
         self.taxis = np.array(taxis)
         self.audit_models = audit

@@ -146,6 +146,24 @@ int fbr_run_f32(const double *fl, const double *fr, const double *fg, const doub
                 int64_t snap_row_stride, int64_t snap_model_stride, float *snap, float *p_final, const int64_t *obs_idx, int n_obs,
                 const double *obs, const double *obs_w, double *misfit, void *stream);
 
+/* K3 with ON-CHIP ASSEMBLY: fbr_assemble_zonal_f64 + fbr_factorize_f64 + fbr_run_f64 in one kernel, for
+ * ensembles whose members share the mesh and differ in n_zones diffusivity values (BASELINE.json
+ * configs[2], [3]).  Each CTA assembles its member's rows with K1's arithmetic (bit-identical diagonals,
+ * src/fiberis/simulator/solver/matbuilder.py:21-81), factorises them in registers (scan of 2x2 Moebius
+ * matrices, csrc/fbr_factor_reg.cuh) and integrates all steps: no (M, nx) coefficient array ever exists in
+ * HBM.  mesh: (nx); zone_value: (M, n_zones); zone_of_cell: (nx) int32; sigma: NULL or (nx) PML damping
+ * (fbr_pml_sigma_f64); singular: NULL or (M) int32 PRESET TO INT32_MAX by the caller, receives
+ * min(1 + zero-pivot row) for members whose matrix is singular.  Remaining arguments as fbr_run_f64.
+ * 256 <= nx <= fbr_run_max_nx(). */
+int fbr_run_zonal_f64(const double *mesh, const double *zone_value, int n_zones,
+                      const int32_t *zone_of_cell, double dt, const double *sigma, int32_t *singular,
+                      const double *p0, int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc,
+                      int rbc, const int64_t *src_idx, int n_src, const double *src_table,
+                      int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
+                      int64_t snap_row_stride, int64_t snap_model_stride, double *snap, double *p_final,
+                      const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
+                      double *misfit, void *stream);
+
 int64_t fbr_run_max_nx(void);
 
 /* The persistent grid of fbr_run_* normally fills every CTA slot of the device.  A caller that has just

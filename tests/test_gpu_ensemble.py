@@ -60,10 +60,39 @@ def test_ensemble_members_and_misfit_vs_oracle(M, nx, dense):
 
 def test_ensemble_member_equals_single_model_api():
     e, c = make_ensemble(3, 5, 300, 30)
-    e.solve(dt=1.0, t_total=c["T"], audit_models=[2])
+    e.solve(dt=1.0, t_total=c["T"], audit_models=[2], on_chip_assembly=False)
     p = e.member(2)
     p.solve(dt=1.0, t_total=c["T"])
     npt.assert_array_equal(e.snapshot[0], p.snapshot)  # same kernels, same arithmetic: bit-equal
+    # default: the matrices are assembled and factorised inside the run kernel (scan-based pivots: last-bit differences)
+    e.solve(dt=1.0, t_total=c["T"], audit_models=[2])
+    assert G.rel_max(e.snapshot[0], p.snapshot) <= 1e-13
+
+
+@pytest.mark.parametrize("nx,lbc,rbc", [(256, "Neumann", "Neumann"), (300, "Dirichlet", "Neumann"), (777, "Neumann", "Dirichlet"),
+                                        (1024, "Dirichlet", "Neumann"), (2049, "Dirichlet", "Dirichlet"), (4096, "Neumann", "Neumann")])
+def test_on_chip_assembly_matches_three_kernel_path_and_oracle(nx, lbc, rbc):
+    """fbr_run_zonal_f64: K1's assembly + a register factorisation inside the run kernel — every team width, padding
+    rows, every boundary type, sources on and next to chunk / warp boundaries; singular members are flagged."""
+    M, n_steps = 7, 40
+    e, c = make_ensemble(4000 + nx, M, nx, n_steps, n_obs=5)
+    e.set_bcs(lbc, rbc)
+    e.set_sourceidx([255 if nx > 300 else 8, 256 if nx > 300 else 9][:len(c["sidx"])] + list(c["sidx"][2:]))
+    rng = np.random.default_rng(nx)
+    e.set_observations(c["obs_idx"], rng.uniform(-1, 1, (n_steps + 1, 5)))
+    mis = e.solve(dt=1.0, t_total=c["T"], audit_models=[0, 3, 6]).copy()
+    snap = e.snapshot.copy()
+    mis3 = e.solve(dt=1.0, t_total=c["T"], audit_models=[0, 3, 6], on_chip_assembly=False)
+    assert G.rel_max(snap, e.snapshot) <= 1e-12
+    npt.assert_allclose(mis, mis3, rtol=1e-11)
+    for k, m in enumerate([0, 3, 6]):
+        want, _ = O.solve_fixed(c["mesh"], c["zv"][m][c["zone"]], np.zeros(nx), lbc, rbc, list(e.sourceidx), c["srcs"], 0.0, 1.0,
+                                c["T"])
+        assert G.rel_max(snap[k], want) <= 1e-10
+    if nx == 300:  # a 'None' boundary leaves a zero row (matbuilder.py:49-69): scipy raises in the reference
+        e.set_bcs("None", "Neumann")
+        with pytest.raises(np.linalg.LinAlgError):
+            e.solve(dt=1.0, t_total=c["T"])
 
 
 def test_ensemble_fp32_mode():
