@@ -613,8 +613,10 @@ def run_gpu_arm(args):
                                          else "K1 assemble_zonal + K1b factorize + K3 run_onchip")
                                         + (" + NCCL all-gather of misfits" if world > 1 else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None if f32 else ncu_traffic(args.workload),
-                         "kernel": "run_onchip_kernel<float,8,4> (K3, fp32 mode)" if f32 else "run_onchip8_kernel<4> (K3, fp64 x8)",
+                         "traffic": ncu_traffic(args.workload) if (on_chip and args.workload == "c3") else None,
+                         "kernel": ("run_onchipx_kernel<float,16,W> (K3, fp32 mode)" if f32 else
+                                    "run_onchipx_kernel<double,8,W,ZONAL> (K3 fp64 x8, on-chip assembly)" if on_chip else
+                                    "run_onchipx_kernel<double,8,W> (K3, fp64 x8)"),
                          "kernel_ms": k3_s * 1e3, "peak_source": peak_src,
                          "note": "algorithmic 16 B/cell-update; K3 keeps pressure+factors on chip for all time "
                                  "steps, so frac > 1 is expected - see traffic (ncu DRAM bytes per launch)"},
