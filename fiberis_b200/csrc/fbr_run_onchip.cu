@@ -77,7 +77,7 @@ __device__ __forceinline__ void assemble_zonal_chunk(const RunArgs &a, int64_t m
         int i = cell0 - 1 + j;
         i = i < 0 ? 0 : (i > nx - 1 ? nx - 1 : i);
         xs[j] = __ldg(a.z_mesh + i);
-        Ds[j] = __ldg(zv + __ldg(a.z_of_cell + i));
+        Ds[j] = __ldg(zv + (a.z_of_cell ? __ldg(a.z_of_cell + i) : i));  // zone value, or the member's own (nx) row
     }
     double he[CPT + 1];  // harmonic means between neighbours: he[j] couples cells cell0 + j - 1 and cell0 + j
 #pragma unroll
@@ -1013,7 +1013,8 @@ extern "C" int fbr_run_zonal_f64(const double *mesh, const double *zone_value, i
                                  double *misfit, void *stream) {
     const double *fl = nullptr, *fr = nullptr, *fg = nullptr;
     FBR_FILL_ARGS();
-    FBR_REQUIRE(mesh && zone_value && zone_of_cell && n_zones >= 1, "NULL mesh / zone arguments");
+    FBR_REQUIRE(mesh && zone_value && n_zones >= 1, "NULL mesh / zone arguments");
+    FBR_REQUIRE(zone_of_cell || n_zones == nx, "zone_of_cell == NULL means one diffusivity per cell: n_zones must equal nx");
     FBR_REQUIRE(nx >= 256 && nx <= fbr_run_max_nx(), "on-chip assembly covers 256 <= nx <= %lld (got %lld)",
                 (long long)fbr_run_max_nx(), (long long)nx);
     a.z_mesh = mesh; a.z_value = zone_value; a.z_of_cell = zone_of_cell; a.z_n = n_zones; a.z_dt = dt; a.z_sigma = sigma;

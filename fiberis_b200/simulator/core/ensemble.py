@@ -161,14 +161,16 @@ class PDS1D_Ensemble:
 
         mesh_d = _engine.to_device(self.mesh)
         sidx_d, n_src = _engine.index_tensor(self.sourceidx)
-        # Zonal members in fp64: the matrices are assembled and factorised inside the run kernel (fbr_run_zonal_f64),
-        # no (M, nx) coefficient array exists.  Dense diffusivities / the fp32 mode / short meshes: K1 + K1b + K3.
+        # fp64 ensembles on a shared mesh: the matrices are assembled and factorised inside the run kernel
+        # (fbr_run_zonal_f64), no (M, nx) coefficient array exists.  The fp32 mode / short meshes: K1 + K1b + K3.
         zonal = flags_d = None
-        on_chip = (self.diffusivity is None and dtype == "float64" and 256 <= nx <= _engine.run_max_nx()
-                   and on_chip_assembly)
+        on_chip = dtype == "float64" and 256 <= nx <= _engine.run_max_nx() and on_chip_assembly
         if on_chip:
-            zonal = (mesh_d, _engine.to_device(self.zone_value[lo:hi]), _engine.to_device(self.zone_of_cell, np.int32),
-                     dt, None)
+            if self.diffusivity is None:
+                zonal = (mesh_d, _engine.to_device(self.zone_value[lo:hi]), _engine.to_device(self.zone_of_cell, np.int32),
+                         dt, None)
+            else:  # one diffusivity per cell and member: the (M, nx) array is read once, 8 B per cell
+                zonal = (mesh_d, _engine.to_device(self.diffusivity[lo:hi]), None, dt, None)
             flags_d = _engine.zonal_flags(M, mesh_d.device)
             factors = None
         else:

@@ -151,7 +151,8 @@ int fbr_run_f32(const double *fl, const double *fr, const double *fg, const doub
  * configs[2], [3]).  Each CTA assembles its member's rows with K1's arithmetic (bit-identical diagonals,
  * src/fiberis/simulator/solver/matbuilder.py:21-81), factorises them in registers (scan of 2x2 Moebius
  * matrices, csrc/fbr_factor_reg.cuh) and integrates all steps: no (M, nx) coefficient array ever exists in
- * HBM.  mesh: (nx); zone_value: (M, n_zones); zone_of_cell: (nx) int32; sigma: NULL or (nx) PML damping
+ * HBM.  mesh: (nx); zone_value: (M, n_zones); zone_of_cell: (nx) int32, or NULL with n_zones == nx for
+ * members that carry a full (nx) diffusivity row each; sigma: NULL or (nx) PML damping
  * (fbr_pml_sigma_f64); singular: NULL or (M) int32 PRESET TO INT32_MAX by the caller, receives
  * min(1 + zero-pivot row) for members whose matrix is singular.  Remaining arguments as fbr_run_f64.
  * 256 <= nx <= fbr_run_max_nx(). */

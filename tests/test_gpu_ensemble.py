@@ -75,7 +75,7 @@ def test_on_chip_assembly_matches_three_kernel_path_and_oracle(nx, lbc, rbc):
     """fbr_run_zonal_f64: K1's assembly + a register factorisation inside the run kernel — every team width, padding
     rows, every boundary type, sources on and next to chunk / warp boundaries; singular members are flagged."""
     M, n_steps = 7, 40
-    e, c = make_ensemble(4000 + nx, M, nx, n_steps, n_obs=5)
+    e, c = make_ensemble(4000 + nx, M, nx, n_steps, n_obs=5, dense=nx in (300, 2049))
     e.set_bcs(lbc, rbc)
     e.set_sourceidx([255 if nx > 300 else 8, 256 if nx > 300 else 9][:len(c["sidx"])] + list(c["sidx"][2:]))
     rng = np.random.default_rng(nx)
