@@ -286,3 +286,27 @@ def test_tiled_factorisation_is_bit_identical_to_the_plain_recurrence(monkeypatc
     dl = np.zeros((70, 40)); d = np.ones((70, 40)); du = np.zeros((70, 40)); d[5, 17] = 0.0
     with pytest.raises(np.linalg.LinAlgError):
         E.factorize(E.to_device(dl), E.to_device(d), E.to_device(du))
+
+
+def test_c4_full_member_count_properties():
+    """BASELINE.json configs[3] at its full member count (1,000,000 x 512 cells), 24 steps: sampled members' misfits
+    equal the banded C oracle's, the generating member's misfit is exactly 0, and the blocks of an 8-way shard are
+    bit-equal to the corresponding part of the unsharded sweep."""
+    from fiberis_b200.simulator.core.ensemble import shard_bounds
+    from oracle import c_oracle as CO
+    M, nx, n_steps = 1_000_000, 512, 24
+    e, c = make_ensemble(404, M, nx, n_steps, n_obs=16)
+    e.solve(dt=1.0, t_total=c["T"], audit_models=[0], models=(0, 8))
+    obs = e.snapshot[0][:, c["obs_idx"]].copy()
+    e.set_observations(c["obs_idx"], obs)
+    mis = e.solve(dt=1.0, t_total=c["T"], audit_models=[0, 999_999]).copy()
+    assert mis.shape == (M,) and mis[0] == 0.0 and np.all(np.isfinite(mis)) and np.count_nonzero(mis) >= M - 1
+    table = np.stack([np.interp(np.arange(n_steps) * 1.0, t, d) for t, d in c["srcs"]], axis=1)  # sampled at step start
+    pick = np.array([1, 2, 77_777, 500_000, 999_998, 999_999])
+    want, _ = CO.run_ensemble(c["mesh"], c["zv"][pick], c["zone"], np.zeros(nx), n_steps, 1.0, "Neumann", "Neumann",
+                              np.asarray(c["sidx"]), table, c["obs_idx"], obs)
+    npt.assert_allclose(mis[pick], want, rtol=1e-9)
+    for r in (0, 3, 7):
+        lo, hi = shard_bounds(M, 8, r)
+        part = e.solve(dt=1.0, t_total=c["T"], models=(lo, hi))
+        npt.assert_array_equal(part, mis[lo:hi])
