@@ -756,7 +756,13 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 for (int n = n_begin; n < n_end; ++n) {
                     // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
                     if (has_ov) {  // only the threads that own an overridden cell
-                        set_at<T, CPT>(x, (int)(desc & 0x1F), (T)lds_f64(src_addr));
+                        const T v = (T)lds_f64(src_addr);
+                        const int jo = (int)(desc & 0x1F);
+                        // boundary rows (and sources that start or end a chunk) sit in the first / last register of a thread:
+                        // one move; any other position goes through the compare-and-move chain
+                        if (jo == 0) x[0] = v;
+                        else if (jo == CPT - 1) x[CPT - 1] = v;
+                        else set_at<T, CPT>(x, jo, v);
                         src_addr += src_inc;
                     }
                     if (SLOW && ov_slow) {  // several overridden cells in this thread: re-derive them (rare)
