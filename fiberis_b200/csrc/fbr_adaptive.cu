@@ -12,6 +12,7 @@
 // the ring is full, t >= t_total or max_iters is reached and leaves (t, dt, state) for a relaunch.
 #include "fbr_common.cuh"
 #include "fbr_moebius.cuh"
+#include "fbr_factor_reg.cuh"
 #include "fbr_sweep.cuh"
 
 namespace fbr {
@@ -338,51 +339,10 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) adaptive_
             if (i >= n - 1) cc = 0.0;
             l[j] = aa; r[j] = bb; g[j] = cc;
         }
-        // super-diagonal entry of the cell in front of my chunk
-        double c_prev = __shfl_up_sync(kAll, g[CPT - 1], 1);
-        if (lane == 31) s_clast[warp] = g[CPT - 1];
-        // composite Moebius matrix of my chunk, inclusive scan over the warp, carry over the warps
-        Mat2 G{1.0, 0.0, 0.0, 1.0};
-        __syncthreads();
-        if (lane == 0) c_prev = warp > 0 ? s_clast[warp - 1] : 0.0;
-        {
-            double cp = c_prev;
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-                const double e = -l[j] * cp;  // e_i = -dl_i du_{i-1} (zero for the first cell: dl_0 = 0)
-                const Mat2 nm{r[j] * G.a + e * G.c, r[j] * G.b + e * G.d, G.a, G.b};
-                G = (j == CPT / 2 - 1) ? rescale(nm) : nm;
-                cp = g[j];
-            }
-        }
-        G = rescale(G);
-        Mat2 inc = G;
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const Mat2 up = shfl_up_mat(inc, s);
-            if (lane >= s) inc = compose(inc, up);
-        }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        Mat2 before{1.0, 0.0, 0.0, 1.0};
-        for (int v = 0; v < warp; ++v) before = compose(s_w[v], before);
-        Mat2 ex = shfl_up_mat(inc, 1);
-        if (lane == 0) ex = Mat2{1.0, 0.0, 0.0, 1.0};
-        ex = compose(ex, before);
-        // reciprocal of the pivot in front of my chunk (any finite value works for the first cell: e_0 = 0)
-        double r_prev = (ex.c + ex.d) / (ex.a + ex.b);
-        int bad = 0;
-#pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            const int i = cell0 + j;
-            const double lj = (i == 0) ? 0.0 : l[j] * r_prev;
-            const double u = r[j] - lj * c_prev;
-            if (!bad && i < n && (u == 0.0 || !isfinite(u))) bad = i + 1;
-            const double rj = 1.0 / u;
-            c_prev = g[j];
-            l[j] = lj; r[j] = rj; g[j] = g[j] * rj;
-            r_prev = rj;
-        }
+        // pivots from a scan of 2x2 Moebius matrices, independent divisions (fbr_factor_reg.cuh; two CTA barriers)
+        const int left = n - cell0;
+        const int bad = factor_rows_in_registers<CPT, W>(l, r, g, cell0, left < 0 ? 0 : (left > CPT ? CPT : left), lane, warp,
+                                                         s_w, s_clast);
         if (bad) s_bad = bad;
         smul = scan_multipliers<double>(chunk_product<double, CPT>(l), chunk_product<double, CPT>(g), lane);
         if (W > 1) {
