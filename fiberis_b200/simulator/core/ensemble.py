@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from fiberis_b200 import _engine
-from fiberis_b200.simulator.core.pds import PDS1D_MultiSource, _ALLOWED_BC
+from fiberis_b200.simulator.core.pds import PDS1D_MultiSource, _ALLOWED_BC, fixed_time_axis
 
 
 def shard_bounds(n_models: int, world_size: int, rank: int):
@@ -144,9 +144,7 @@ class PDS1D_Ensemble:
         nx = len(self.mesh)
         if t_total is None:
             t_total = self.source[0].taxis[-1] + self.t0
-        taxis = [self.t0]
-        while taxis[-1] < t_total:  # same fp64 accumulation as the single-model path
-            taxis.append(taxis[-1] + dt)
+        taxis = fixed_time_axis(self.t0, dt, t_total)  # same fp64 accumulation as the single-model path
         n_steps = len(taxis) - 1
 
         dist = _dist(process_group)

@@ -57,6 +57,31 @@ def _uses_stock_interp(src) -> bool:
         and np.size(src.taxis) > 1
 
 
+
+def fixed_time_axis(t0, dt, t_total):
+    """The time axis the reference's loop builds (``while taxis[-1] < t_total: taxis.append(taxis[-1] + dt)``,
+    src/fiberis/simulator/core/pds.py:287,309), as a list.  The fp64 accumulation decides the step count (dt = 0.1,
+    t_total = 1 gives 11 steps), so it is reproduced bit for bit: ``np.cumsum`` adds sequentially in the same order;
+    long axes are built in chunks instead of one interpreter iteration per step."""
+    taxis = [t0]
+    try:
+        f0, fdt, ft = float(t0), float(dt), float(t_total)
+        plain = isinstance(t0, (int, float)) and isinstance(dt, (int, float)) and isinstance(t_total, (int, float))
+    except (TypeError, ValueError):
+        plain = False
+    if not plain or not (fdt > 0.0) or not np.isfinite(ft - f0) or (ft - f0) / fdt < 64:
+        while taxis[-1] < t_total:  # short or unusual axes: literally the reference's loop
+            taxis.append(taxis[-1] + dt)
+        return taxis
+    taxis = [f0]
+    while taxis[-1] < ft:
+        guess = int(min(max((ft - taxis[-1]) / fdt, 1.0), 1e6)) + 2
+        block = np.cumsum(np.concatenate(([taxis[-1]], np.full(guess, fdt))))[1:]  # ((t + dt) + dt) + ... in order
+        stop = np.nonzero(block >= ft)[0]
+        taxis.extend(block[: stop[0] + 1].tolist() if len(stop) else block.tolist())
+    taxis[0] = t0
+    return taxis
+
 class PDS1D_SingleSource:
     """One mesh, one pressure source pinned at ``sourceidx`` (a Dirichlet-in-time row)."""
 
@@ -271,9 +296,7 @@ class PDS1D_SingleSource:
         if every < 1:
             raise ValueError("snapshot_every must be >= 1.")
         # exact replica of the reference's time axis (fp64 accumulation decides the step count)
-        taxis = [self.t0]
-        while taxis[-1] < t_total:
-            taxis.append(taxis[-1] + dt)
+        taxis = fixed_time_axis(self.t0, dt, t_total)
         n_steps = len(taxis) - 1
         self.record_log("Start to solve the problem.")
         initial = np.asarray(self.initial, dtype=np.float64)

@@ -300,3 +300,24 @@ def test_sweep_candidate_generators():
     assert r.shape == (100, 3) and np.all(r >= [-1, 0, 2]) and np.all(r <= [1, 0.5, 3])
     np.testing.assert_array_equal(r, sweep.random_candidates(100, [-1, 0, 2], [1, 0.5, 3], seed=3))
     assert not np.array_equal(r, sweep.random_candidates(100, [-1, 0, 2], [1, 0.5, 3], seed=4))
+
+
+def test_fixed_time_axis_is_the_reference_loop_bit_for_bit():
+    """pds.py:287,309 accumulates taxis[-1] + dt in fp64 and stops at the first value >= t_total; the chunked
+    np.cumsum version must give the same list (length and every entry) for dyadic and non-dyadic steps."""
+    from fiberis_b200.simulator.core.pds import fixed_time_axis
+    rng = np.random.default_rng(0)
+
+    def loop(t0, dt, tt):
+        t = [t0]
+        while t[-1] < tt:
+            t.append(t[-1] + dt)
+        return t
+    for _ in range(400):
+        t0 = float(rng.choice([0.0, rng.uniform(-5, 5)]))
+        dt = float(rng.choice([0.1, 0.5, 1.0, 1 / 3, rng.uniform(1e-3, 2.0)]))
+        n = int(rng.integers(1, 3000))
+        tt = float(rng.choice([t0 + n * dt, t0 + rng.uniform(0, 1) * n * dt, round(t0 + n * dt, 3)]))
+        assert fixed_time_axis(t0, dt, tt) == loop(t0, dt, tt)
+    assert len(fixed_time_axis(0, 0.1, 1)) == 12 and fixed_time_axis(3.0, 1.0, 2.0) == [3.0]
+    assert fixed_time_axis(0.0, 0.1, 100.0) == loop(0.0, 0.1, 100.0)
