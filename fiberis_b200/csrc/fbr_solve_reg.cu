@@ -3,7 +3,8 @@
 // of a persistent CTA through shared memory with cp.async was measured and dropped: the kernel's shuffles
 // already load the MIO queue, the extra LDGSTS / LDS traffic cost more than the hidden latency gave back —
 // 65536 x 512: 0.40 ms staged against 0.31 ms with plain 16-byte loads.  16 cells per thread — half the
-// shuffles per cell, but 225 registers — was slower as well: 0.38 ms.)
+// shuffles per cell, but 225 registers — was slower as well: 0.38 ms; prefetch.global.L2 of the CTA's next system: no
+// change (0.276 vs 0.274 ms); 20 warps per SM at 96 registers with spills: 0.29 ms.)
 //
 // A thread owns CPT consecutive cells of one system (64 bytes per array, 16-byte loads), W warps own a
 // system.  The elimination is made parallel along the mesh the same way as in the adaptive loop
