@@ -47,19 +47,29 @@ __device__ __forceinline__ double div_fast(double num, double den) {
 
 // In: rows (dl, d, du) of my CPT cells in (l, r, g), identity rows beyond the mesh, dl of row 0 and du of the last row
 // already zero.  Out: the un-pivoted LU factors the run kernels use — l_i = dl_i / u_{i-1}, r_i = 1 / u_i,
-// g_i = du_i / u_i — and `bad` = 1 + first row among my first `nvalid` with a zero / non-finite pivot (0: none).
+// g_i = du_i / u_i — and the return value = 1 + first row among my first `nvalid` with a zero / non-finite pivot (0: none).
+// cell0 = my first row within the team's tile, first_row = global row of the tile's first cell (0 for a whole system).
+// A tile in the middle of a longer system passes TileLink: the super-diagonal entry in front of the tile and the
+// (p, q) = (p_{i-1}, p_{i-2}) pair in front of it (from a scan over the tiles); `total`, when non-NULL, receives the
+// tile's composite matrix and the function returns right after (first pass of a two-pass factorisation).
 // s_w: W matrices, s_c: W doubles of shared scratch; contains two CTA barriers when W > 1 (CTA-uniform call).
+struct TileLink {
+    double c_front = 0.0, p = 1.0, q = 1.0;
+    int64_t first_row = 0;
+    Mat2 *total = nullptr;
+};
 template <int CPT, int W>
 __device__ __forceinline__ int factor_rows_in_registers(double (&l)[CPT], double (&r)[CPT], double (&g)[CPT], int cell0,
-                                                        int nvalid, int lane, int warp, Mat2 *s_w, double *s_c) {
+                                                        int nvalid, int lane, int warp, Mat2 *s_w, double *s_c,
+                                                        const TileLink &link = TileLink()) {
     // super-diagonal entry of the row in front of my chunk
     double c_prev = __shfl_up_sync(kAll, g[CPT - 1], 1);
     if (W > 1) {
         if (lane == 31) s_c[warp] = g[CPT - 1];
         __syncthreads();
-        if (lane == 0) c_prev = warp > 0 ? s_c[warp - 1] : 0.0;
+        if (lane == 0) c_prev = warp > 0 ? s_c[warp - 1] : link.c_front;
     } else if (lane == 0) {
-        c_prev = 0.0;
+        c_prev = link.c_front;
     }
     double ee[CPT];
     {
@@ -90,16 +100,26 @@ __device__ __forceinline__ int factor_rows_in_registers(double (&l)[CPT], double
         if (lane == 31) s_w[warp] = inc;
         __syncthreads();
         Mat2 before{1.0, 0.0, 0.0, 1.0};
+        if (link.total) {  // first pass: only the composite of the whole tile is wanted
+            if (warp == 0 && lane == 0) {
+                for (int q = 0; q < W; ++q) before = rescale_fast(compose_raw(s_w[q], before));
+                *link.total = before;
+            }
+            return 0;
+        }
         for (int q = 0; q < warp; ++q) before = rescale_fast(compose_raw(s_w[q], before));
         ex = compose_raw(ex, before);
+    } else if (link.total) {
+        if (lane == 31) *link.total = inc;
+        return 0;
     }
-    double p1 = ex.a + ex.b, p2 = ex.c + ex.d;  // p_{i-1}, p_{i-2} in front of my chunk
+    double p1 = fma(ex.a, link.p, ex.b * link.q), p2 = fma(ex.c, link.p, ex.d * link.q);  // p_{i-1}, p_{i-2} in front of my chunk
     {
         const double s = pow2_scale_for(max(exp_field(p1), exp_field(p2)));
         p1 *= s; p2 *= s;
     }
     double r_prev = div_fast(p2, p1);  // 1 / u of the row in front of my chunk (unused by row 0: dl_0 = 0)
-    if (cell0 == 0) r_prev = 0.0;
+    if (cell0 == 0 && link.first_row == 0) r_prev = 0.0;
     double nanacc = 0.0;
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
@@ -116,7 +136,7 @@ __device__ __forceinline__ int factor_rows_in_registers(double (&l)[CPT], double
     if (nanacc != nanacc) {
 #pragma unroll
         for (int j = CPT - 1; j >= 0; --j)
-            if (j < nvalid && !isfinite(r[j])) bad = cell0 + j + 1;
+            if (j < nvalid && !isfinite(r[j])) bad = (int)(link.first_row + cell0) + j + 1;
     }
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {

@@ -9,17 +9,18 @@
 //     is a Moebius map of u_{i-1}; with u = p/q it is the linear map (p,q)_i = [[d_i, e_i],[1, 0]] (p,q)_{i-1},
 //     e_i = -dl_i du_{i-1}, so pivots at arbitrary positions follow from a scan of 2x2 matrix products
 //     (matrices are projective: each product is rescaled by a power of two, so nothing overflows).
-//     The scan is only used to obtain the pivot IN FRONT of every 8-cell chunk; inside its chunk every
-//     thread then runs the plain sequential recurrence, so all factors come out of the same
-//     formulas as in the sequential variant (the chunk start differs from it by a few ulps at most).
+//     The scan yields the pair (p_{i-1}, p_{i-2}) IN FRONT of every 8-cell chunk; inside its chunk a thread
+//     runs the two-term recurrence and takes r_i = p_{i-1} / p_i with independent divisions
+//     (fbr_factor_reg.cuh); the factors agree with the sequential variant to a few ulps.
 #include "fbr_common.cuh"
 #include "fbr_moebius.cuh"
+#include "fbr_factor_reg.cuh"
+
+#include <type_traits>
 
 namespace fbr {
 
 constexpr int kFacCPT = 8;
-constexpr int kFacW = 4;
-constexpr int kFacTile = 32 * kFacW * kFacCPT;
 
 // ---- sequential variant ----
 __global__ void __launch_bounds__(128) factorize_kernel(const double *__restrict__ dl, const double *__restrict__ d,
@@ -107,112 +108,134 @@ __global__ void __launch_bounds__(32 * kTileWarps) factorize_tiled_kernel(
 }
 
 // ---- parallel variant ----
-// Composite of the thread's chunk, then inclusive scan over the tile.  Returns the EXCLUSIVE prefix of
-// this thread within the tile (identity for thread 0); *tile_total receives the whole-tile composite
-// (valid in every thread).
-__device__ Mat2 tile_prefix(const double *__restrict__ dl, const double *__restrict__ d,
-                            const double *__restrict__ du, int64_t nx, int64_t cell0, Mat2 *tile_total,
-                            Mat2 (*s_w)[kFacW]) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Mat2 g{1.0, 0.0, 0.0, 1.0};
+// Two passes over tiles of 256 * W cells (a thread owns 8 consecutive cells, fbr_factor_reg.cuh):
+//   pass 1  every tile composes the 2x2 matrix that carries (p_{i-1}, p_{i-2}) across it,
+//   scan    one CTA per model scans the tile matrices: the (p, q) pair in front of every tile,
+//   pass 2  every tile factorises its rows from that pair and writes l, r, g with 16-byte stores.
+// 72 B of traffic per cell (rows read twice, factors written once).
+template <int W>
+__device__ __forceinline__ void load_tile_rows(const double *__restrict__ dl, const double *__restrict__ d,
+                                               const double *__restrict__ du, int64_t o, int64_t nx, int64_t gi, int nvalid,
+                                               double (&l)[kFacCPT], double (&r)[kFacCPT], double (&g)[kFacCPT]) {
+    const bool vec = nvalid == kFacCPT && ((o + gi) & 1) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(dl) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(du)) & 15) == 0;
+    if (vec) {
+        const double2 *ql = reinterpret_cast<const double2 *>(dl + o + gi), *qd = reinterpret_cast<const double2 *>(d + o + gi),
+                      *qu = reinterpret_cast<const double2 *>(du + o + gi);
 #pragma unroll
-    for (int j = 0; j < kFacCPT; ++j) {
-        const int64_t i = cell0 + j;
-        if (i < nx) {
-            const double di = d[i];
-            const double e = i > 0 ? -dl[i] * du[i - 1] : 0.0;
-            // [[di, e],[1, 0]] * g
-            const Mat2 n{di * g.a + e * g.c, di * g.b + e * g.d, g.a, g.b};
-            g = (j == kFacCPT / 2 - 1) ? rescale(n) : n;  // keep extreme dt / dx^2 ratios in range
+        for (int j = 0; j < kFacCPT / 2; ++j) {
+            const double2 a = __ldg(ql + j), b = __ldg(qd + j), c = __ldg(qu + j);
+            l[2 * j] = a.x; l[2 * j + 1] = a.y; r[2 * j] = b.x; r[2 * j + 1] = b.y; g[2 * j] = c.x; g[2 * j + 1] = c.y;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kFacCPT; ++j) {
+            const bool in = j < nvalid;
+            l[j] = in ? __ldg(dl + o + gi + j) : 0.0;
+            r[j] = in ? __ldg(d + o + gi + j) : 1.0;
+            g[j] = in ? __ldg(du + o + gi + j) : 0.0;
         }
     }
-    g = rescale(g);
-    Mat2 inc = g;
+    if (gi == 0) l[0] = 0.0;  // outside the matrix
+#pragma unroll
+    for (int j = 0; j < kFacCPT; ++j)
+        if (gi + j == nx - 1) g[j] = 0.0;
+}
+
+template <int W>
+__global__ void __launch_bounds__(32 * W) factor_tile_total_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                                   const double *__restrict__ du, int64_t nx, int n_tiles,
+                                                                   double *__restrict__ tile_mat) {
+    __shared__ Mat2 s_w[W], s_total;
+    __shared__ double s_c[W];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t o = (int64_t)blockIdx.y * nx, first = (int64_t)blockIdx.x * (256 * W), gi = first + (int64_t)tid * kFacCPT;
+    const int64_t left = nx - gi;
+    const int nvalid = left < 0 ? 0 : (left > kFacCPT ? kFacCPT : (int)left);
+    double l[kFacCPT], r[kFacCPT], g[kFacCPT];
+    load_tile_rows<W>(dl, d, du, o, nx, gi, nvalid, l, r, g);
+    TileLink link;
+    link.first_row = first;
+    link.c_front = (tid == 0 && first > 0) ? __ldg(du + o + first - 1) : 0.0;
+    link.total = &s_total;
+    factor_rows_in_registers<kFacCPT, W>(l, r, g, tid * kFacCPT, nvalid, lane, warp, s_w, s_c, link);
+    __syncthreads();
+    if (tid < 4) {
+        const double v = tid == 0 ? s_total.a : tid == 1 ? s_total.b : tid == 2 ? s_total.c : s_total.d;
+        tile_mat[((int64_t)blockIdx.y * n_tiles + blockIdx.x) * 4 + tid] = v;
+    }
+}
+
+// one CTA per model: (p, q) in front of every tile = (exclusive prefix of the tile matrices) applied to (1, 1)
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) factor_tile_scan_kernel(const double *__restrict__ tile_mat, int n_tiles,
+                                                                        double *__restrict__ tile_vec) {
+    __shared__ Mat2 s_warp[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *mats = tile_mat + (int64_t)blockIdx.x * n_tiles * 4;
+    double *vecs = tile_vec + (int64_t)blockIdx.x * n_tiles * 2;
+    const int per = (n_tiles + kScanThreads - 1) / kScanThreads, t0 = tid * per, t1 = min(n_tiles, t0 + per);
+    Mat2 mine{1.0, 0.0, 0.0, 1.0};
+    for (int t = t0; t < t1; ++t) mine = rescale_fast(compose_raw(Mat2{mats[4 * t], mats[4 * t + 1], mats[4 * t + 2], mats[4 * t + 3]}, mine));
+    Mat2 inc = mine;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
         const Mat2 up = shfl_up_mat(inc, s);
-        if (lane >= s) inc = compose(inc, up);
+        if (lane >= s) inc = rescale_fast(compose_raw(inc, up));
     }
-    if (lane == 31) (*s_w)[warp] = inc;
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    Mat2 before{1.0, 0.0, 0.0, 1.0};  // composite of the warps before mine
-    Mat2 total{1.0, 0.0, 0.0, 1.0};
-    for (int v = 0; v < kFacW; ++v) {
-        if (v == warp) before = total;
-        total = compose((*s_w)[v], total);
-    }
-    *tile_total = total;
+    Mat2 before{1.0, 0.0, 0.0, 1.0};
+    for (int q = 0; q < warp; ++q) before = rescale_fast(compose_raw(s_warp[q], before));
     Mat2 ex = shfl_up_mat(inc, 1);
     if (lane == 0) ex = Mat2{1.0, 0.0, 0.0, 1.0};
-    return compose(ex, before);
-}
-
-__global__ void __launch_bounds__(32 * kFacW) factor_compose_kernel(const double *__restrict__ dl,
-                                                                    const double *__restrict__ d,
-                                                                    const double *__restrict__ du, int64_t nx,
-                                                                    int n_tiles, double *__restrict__ tile_mat) {
-    __shared__ Mat2 s_w[kFacW];
-    const int64_t o = (int64_t)blockIdx.y * nx;
-    const int64_t cell0 = ((int64_t)blockIdx.x * (32 * kFacW) + threadIdx.x) * kFacCPT;
-    Mat2 total;
-    tile_prefix(dl + o, d + o, du + o, nx, cell0, &total, &s_w);
-    if (threadIdx.x == 0) {
-        double *dst = tile_mat + ((int64_t)blockIdx.y * n_tiles + blockIdx.x) * 4;
-        dst[0] = total.a; dst[1] = total.b; dst[2] = total.c; dst[3] = total.d;
+    ex = compose_raw(ex, before);
+    double p = ex.a + ex.b, q = ex.c + ex.d;
+    for (int t = t0; t < t1; ++t) {
+        const double s = pow2_scale_for(max(exp_field(p), exp_field(q)));
+        p *= s; q *= s;
+        vecs[2 * t] = p; vecs[2 * t + 1] = q;
+        const double np = fma(mats[4 * t], p, mats[4 * t + 1] * q), nq = fma(mats[4 * t + 2], p, mats[4 * t + 3] * q);
+        p = np; q = nq;
     }
 }
 
-// one thread per model walks the tile composites: (p, q) in front of every tile
-__global__ void factor_tile_walk_kernel(const double *__restrict__ tile_mat, int n_tiles, int64_t M,
-                                        double *__restrict__ tile_vec) {
-    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (m >= M) return;
-    double p = 1.0, q = 1.0;
-    for (int t = 0; t < n_tiles; ++t) {
-        tile_vec[(m * n_tiles + t) * 2 + 0] = p;
-        tile_vec[(m * n_tiles + t) * 2 + 1] = q;
-        const double *g = tile_mat + (m * n_tiles + t) * 4;
-        const double np = g[0] * p + g[1] * q, nq = g[2] * p + g[3] * q;
-        const double big = fmax(fabs(np), fabs(nq));
-        const int e = (big > 0.0 && isfinite(big)) ? -ilogb(big) : 0;
-        p = scalbn(np, e);
-        q = scalbn(nq, e);
-    }
-}
-
-__global__ void __launch_bounds__(32 * kFacW) factor_apply_kernel(const double *__restrict__ dl,
-                                                                  const double *__restrict__ d,
-                                                                  const double *__restrict__ du, int64_t nx,
-                                                                  int n_tiles, const double *__restrict__ tile_vec,
-                                                                  double *__restrict__ fl, double *__restrict__ fr,
-                                                                  double *__restrict__ fg,
-                                                                  int32_t *__restrict__ singular) {
-    __shared__ Mat2 s_w[kFacW];
-    const int64_t o = (int64_t)blockIdx.y * nx;
-    const int64_t cell0 = ((int64_t)blockIdx.x * (32 * kFacW) + threadIdx.x) * kFacCPT;
-    Mat2 total;
-    const Mat2 ex = tile_prefix(dl + o, d + o, du + o, nx, cell0, &total, &s_w);
-    if (cell0 >= nx) return;
+template <int W>
+__global__ void __launch_bounds__(32 * W) factor_tile_apply_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                                   const double *__restrict__ du, int64_t nx, int n_tiles,
+                                                                   const double *__restrict__ tile_vec, double *__restrict__ fl,
+                                                                   double *__restrict__ fr, double *__restrict__ fg,
+                                                                   int32_t *__restrict__ singular) {
+    __shared__ Mat2 s_w[W];
+    __shared__ double s_c[W];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t o = (int64_t)blockIdx.y * nx, first = (int64_t)blockIdx.x * (256 * W), gi = first + (int64_t)tid * kFacCPT;
+    const int64_t left = nx - gi;
+    const int nvalid = left < 0 ? 0 : (left > kFacCPT ? kFacCPT : (int)left);
+    double l[kFacCPT], r[kFacCPT], g[kFacCPT];
+    load_tile_rows<W>(dl, d, du, o, nx, gi, nvalid, l, r, g);
+    TileLink link;
+    link.first_row = first;
+    link.c_front = (tid == 0 && first > 0) ? __ldg(du + o + first - 1) : 0.0;
     const double *v = tile_vec + ((int64_t)blockIdx.y * n_tiles + blockIdx.x) * 2;
-    const double p = ex.a * v[0] + ex.b * v[1], q = ex.c * v[0] + ex.d * v[1];
-    double r_prev = q / p;  // reciprocal of the pivot in front of my chunk (unused for the very first cell)
-    double c_prev = cell0 > 0 ? du[o + cell0 - 1] : 0.0;
-    int bad = 0;
+    link.p = __ldg(v);
+    link.q = __ldg(v + 1);
+    const int bad = factor_rows_in_registers<kFacCPT, W>(l, r, g, tid * kFacCPT, nvalid, lane, warp, s_w, s_c, link);
+    const bool vec = nvalid == kFacCPT && ((o + gi) & 1) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(fl) | reinterpret_cast<uintptr_t>(fr) | reinterpret_cast<uintptr_t>(fg)) & 15) == 0;
+    if (vec) {
+        double2 *ql = reinterpret_cast<double2 *>(fl + o + gi), *qr = reinterpret_cast<double2 *>(fr + o + gi),
+                *qg = reinterpret_cast<double2 *>(fg + o + gi);
 #pragma unroll
-    for (int j = 0; j < kFacCPT; ++j) {
-        const int64_t i = cell0 + j;
-        if (i < nx) {
-            const double a = dl[o + i], b = d[o + i], c = du[o + i];
-            const double l = (i == 0) ? 0.0 : a * r_prev;
-            const double u = b - l * c_prev;
-            if (!bad && (u == 0.0 || !isfinite(u))) bad = (int)(i + 1);
-            const double r = 1.0 / u;
-            fl[o + i] = l;
-            fr[o + i] = r;
-            fg[o + i] = c * r;
-            r_prev = r;
-            c_prev = c;
+        for (int j = 0; j < kFacCPT / 2; ++j) {
+            ql[j] = make_double2(l[2 * j], l[2 * j + 1]);
+            qr[j] = make_double2(r[2 * j], r[2 * j + 1]);
+            qg[j] = make_double2(g[2 * j], g[2 * j + 1]);
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kFacCPT; ++j)
+            if (j < nvalid) { fl[o + gi + j] = l[j]; fr[o + gi + j] = r[j]; fg[o + gi + j] = g[j]; }
     }
     if (bad && singular) atomicMin(singular + blockIdx.y, bad);  // the caller preset the flag to INT_MAX
 }
@@ -230,8 +253,12 @@ __global__ void flag_finish_kernel(int32_t *flag, int64_t M) {
 
 using namespace fbr;
 
+// warps per tile team of the parallel variant: the shortest team that covers the system, 16 (4096 cells) at most
+static int fac_team_warps(int64_t nx) { return nx <= 512 ? 2 : nx <= 1024 ? 4 : nx <= 2048 ? 8 : 16; }
+
 extern "C" int64_t fbr_factorize_work_bytes(int64_t M, int64_t nx) {
-    const int64_t tiles = (nx + kFacTile - 1) / kFacTile;
+    const int W = fac_team_warps(nx);
+    const int64_t tiles = (nx + 256 * W - 1) / (256 * W);
     return M * tiles * 6 * (int64_t)sizeof(double);
 }
 
@@ -259,7 +286,8 @@ extern "C" int fbr_factorize_f64(const double *dl, const double *d, const double
         factorize_kernel<<<(unsigned)((M + block - 1) / block), block, 0, st>>>(dl, d, du, M, nx, fl, fr, fg, singular);
         return check_launch("fbr_factorize_f64");
     }
-    const int64_t tiles = (nx + kFacTile - 1) / kFacTile;
+    const int W = fac_team_warps(nx);
+    const int64_t tiles = (nx + 256 * W - 1) / (256 * W);
     FBR_REQUIRE(M <= 65535 && tiles <= 0x7fffffff, "too many models / tiles for the parallel factorisation");
     double *tile_mat = work, *tile_vec = work + M * tiles * 4;
     const dim3 grid((unsigned)tiles, (unsigned)M);
@@ -267,12 +295,23 @@ extern "C" int fbr_factorize_f64(const double *dl, const double *d, const double
         flag_preset_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(singular, M, 0x7fffffff);
         if (int rc = check_launch("fbr_factorize_f64 (flag preset)")) return rc;
     }
-    factor_compose_kernel<<<grid, 32 * kFacW, 0, st>>>(dl, d, du, nx, (int)tiles, tile_mat);
-    if (int rc = check_launch("fbr_factorize_f64 (compose)")) return rc;
-    factor_tile_walk_kernel<<<(unsigned)((M + 31) / 32), 32, 0, st>>>(tile_mat, (int)tiles, M, tile_vec);
-    if (int rc = check_launch("fbr_factorize_f64 (tile walk)")) return rc;
-    factor_apply_kernel<<<grid, 32 * kFacW, 0, st>>>(dl, d, du, nx, (int)tiles, tile_vec, fl, fr, fg, singular);
-    if (int rc = check_launch("fbr_factorize_f64 (apply)")) return rc;
+    auto go = [&](auto wtag) -> int {
+        constexpr int WW = decltype(wtag)::value;
+        factor_tile_total_kernel<WW><<<grid, 32 * WW, 0, st>>>(dl, d, du, nx, (int)tiles, tile_mat);
+        if (int rc = check_launch("fbr_factorize_f64 (tile totals)")) return rc;
+        factor_tile_scan_kernel<<<(unsigned)M, kScanThreads, 0, st>>>(tile_mat, (int)tiles, tile_vec);
+        if (int rc = check_launch("fbr_factorize_f64 (tile scan)")) return rc;
+        factor_tile_apply_kernel<WW><<<grid, 32 * WW, 0, st>>>(dl, d, du, nx, (int)tiles, tile_vec, fl, fr, fg, singular);
+        return check_launch("fbr_factorize_f64 (apply)");
+    };
+    int rc;
+    switch (W) {
+        case 2: rc = go(std::integral_constant<int, 2>{}); break;
+        case 4: rc = go(std::integral_constant<int, 4>{}); break;
+        case 8: rc = go(std::integral_constant<int, 8>{}); break;
+        default: rc = go(std::integral_constant<int, 16>{}); break;
+    }
+    if (rc) return rc;
     if (singular) {
         flag_finish_kernel<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(singular, M);
         if (int rc = check_launch("fbr_factorize_f64 (flag finish)")) return rc;

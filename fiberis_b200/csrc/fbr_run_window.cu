@@ -378,8 +378,14 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
 // acc[0..3] = max local growth fwd, max q fwd, max local growth bwd, max q bwd (as ordered bit patterns).
 constexpr int kProbe = 64;
 
-__device__ __forceinline__ void atomic_max_pos(double *addr, double v) {  // v >= 0: bit patterns are ordered
-    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+// v >= 0: bit patterns are ordered.  The maxima settle after the first few warps; everybody else only LOOKS (one L2
+// read) instead of queueing an atomic on the same four addresses (312 500 warps at 1e7 cells: 1.3 ms -> 0.1 ms).
+__device__ __forceinline__ void atomic_max_pos(double *addr, double v) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    if (bits > __ldcg(reinterpret_cast<const unsigned long long *>(addr))) atomicMax(reinterpret_cast<unsigned long long *>(addr), bits);
+}
+__device__ __forceinline__ void atomic_max_seen(unsigned long long *addr, unsigned long long v) {
+    if (v > __ldcg(addr)) atomicMax(addr, v);
 }
 
 __global__ void probe_kernel(const double *__restrict__ fl, const double *__restrict__ fg, int64_t nx, double *acc) {
@@ -452,8 +458,8 @@ __global__ void horizon_kernel(const double *__restrict__ fl, const double *__re
         nb = max(nb, __shfl_xor_sync(kFullW, nb, s));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMax(horizon, (unsigned long long)nf);
-        atomicMax(horizon + 1, (unsigned long long)nb);
+        atomic_max_seen(horizon, (unsigned long long)nf);
+        atomic_max_seen(horizon + 1, (unsigned long long)nb);
     }
 }
 
