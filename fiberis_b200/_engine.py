@@ -113,7 +113,7 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
 
     ``factors`` = (fl, fr, fg) from ``factorize``; or ``factors=None`` and ``zonal=(mesh, zone_value (M, n_zones),
     zone_of_cell int32 (nx), dt, sigma | None)``: assembly and factorisation happen inside the kernel
-    (``fbr_run_zonal_f64``, fp64, 256 <= nx <= 4096).  Singular members raise ``LinAlgError`` here, unless the
+    (``fbr_run_zonal_f64``, fp64, 128 < nx <= 4096).  Singular members raise ``LinAlgError`` here, unless the
     caller passes ``singular_flags`` (from ``zonal_flags(M)``) and checks them later with
     ``raise_if_singular_zonal`` — which keeps the launch asynchronous.
 

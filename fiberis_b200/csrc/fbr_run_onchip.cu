@@ -857,6 +857,174 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     }
 }
 
+// ---- short meshes: several members per warp ---------------------------------------------------------------------
+// Meshes of up to 64 / 128 cells (the reference's own models have 200) would leave most lanes of a warp idle with 8
+// cells per thread, and most of a thread's registers idle with fewer.  Here a member is owned by a GROUP of L = 2 .. 16
+// lanes (8 cells per thread), a warp integrates 32 / L members in lock-step (all members share n_steps), shuffles stay
+// inside a group (log2 L scan stages), and nothing in the time loop touches shared memory or a barrier.  Per-step
+// scalars (source values, observations) are prefetched one step ahead by the threads that own the cell.
+template <typename T, int L>
+__global__ void __launch_bounds__(128, 4) run_group_kernel(const RunArgs a) {
+    constexpr int CPT = 8, GPW = 32 / L, NS = L == 16 ? 4 : L == 8 ? 3 : L == 4 ? 2 : 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane & (L - 1), grp = lane / L;
+    const int nx = (int)a.nx, cell0 = sub * CPT;
+    const int64_t n_groups = (int64_t)gridDim.x * 4 * GPW;
+    // which of my cells are overridden / observed (member-independent)
+    int ov_j = -1, ob_j = -1, ov_col = -1, ob_col = -1;
+    bool ov_slow = false, ob_slow = false;
+    if (cell0 < nx) {
+        uint64_t ov = ~0ull;
+        if (cell0 == 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~0xFFull) | kSlotZero;
+        const int jl = nx - 1 - cell0;
+        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kSlotZero << (8 * jl));
+#pragma unroll 1
+        for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win (matbuilder.py:156-161)
+            const int64_t jj = a.src_idx[k] - cell0;
+            if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)k << (8 * jj));
+        }
+        int n_ov = 0, n_ob = 0;
+#pragma unroll 1
+        for (int j = 0; j < CPT; ++j) {
+            const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
+            if (so != kSlotNone) { ++n_ov; ov_j = j; ov_col = so == kSlotZero ? -1 : (int)so; }
+        }
+#pragma unroll 1
+        for (int k = 0; k < a.n_obs; ++k) {
+            const int64_t jj = a.obs_idx[k] - cell0;
+            if (jj >= 0 && jj < CPT && a.obs_idx[k] < nx) { ++n_ob; ob_j = (int)jj; ob_col = k; }
+        }
+        if (n_ov > 1) { ov_slow = true; ov_j = -1; ov_col = -1; }
+        if (n_ob > 1) { ob_slow = true; ob_j = -1; ob_col = -1; }
+    }
+    const double ob_w = (ob_j >= 0 && a.obs_w) ? a.obs_w[ob_col] : 1.0;
+    const int keep_f = sub == 0 ? 0 : -1, keep_b = sub == L - 1 ? 0 : -1;
+    const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
+
+    // the loop bound is uniform over the warp; groups past the last member redo member M - 1 and write nothing
+    for (int64_t m_raw = ((int64_t)blockIdx.x * 4 + warp) * GPW + grp; m_raw - grp < a.M; m_raw += n_groups) {
+        const bool live = m_raw < a.M;
+        const int64_t m = live ? m_raw : a.M - 1;
+        T l[CPT], r[CPT], g[CPT], x[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int i = cell0 + j;
+            if (i < nx) {
+                l[j] = (T)__ldg(a.fl + m * nx + i);
+                r[j] = (T)__ldg(a.fr + m * nx + i);
+                g[j] = (T)__ldg(a.fg + m * nx + i);
+                x[j] = (T)__ldg(a.p0 + m * a.p0_stride + i);
+            } else {  // padding cell: identity row, decoupled
+                l[j] = (T)0; r[j] = (T)1; g[j] = (T)0; x[j] = (T)0;
+            }
+        }
+        // stage multipliers of the group scans (zero where a stage does not reach: no predicates in the loop)
+        T Pf[NS], Pb[NS], PfEx, PbEx;
+        {
+            T pf = chunk_product<T, CPT>(l), pb = chunk_product<T, CPT>(g);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const bool fa = sub >= (1 << s), ba = sub + (1 << s) < L;
+                Pf[s] = fa ? pf : (T)0;
+                Pb[s] = ba ? pb : (T)0;
+                const T upf = __shfl_up_sync(kFull, pf, 1 << s, L), dnb = __shfl_down_sync(kFull, pb, 1 << s, L);
+                if (fa) pf *= upf;
+                if (ba) pb *= dnb;
+            }
+        }
+        // snapshot slot of this member (-1: not recorded)
+        long long slot = -1;
+        if (live && a.snap) {
+            if (!a.snap_models) slot = m;
+            else
+                for (int64_t q = 0; q < a.n_snap_models; ++q)
+                    if (a.snap_models[q] == m) slot = q;
+        }
+        int snap_countdown = slot >= 0 ? snap_every : 0x7fffffff;
+        T *snap_dst = reinterpret_cast<T *>(a.snap) + (slot >= 0 ? slot : 0) * a.snap_model_stride + cell0;
+        const double *ovp = ov_col >= 0 ? a.src_table + ov_col : &kZero, *obp = ob_col >= 0 ? a.obs + a.n_obs + ob_col : &kZero;
+        int ov_stride = ov_col >= 0 ? a.n_src : 0, ob_stride = ob_col >= 0 ? a.n_obs : 0;
+        double ov_val = a.n_steps > 0 ? __ldg(ovp) : 0.0, ob_val = a.n_steps > 0 ? __ldg(obp) : 0.0, acc = 0.0;
+
+#pragma unroll 1
+        for (int left = (int)a.n_steps; left > 0; --left) {
+            if (left == 1) { ov_stride = 0; ob_stride = 0; }  // no row after the last one
+            ovp += ov_stride;
+            obp += ob_stride;
+            const double ov_next = __ldg(ovp), ob_next = __ldg(obp);
+            if (ov_j >= 0) set_at<T, CPT>(x, ov_j, (T)ov_val);
+            if (ov_slow) {  // several overridden cells in this thread: re-derive them (rare)
+                const int64_t n = a.n_steps - left;
+                if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (T)0;
+                const int jl = nx - 1 - cell0;
+                if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) set_at<T, CPT>(x, jl, (T)0);
+#pragma unroll 1
+                for (int k = 0; k < a.n_src; ++k) {
+                    const int64_t jj = a.src_idx[k] - cell0;
+                    if (jj >= 0 && jj < CPT) set_at<T, CPT>(x, (int)jj, (T)__ldg(a.src_table + n * a.n_src + k));
+                }
+            }
+            {   // forward sweep
+                T y = chunk_end_fwd_plain<T, CPT>(x, l);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) y = fma_any<T>(Pf[s], __shfl_up_sync(kFull, y, 1 << s, L), y);
+                const T c = and_mask(__shfl_up_sync(kFull, y, 1, L), keep_f);
+                chunk_apply_fwd_plain<T, CPT>(x, l, r, c);
+            }
+            {   // backward sweep
+                T z = chunk_end_bwd_plain<T, CPT>(x, g);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) z = fma_any<T>(Pb[s], __shfl_down_sync(kFull, z, 1 << s, L), z);
+                const T c = and_mask(__shfl_down_sync(kFull, z, 1, L), keep_b);
+                chunk_apply_bwd_plain<T, CPT>(x, g, c);
+            }
+            if (ob_j >= 0) {  // one observed cell: its weight is applied once, after the loop
+                const double res = (double)get_at<T, CPT>(x, ob_j) - ob_val;
+                acc = fma(res, res, acc);
+            }
+            if (ob_slow) {
+                const int64_t n = a.n_steps - left;
+#pragma unroll 1
+                for (int k = 0; k < a.n_obs; ++k) {
+                    const int64_t jj = a.obs_idx[k] - cell0;
+                    if (jj >= 0 && jj < CPT) {
+                        const double res = (double)get_at<T, CPT>(x, (int)jj) - __ldg(a.obs + (n + 1) * a.n_obs + k);
+                        acc = fma((a.obs_w ? a.obs_w[k] : 1.0) * res, res, acc);
+                    }
+                }
+            }
+            if (--snap_countdown == 0) {
+                snap_countdown = snap_every;
+                store_row_direct<T, CPT>(snap_dst, cell0, nx, x);
+                snap_dst += a.snap_row_stride;
+            }
+            ov_val = ov_next;
+            ob_val = ob_next;
+        }
+        if (a.p_final && live) store_row_direct<T, CPT>(reinterpret_cast<T *>(a.p_final) + m * nx + cell0, cell0, nx, x);
+        if (a.misfit) {
+            acc *= ob_w;
+#pragma unroll
+            for (int s = 1; s < L; s <<= 1) acc += __shfl_xor_sync(kFull, acc, s, L);
+            if (sub == 0 && live) a.misfit[m] = acc;
+        }
+    }
+}
+
+template <typename T, int L>
+static int launch_group(const RunArgs &a, cudaStream_t stream) {
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    auto kern = run_group_kernel<T, L>;
+    int occ = 0;
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0));
+    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "group run kernel does not fit on an SM");
+    const int64_t per_cta = 4 * (32 / L);
+    int64_t grid = (int64_t)occ * f.sm_count;
+    if (grid > (a.M + per_cta - 1) / per_cta) grid = (a.M + per_cta - 1) / per_cta;
+    kern<<<(unsigned)grid, 128, 0, stream>>>(a);
+    return check_launch("fbr_run (member groups)");
+}
+
 // CTA slots the next launch of this thread leaves free (fbr_run_reserve_ctas): lets a small launch
 // enqueued just before on another stream stay resident next to the persistent grid.
 static int &reserved_ctas() {
@@ -953,10 +1121,17 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
         const int v = atoi(e);
         if ((v == 1 || v == 2 || v == 4 || v == 8) && (a.nx + v - 1) / v <= 32 * kMaxWarps) cpt = v;
     }
-    // 256 cells (fp64) / 512 cells (fp32 mode) and up: the 64-byte-per-thread kernel
+    // fp64 above 128 cells / fp32 mode from 512 cells: the 64-byte-per-thread kernel (a partly filled warp of 8-cell
+    // threads still beats narrower chunks: 32768 members x 200 cells 17.1 -> 10.3 ms)
     const char *min_env = getenv("FBR_K3_X_MIN_NX");  // tuning aid
-    const int64_t x_min = min_env ? atoll(min_env) : 32 * (int64_t)(64 / sizeof(T));
+    const int64_t x_min = min_env ? atoll(min_env) : (sizeof(T) == 8 ? 129 : 512);
     if (a.nx >= x_min && !getenv("FBR_K3_GENERIC")) return launch_x<T>(a, stream);
+    // short meshes, more than a handful of members: groups of 8 / 16 lanes per member, several members per warp
+    if (a.nx > 8 && a.nx <= 128 && a.M >= 8 && !a.z_mesh && !getenv("FBR_K3_GENERIC") && !getenv("FBR_K3_NO_GROUPS")) {
+        if (a.nx <= 16) return launch_group<T, 2>(a, stream);
+        if (a.nx <= 32) return launch_group<T, 4>(a, stream);
+        return a.nx <= 64 ? launch_group<T, 8>(a, stream) : launch_group<T, 16>(a, stream);
+    }
     switch (cpt) {
         case 1: return launch_cpt<T, 1>(a, stream);
         case 2: return launch_cpt<T, 2>(a, stream);
@@ -1021,7 +1196,7 @@ extern "C" int fbr_run_zonal_f64(const double *mesh, const double *zone_value, i
     FBR_FILL_ARGS();
     FBR_REQUIRE(mesh && zone_value && n_zones >= 1, "NULL mesh / zone arguments");
     FBR_REQUIRE(zone_of_cell || n_zones == nx, "zone_of_cell == NULL means one diffusivity per cell: n_zones must equal nx");
-    FBR_REQUIRE(nx >= 256 && nx <= fbr_run_max_nx(), "on-chip assembly covers 256 <= nx <= %lld (got %lld)",
+    FBR_REQUIRE(nx > 128 && nx <= fbr_run_max_nx(), "on-chip assembly covers 128 < nx <= %lld (got %lld)",
                 (long long)fbr_run_max_nx(), (long long)nx);
     a.z_mesh = mesh; a.z_value = zone_value; a.z_of_cell = zone_of_cell; a.z_n = n_zones; a.z_dt = dt; a.z_sigma = sigma;
     a.z_singular = singular;

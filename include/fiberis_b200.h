@@ -155,7 +155,7 @@ int fbr_run_f32(const double *fl, const double *fr, const double *fg, const doub
  * members that carry a full (nx) diffusivity row each; sigma: NULL or (nx) PML damping
  * (fbr_pml_sigma_f64); singular: NULL or (M) int32 PRESET TO INT32_MAX by the caller, receives
  * min(1 + zero-pivot row) for members whose matrix is singular.  Remaining arguments as fbr_run_f64.
- * 256 <= nx <= fbr_run_max_nx(). */
+ * 128 < nx <= fbr_run_max_nx(). */
 int fbr_run_zonal_f64(const double *mesh, const double *zone_value, int n_zones,
                       const int32_t *zone_of_cell, double dt, const double *sigma, int32_t *singular,
                       const double *p0, int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc,

@@ -35,7 +35,8 @@ def make_ensemble(seed, M, nx, n_steps, zones=8, n_obs=5, dt=1.0, dense=False):
     return e, dict(mesh=mesh, zone=zone, zv=zv, srcs=srcs, sidx=sidx, obs_idx=obs_idx, T=T, dt=dt)
 
 
-@pytest.mark.parametrize("M,nx,dense", [(37, 200, False), (9, 1024, False), (20, 96, True), (300, 64, False)])
+@pytest.mark.parametrize("M,nx,dense", [(37, 200, False), (9, 1024, False), (20, 96, True), (300, 64, False), (77, 24, False),
+                                         (50, 12, False), (33, 130, True), (5, 40, False)])
 def test_ensemble_members_and_misfit_vs_oracle(M, nx, dense):
     n_steps = 48
     e, c = make_ensemble(11 + nx, M, nx, n_steps, dense=dense)
