@@ -1125,7 +1125,10 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     // threads still beats narrower chunks: 32768 members x 200 cells 17.1 -> 10.3 ms)
     const char *min_env = getenv("FBR_K3_X_MIN_NX");  // tuning aid
     const int64_t x_min = min_env ? atoll(min_env) : (sizeof(T) == 8 ? 129 : 512);
-    if (a.nx >= x_min && !getenv("FBR_K3_GENERIC")) return launch_x<T>(a, stream);
+    // (a handful of members below 256 cells is a latency problem, not a throughput one: the generic kernel's shorter
+    // chains over more threads win there — C1, one 200-cell model: 0.50 against 0.75 us per step)
+    const bool few_short = sizeof(T) == 8 && a.nx < 256 && a.M < 32 && !a.z_mesh && !min_env;
+    if (a.nx >= x_min && !few_short && !getenv("FBR_K3_GENERIC")) return launch_x<T>(a, stream);
     // short meshes, more than a handful of members: groups of 8 / 16 lanes per member, several members per warp
     if (a.nx > 8 && a.nx <= 128 && a.M >= 8 && !a.z_mesh && !getenv("FBR_K3_GENERIC") && !getenv("FBR_K3_NO_GROUPS")) {
         if (a.nx <= 16) return launch_group<T, 2>(a, stream);

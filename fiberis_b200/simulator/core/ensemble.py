@@ -162,7 +162,7 @@ class PDS1D_Ensemble:
         # fp64 ensembles on a shared mesh: the matrices are assembled and factorised inside the run kernel
         # (fbr_run_zonal_f64), no (M, nx) coefficient array exists.  The fp32 mode / short meshes: K1 + K1b + K3.
         zonal = flags_d = None
-        on_chip = dtype == "float64" and 128 < nx <= _engine.run_max_nx() and on_chip_assembly
+        on_chip = dtype == "float64" and 128 < nx <= _engine.run_max_nx() and on_chip_assembly and (nx >= 256 or M >= 32)
         if on_chip:
             if self.diffusivity is None:
                 zonal = (mesh_d, _engine.to_device(self.zone_value[lo:hi]), _engine.to_device(self.zone_of_cell, np.int32),

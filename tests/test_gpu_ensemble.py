@@ -104,6 +104,17 @@ def test_ensemble_fp32_mode():
     assert G.rel_max(e.snapshot[0], want) <= 1e-5
 
 
+@pytest.mark.parametrize("nx", [48, 100, 200])
+def test_ensemble_fp32_mode_short_meshes(nx):
+    """fp32 mode on the member-group kernel (<= 128 cells) and on the generic kernel (200 cells)."""
+    e, c = make_ensemble(40 + nx, 33, nx, 40)
+    e.solve(dt=1.0, t_total=c["T"], audit_models=[0, 32], dtype="float32")
+    for k, m in enumerate([0, 32]):
+        want, _ = O.solve_fixed(c["mesh"], c["zv"][m][c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"], c["srcs"],
+                                0.0, 1.0, c["T"])
+        assert G.rel_max(e.snapshot[k], want) <= 1e-5
+
+
 def test_c3_full_shape_properties():
     """BASELINE.json configs[2] at full width (4096 models x 1024 cells), 200 steps:
     (1) audited members match the oracle, (2) the member that generated the observations has
