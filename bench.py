@@ -49,6 +49,25 @@ B_ALG = 16.0  # bytes per cell-update, fp64: read p^n + write p^{n+1} (SURVEY.md
 
 
 # ------------------------------------------------------------------------------------------------
+# stdout carries exactly ONE JSON line (the driver parses it): everything else any library writes to file descriptor 1 —
+# NCCL's version banner, for one — is sent to stderr for the whole run, and the line goes out through the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def make_workload(name, world=1):
     """Synthetic inputs of SURVEY.md 8(d) (C3 recipe; C4 is the same recipe at 512 cells).  With
     world > 1 the ensemble has world x (members per GPU) members; rank r owns the r-th block."""
@@ -283,7 +302,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_single_reference_arm(args):
@@ -306,13 +325,13 @@ def run_single_reference_arm(args):
     value = w["nx"] * ss / float(np.mean(times))
     sample = (f"{w['nx']} cells x {ss} steps; " + ("reference algorithm (dense A rebuilt every step + scipy.linalg.solve)"
               if dense else "reference cannot run at this size (dense nx^2 matrix); banded NumPy oracle (dgttrs per step) timed instead"))
-    print(json.dumps({"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
+    emit({"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": w["desc"], "seed": w["seed"], "sample": sample},
                       "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample},
                       "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}))
+                      "gpu_launches": 0})
 
 
 # ------------------------------------------------------------------------------------------------
@@ -458,7 +477,7 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
                                 "sample": f"{nx} cells x {ss} steps of the same model, banded C oracle (one system is "
                                           f"sequential: 1 thread), {el:.1f} s"}
     if emit:
-        print(json.dumps(line))
+        emit(line)
     return line
 
 
@@ -644,13 +663,14 @@ def run_gpu_arm(args):
                     "roofline_frac_16B": r["roofline"]["frac"], "roofline_frac_32B": 2.0 * r["roofline"]["frac"], "e2e": r["e2e"]["value"], "window_plan": r["config"]["window_plan"]}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(w)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
