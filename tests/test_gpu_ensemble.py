@@ -322,3 +322,37 @@ def test_c4_full_member_count_properties():
         lo, hi = shard_bounds(M, 8, r)
         part = e.solve(dt=1.0, t_total=c["T"], models=(lo, hi))
         npt.assert_array_equal(part, mis[lo:hi])
+
+
+@pytest.mark.parametrize("M,nx,every", [(70, 40, 3), (9, 64, 1), (130, 100, 7), (41, 16, 2), (300, 128, 5)])
+def test_member_group_kernel_records_every_member(M, nx, every):
+    """Short meshes: groups of lanes per member (run_group_kernel) straight through the engine — snapshots of ALL
+    members (snap_models = None), a snapshot interval, the final state, a source on a boundary row and a duplicated
+    source index, member counts that leave the last warp partly filled."""
+    from fiberis_b200 import _engine as E
+    rng = np.random.default_rng(M + nx)
+    n_steps = 23
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    D = 10 ** rng.uniform(-1, 1, (M, nx))
+    p0 = rng.uniform(0, 1, (M, nx))
+    sidx = np.array([nx // 3, nx - 1, nx // 3])  # later duplicate wins; the last one overrides the Dirichlet row
+    table = rng.uniform(-5, 5, (n_steps, 3))
+    sidx_d, n_src = E.index_tensor(sidx)
+    fac = E.factorize(*E.assemble(E.to_device(mesh), E.to_device(D), M, nx, 0.5, "Neumann", "Dirichlet", sidx_d, n_src))
+    snap, final, _ = E.run(fac, E.to_device(p0), M, nx, n_steps, "Neumann", "Dirichlet", sidx_d, n_src, E.to_device(table),
+                           snapshot_every=every, want_final=True)
+    snap, final = snap.cpu().numpy(), final.cpu().numpy()
+    assert snap.shape == (M, n_steps // every + 1, nx)
+    for m in range(0, M, max(1, M // 6)):
+        dl, d, du = O.assemble_tridiag(mesh, D[m], 0.5, "Neumann", "Dirichlet", list(sidx))
+        p = p0[m].copy()
+        rows = [p.copy()]
+        for n in range(n_steps):
+            b = p.copy(); b[0] = 0.0; b[-1] = 0.0
+            for k, s_ in enumerate(sidx):
+                b[s_] = table[n, k]
+            p = O.solve_tridiag(dl, d, du, b)
+            if (n + 1) % every == 0:
+                rows.append(p.copy())
+        assert G.rel_max(snap[m], np.stack(rows)) <= 1e-10, m
+        assert G.rel_max(final[m], p) <= 1e-10
