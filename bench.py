@@ -62,7 +62,7 @@ def _guard_stdout():
         os.dup2(2, 1)
 
 
-def emit(line):
+def emit_line(line):
     sys.stdout.flush()
     data = (json.dumps(line) + "\n").encode()
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
@@ -302,7 +302,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    emit(line)
+    emit_line(line)
 
 
 def run_single_reference_arm(args):
@@ -325,7 +325,7 @@ def run_single_reference_arm(args):
     value = w["nx"] * ss / float(np.mean(times))
     sample = (f"{w['nx']} cells x {ss} steps; " + ("reference algorithm (dense A rebuilt every step + scipy.linalg.solve)"
               if dense else "reference cannot run at this size (dense nx^2 matrix); banded NumPy oracle (dgttrs per step) timed instead"))
-    emit({"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
+    emit_line({"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": w["desc"], "seed": w["seed"], "sample": sample},
@@ -477,7 +477,7 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
                                 "sample": f"{nx} cells x {ss} steps of the same model, banded C oracle (one system is "
                                           f"sequential: 1 thread), {el:.1f} s"}
     if emit:
-        emit(line)
+        emit_line(line)
     return line
 
 
@@ -663,7 +663,7 @@ def run_gpu_arm(args):
                     "roofline_frac_16B": r["roofline"]["frac"], "roofline_frac_32B": 2.0 * r["roofline"]["frac"], "e2e": r["e2e"]["value"], "window_plan": r["config"]["window_plan"]}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(w)
-        emit(line)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

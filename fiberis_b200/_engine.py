@@ -35,6 +35,77 @@ def to_device(x, dtype=np.float64, dev=None, pinned=False):
     return t.to(device(dev), non_blocking=pinned)
 
 
+_upload_cache = {}  # device -> ([side streams], [pinned staging buffers])
+
+
+def _upload_lanes(d, n, nbytes):
+    torch = _torch()
+    streams, staging = _upload_cache.setdefault(str(d), ([], []))
+    while len(streams) < n:
+        streams.append(torch.cuda.Stream(d))
+        staging.append(None)
+    for i in range(n):
+        if staging[i] is None or staging[i].numel() < nbytes[i]:
+            staging[i] = torch.empty(nbytes[i], dtype=torch.uint8, pin_memory=True)
+    return streams[:n], staging[:n]
+
+
+def to_device_many(arrays, dtype=np.float64, dev=None):
+    """Several LARGE host arrays -> device tensors.  A copy from pageable memory is paced by a single-threaded
+    host-side staging memcpy (~10 GB/s, a fifth of the PCIe rate; several threads calling cudaMemcpy do not
+    overlap).  Here every array gets a host thread that copies it chunk by chunk into its own cached page-locked
+    buffer (NumPy releases the GIL for the copy) and queues one DMA per chunk on its own stream, so the staging
+    copies of the arrays run side by side and overlap the transfers (C5: three 80 MB arrays 23.5 -> ~9 ms).
+    Returns when the data is on the device.  Small arrays: plain copies."""
+    torch = _torch()
+    d = device(dev)
+    arrs = [np.ascontiguousarray(np.asarray(x, dtype=dtype)) for x in arrays]
+    if len(arrs) < 2 or min(a.nbytes for a in arrs) < (8 << 20):
+        return [to_device(a, dtype, dev) for a in arrs]
+    import threading
+    main = torch.cuda.current_stream(d)
+    # destinations come from the current stream's allocator pool (a side stream would cudaMalloc afresh every call)
+    outs = [torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, device=d) for a in arrs]
+    # lanes: every array is cut into a few byte ranges, one host thread + stream + staging buffer per range
+    parts = max(1, min(4, 12 // len(arrs)))
+    lanes = []
+    for i, a in enumerate(arrs):
+        step = -(-a.nbytes // parts)
+        step = (step + 4095) // 4096 * 4096
+        lanes += [(i, o, min(o + step, a.nbytes)) for o in range(0, a.nbytes, step)]
+    streams, staging = _upload_lanes(d, len(lanes), [e - o for _, o, e in lanes])
+    for s in streams:
+        s.wait_stream(main)
+    errors = []
+    chunk = 8 << 20
+
+    def work(k):
+        try:
+            i, lo, hi = lanes[k]
+            torch.cuda.set_device(d)
+            src = arrs[i].reshape(-1).view(np.uint8)[lo:hi]
+            pin = staging[k][: hi - lo]
+            pin_np = pin.numpy()
+            dst = outs[i].view(-1).view(torch.uint8)[lo:hi]
+            with torch.cuda.stream(streams[k]):
+                for o in range(0, hi - lo, chunk):
+                    e = min(o + chunk, hi - lo)
+                    np.copyto(pin_np[o:e], src[o:e])
+                    dst[o:e].copy_(pin[o:e], non_blocking=True)
+            streams[k].synchronize()  # the staging buffer is reused by the next call
+        except Exception as ex:  # re-raised on the calling thread
+            errors.append(ex)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(lanes))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return outs
+
+
 def index_tensor(idx, dev=None):
     idx = np.atleast_1d(np.asarray(idx)).astype(np.int64)
     if idx.size == 0:

@@ -276,16 +276,20 @@ class PDS1D_SingleSource:
         print("Problem solved.")
         return None
 
-    def _device_model(self, kwargs):
+    def _device_model(self, kwargs, initial=None):
+        """Model arrays on the device; with ``initial`` its tensor is appended to the result (long meshes upload
+        the three big arrays on parallel host threads, ``_engine.to_device_many``)."""
         nx = len(self.mesh)
         sidx = self._source_indices()
         sidx = np.where(sidx < 0, sidx + nx, sidx)
-        mesh_d = _engine.to_device(self.mesh)
-        diff_d = _engine.to_device(self.diffusivity)
+        big = [self.mesh, self.diffusivity] + ([] if initial is None else [initial])
+        dev = _engine.to_device_many(big)
+        mesh_d, diff_d = dev[0], dev[1]
         sidx_d, n_src = _engine.index_tensor(sidx)
         pml = float(kwargs.get("pml_thickness", 0.0))
         smax = float(kwargs.get("sigma_max", 10 if self._multi else 2))
-        return nx, mesh_d, diff_d, sidx_d, n_src, pml, smax
+        out = (nx, mesh_d, diff_d, sidx_d, n_src, pml, smax)
+        return out if initial is None else out + (dev[2],)
 
     def _solve_fixed(self, dt, t_total, kwargs):
         mode = kwargs.get("mode", "implicit")
@@ -304,10 +308,9 @@ class PDS1D_SingleSource:
             self.snapshot = np.array([self.initial])
             self.taxis = np.array(taxis)
             return
-        nx, mesh_d, diff_d, sidx_d, n_src, pml, smax = self._device_model(kwargs)
+        nx, mesh_d, diff_d, sidx_d, n_src, pml, smax, p0_d = self._device_model(kwargs, initial[None, :])
         table = self._source_table(taxis[:-1])
         dl, d, du = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
-        p0_d = _engine.to_device(initial[None, :])
         if mode == "implicit":
             factors = _engine.factorize(dl, d, du)
             table_d = _engine.to_device(table)
