@@ -356,3 +356,19 @@ def test_member_group_kernel_records_every_member(M, nx, every):
                 rows.append(p.copy())
         assert G.rel_max(snap[m], np.stack(rows)) <= 1e-10, m
         assert G.rel_max(final[m], p) <= 1e-10
+
+
+@pytest.mark.parametrize("nx,dt", [(1024, 30.0), (200, 30.0), (64, 30.0), (1024, 1e-4)])
+def test_stiff_and_nearly_explicit_ensembles(nx, dt):
+    """alpha = D dt / dx^2 up to ~1.2e3 (multipliers close to one: slow decay, every scan stage and cross-warp carry
+    matters) and down to ~1e-6 (multipliers ~1e-6: products underflow towards zero) on the on-chip-assembly path, the
+    partly filled x8 warp and the member-group kernel."""
+    M, n_steps = 12, 30
+    e, c = make_ensemble(77 + nx, M, nx, n_steps, dt=dt)
+    e.set_initial(np.random.default_rng(nx).uniform(0, 1, nx))
+    e.solve(dt=dt, t_total=c["T"], audit_models=[0, 5, 11])
+    for k, m in enumerate([0, 5, 11]):
+        want, taxis = O.solve_fixed(c["mesh"], c["zv"][m][c["zone"]], e.initial, "Neumann", "Neumann", c["sidx"], c["srcs"],
+                                    0.0, dt, c["T"])
+        assert e.snapshot[k].shape == want.shape
+        assert G.rel_max(e.snapshot[k], want) <= 1e-10
