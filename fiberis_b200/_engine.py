@@ -522,6 +522,10 @@ def solve_tridiag(dl, d, du, b, variant=_cabi.SOLVER_AUTO, check_singular=True):
     check(lib.fbr_solve_tridiag_f64(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(x), M, nx, int(variant), ptr(work),
                                     ptr(flags), current_stream()))
     if check_singular:
+        if variant == _cabi.SOLVER_AUTO and nx <= 4096 and bool(flags.any()):
+            # the register-resident variant also flags systems whose leading minors leave the fp64 range between two
+            # rescalings (rows scaled by ~1e77 and more): the elimination without products of pivots decides
+            return solve_tridiag(dl, d, du, b, _cabi.SOLVER_THOMAS, True)
         raise_if_singular(flags, "system")
     return x
 
@@ -541,6 +545,8 @@ def step(dl, d, du, p, lbc, rbc, src_idx, n_src, src_val, variant=_cabi.SOLVER_A
     check(lib.fbr_step_f64(ptr(dl), ptr(d), ptr(du), ptr(p), M, nx, BC_CODES[lbc], BC_CODES[rbc], ptr(src_idx), n_src,
                            ptr(src_val), stride, ptr(x), int(variant), ptr(work), ptr(flags), current_stream()))
     if check_singular:
+        if variant == _cabi.SOLVER_AUTO and nx <= 4096 and stride == 0 and x is not p and bool(flags.any()):
+            return step(dl, d, du, p, lbc, rbc, src_idx, n_src, src_val, _cabi.SOLVER_THOMAS, out, True)  # see solve_tridiag
         raise_if_singular(flags, "system")
     return x
 

@@ -125,7 +125,7 @@ __device__ __forceinline__ int factor_rows_in_registers(double (&l)[CPT], double
     for (int j = 0; j < CPT; ++j) {
         const double p0 = fma(r[j], p1, ee[j] * p2);
         r[j] = div_fast(p1, p0);
-        nanacc = fma(r[j], 0.0, nanacc);
+        nanacc = fma(r[j], 0.0, fma(p0, 0.0, nanacc));  // NaN <=> a zero pivot (r = inf) or an overflowed minor (p0 = inf)
         p2 = p1; p1 = p0;
         if (j == CPT / 2 - 1) {
             const double s = pow2_scale_for(max(exp_field(p1), exp_field(p2)));
@@ -136,7 +136,7 @@ __device__ __forceinline__ int factor_rows_in_registers(double (&l)[CPT], double
     if (nanacc != nanacc) {
 #pragma unroll
         for (int j = CPT - 1; j >= 0; --j)
-            if (j < nvalid && !isfinite(r[j])) bad = (int)(link.first_row + cell0) + j + 1;
+            if (j < nvalid && (!isfinite(r[j]) || r[j] == 0.0)) bad = (int)(link.first_row + cell0) + j + 1;
     }
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
         for (int j = 0; j < CPT; ++j) {
             const double p0 = fma(dd[j], p1, ee[j] * p2);
             r[j] = div_fast(p1, p0);  // off the chain: the recurrence continues with p0
-            nanacc = fma(r[j], 0.0, nanacc);
+            nanacc = fma(r[j], 0.0, fma(p0, 0.0, nanacc));  // NaN <=> a zero pivot (r = inf) or an overflowed minor (p0 = inf)
             p2 = p1; p1 = p0;
             if (j == CPT / 2 - 1) {
                 const double s = pow2_scale_for(max(exp_field(p1), exp_field(p2)));
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
         if (nanacc != nanacc) {  // a zero (or non-finite) pivot makes its quotient non-finite: find the first such row
 #pragma unroll
             for (int j = CPT - 1; j >= 0; --j)
-                if (j < nvalid && !isfinite(r[j])) bad = cell0 + j + 1;
+                if (j < nvalid && (!isfinite(r[j]) || r[j] == 0.0)) bad = cell0 + j + 1;
         }
         // normalised rows: z_i = r_i b_i - (r_i dl_i) z_{i-1};  x_i = z_i - (r_i du_i) x_{i+1}
 #pragma unroll
