@@ -48,6 +48,7 @@ class PDS1D_Ensemble:
         self.misfit = None
         self.snapshot = None         # (n_audit, n_t, nx)
         self.taxis = None
+        self.snapshot_taxis = None
         self.audit_models = None
         self.history = []
 
@@ -237,6 +238,8 @@ class PDS1D_Ensemble:
             _engine.raise_if_singular_zonal(flags_d)
 
         self.taxis = np.array(taxis)
+        # times of the recorded rows of ``snapshot`` (row 0 = initial state, then every ``snapshot_every`` steps)
+        self.snapshot_taxis = self.taxis[np.arange(0, n_steps + 1, snapshot_every)[: 1 + n_steps // snapshot_every]]
         self.audit_models = audit
         if n_audit and snap_d is not None:  # (n_audit, n_t, nx), row 0 = initial, straight from the kernel
             if host_snap is not None:
@@ -246,6 +249,9 @@ class PDS1D_Ensemble:
                 self.snapshot = _engine.to_host(_engine.as_f64(snap_d))  # fp32 mode: widened on the device, not on the host
             if len(audit_unique) != len(audit) or np.any(audit_slot != np.arange(len(audit))):
                 self.snapshot = self.snapshot[audit_slot]  # back to the order (and repeats) the caller listed
+        elif n_audit:  # snapshot_every > n_steps: only the initial state is kept, as in the single-model path
+            rows = np.asarray(self.initial, dtype=np.float64)
+            self.snapshot = np.stack([(rows if rows.ndim == 1 else rows[a]).copy() for a in audit])[:, None, :]
         else:
             self.snapshot = None
         if misfit_d is not None:

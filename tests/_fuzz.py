@@ -1,0 +1,75 @@
+"""One randomly drawn fixed-dt configuration (single model of any length, or an ensemble: zonal / dense, on-chip
+assembly on or off, any member-group width) solved on the GPU and compared with the NumPy oracle.  Shared by
+tests/test_gpu_fuzz.py and scratch/fuzz_parity.py."""
+import contextlib
+import io
+
+import numpy as np
+
+from oracle import pds_oracle as O
+from tests import _golden as G
+from tests import _models as Mo
+
+
+def run_case(rng):
+    """Returns (relative max-norm error, description); raises AssertionError on a taxis / misfit mismatch."""
+    from fiberis_b200.simulator.core.ensemble import PDS1D_Ensemble
+    kind = rng.choice(["single", "single", "ensemble", "ensemble", "long"])
+    if kind == "single":
+        nx = int(rng.choice([2, 3, 5, 9, 31, 64, 200, 255, 256, 257, 700, 1024, 2049, 4096]))
+    elif kind == "long":
+        nx = int(rng.choice([4097, 6000, 20001]))
+    else:
+        nx = int(rng.choice([9, 16, 17, 40, 64, 65, 128, 129, 200, 256, 300, 512, 1000, 2048]))
+    lbc, rbc = (str(rng.choice(["Dirichlet", "Neumann"])) for _ in range(2))
+    n_src = int(rng.integers(1, 5)) if nx > 6 else 1
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    init = rng.uniform(0, 1, nx) if rng.random() < 0.7 else np.zeros(nx)
+    dt = float(rng.choice([0.1, 0.5, 1.0, 1 / 3, 2.5]))
+    n_steps = int(rng.integers(1, 70))
+    T = dt * n_steps if rng.random() < 0.7 else dt * (n_steps - 0.5)
+    t0 = float(rng.choice([0.0, 0.0, 1.5, -2.0]))
+    every = int(rng.choice([1, 1, 2, 7]))
+    cand = np.arange(0, nx) if nx <= 6 else np.arange(1, nx - 1)
+    sidx = rng.choice(cand, size=min(n_src, len(cand)), replace=bool(rng.random() < 0.2)).tolist()
+    if rng.random() < 0.15:
+        sidx[0] = int(rng.choice([0, nx - 1]))
+    srcs = [(np.linspace(0, max(T, dt), 7), rng.uniform(-10, 10, 7)) for _ in sidx]
+    desc = f"{kind} nx={nx} {lbc}/{rbc} src={sidx} dt={dt} steps~{n_steps} t0={t0} every={every}"
+    if kind in ("single", "long"):
+        D = 10 ** rng.uniform(-1, 1, nx)
+        p = Mo.model(mesh, D, init, lbc, rbc, sidx, srcs, t0, True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            p.solve(dt=dt, t_total=T + t0, snapshot_every=every)
+        want, taxis = O.solve_fixed(mesh, D, init, lbc, rbc, sidx, srcs, t0, dt, T + t0)
+        kept = np.arange(0, len(taxis), every)[: 1 + (len(taxis) - 1) // every]
+        assert np.array_equal(p.taxis, taxis[kept]), "taxis"
+        err = G.rel_max(p.snapshot, want[kept])
+    else:
+        M = int(rng.choice([1, 3, 8, 33, 70, 300]))
+        dense = rng.random() < 0.4
+        zones = int(rng.choice([1, 3, 8]))
+        zone = (np.arange(nx) * zones) // nx
+        zv = 10 ** rng.uniform(-1, 1, (M, zones))
+        e = PDS1D_Ensemble()
+        e.set_mesh(mesh); e.set_source(Mo.sources_of(srcs)); e.set_sourceidx(sidx); e.set_bcs(lbc, rbc)
+        e.set_initial(init); e.t0 = t0
+        if dense: e.set_diffusivity(zv[:, zone])
+        else: e.set_zonal_diffusivity(zv, zone)
+        n_obs = int(rng.integers(1, 6))
+        oidx = rng.choice(nx, size=min(n_obs, nx), replace=False)
+        taxis_o = O.solve_fixed(mesh, zv[0][zone], init, lbc, rbc, sidx, srcs, t0, dt, T + t0)[1]
+        obs = rng.uniform(-1, 1, (len(taxis_o), len(oidx)))
+        w = rng.uniform(0.5, 2, len(oidx)) if rng.random() < 0.5 else None
+        e.set_observations(oidx, obs, w)
+        audit = sorted(set(int(a) for a in rng.choice(M, size=min(3, M), replace=False)))
+        mis = e.solve(dt=dt, t_total=T + t0, audit_models=audit, snapshot_every=every, on_chip_assembly=bool(rng.random() < 0.7))
+        err = 0.0
+        for k, m in enumerate(audit):
+            want, taxis = O.solve_fixed(mesh, zv[m][zone], init, lbc, rbc, sidx, srcs, t0, dt, T + t0)
+            kept = np.arange(0, len(taxis), every)[: 1 + (len(taxis) - 1) // every]
+            assert np.array_equal(e.snapshot_taxis, taxis[kept]), "snapshot_taxis"
+            err = max(err, G.rel_max(e.snapshot[k], want[kept]))
+            ref_mis = O.ensemble_misfit(want, oidx, obs, w)
+            assert abs(mis[m] - ref_mis) <= 1e-9 * max(1.0, abs(ref_mis)), f"misfit {mis[m]} vs {ref_mis}"
+    return err, desc

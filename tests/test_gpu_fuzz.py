@@ -1,0 +1,14 @@
+"""Randomised parity: 150 configurations drawn with a fixed seed over every fixed-dt path (tests/_fuzz.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_configurations_match_the_oracle(seed):
+    from tests._fuzz import run_case
+    rng = np.random.default_rng(seed)
+    for _ in range(50):
+        err, desc = run_case(rng)
+        assert err <= 1e-10, f"{desc}: {err:.2e}"
