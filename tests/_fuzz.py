@@ -73,3 +73,27 @@ def run_case(rng):
             ref_mis = O.ensemble_misfit(want, oidx, obs, w)
             assert abs(mis[m] - ref_mis) <= 1e-9 * max(1.0, abs(ref_mis)), f"misfit {mis[m]} vs {ref_mis}"
     return err, desc
+
+
+def run_adaptive_case(rng):
+    """optimizer=True (step doubling, on the device) for one random model against the oracle's loop: identical
+    accept / reject history (same number of rows), times to 1e-9, rows to 1e-9.  Returns (error, description)."""
+    nx = int(rng.choice([5, 9, 40, 200, 256, 257, 600, 1024, 1500, 3000]))
+    lbc, rbc = (str(rng.choice(["Dirichlet", "Neumann"])) for _ in range(2))
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    D = 10 ** rng.uniform(-1, 1, nx)
+    init = rng.uniform(0, 1, nx)
+    T = float(rng.choice([5.0, 20.0, 60.0]))
+    n_src = int(rng.integers(1, 4)) if nx > 6 else 1
+    sidx = sorted(rng.choice(np.arange(1, nx - 1), size=n_src, replace=False).tolist())
+    srcs = [(np.linspace(0, T, 9), rng.uniform(-10, 10, 9)) for _ in sidx]
+    kw = dict(tol=float(rng.choice([1e-3, 5e-3, 2e-2])), max_dt=float(rng.choice([0.5, 2.0, 40.0])))
+    dt_init = float(rng.choice([0.01, 0.05, 0.3]))
+    desc = f"adaptive nx={nx} {lbc}/{rbc} src={sidx} T={T} dt_init={dt_init} {kw}"
+    p = Mo.model(mesh, D, init, lbc, rbc, sidx, srcs, 0.0, True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        p.solve(optimizer=True, dt_init=dt_init, t_total=T, **kw)
+    snap, taxis, _ = O.solve_adaptive(mesh, D, init, lbc, rbc, sidx, srcs, 0.0, dt_init, T, **kw)
+    assert p.taxis.shape == taxis.shape, f"{desc}: {p.taxis.shape} vs {taxis.shape} accepted steps"
+    np.testing.assert_allclose(p.taxis, taxis, rtol=1e-9, atol=0, err_msg=desc)
+    return G.rel_max(p.snapshot, snap), desc

@@ -12,3 +12,11 @@ def test_random_configurations_match_the_oracle(seed):
     for _ in range(50):
         err, desc = run_case(rng)
         assert err <= 1e-10, f"{desc}: {err:.2e}"
+
+
+def test_random_adaptive_runs_match_the_oracle():
+    from tests._fuzz import run_adaptive_case
+    rng = np.random.default_rng(21)
+    for _ in range(12):
+        err, desc = run_adaptive_case(rng)
+        assert err <= 1e-9, f"{desc}: {err:.2e}"
