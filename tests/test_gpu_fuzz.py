@@ -20,3 +20,12 @@ def test_random_adaptive_runs_match_the_oracle():
     for _ in range(12):
         err, desc = run_adaptive_case(rng)
         assert err <= 1e-9, f"{desc}: {err:.2e}"
+
+
+def test_random_configurations_fp32_mode():
+    """fp32 mode (north_star: stated separately at 1e-5) over random single models and ensembles up to 4096 cells."""
+    from tests._fuzz import run_case
+    rng = np.random.default_rng(31)
+    for _ in range(60):
+        err, desc = run_case(rng, "float32")
+        assert err <= 1e-5, f"{desc}: {err:.2e}"
