@@ -18,8 +18,11 @@
 //   (3) a carry across the warps of the team through shared memory (W-1 FMAs),
 //   (4) a second local pass with the true carry-in.
 // No divisions, no HBM traffic and two __syncthreads per step (none for single-warp teams).
-// Source values and observations are read by the one thread that owns the cell, prefetched one
-// step ahead straight from global memory (L2), so the time loop has no staging code at all.
+// Three kernels share this scheme: run_onchipx_kernel (64 bytes of state per thread, per-step scalars staged through
+// shared memory; with ZONAL the matrices are assembled and factorised in the per-member prologue), run_group_kernel
+// (short meshes: groups of 2..16 lanes per member, several members per warp) and the generic run_onchip_kernel
+// (1..8 cells per thread; single short models and the fp32 mode below 512 cells), whose per-step scalars are
+// prefetched one step ahead straight from global memory (L2) by the thread that owns the cell.
 #include "fbr_common.cuh"
 #include "fbr_sweep.cuh"
 #include "fbr_factor_reg.cuh"

@@ -1,5 +1,5 @@
 // K2  bare batched tridiagonal solves (matrix changes every call: adaptive time stepping) and the
-// Jacobi "explicit" mode.  Two variants, chosen by shape (north_star: "variant chosen by mesh length"):
+// Jacobi "explicit" mode.  Three variants, chosen by shape (north_star: "variant chosen by mesh length"):
 //   THOMAS  one thread per system, sequential elimination      -> systems longer than 4096 cells
 //   PCR     one CTA per system, shared-memory parallel cyclic reduction, log2(nx) levels
 //   REG     register-resident Moebius-scan pivots + scan sweeps (fbr_solve_reg.cu) -> AUTO's choice up to 4096 cells
