@@ -458,8 +458,9 @@ class _PinnedPool:
         fits = [e for e in free if nbytes <= e[0].numel() <= 2 * nbytes + 4096]
         if fits:
             return min(fits, key=lambda e: e[0].numel())
-        for e in free[: max(0, len(self.entries) - 7)]:  # bound the pool: drop unused buffers first
-            self.entries.remove(e)
+        drop = free[: max(0, len(self.entries) - 7)]  # bound the pool: drop unused buffers first
+        if drop:  # by identity: list.remove would compare the tensors inside the entries element by element
+            self.entries = [x for x in self.entries if not any(x is e for e in drop)]
         entry = [torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True), lambda: None]
         self.entries.append(entry)
         return entry

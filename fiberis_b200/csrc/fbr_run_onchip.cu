@@ -1043,11 +1043,30 @@ static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     auto kern = run_onchipx_kernel<T, CPT, W, kFull16, ZONAL>;
     RunArgs b = a;
     const int cols = a.n_src + 2 * a.n_obs;
-    b.blk_steps = cols <= 64 ? 32 : 8;  // keeps the staging area <= 32 KB per CTA
-    const size_t smem = (2 * (size_t)b.blk_steps * (size_t)cols + (size_t)W * 32 * 9) * sizeof(double);
-    if (smem > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
+    // Time steps per staged block of per-step scalars: the longest block that costs no resident CTA (block boundaries
+    // carry three barriers and the residual sums; C3: 64 steps 25.2 ms, 32 steps 25.5 ms, 128 steps lose a CTA: 42.7 ms).
+    // The audited side launch of an ensemble must end up with the SAME footprint as the sweep (see ensemble.py): the
+    // choice depends only on the column count and the team width, not on M.
+    auto smem_for = [&](int blk) { return (2 * (size_t)blk * (size_t)cols + (size_t)W * 32 * 9) * sizeof(double); };
+    int occ = 0, occ_ref = 0;
+    size_t smem = smem_for(8);
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ref, kern, 32 * W, smem));
+    b.blk_steps = 8;
+    occ = occ_ref;
+    for (int blk : {64, 32, 16}) {
+        const size_t need = smem_for(blk);
+        if (need > (size_t)f.smem_optin) continue;
+        if (need > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        int o = 0;
+        FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 32 * W, need));
+        if (o == occ_ref) { b.blk_steps = blk; smem = need; occ = o; break; }
+    }
+    if (const char *e = getenv("FBR_K3_BLK")) {  // tuning aid
+        b.blk_steps = atoi(e) > 0 ? atoi(e) : 8;
+        smem = smem_for(b.blk_steps);
+        if (smem > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
+    }
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d)", 32 * W);
     int64_t grid = (int64_t)occ * f.sm_count - reserved_ctas();
     reserved_ctas() = 0;

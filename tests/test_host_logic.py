@@ -321,3 +321,21 @@ def test_fixed_time_axis_is_the_reference_loop_bit_for_bit():
         assert fixed_time_axis(t0, dt, tt) == loop(t0, dt, tt)
     assert len(fixed_time_axis(0, 0.1, 1)) == 12 and fixed_time_axis(3.0, 1.0, 2.0) == [3.0]
     assert fixed_time_axis(0.0, 0.1, 100.0) == loop(0.0, 0.1, 100.0)
+
+
+def test_pinned_pool_drops_unused_buffers_by_identity():
+    """More than 7 pooled buffers: the oldest unused ones are dropped — by identity (the entries hold tensors, and
+    list.remove would compare them element by element and raise on different sizes)."""
+    import torch
+    from fiberis_b200 import _engine as E
+    pool = E._PinnedPool()
+    real_empty = torch.empty
+    try:  # no GPU here: page-locked allocation is replaced by a plain one
+        torch.empty = lambda *a, pin_memory=False, **k: real_empty(*a, **k)
+        sizes = [1000 * (k + 1) ** 2 for k in range(12)]
+        for n in sizes:
+            e = pool.take(n)
+            assert e[0].numel() >= n
+        assert len(pool.entries) <= 8
+    finally:
+        torch.empty = real_empty
