@@ -29,3 +29,11 @@ def test_random_configurations_fp32_mode():
     for _ in range(60):
         err, desc = run_case(rng, "float32")
         assert err <= 1e-5, f"{desc}: {err:.2e}"
+
+
+def test_random_pml_jacobi_and_host_driven_adaptive_runs():
+    from tests._fuzz import run_misc_case
+    rng = np.random.default_rng(41)
+    for _ in range(24):
+        err, gate, desc = run_misc_case(rng)
+        assert err <= gate, f"{desc}: {err:.2e}"
