@@ -35,7 +35,10 @@ def to_device(x, dtype=np.float64, dev=None, pinned=False):
     return t.to(device(dev), non_blocking=pinned)
 
 
+import threading as _threading
+
 _upload_cache = {}  # device -> ([side streams], [pinned staging buffers])
+_upload_lock = _threading.Lock()  # one upload at a time per process: the lanes' staging buffers are shared state
 
 
 def _upload_lanes(d, n, nbytes):
@@ -62,7 +65,13 @@ def to_device_many(arrays, dtype=np.float64, dev=None):
     arrs = [np.ascontiguousarray(np.asarray(x, dtype=dtype)) for x in arrays]
     if len(arrs) < 2 or min(a.nbytes for a in arrs) < (8 << 20):
         return [to_device(a, dtype, dev) for a in arrs]
+    with _upload_lock:
+        return _to_device_many_locked(arrs, d)
+
+
+def _to_device_many_locked(arrs, d):
     import threading
+    torch = _torch()
     main = torch.cuda.current_stream(d)
     # destinations come from the current stream's allocator pool (a side stream would cudaMalloc afresh every call)
     outs = [torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, device=d) for a in arrs]
@@ -451,8 +460,13 @@ class _PinnedPool:
 
     def __init__(self):
         self.entries = []  # [pinned uint8 tensor, weakref to the last ndarray handed out]
+        self.lock = _threading.Lock()
 
     def take(self, nbytes):
+        with self.lock:
+            return self._take(nbytes)
+
+    def _take(self, nbytes):
         torch = _torch()
         free = [e for e in self.entries if e[1]() is None]
         fits = [e for e in free if nbytes <= e[0].numel() <= 2 * nbytes + 4096]
