@@ -24,23 +24,55 @@ _i64 = C.c_int64
 _i32 = C.c_int
 _f64 = C.c_double
 
+class RunOpts(C.Structure):
+    """``fbr_run_opts`` of include/fiberis_b200.h (options of the fbr_run_* family; all zero = defaults)."""
+    _fields_ = [("struct_bytes", C.c_int32), ("reserve_ctas", C.c_int32), ("snap_cell_stride", C.c_int64),
+                ("scan_log2_eps", C.c_double), ("n_samples", C.c_int64), ("sample_row", C.c_void_p),
+                ("sample_w", C.c_void_p), ("row_first_sample", C.c_void_p), ("base_sample", C.c_int32),
+                ("first_sample", C.c_int32), ("last_sample", C.c_int32), ("reserved_", C.c_int32),
+                ("scan_mode", C.c_void_p)]
+
+
+def run_opts(reserve_ctas=0, snap_cell_stride=0, scan_log2_eps=0.0, sampling=None, scan_mode=None):
+    """Build an ``fbr_run_opts``.  ``sampling``: None, or a dict with device tensors ``sample_row`` (int32),
+    ``sample_w`` (float64), ``row_first_sample`` (int32) and ints ``base_sample``, ``first_sample``, ``last_sample``."""
+    o = RunOpts()
+    o.struct_bytes = C.sizeof(RunOpts)
+    o.reserve_ctas = int(reserve_ctas)
+    o.snap_cell_stride = int(snap_cell_stride)
+    o.scan_log2_eps = float(scan_log2_eps)
+    if scan_mode is not None:
+        o.scan_mode = scan_mode.data_ptr()
+    if sampling is not None:
+        o.n_samples = int(sampling["sample_row"].numel())
+        o.sample_row = sampling["sample_row"].data_ptr()
+        o.sample_w = sampling["sample_w"].data_ptr()
+        o.row_first_sample = sampling["row_first_sample"].data_ptr()
+        o.base_sample = int(sampling["base_sample"])
+        o.first_sample = int(sampling["first_sample"])
+        o.last_sample = int(sampling["last_sample"])
+    return o
+
+
 # name -> (restype, argtypes); mirrors include/fiberis_b200.h one to one
 SIGNATURES = {
     "fbr_version": (_i32, []),
     "fbr_last_error": (C.c_char_p, []),
     "fbr_last_launch_count": (_i32, []),
+    "fbr_probe_fp64_peak": (_i32, [C.POINTER(_f64), _p, _p]),
     "fbr_device_info": (_i32, [C.POINTER(_i32)] * 3 + [C.POINTER(_i64)] * 3),
     "fbr_assemble_f64": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
     "fbr_assemble_zonal_f64": (_i32, [_p, _p, _i32, _p, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
     "fbr_pml_sigma_f64": (_i32, [_p, _i64, _f64, _f64, _p, _p]),
     "fbr_factorize_work_bytes": (_i64, [_i64, _i64]),
     "fbr_factorize_f64": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
-    "fbr_run_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
-    "fbr_run_f32": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
+    "fbr_run_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p,
+                           C.POINTER(RunOpts), _p]),
+    "fbr_run_f32": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p,
+                           C.POINTER(RunOpts), _p]),
     "fbr_run_zonal_f64": (_i32, [_p, _p, _i32, _p, _f64, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p,
-                                 _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, _p]),
+                                 _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, C.POINTER(RunOpts), _p]),
     "fbr_run_max_nx": (_i64, []),
-    "fbr_run_reserve_ctas": (_i32, [_i32]),
     "fbr_run_long_max_nx": (_i64, []),
     "fbr_run_long_work_bytes": (_i64, [_i64]),
     "fbr_run_long_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _i64, _p, _p, _p, _p]),

@@ -188,7 +188,8 @@ def factorize(dl, d, du, check_singular=True, parallel=None):
 
 def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, snap_models=None,
         n_snap_models=None, want_final=False, obs_idx=None, n_obs=0, obs=None, obs_w=None, dtype="float64",
-        with_initial_row=True, misfit_out=None, snap_out=None, zonal=None, singular_flags=None):
+        with_initial_row=True, misfit_out=None, snap_out=None, zonal=None, singular_flags=None, reserve_ctas=0,
+        cell_major=False, scan_log2_eps=0.0, sampling=None, scan_mode_out=None):
     """K3: persistent on-chip integration.
 
     ``factors`` = (fl, fr, fg) from ``factorize``; or ``factors=None`` and ``zonal=(mesh, zone_value (M, n_zones),
@@ -198,9 +199,13 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     ``raise_if_singular_zonal`` — which keeps the launch asynchronous.
 
     Returns (snap | None, p_final | None, misfit | None).  ``snap`` has shape
-    (n_recorded_models, rows, nx) — the layout the result objects want, written directly by the
-    kernel — where rows = n_steps // snapshot_every (+ 1 leading row holding the initial state when
-    ``with_initial_row``).  ``snapshot_every=0`` disables snapshots.
+    (n_recorded_models, rows, nx) — the reference's ``snapshot`` layout, written directly by the
+    kernel — or, with ``cell_major``, (n_recorded_models, nx, rows): the (cell, time) layout of ``Data2D`` /
+    ``pack_result`` (``fbr_run_opts.snap_cell_stride``).  rows = n_steps // snapshot_every (+ 1 leading row holding
+    the initial state when ``with_initial_row``).  ``snapshot_every=0`` disables snapshots.
+
+    ``sampling`` (from ``sample_plan``): the observations ``obs`` (n_samples, n_obs) sit on their own time axis.
+    ``reserve_ctas``: CTA slots the persistent grid leaves free.  ``scan_log2_eps``: see ``fbr_run_opts``.
     """
     torch = _torch()
     lib = _cabi.load()
@@ -215,26 +220,38 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     fn = lib.fbr_run_f64 if dtype == "float64" else lib.fbr_run_f32
     n_rows = n_steps // snapshot_every if snapshot_every else 0
     snap = snap_ptr = None
-    row_stride = model_stride = 0
+    row_stride = model_stride = cell_stride = 0
     if n_rows > 0:
         ns = M if snap_models is None else n_snap_models
         lead = 1 if with_initial_row else 0
-        snap = snap_out if snap_out is not None else torch.empty((ns, n_rows + lead, nx), dtype=tdt, device=dev)
-        assert snap.shape == (ns, n_rows + lead, nx) and snap.dtype == tdt
+        rows = n_rows + lead
+        shape = (ns, nx, rows) if cell_major else (ns, rows, nx)
+        snap = snap_out if snap_out is not None else torch.empty(shape, dtype=tdt, device=dev)
+        assert snap.shape == shape and snap.dtype == tdt
         if lead:
             first = p0 if p0.dim() == 1 else (p0 if snap_models is None else p0[snap_models])
-            snap[:, 0, :] = first.to(tdt)
-        row_stride, model_stride, n_snap_models = nx, (n_rows + lead) * nx, ns
-        snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * snap.element_size())
+            if cell_major:
+                snap[:, :, 0] = first.to(tdt)
+            else:
+                snap[:, 0, :] = first.to(tdt)
+        if cell_major:
+            row_stride, model_stride, cell_stride, n_snap_models = 1, rows * nx, rows, ns
+            snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * snap.element_size())
+        else:
+            row_stride, model_stride, n_snap_models = nx, rows * nx, ns
+            snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * snap.element_size())
     p_final = torch.empty((M, nx), dtype=tdt, device=dev) if want_final else None
     misfit = misfit_out
     if misfit is None and obs_idx is not None:
         misfit = torch.empty(M, dtype=torch.float64, device=dev)
     p0_stride = 0 if p0.dim() == 1 else nx
+    opts = None
+    if reserve_ctas or cell_stride or scan_log2_eps or sampling is not None or scan_mode_out is not None:
+        opts = _cabi.C.byref(_cabi.run_opts(reserve_ctas, cell_stride, scan_log2_eps, sampling, scan_mode_out))
     tail = (ptr(p0), p0_stride, M, nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
             ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), ptr(snap_models),
             int(n_snap_models or 0), row_stride, model_stride, snap_ptr, ptr(p_final), ptr(obs_idx), int(n_obs),
-            ptr(obs), ptr(obs_w), ptr(misfit), current_stream())
+            ptr(obs), ptr(obs_w), ptr(misfit), opts, current_stream())
     if zonal is not None:
         flags = zonal_flags(M, dev) if singular_flags is None else singular_flags
         check(lib.fbr_run_zonal_f64(ptr(z_mesh), ptr(z_value), int(z_value.shape[1]), ptr(z_of_cell), float(z_dt), ptr(z_sigma),
@@ -246,6 +263,58 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     return snap, p_final, misfit
 
 
+def sample_plan(taxis, obs_taxis, baseline_index=None, window=None, dev=None):
+    """Bracket every observed time between two simulated states (host, NumPy — the arithmetic of ``np.interp``'s
+    index search, src/fiberis/analyzer/Data1D/core1D.py:791-800 in the reference) and upload the plan
+    ``fbr_run_opts`` wants.  ``taxis``: (n_steps + 1) times of the simulated states (row 0 = initial);
+    ``obs_taxis``: (n_samples) non-decreasing, in the same time frame; ``window`` = (first, last) sample range that
+    is summed (default: all); ``baseline_index``: sample subtracted from the simulated channel (None: nothing).
+    Times outside [taxis[0], taxis[-1]] give NaN misfits when they fall inside the window, as the reference's
+    ``interpolate`` (left / right = NaN) does."""
+    taxis = np.asarray(taxis, dtype=np.float64)
+    t = np.asarray(obs_taxis, dtype=np.float64)
+    n_steps, J = len(taxis) - 1, len(t)
+    if J == 0 or np.any(np.diff(t) < 0):
+        raise ValueError("Observed times must be a non-empty, non-decreasing sequence.")
+    row = np.searchsorted(taxis, t, side="right") - 1          # taxis[row] <= t < taxis[row + 1]
+    row = np.clip(row, 0, max(n_steps - 1, 0))
+    if n_steps > 0:
+        w = (t - taxis[row]) / (taxis[row + 1] - taxis[row])
+    else:
+        w = np.zeros(J)
+    at_end = t == taxis[-1]                                     # the last state itself: row n_steps, nothing beyond it
+    row = np.where(at_end, n_steps, row)
+    w = np.where(at_end, 0.0, w)
+    outside = (t < taxis[0]) | (t > taxis[-1])
+    row = np.where(outside, -1, row).astype(np.int32)
+    w = np.where(outside, 0.0, w)
+    done = np.where(outside, 0, row + (w > 0))                  # last state a sample needs
+    done = np.maximum.accumulate(done)                          # (outside samples ride along with their neighbours)
+    row_first = np.searchsorted(done, np.arange(n_steps + 2), side="left").astype(np.int32)
+    first, last = (0, J) if window is None else (int(window[0]), int(window[1]))
+    if first < 0:
+        first += J
+    if last <= 0:
+        last += J
+    base = -1 if baseline_index is None else int(baseline_index) % J
+    if not (0 <= first <= last <= J):
+        raise ValueError("Observation window outside the samples.")
+    if base >= 0 and base > first:
+        raise ValueError("The baseline sample must not lie behind the first sample of the window.")
+    return dict(sample_row=to_device(row, np.int32, dev), sample_w=to_device(w, np.float64, dev),
+                row_first_sample=to_device(row_first, np.int32, dev), base_sample=base, first_sample=first,
+                last_sample=last, host=dict(row=row, w=w, done=done))
+
+
+def fp64_peak():
+    """Measured fp64 issue peak of the current device, lane-level DFMA per second (fbr_probe_fp64_peak)."""
+    torch = _torch()
+    out = _cabi.C.c_double(0.0)
+    sink = torch.zeros(1, dtype=torch.float64, device=device())
+    check(_cabi.load().fbr_probe_fp64_peak(_cabi.C.byref(out), ptr(sink), current_stream()))
+    return float(out.value)
+
+
 def zonal_flags(M, dev=None):
     """Per-member flag array for fbr_run_zonal_f64 (the kernel takes the minimum with 1 + zero-pivot row)."""
     return _torch().full((M,), 2**31 - 1, dtype=_torch().int32, device=device(dev))
@@ -254,11 +323,6 @@ def zonal_flags(M, dev=None):
 def raise_if_singular_zonal(flags):
     """Flags of fbr_run_zonal_f64 (INT32_MAX = fine) -> the exception the reference's scipy.linalg.solve raises."""
     raise_if_singular(flags * (flags != 2**31 - 1), "system")
-
-
-def reserve_ctas(n):
-    """Ask the next ``run`` of this thread to leave ``n`` CTA slots free (see fbr_run_reserve_ctas)."""
-    check(_cabi.load().fbr_run_reserve_ctas(int(n)))
 
 
 def run_long_max_nx() -> int:

@@ -284,6 +284,49 @@ extern "C" int fbr_version(void) { return FBR_VERSION; }
 extern "C" const char *fbr_last_error(void) { return last_error_ref().c_str(); }
 extern "C" int fbr_last_launch_count(void) { return launch_count_ref(); }
 
+// fp64 issue peak of this device, measured: every thread runs 8 independent DFMA chains, 16 warps per SM (the
+// residency of K3), so the fp64 pipe — not latency — bounds the loop.  The denominator of bench.py's compute roofline.
+__global__ void __launch_bounds__(512, 1) fp64_peak_kernel(double *sink, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 0.999999, c = 1e-9 * threadIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) sink[0] = s;  // keeps the chains alive
+}
+
+extern "C" int fbr_probe_fp64_peak(double *h_dfma_per_s, double *d_sink, void *stream_v) {
+    FBR_REQUIRE(h_dfma_per_s && d_sink, "NULL output pointer");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    cudaStream_t stream = as_stream(stream_v);
+    cudaEvent_t e0, e1;
+    FBR_CUDA(cudaEventCreate(&e0));
+    FBR_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {  // the first repetition warms up
+        FBR_CUDA(cudaEventRecord(e0, stream));
+        fp64_peak_kernel<<<f.sm_count, 512, 0, stream>>>(d_sink, iters, 1.0);
+        FBR_CUDA(cudaEventRecord(e1, stream));
+        FBR_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        FBR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (int rc = check_launch("fbr_probe_fp64_peak")) return rc;
+    *h_dfma_per_s = (double)f.sm_count * 512.0 * iters * 64.0 / (best * 1e-3);  // lane-level DFMA per second
+    return FBR_OK;
+}
+
 extern "C" int fbr_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_per_block_optin,
                                int64_t *l2_bytes, int64_t *hbm_bytes) {
     DeviceFacts f;

@@ -27,6 +27,8 @@
 #include "fbr_sweep.cuh"
 #include "fbr_factor_reg.cuh"
 
+#include <cmath>
+#include <cstring>
 #include <type_traits>
 
 namespace fbr {
@@ -66,6 +68,16 @@ struct RunArgs {
     double z_dt;
     const double *z_sigma;       // (nx) PML damping or NULL
     int32_t *z_singular;         // (M) preset to INT32_MAX by the caller; atomicMin of 1 + zero-pivot row; may be NULL
+    // fbr_run_opts
+    int64_t snap_cell_stride;    // element stride between the cells of a recorded row (1: contiguous)
+    double scan_eps;             // skip scan stages / carry chains whose multiplier products are all below this; < 0: never
+    int reserve_ctas;
+    int64_t n_samples;           // 0: observations on the step times
+    const int32_t *sample_row;
+    const double *sample_w;
+    const int32_t *row_first_sample;
+    int base_sample, first_sample, last_sample;
+    int32_t *scan_mode;          // (M) or NULL: how each member was scanned
 };
 
 // Rows of A(dt) for CPT consecutive cells of member m, exactly K1's arithmetic (fbr_assemble.cu, matbuilder.py:21-81).
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
         double acc = 0.0;
         const int snap_every = a.snapshot_every > 0x7fffffff ? 0x7fffffff : (int)a.snapshot_every;
         int snap_countdown = snap_slot >= 0 ? snap_every : 0x7fffffff;  // never reaches 0 when not recorded
-        T *snap_dst = reinterpret_cast<T *>(a.snap) + (snap_slot >= 0 ? snap_slot : 0) * a.snap_model_stride + cell0;
+        T *snap_dst = reinterpret_cast<T *>(a.snap) + (snap_slot >= 0 ? snap_slot : 0) * a.snap_model_stride + cell0 * a.snap_cell_stride;
         const int64_t snap_stride = a.snap_row_stride;
         // per-step scalars are prefetched one step ahead straight from global memory (L2) by the
         // threads that own an overridden / observed cell; everybody else re-reads a constant
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 snap_countdown = snap_every;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j)
-                    if (cell0 + j < nx) snap_dst[j] = x[j];
+                    if (cell0 + j < nx) snap_dst[j * a.snap_cell_stride] = x[j];
                 snap_dst += snap_stride;
             }
             ov_val = ov_next;
@@ -486,8 +498,10 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
 //     generic path guarded by one CTA-uniform flag.
 // descriptor: [4:0] overridden cell (31 none)  [12:5] src column (0xFE: constant zero)
 //             [17:13] observed cell (31 none)  [25:18] obs column
+//             [26] the thread's FIRST cell is a boundary row (right-hand side 0)   [27] its LAST cell is one
 constexpr unsigned kDescNone = 0x1F;  // "no cell" in a descriptor's cell field
 constexpr unsigned kDescObShift = 13, kDescSrcColShift = 5, kDescObColShift = 18;
+constexpr unsigned kDescZeroFirst = 1u << 26, kDescZeroLast = 1u << 27;
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -508,7 +522,13 @@ __device__ __forceinline__ T pick_at(const T (&x)[CPT], int j) {
 
 // A thread's 64 bytes straight to global memory (16-byte stores when aligned).
 template <typename T, int CPT>
-__device__ __forceinline__ void store_row_direct(T *__restrict__ dst, int64_t cell0, int64_t nx, const T (&x)[CPT]) {
+__device__ __forceinline__ void store_row_direct(T *__restrict__ dst, int64_t cell0, int64_t nx, const T (&x)[CPT], int64_t cs = 1) {
+    if (cs != 1) {  // cell-major result layout (Data2D's (cell, time)): one element per cell, cs elements apart
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (cell0 + j < nx) dst[j * cs] = x[j];
+        return;
+    }
     if (cell0 + CPT <= nx && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         constexpr int PER = 16 / sizeof(T);
 #pragma unroll
@@ -531,7 +551,7 @@ __device__ __forceinline__ void store_row_direct(T *__restrict__ dst, int64_t ce
 // writes 32 consecutive elements.
 template <typename T, int CPT>
 __device__ __forceinline__ void store_row_coalesced(T *__restrict__ row, int64_t warp_cell0, int64_t nx, const T (&x)[CPT],
-                                                    T *patch, int lane) {
+                                                    T *patch, int lane, int64_t cs = 1) {
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < CPT; ++j) patch[lane * (CPT + 1) + j] = x[j];
@@ -540,9 +560,19 @@ __device__ __forceinline__ void store_row_coalesced(T *__restrict__ row, int64_t
     for (int i = 0; i < CPT; ++i) {
         const int c = 32 * i + lane;  // cell within the warp's 32 * CPT
         const T v = patch[(c / CPT) * (CPT + 1) + (c % CPT)];
-        if (warp_cell0 + c < nx) row[warp_cell0 + c] = v;
+        if (warp_cell0 + c < nx) row[(warp_cell0 + c) * cs] = v;
     }
 }
+
+// How a member's sweeps are scanned (decided per member from its own factors, CTA-uniform):
+//   kScanExact : 5 Kogge-Stone stages per warp and the W x W table of warp-total products across warps — exact;
+//   kScanNear  : 5 stages, carry from the neighbouring warp only — every interior warp's total product (32 * CPT
+//                consecutive multipliers) is below the threshold, so longer carry chains vanish;
+//   kScanNear4 : as kScanNear with 4 stages — every product of 16 consecutive chunks is below the threshold too.
+// The threshold (RunArgs::scan_eps, default 2^-80) sits 8 orders of magnitude below fp64 rounding; the skipped terms
+// are products of that size with partial sums of the sweep.  B200: 18.3 / 16.4 / 15.4 ms per C3 sweep for the bare
+// loops (scratch/ubench_k3v.cu) — the table costs 6 shared loads and 3 dependent FMAs behind every barrier.
+constexpr int kScanExact = 0, kScanNear = 1, kScanNear4 = 2;
 
 template <typename T, int CPT, int W, int MINB, bool ZONAL>
 __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs a) {
@@ -550,19 +580,22 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     __shared__ double s_zc[ZONAL ? W : 1];
     static_assert(CPT * sizeof(T) == 64, "a thread owns 64 bytes of state: 8 doubles or 16 floats");
     __shared__ __align__(16) T s_K[2][W][W];
-    __shared__ __align__(16) T s_E[2][W];
+    // zero-carry warp totals of the current sweep: forward total of warp v at [0][1 + v] ([0][0] stays zero),
+    // backward total of warp v at [1][1 + v] ([1][W + 1] stays zero) — a warp's neighbour is one fixed slot away
+    __shared__ __align__(16) T s_E[2][W + 2];
     __shared__ T s_dummy;
     __shared__ double s_zero, s_trash;  // constant zero source value; where non-observers "record"
     __shared__ T s_T[2][W];
     __shared__ double s_red[W];
     __shared__ long long s_snap_slot;
+    __shared__ double s_prev[kMaxObs], s_base[kMaxObs];  // observed cells: last row of the previous block; baseline sample
     extern __shared__ __align__(16) double s_dyn[];  // staged per-step scalars, see the time loop
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nx = a.nx;
     const int64_t cell0 = (int64_t)tid * CPT;
-    if (tid == 0) s_zero = 0.0;
-    const unsigned st_f = smem_addr(lane == 31 ? &s_E[0][warp] : &s_dummy);
-    const unsigned st_b = smem_addr(lane == 0 ? &s_E[1][warp] : &s_dummy);
+    if (tid == 0) { s_zero = 0.0; s_E[0][0] = (T)0; s_E[1][W + 1] = (T)0; }
+    const unsigned st_f = smem_addr(lane == 31 ? &s_E[0][1 + warp] : &s_dummy);
+    const unsigned st_b = smem_addr(lane == 0 ? &s_E[1][1 + warp] : &s_dummy);
     const int keep_f = lane == 0 ? 0 : -1, keep_b = lane == 31 ? 0 : -1;
     const int n_steps = (int)a.n_steps;
 
@@ -579,9 +612,23 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             if (n_ov == 1 || j == last) { last = j; slot_of_last = so; }
             else last = -2;  // several cells: the generic path re-derives them every step
         };
-        if (cell0 == 0 && a.lbc != FBR_BC_NONE) claim(0, kSlotZero);
+        auto is_source = [&](int64_t cell) {
+            for (int k = 0; k < a.n_src; ++k)
+                if (a.src_idx[k] == cell) return true;
+            return false;
+        };
+        // A boundary row that sits in a thread's first / last register (cell 0 always does; cell nx - 1 when nx is a
+        // multiple of the chunk) is zeroed by a mask every thread applies — two instructions, no shared-memory read, no
+        // divergent branch; any other position takes the override path below.
         const int64_t jl = nx - 1 - cell0;
-        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) claim((int)jl, kSlotZero);
+        if (cell0 == 0 && a.lbc != FBR_BC_NONE) {
+            if (!is_source(0)) desc |= kDescZeroFirst;
+            else claim(0, kSlotZero);
+        }
+        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) {
+            if (jl == CPT - 1 && !is_source(nx - 1)) desc |= kDescZeroLast;
+            else claim((int)jl, kSlotZero);
+        }
 #pragma unroll 1
         for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win
             const int64_t jj = a.src_idx[k] - cell0;
@@ -626,6 +673,22 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) src_rows |= 1u << jj;
         }
     }
+    const bool has_ov = (desc & 0x1F) != kDescNone, has_ob = ((desc >> kDescObShift) & 0x1F) != kDescNone;
+    const bool ov_zero = ((desc >> kDescSrcColShift) & 0xFF) == kSlotZero;
+    const int keep_first = (desc & kDescZeroFirst) ? 0 : -1, keep_last = (desc & kDescZeroLast) ? 0 : -1;
+    // Per-step scalars never travel through a global load inside the sweeps: a load in flight across a sweep
+    // shares a scoreboard with its shuffles / shared-memory reads and stalls them (+25 % per step on B200,
+    // scratch/ubench_k3.cu), and a load consumed on the spot exposes L2 latency on an in-order warp.  Instead the
+    // time axis is cut into blocks of `blk` steps:
+    //   * the block's source values stream into shared memory (cp.async) while the previous block is integrated;
+    //   * observed pressures are only WRITTEN during the block (a store has no result latency) into a trace, and
+    //     the residuals of the observation samples a block completes are summed cooperatively at the next block
+    //     boundary (samples on the step times, or interpolated onto the observations' own time axis).
+    const int blk = a.blk_steps;
+    double *s_src = s_dyn;                                  // [2][blk][n_src]
+    double *s_tr = s_src + 2 * blk * a.n_src;               // [2][blk][n_obs]
+    T *s_patch = reinterpret_cast<T *>(s_tr + 2 * blk * a.n_obs + warp * (32 * 9));  // [W] row-transposition patches (2304 B each)
+    const int64_t cs = a.snap_cell_stride;
 
     ModelCursor cursor = model_cursor(a);
     int64_t m;
@@ -677,46 +740,64 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             }
             s_snap_slot = slot;
         }
-        __syncthreads();
+        // observed cells: the initial state is "row 0" of the trace; no baseline yet
+        if (has_ob) s_prev[(desc >> kDescObColShift) & 0xFF] = (double)pick_at<T, CPT>(x, (int)((desc >> kDescObShift) & (CPT - 1)));
+        if (ob_slow) {
+#pragma unroll 1
+            for (int k = 0; k < a.n_obs; ++k) {
+                const int64_t jj = a.obs_idx[k] - cell0;
+                if (jj >= 0 && jj < CPT) s_prev[k] = (double)pick_at<T, CPT>(x, (int)jj);
+            }
+        }
+        for (int k = tid; k < a.n_obs; k += 32 * W) s_base[k] = 0.0;
+        // scan mode of this member (CTA-uniform): which far terms vanish below the threshold?
+        bool far_ok = false;
+        if (a.scan_eps > 0.0) far_ok = fabs((double)sm.f[4]) <= a.scan_eps && fabs((double)sm.b[4]) <= a.scan_eps;
+        far_ok = __syncthreads_and(far_ok);
+        int scan_mode = kScanExact;
+        if (a.scan_eps > 0.0 && !any_slow) {
+            bool near_ok = true;
+            for (int v = 1; v + 1 < W; ++v)
+                near_ok = near_ok && fabs((double)s_T[0][v]) <= a.scan_eps && fabs((double)s_T[1][v]) <= a.scan_eps;
+            if (near_ok) scan_mode = far_ok ? kScanNear4 : kScanNear;
+        }
+        if (a.scan_mode && tid == 0) a.scan_mode[m] = scan_mode;
         const long long snap_slot = s_snap_slot;
         double acc = 0.0;
-        // Per-step scalars never travel through a global load inside the sweeps: a load in flight across a
-        // sweep shares a scoreboard with its shuffles / shared-memory reads and stalls them (+25 % per
-        // step on B200, scratch/ubench_k3.cu), and a load consumed on the spot exposes L2 latency on
-        // an in-order warp.  Instead the time axis is cut into blocks of `blk` steps:
-        //   * the block's source values and observations stream into shared memory (cp.async) while
-        //     the previous block is integrated;
-        //   * observed pressures are only WRITTEN during the block (a store has no result latency)
-        //     into a trace, and the squared residuals of a whole block are summed cooperatively at
-        //     the next block boundary.
-        const bool has_ov = (desc & 0x1F) != kDescNone, has_ob = ((desc >> kDescObShift) & 0x1F) != kDescNone;
-        const bool ov_zero = ((desc >> kDescSrcColShift) & 0xFF) == kSlotZero;
-        const int blk = a.blk_steps;
-        double *s_src = s_dyn;                                  // [2][blk][n_src]
-        double *s_obs = s_src + 2 * blk * a.n_src;              // [2][blk][n_obs]
-        double *s_tr = s_obs + 2 * blk * a.n_obs;               // [2][blk][n_obs]
-        T *s_patch = reinterpret_cast<T *>(s_tr + 2 * blk * a.n_obs + warp * (32 * 9));  // [W] row-transposition patches (2304 B each)
-        auto stage_block = [&](int b) {  // sources of steps [b blk, ..) and observations of the states after them
+
+        auto stage_block = [&](int b) {  // source values of steps [b blk, ..)
             const int n0 = b * blk;
             const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
             if (rows <= 0) return;
             const int buf = b & 1;
             for (int e = tid; e < rows * a.n_src; e += 32 * W)
                 cp_async8(s_src + buf * blk * a.n_src + e, a.src_table + (int64_t)n0 * a.n_src + e);
-            for (int e = tid; e < rows * a.n_obs; e += 32 * W) {
-                cp_async8(s_obs + buf * blk * a.n_obs + e, a.obs + (int64_t)(n0 + 1) * a.n_obs + e);
-                // the trace starts out equal to the observations: a column nobody owns (index outside
-                // the mesh) then contributes exactly nothing
-                cp_async8(s_tr + buf * blk * a.n_obs + e, a.obs + (int64_t)(n0 + 1) * a.n_obs + e);
-            }
         };
-        auto flush_block = [&](int b) {  // sum of weighted squared residuals of block b
-            const int n0 = b * blk;
-            const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
-            const int buf = b & 1;
-            for (int e = tid; e < rows * a.n_obs; e += 32 * W) {
-                const double res = s_tr[buf * blk * a.n_obs + e] - s_obs[buf * blk * a.n_obs + e];
-                const double wgt = a.obs_w ? __ldg(a.obs_w + e % a.n_obs) : 1.0;
+        // Residuals of the observation samples whose last needed state lies in rows (lo, hi] — the block just integrated
+        // (trace buffer `buf`; row lo itself is s_prev) — plus, for lo == 0, those that only need the initial state.
+        auto flush_rows = [&](int lo, int hi, int buf) {
+            int ja, jb;
+            if (a.sample_row) { ja = __ldg(a.row_first_sample + (lo == 0 ? 0 : lo + 1)); jb = __ldg(a.row_first_sample + hi + 1); }
+            else { ja = lo == 0 ? 0 : lo + 1; jb = hi + 1; }
+            auto sample = [&](int j, int k) -> double {  // simulated channel k at observation sample j
+                const int row = a.sample_row ? __ldg(a.sample_row + j) : j;
+                const double w = a.sample_w ? __ldg(a.sample_w + j) : 0.0;
+                if (row < 0) return __longlong_as_double(0x7ff8000000000000ll);  // outside the simulated time range
+                const double *tr = s_tr + (buf * blk - lo - 1) * a.n_obs + k;
+                const double p_lo = row == lo ? s_prev[k] : tr[row * a.n_obs];
+                if (w == 0.0) return p_lo;
+                return fma(w, tr[(row + 1) * a.n_obs] - p_lo, p_lo);
+            };
+            if (a.base_sample >= ja && a.base_sample < jb) {  // "initial time calibration" (baseline_model_generator.py:398)
+                for (int k = tid; k < a.n_obs; k += 32 * W) s_base[k] = sample(a.base_sample, k);
+                __syncthreads();
+            }
+            ja = ja < a.first_sample ? a.first_sample : ja;
+            jb = jb > a.last_sample ? a.last_sample : jb;
+            for (int e = tid; e < (jb - ja) * a.n_obs; e += 32 * W) {
+                const int j = ja + e / a.n_obs, k = e % a.n_obs;
+                const double res = (sample(j, k) - s_base[k]) - __ldg(a.obs + (int64_t)j * a.n_obs + k);
+                const double wgt = a.obs_w ? __ldg(a.obs_w + k) : 1.0;
                 acc = fma(wgt * res, res, acc);
             }
         };
@@ -740,8 +821,9 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 cp_async_wait_all_k3();
                 __syncthreads();  // block b's inputs have landed; everybody is done with block b - 1
                 if (b > 0 && a.n_obs > 0) {
-                    flush_block(b - 1);
-                    __syncthreads();  // block b + 1 is staged into the observation buffer just read
+                    flush_rows((b - 1) * blk, b * blk, (b - 1) & 1);
+                    __syncthreads();  // s_prev is replaced; block b + 1 is staged
+                    for (int k = tid; k < a.n_obs; k += 32 * W) s_prev[k] = s_tr[(((b - 1) & 1) * blk + blk - 1) * a.n_obs + k];
                 }
                 stage_block(b + 1);
                 cp_async_commit_k3();
@@ -751,22 +833,27 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             }
             int run = blk - done % blk;
             if (run > n_steps - done) run = n_steps - done;
-            // two copies of the step loop: the common one carries no code for threads that own several
-            // overridden / observed cells, which keeps its instruction footprint small
-            auto steps = [&](auto slow_tag, auto rec_tag, int n_begin, int n_end) {
+            // several copies of the step loop: the common ones carry no code for threads that own several
+            // overridden / observed cells, nor for snapshots, and only the scan stages their mode needs
+            auto steps = [&](auto mode_tag, auto slow_tag, auto rec_tag, int n_begin, int n_end) {
+                constexpr int MODE = decltype(mode_tag)::value;
                 constexpr bool SLOW = decltype(slow_tag)::value, REC = decltype(rec_tag)::value;
+                constexpr int NS = MODE == kScanNear4 ? 4 : 5;
+                // the value overriding this thread's cell (a source sample, or the constant zero) is read from shared
+                // memory one step AHEAD, next to the backward sweep's barrier, whose wait hides the read's latency
+                T v_ov = (T)lds_f64(src_addr);
 #pragma unroll 1
                 for (int n = n_begin; n < n_end; ++n) {
                     // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
+                    x[0] = and_mask(x[0], keep_first);
+                    x[CPT - 1] = and_mask(x[CPT - 1], keep_last);
                     if (has_ov) {  // only the threads that own an overridden cell
-                        const T v = (T)lds_f64(src_addr);
                         const int jo = (int)(desc & 0x1F);
-                        // boundary rows (and sources that start or end a chunk) sit in the first / last register of a thread:
-                        // one move; any other position goes through the compare-and-move chain
-                        if (jo == 0) x[0] = v;
-                        else if (jo == CPT - 1) x[CPT - 1] = v;
-                        else set_at<T, CPT>(x, jo, v);
-                        src_addr += src_inc;
+                        // sources that start or end a chunk sit in the first / last register of a thread: one move;
+                        // any other position goes through the compare-and-move chain
+                        if (jo == 0) x[0] = v_ov;
+                        else if (jo == CPT - 1) x[CPT - 1] = v_ov;
+                        else set_at<T, CPT>(x, jo, v_ov);
                     }
                     if (SLOW && ov_slow) {  // several overridden cells in this thread: re-derive them (rare)
                         if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (T)0;
@@ -782,15 +869,17 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                     {
                         T y = chunk_end_fwd_plain<T, CPT>(x, l);
 #pragma unroll
-                        for (int s = 0; s < 5; ++s) y = fma_any<T>(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+                        for (int s = 0; s < NS; ++s) y = fma_any<T>(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
                         T c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
                         if (W > 1) {
                             sts_any(st_f, y);
                             __syncthreads();
-                            T cw = (T)0;
+                            if (MODE == kScanExact) {
+                                T cw = (T)0;
 #pragma unroll
-                            for (int v = 0; v < W - 1; ++v) cw = fma_any<T>(s_K[0][warp][v], s_E[0][v], cw);
-                            c = fma_any<T>(sm.ex_f, cw, c);
+                                for (int v = 0; v < W - 1; ++v) cw = fma_any<T>(s_K[0][warp][v], s_E[0][1 + v], cw);
+                                c = fma_any<T>(sm.ex_f, cw, c);
+                            } else c = fma_any<T>(sm.ex_f, s_E[0][warp], c);
                         }
                         chunk_apply_fwd_plain<T, CPT>(x, l, r, c);
                     }
@@ -798,15 +887,19 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                     {
                         T z = chunk_end_bwd_plain<T, CPT>(x, g);
 #pragma unroll
-                        for (int s = 0; s < 5; ++s) z = fma_any<T>(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+                        for (int s = 0; s < NS; ++s) z = fma_any<T>(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
                         T c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+                        src_addr += src_inc;
+                        v_ov = (T)lds_f64(src_addr);  // next step's override value (one row past the block's last is never used)
                         if (W > 1) {
                             sts_any(st_b, z);
                             __syncthreads();
-                            T cw = (T)0;
+                            if (MODE == kScanExact) {
+                                T cw = (T)0;
 #pragma unroll
-                            for (int v = 1; v < W; ++v) cw = fma_any<T>(s_K[1][warp][v], s_E[1][v], cw);
-                            c = fma_any<T>(sm.ex_b, cw, c);
+                                for (int v = 1; v < W; ++v) cw = fma_any<T>(s_K[1][warp][v], s_E[1][1 + v], cw);
+                                c = fma_any<T>(sm.ex_b, cw, c);
+                            } else c = fma_any<T>(sm.ex_b, s_E[1][warp + 2], c);
                         }
                         chunk_apply_bwd_plain<T, CPT>(x, g, c);
                     }
@@ -824,24 +917,38 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                     // ---- sampled snapshot (CTA-uniform countdown; never fires for unrecorded members) ----
                     if (REC && --to_snap == 0) {
                         to_snap = snap_every;
-                        if (direct_rows) store_row_direct<T, CPT>(snap_row + cell0, cell0, nx, x);
-                        else store_row_coalesced<T, CPT>(snap_row, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane);
+                        if (direct_rows) store_row_direct<T, CPT>(snap_row + cell0 * cs, cell0, nx, x, cs);
+                        else store_row_coalesced<T, CPT>(snap_row, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane, cs);
                         snap_row += a.snap_row_stride;
                     }
                 }
             };
-            if (snap_slot >= 0) {  // (the copy for unrecorded members carries no snapshot code)
-                if (any_slow) steps(std::true_type{}, std::true_type{}, done, done + run);
-                else steps(std::false_type{}, std::true_type{}, done, done + run);
+            using I0 = std::integral_constant<int, kScanExact>;
+            using I1 = std::integral_constant<int, kScanNear>;
+            using I2 = std::integral_constant<int, kScanNear4>;
+            if (scan_mode == kScanExact) {
+                if (snap_slot >= 0) {  // (the copies for unrecorded members carry no snapshot code)
+                    if (any_slow) steps(I0{}, std::true_type{}, std::true_type{}, done, done + run);
+                    else steps(I0{}, std::false_type{}, std::true_type{}, done, done + run);
+                } else {
+                    if (any_slow) steps(I0{}, std::true_type{}, std::false_type{}, done, done + run);
+                    else steps(I0{}, std::false_type{}, std::false_type{}, done, done + run);
+                }
+            } else if (scan_mode == kScanNear) {
+                if (snap_slot >= 0) steps(I1{}, std::false_type{}, std::true_type{}, done, done + run);
+                else steps(I1{}, std::false_type{}, std::false_type{}, done, done + run);
             } else {
-                if (any_slow) steps(std::true_type{}, std::false_type{}, done, done + run);
-                else steps(std::false_type{}, std::false_type{}, done, done + run);
+                if (snap_slot >= 0) steps(I2{}, std::false_type{}, std::true_type{}, done, done + run);
+                else steps(I2{}, std::false_type{}, std::false_type{}, done, done + run);
             }
             done += run;
         }
         cp_async_wait_all_k3();
         __syncthreads();
-        if (n_steps > 0 && a.n_obs > 0) flush_block((n_steps - 1) / blk);
+        if (n_steps > 0 && a.n_obs > 0) {
+            const int b_last = (n_steps - 1) / blk;
+            flush_rows(b_last * blk, n_steps, b_last & 1);
+        }
 
         // ---------------- per-model epilogue ----------------
         if (a.p_final)
@@ -943,7 +1050,7 @@ __global__ void __launch_bounds__(128, 4) run_group_kernel(const RunArgs a) {
                     if (a.snap_models[q] == m) slot = q;
         }
         int snap_countdown = slot >= 0 ? snap_every : 0x7fffffff;
-        T *snap_dst = reinterpret_cast<T *>(a.snap) + (slot >= 0 ? slot : 0) * a.snap_model_stride + cell0;
+        T *snap_dst = reinterpret_cast<T *>(a.snap) + (slot >= 0 ? slot : 0) * a.snap_model_stride + cell0 * a.snap_cell_stride;
         const double *ovp = ov_col >= 0 ? a.src_table + ov_col : &kZero, *obp = ob_col >= 0 ? a.obs + a.n_obs + ob_col : &kZero;
         int ov_stride = ov_col >= 0 ? a.n_src : 0, ob_stride = ob_col >= 0 ? a.n_obs : 0;
         double ov_val = a.n_steps > 0 ? __ldg(ovp) : 0.0, ob_val = a.n_steps > 0 ? __ldg(obp) : 0.0, acc = 0.0;
@@ -997,7 +1104,7 @@ __global__ void __launch_bounds__(128, 4) run_group_kernel(const RunArgs a) {
             }
             if (--snap_countdown == 0) {
                 snap_countdown = snap_every;
-                store_row_direct<T, CPT>(snap_dst, cell0, nx, x);
+                store_row_direct<T, CPT>(snap_dst, cell0, nx, x, a.snap_cell_stride);
                 snap_dst += a.snap_row_stride;
             }
             ov_val = ov_next;
@@ -1028,13 +1135,6 @@ static int launch_group(const RunArgs &a, cudaStream_t stream) {
     return check_launch("fbr_run (member groups)");
 }
 
-// CTA slots the next launch of this thread leaves free (fbr_run_reserve_ctas): lets a small launch
-// enqueued just before on another stream stay resident next to the persistent grid.
-static int &reserved_ctas() {
-    static thread_local int n = 0;
-    return n;
-}
-
 template <typename T, int CPT, int W, bool ZONAL = false>
 static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
@@ -1042,7 +1142,7 @@ static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     constexpr int kFull16 = (16 / W) > 0 ? (16 / W) : 1;
     auto kern = run_onchipx_kernel<T, CPT, W, kFull16, ZONAL>;
     RunArgs b = a;
-    const int cols = a.n_src + 2 * a.n_obs;
+    const int cols = a.n_src + a.n_obs;
     // Time steps per staged block of per-step scalars: the longest block that costs no resident CTA (block boundaries
     // carry three barriers and the residual sums; C3: 64 steps 25.2 ms, 32 steps 25.5 ms, 128 steps lose a CTA: 42.7 ms).
     // The audited side launch of an ensemble must end up with the SAME footprint as the sweep (see ensemble.py): the
@@ -1068,8 +1168,7 @@ static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
         FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, smem));
     }
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d)", 32 * W);
-    int64_t grid = (int64_t)occ * f.sm_count - reserved_ctas();
-    reserved_ctas() = 0;
+    int64_t grid = (int64_t)occ * f.sm_count - a.reserve_ctas;  // fbr_run_opts::reserve_ctas
     if (grid < 1) grid = 1;
     if (grid > a.M) grid = a.M;
     kern<<<(unsigned)grid, 32 * W, smem, stream>>>(b);
@@ -1134,7 +1233,15 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     FBR_REQUIRE(a.n_obs == 0 || (a.obs_idx && a.obs && a.misfit), "observations given without obs / misfit");
     FBR_REQUIRE(!a.snap || (a.snapshot_every >= 1 && a.n_snap_models >= 1), "snapshot_every / n_snap_models must be >= 1");
     FBR_REQUIRE(!a.snap || a.snap_models || a.n_snap_models == a.M, "snap_models == NULL needs n_snap_models == M");
-    FBR_REQUIRE(!a.snap || (a.snap_row_stride >= a.nx && a.snap_model_stride >= a.nx), "snapshot strides must be >= nx");
+    FBR_REQUIRE(!a.snap || a.snap_cell_stride != 1 || (a.snap_row_stride >= a.nx && a.snap_model_stride >= a.nx),
+                "snapshot strides must be >= nx");
+    FBR_REQUIRE(!a.snap || a.snap_cell_stride >= 1, "snap_cell_stride must be >= 1");
+    FBR_REQUIRE(a.n_samples == 0 || (a.n_obs > 0 && a.sample_row && a.sample_w && a.row_first_sample),
+                "sampled observations need obs_idx, sample_row, sample_w and row_first_sample");
+    FBR_REQUIRE(a.n_samples == 0 || (a.first_sample >= 0 && a.last_sample <= a.n_samples && a.base_sample < a.n_samples),
+                "sample window / baseline index outside [0, n_samples)");
+    FBR_REQUIRE(a.n_samples == 0 || a.base_sample < 0 || a.base_sample <= a.first_sample,
+                "base_sample must not lie behind first_sample");
     if (a.nx > fbr_run_max_nx())
         return fail(FBR_ERR_UNSUPPORTED, "nx=%lld exceeds the on-chip run kernel limit %lld", (long long)a.nx,
                     (long long)fbr_run_max_nx());
@@ -1153,7 +1260,9 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     // (a handful of members below 256 cells is a latency problem, not a throughput one: the generic kernel's shorter
     // chains over more threads win there — C1, one 200-cell model: 0.50 against 0.75 us per step)
     const bool few_short = sizeof(T) == 8 && a.nx < 256 && a.M < 32 && !a.z_mesh && !min_env;
-    if (a.nx >= x_min && !few_short && !getenv("FBR_K3_GENERIC")) return launch_x<T>(a, stream);
+    // observations on their own time axis are evaluated by the 64-byte-per-thread kernel only
+    const bool needs_x = a.n_samples > 0;
+    if (needs_x || (a.nx >= x_min && !few_short && !getenv("FBR_K3_GENERIC"))) return launch_x<T>(a, stream);
     // short meshes, more than a handful of members: groups of 8 / 16 lanes per member, several members per warp
     if (a.nx > 8 && a.nx <= 128 && a.M >= 8 && !a.z_mesh && !getenv("FBR_K3_GENERIC") && !getenv("FBR_K3_NO_GROUPS")) {
         if (a.nx <= 16) return launch_group<T, 2>(a, stream);
@@ -1168,17 +1277,38 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     }
 }
 
+// fbr_run_opts -> RunArgs (NULL: all defaults).  Callers compiled against an older, shorter struct are accepted.
+static int apply_opts(RunArgs &a, const fbr_run_opts *opts) {
+    fbr_run_opts o;
+    memset(&o, 0, sizeof(o));
+    if (opts) {
+        FBR_REQUIRE(opts->struct_bytes >= 8 && opts->struct_bytes <= (int)sizeof(o), "fbr_run_opts.struct_bytes=%d is not a size this library knows",
+                    opts->struct_bytes);
+        memcpy(&o, opts, (size_t)opts->struct_bytes);
+    }
+    FBR_REQUIRE(o.reserve_ctas >= 0, "cannot reserve a negative number of CTA slots");
+    a.reserve_ctas = o.reserve_ctas;
+    a.snap_cell_stride = o.snap_cell_stride == 0 ? 1 : o.snap_cell_stride;
+    const double log2_eps = o.scan_log2_eps == 0.0 ? -80.0 : o.scan_log2_eps;
+    a.scan_eps = log2_eps > 0.0 ? -1.0 : exp2(log2_eps);
+    if (getenv("FBR_K3_EXACT")) a.scan_eps = -1.0;  // tuning aid
+    a.scan_mode = o.scan_mode;
+    a.n_samples = o.n_samples;
+    if (o.n_samples > 0) {
+        a.sample_row = o.sample_row; a.sample_w = o.sample_w; a.row_first_sample = o.row_first_sample;
+        a.base_sample = o.base_sample; a.first_sample = o.first_sample; a.last_sample = o.last_sample;
+    } else {  // observations on the step times: sample j is the state after step j, all of them count, nothing subtracted
+        a.sample_row = nullptr; a.sample_w = nullptr; a.row_first_sample = nullptr;
+        a.base_sample = -1; a.first_sample = 1; a.last_sample = (int)(a.n_steps + 1);
+    }
+    return FBR_OK;
+}
+
 }  // namespace fbr
 
 using namespace fbr;
 
 extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
-
-extern "C" int fbr_run_reserve_ctas(int n) {
-    FBR_REQUIRE(n >= 0, "cannot reserve a negative number of CTA slots");
-    reserved_ctas() = n;
-    return FBR_OK;
-}
 
 #define FBR_FILL_ARGS()                                                                                   \
     RunArgs a;                                                                                            \
@@ -1189,7 +1319,8 @@ extern "C" int fbr_run_reserve_ctas(int n) {
     a.snap_model_stride = snap_model_stride; a.snap = snap; a.p_final = p_final; a.obs_idx = obs_idx;             \
     a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit; a.blk_steps = 0;     \
     a.z_mesh = nullptr; a.z_value = nullptr; a.z_of_cell = nullptr; a.z_n = 0; a.z_dt = 0.0;              \
-    a.z_sigma = nullptr; a.z_singular = nullptr;
+    a.z_sigma = nullptr; a.z_singular = nullptr;                                                         \
+    if (int rc_opts = apply_opts(a, opts)) return rc_opts;
 
 extern "C" int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,
                            int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
@@ -1197,7 +1328,7 @@ extern "C" int fbr_run_f64(const double *fl, const double *fr, const double *fg,
                            const int64_t *snap_models, int64_t n_snap_models, int64_t snap_row_stride,
                            int64_t snap_model_stride, double *snap, double *p_final,
                            const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
-                           double *misfit, void *stream) {
+                           double *misfit, const fbr_run_opts *opts, void *stream) {
     FBR_FILL_ARGS();
     return run_dispatch<double>(a, as_stream(stream));
 }
@@ -1208,7 +1339,7 @@ extern "C" int fbr_run_f32(const double *fl, const double *fr, const double *fg,
                            const int64_t *snap_models, int64_t n_snap_models, int64_t snap_row_stride,
                            int64_t snap_model_stride, float *snap, float *p_final,
                            const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
-                           double *misfit, void *stream) {
+                           double *misfit, const fbr_run_opts *opts, void *stream) {
     FBR_FILL_ARGS();
     return run_dispatch<float>(a, as_stream(stream));
 }
@@ -1219,7 +1350,7 @@ extern "C" int fbr_run_zonal_f64(const double *mesh, const double *zone_value, i
                                  const double *src_table, int64_t snapshot_every, const int64_t *snap_models,
                                  int64_t n_snap_models, int64_t snap_row_stride, int64_t snap_model_stride, double *snap,
                                  double *p_final, const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
-                                 double *misfit, void *stream) {
+                                 double *misfit, const fbr_run_opts *opts, void *stream) {
     const double *fl = nullptr, *fr = nullptr, *fg = nullptr;
     FBR_FILL_ARGS();
     FBR_REQUIRE(mesh && zone_value && n_zones >= 1, "NULL mesh / zone arguments");

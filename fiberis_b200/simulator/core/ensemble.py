@@ -45,6 +45,9 @@ class PDS1D_Ensemble:
         self.obs_idx = None
         self.obs = None              # (n_steps + 1, n_obs), row 0 unused
         self.obs_weights = None
+        self.obs_taxis = None        # observations on their own time axis (None: on the step times)
+        self.obs_baseline = None
+        self.obs_window = None
         self.misfit = None
         self.snapshot = None         # (n_audit, n_t, nx)
         self.taxis = None
@@ -94,16 +97,52 @@ class PDS1D_Ensemble:
             raise ValueError("zone_of_cell refers to a zone outside zone_value.")
         self.zone_value, self.zone_of_cell, self.diffusivity = zv, zc.astype(np.int32), None
 
-    def set_observations(self, obs_idx, obs, weights=None):
-        """obs[n, k]: observed pressure at cell obs_idx[k] at time taxis[n] (row 0 is not used)."""
+    def set_observations(self, obs_idx, obs, weights=None, taxis=None, baseline_index=None, window=None):
+        """Observed channels for the fused misfit.
+
+        Without ``taxis``: ``obs[n, k]`` is the observed pressure at cell ``obs_idx[k]`` at the step time
+        ``taxis[n]`` of the run (row 0 is not used) and ``misfit = sum_n sum_k w_k (p - obs)^2``.
+
+        With ``taxis`` (seconds on the run's own time axis ``self.taxis``, i.e. including ``t0``; non-decreasing): the observations keep their OWN time
+        axis, ``obs`` is ``(len(taxis), n_obs)`` and the misfit is the reference's
+        (src/fiberis/moose/templates/baseline_model_generator.py:394-403): every simulated channel is interpolated
+        linearly onto ``taxis`` (``Data1D.interpolate``), the sample ``baseline_index`` is subtracted from it (the
+        reference uses 1; ``None``: nothing), and ``w_k (sim - obs)^2`` is summed over the samples of ``window =
+        (first, last)`` (the reference uses ``(1, -1)``; default: all samples).  Observed times outside the simulated
+        range inside the window make the misfit NaN, as the reference's interpolation (fill = NaN) does."""
         idx = np.atleast_1d(np.asarray(obs_idx)).astype(np.int64)
         if len(np.unique(idx)) != len(idx):
             raise ValueError("Observation cells must be distinct.")
+        if self.mesh is not None and (idx.min() < 0 or idx.max() >= len(self.mesh)):
+            raise ValueError("Observation cells must lie in the mesh.")
         obs = np.asarray(obs, dtype=np.float64)
         if obs.ndim != 2 or obs.shape[1] != len(idx):
-            raise ValueError("obs must have shape (n_steps + 1, n_obs).")
+            raise ValueError("obs must have shape (n_samples, n_obs).")
+        if taxis is not None:
+            taxis = np.asarray(taxis, dtype=np.float64)
+            if taxis.shape != (obs.shape[0],) or np.any(np.diff(taxis) < 0):
+                raise ValueError("Observed taxis must be non-decreasing with one entry per row of obs.")
+        elif baseline_index is not None or window is not None:
+            raise ValueError("baseline_index / window need the observations' own taxis.")
         self.obs_idx, self.obs = idx, obs
         self.obs_weights = None if weights is None else np.asarray(weights, dtype=np.float64)
+        self.obs_taxis, self.obs_baseline, self.obs_window = taxis, baseline_index, window
+
+    def set_observed_data(self, observed, obs_idx, channels=None, weights=None, baseline_index=1, window=(1, -1)):
+        """Observations from a ``Data2D``-like object (``data (n_channels, n_time)``, ``taxis`` in seconds after
+        ``start_time``) with the reference's misfit conventions as defaults.  ``channels``: rows of ``observed.data``
+        matched with the cells ``obs_idx`` (default: the first ``len(obs_idx)``).  The observed ``start_time`` is
+        aligned with the first source's ``start_time`` when both are set (``Data1D.interpolate``'s time offset)."""
+        idx = np.atleast_1d(np.asarray(obs_idx)).astype(np.int64)
+        rows = np.arange(len(idx)) if channels is None else np.atleast_1d(np.asarray(channels)).astype(np.int64)
+        data = np.asarray(observed.data, dtype=np.float64)[rows]
+        taxis = np.asarray(observed.taxis, dtype=np.float64).copy()
+        sim_start = getattr(self.source[0], "start_time", None) if self.source else None
+        obs_start = getattr(observed, "start_time", None)
+        if sim_start is not None and obs_start is not None:
+            taxis = taxis + (obs_start - sim_start).total_seconds()
+        self.set_observations(idx, np.ascontiguousarray(data.T), weights=weights, taxis=taxis,
+                              baseline_index=baseline_index, window=window)
 
     @property
     def n_models(self):
@@ -129,11 +168,14 @@ class PDS1D_Ensemble:
 
     # -- solve ------------------------------------------------------------------------------------
     def solve(self, dt, t_total=None, audit_models=(), snapshot_every=1, dtype="float64", models=None,
-              process_group=None, gather=True, split_audit=True, on_chip_assembly=True):
+              process_group=None, gather=True, split_audit=True, on_chip_assembly=True, scan_log2_eps=0.0):
         """Integrate every member with a fixed ``dt``.
 
         Ensembles in fp64 with 129..4096 cells assemble and factorise their matrices inside the run
         kernel (``fbr_run_zonal_f64``; ``on_chip_assembly=False`` selects the three-kernel path K1 + K1b + K3).
+
+        ``scan_log2_eps``: threshold below which a member's far scan terms are skipped (``fbr_run_opts``; default
+        2^-80, a positive value keeps every member's scans exact).
 
         ``models=(lo, hi)`` restricts the run to a contiguous block (multi-GPU sharding does this
         per rank when ``process_group`` / an initialised default group is given); ``misfit`` is then
@@ -192,14 +234,18 @@ class PDS1D_Ensemble:
         snap_models_d, n_audit = _engine.index_tensor(audit_unique - lo) if audit else (None, 0)
         obs_idx_d = obs_d = w_d = None
         n_obs = 0
+        sampling = None
         if self.obs_idx is not None:
-            if self.obs.shape[0] != n_steps + 1:
+            if self.obs_taxis is not None:  # interpolation plan of the observed times on this run's time axis
+                sampling = _engine.sample_plan(np.asarray(taxis), self.obs_taxis, self.obs_baseline, self.obs_window)
+            elif self.obs.shape[0] != n_steps + 1:
                 raise ValueError(f"obs has {self.obs.shape[0]} rows, the run has {n_steps + 1} time samples.")
             obs_idx_d, n_obs = _engine.index_tensor(self.obs_idx)
             obs_d = _engine.to_device(self.obs)
             w_d = None if self.obs_weights is None else _engine.to_device(self.obs_weights)
 
-        run_kw = dict(obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, obs_w=w_d, dtype=dtype)
+        run_kw = dict(obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, obs_w=w_d, dtype=dtype, sampling=sampling,
+                      scan_log2_eps=scan_log2_eps)
         n_rows = n_steps // snapshot_every if n_audit else 0
         host_snap = None
         if n_rows and M >= 8 * n_audit and M >= 512 and split_audit:
@@ -224,9 +270,10 @@ class PDS1D_Ensemble:
                 snap_a, _, _ = _engine.run(fac_a, p0_a, n_audit, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                                            snapshot_every=snapshot_every, zonal=zon_a, singular_flags=flags_a, **run_kw)
                 host_snap = _engine.to_host(_engine.as_f64(snap_a), sync=False)
-            _engine.reserve_ctas(n_audit)  # the audited members' CTAs stay resident next to the sweep's grid
+            # reserve_ctas: the audited members' CTAs stay resident next to the sweep's grid
             _, _, misfit_d = _engine.run(factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                         snapshot_every=0, zonal=zonal, singular_flags=flags_d, **run_kw)
+                                         snapshot_every=0, zonal=zonal, singular_flags=flags_d, reserve_ctas=n_audit,
+                                         **run_kw)
             main.wait_stream(side)
             snap_d = snap_a
         else:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FBR_VERSION 100 /* 0.1.0 */
+#define FBR_VERSION 200 /* 0.2.0: fbr_run_opts */
 
 typedef enum {
     FBR_OK = 0,
@@ -55,6 +55,11 @@ enum {
 
 int fbr_version(void);
 const char *fbr_last_error(void);
+
+/* Measurement aid: the fp64 issue peak of the current device in lane-level DFMA per second (8 independent chains per
+ * thread, 16 warps per SM, timed with CUDA events on `stream`; synchronous).  bench.py's compute-side roofline divides
+ * the fp64 operations K3 executes by this figure.  h_dfma_per_s: host; d_sink: 8 bytes of device scratch. */
+int fbr_probe_fp64_peak(double *h_dfma_per_s, double *d_sink, void *stream);
 
 /* Device facts the host layer sizes launches with.  Any out pointer may be NULL. */
 int fbr_device_info(int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_per_block_optin,
@@ -126,25 +131,71 @@ int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64
  *                 in elements), so the caller chooses (time, model, cell) or (model, time, cell)
  *                 order and can reserve a leading row for the initial state by offsetting snap.
  *   p_final     : NULL or (M, nx): state after the last step
- *   obs_idx/obs/obs_w/misfit : fused objective (NULL obs_idx disables it):
+ *   obs_idx/obs/obs_w/misfit : fused objective (NULL obs_idx disables it).  Without opts->n_samples the
+ *                 observations sit on the step times:
  *                 misfit[m] = sum_{n=1..n_steps} sum_k obs_w[k] (p^n[m, obs_idx[k]] - obs[n, k])^2
- *                 obs: (n_steps + 1, n_obs), row 0 unused; obs_w may be NULL (all ones)
+ *                 obs: (n_steps + 1, n_obs), row 0 unused; obs_w may be NULL (all ones).
+ *                 With opts->n_samples > 0 the observations have their OWN time axis (see fbr_run_opts).
+ *   opts        : NULL (all defaults) or a pointer to a struct fbr_run_opts in host memory, read during the call
  * The _f32 variant keeps state and factors in float (fp32 mode of north_star, gated at 1e-5).
  * Limits of this on-chip variant: nx <= fbr_run_max_nx(), n_src <= 64, n_obs <= 64.
  * ------------------------------------------------------------------------------------------ */
+
+/* Options of fbr_run_f64 / fbr_run_f32 / fbr_run_zonal_f64.  A zero-filled struct (with struct_bytes set) means
+ * "all defaults"; the library holds no state between calls.
+ *
+ * Observations on their own time axis — the misfit of the reference's history-matching workflow
+ * (src/fiberis/moose/templates/baseline_model_generator.py:394-403 with Data1D.interpolate,
+ * src/fiberis/analyzer/Data1D/core1D.py:732-822): the simulated channel is interpolated linearly onto the
+ * observed times, the sample at index `base_sample` is subtracted ("initial time calibration", :398), and the
+ * squared residuals of samples [first_sample, last_sample) are summed (:401, the reference uses [1:-1]) with one
+ * weight per channel (:403).  The host brackets every observed time t_j between two stored states once:
+ *     sample_row[j] = n  with taxis[n] <= t_j <= taxis[n + 1]   (-1: t_j outside the simulated range -> NaN,
+ *                                                                the reference's np.interp(left=nan, right=nan))
+ *     sample_w[j]   = (t_j - taxis[n]) / (taxis[n + 1] - taxis[n])   (0 when t_j == taxis[n]: row n + 1 is not read)
+ *     s_j[k] = p^n[k] + sample_w[j] (p^{n+1}[k] - p^n[k]),  p^0 = initial state
+ *     misfit[m] = sum_k obs_w[k] sum_{j = first_sample}^{last_sample - 1} ((s_j[k] - s_base[k]) - obs[j, k])^2
+ * obs is then (n_samples, n_obs).  row_first_sample: (n_steps + 2) int32, row_first_sample[r] = the first sample
+ * whose last needed state (row n + 1, or n when sample_w == 0) is >= r — samples must be ordered in time.
+ * Requires base_sample <= first_sample (or base_sample < 0: nothing is subtracted).  Sampled observations are
+ * evaluated by the 64-byte-per-thread kernel family only (fp64: any nx <= fbr_run_max_nx(); the call picks it). */
+typedef struct fbr_run_opts {
+    int32_t struct_bytes;            /* sizeof(fbr_run_opts) of the caller */
+    int32_t reserve_ctas;            /* leave this many CTA slots of the persistent grid free: a SMALL fbr_run_* launch
+                                        enqueued just before on another stream (the few recorded members of a sweep, whose
+                                        snapshots travel to the host while the sweep runs) then stays resident beside it */
+    int64_t snap_cell_stride;        /* 0 or 1: the cells of a snapshot row are contiguous.  Otherwise sample r of slot q,
+                                        cell i goes to snap[r * snap_row_stride + q * snap_model_stride + i * snap_cell_stride]:
+                                        snap_row_stride = 1, snap_cell_stride = n_rows writes the (cell, time) layout of
+                                        Data2D / pack_result directly (src/fiberis/simulator/core/pds.py:415) */
+    double scan_log2_eps;            /* far scan stages / cross-warp carry chains of a member are skipped when every
+                                        multiplier product they carry is below 2^scan_log2_eps in magnitude (decided per
+                                        member from its own factors); 0 = default (-80), > 0 = never skip (exact scans) */
+    int64_t n_samples;               /* 0: observations on the step times (see above) */
+    const int32_t *sample_row;       /* device (n_samples) */
+    const double *sample_w;          /* device (n_samples) */
+    const int32_t *row_first_sample; /* device (n_steps + 2) */
+    int32_t base_sample;             /* < 0: no baseline subtraction */
+    int32_t first_sample, last_sample;
+    int32_t reserved_;
+    int32_t *scan_mode;              /* NULL, or device (M) int32: receives how each member's sweeps were scanned
+                                        (0 exact, 1 neighbour-warp carry, 2 neighbour-warp carry + 4 scan stages);
+                                        written by the 64-byte-per-thread kernels only */
+} fbr_run_opts;
+
 int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,
                 int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
                 const int64_t *src_idx, int n_src, const double *src_table,
                 int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
                 int64_t snap_row_stride, int64_t snap_model_stride, double *snap, double *p_final, const int64_t *obs_idx, int n_obs,
-                const double *obs, const double *obs_w, double *misfit, void *stream);
+                const double *obs, const double *obs_w, double *misfit, const fbr_run_opts *opts, void *stream);
 
 int fbr_run_f32(const double *fl, const double *fr, const double *fg, const double *p0,
                 int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,
                 const int64_t *src_idx, int n_src, const double *src_table,
                 int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
                 int64_t snap_row_stride, int64_t snap_model_stride, float *snap, float *p_final, const int64_t *obs_idx, int n_obs,
-                const double *obs, const double *obs_w, double *misfit, void *stream);
+                const double *obs, const double *obs_w, double *misfit, const fbr_run_opts *opts, void *stream);
 
 /* K3 with ON-CHIP ASSEMBLY: fbr_assemble_zonal_f64 + fbr_factorize_f64 + fbr_run_f64 in one kernel, for
  * ensembles whose members share the mesh and differ in n_zones diffusivity values (BASELINE.json
@@ -163,16 +214,9 @@ int fbr_run_zonal_f64(const double *mesh, const double *zone_value, int n_zones,
                       int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
                       int64_t snap_row_stride, int64_t snap_model_stride, double *snap, double *p_final,
                       const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
-                      double *misfit, void *stream);
+                      double *misfit, const fbr_run_opts *opts, void *stream);
 
 int64_t fbr_run_max_nx(void);
-
-/* The persistent grid of fbr_run_* normally fills every CTA slot of the device.  A caller that has just
- * enqueued a SMALL fbr_run_* launch on another stream (e.g. the few recorded members of a sweep, whose
- * snapshots should travel to the host while the sweep is still running) asks the NEXT fbr_run_* call
- * of this thread to leave n slots free, so that both launches are resident together instead of the
- * small one delaying n persistent CTAs.  The reservation is consumed by that one call. */
-int fbr_run_reserve_ctas(int n);
 
 /* ------------------------------------------------------------------------------------------
  * K3L the same persistent integration for LONG meshes (fbr_run_max_nx() < nx <=

@@ -3,8 +3,9 @@
 TEST INFRASTRUCTURE ONLY.  This module exists so that (a) ``oracle/gen_golden.py`` can run the real
 reference in the build container to produce the committed fixtures under ``tests/golden/`` and
 (b) the optional ``tests/test_oracle_vs_reference.py`` can compare the oracle with the live
-reference when (and only when) ``/root/reference`` is present.  Nothing in ``fiberis_b200/``,
-``bench.py`` or the ``-m gpu`` tests imports it: ``/root/reference`` does not exist on the GPU box.
+reference when (and only when) ``/root/reference`` is present.  (c) ``bench.py --impl reference`` and ``tests/test_reference_suite.py`` can use the byte-identical copies
+that ``oracle/make_ref.py`` places in the git-ignored ``oracle/_ref/`` (``/root/reference`` does not exist
+on the GPU box).  Nothing in ``fiberis_b200/`` imports it.
 
 The reference imports ``matplotlib`` at module top (``src/fiberis/simulator/core/pds.py:5``,
 ``src/fiberis/analyzer/Data1D/core1D.py:6``) and matplotlib is not installed in this image, so a
@@ -17,11 +18,27 @@ import os
 import sys
 import types
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_SRC = os.environ.get("FIBERIS_REFERENCE_SRC", "/root/reference/src")
+# byte-identical copies made by oracle/make_ref.py (git-ignored; they travel to the GPU box)
+TRAVEL_SRC = os.path.join(_HERE, "_ref", "src")
+
+
+def _has(src) -> bool:
+    return os.path.isdir(os.path.join(src, "fiberis", "simulator"))
+
+
+def reference_src():
+    """Where the unmodified reference can be imported from: the mounted tree, else the travelling copy."""
+    if _has(REFERENCE_SRC):
+        return REFERENCE_SRC
+    if _has(TRAVEL_SRC):
+        return TRAVEL_SRC
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "fiberis", "simulator"))
+    return reference_src() is not None
 
 
 class _Anything:
@@ -60,11 +77,12 @@ def _install_matplotlib_stub() -> None:
 
 def import_reference():
     """Return the reference's (pds, matbuilder, tso, Data1D, Data2D, PDESolver_IMP, PDESolver_EXP)."""
-    if not reference_available():
-        raise ImportError(f"reference not mounted at {REFERENCE_SRC}")
+    src = reference_src()
+    if src is None:
+        raise ImportError(f"reference neither mounted at {REFERENCE_SRC} nor copied to {TRAVEL_SRC} (oracle/make_ref.py)")
     _install_matplotlib_stub()
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     from fiberis.simulator.core import pds  # type: ignore
     from fiberis.simulator.solver import matbuilder, PDESolver_IMP, PDESolver_EXP  # type: ignore
     from fiberis.simulator.optimizer import tso  # type: ignore

@@ -1,0 +1,222 @@
+// Round-2 experiment: restructured warp scan for the K3 sweep (scratch tool).
+//
+// OLD  : 5 Kogge-Stone stages (inclusive) + 1 shuffle for the exclusive carry  = 6 dependent shuffle levels, 6 shfl64.
+// FUSED: K stages, then the exclusive carry straight from two INDEPENDENT shuffles of the K-stage partials,
+//            c(lane) = Y_K(lane-1) + G_K(lane) * Y_K(lane-1-2^K),
+//        K = 4: exact over the warp, 5 levels / 6 shfl64;  K = 3: reach 16 chunks (128 cells), 4 levels / 5 shfl64.
+// NEAR : cross-warp carry from the neighbouring warp only (1 LDS + 1 FMA instead of the W x W table).
+// SPLIT: chunk-end pass as two half chains (depth 4 + 1 instead of 7).
+#include <cstdio>
+#include <cmath>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "../fiberis_b200/csrc/fbr_sweep.cuh"
+using namespace fbr;
+
+template <int K>
+struct Scan2 {
+    double f[K], b[K], gf, gb, ex_f, ex_b;
+};
+template <int K>
+__device__ __forceinline__ Scan2<K> scan2(double cf, double cb, int lane) {
+    Scan2<K> m;
+    double pf = cf, pb = cb;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const bool fa = lane >= (1 << s), ba = lane + (1 << s) < 32;
+        if (s < K) { m.f[s] = fa ? pf : 0.0; m.b[s] = ba ? pb : 0.0; }
+        if (s == K) {
+            const double uf = __shfl_up_sync(kAllLanes, pf, 1), ub = __shfl_down_sync(kAllLanes, pb, 1);
+            m.gf = lane >= 1 + (1 << K) ? uf : 0.0;
+            m.gb = lane + 1 + (1 << K) < 32 ? ub : 0.0;
+        }
+        const double upf = __shfl_up_sync(kAllLanes, pf, 1 << s), dnb = __shfl_down_sync(kAllLanes, pb, 1 << s);
+        if (fa) pf *= upf;
+        if (ba) pb *= dnb;
+    }
+    m.ex_f = __shfl_up_sync(kAllLanes, pf, 1);
+    m.ex_b = __shfl_down_sync(kAllLanes, pb, 1);
+    if (lane == 0) m.ex_f = 1.0;
+    if (lane == 31) m.ex_b = 1.0;
+    return m;
+}
+
+// MODE 0: old scheme.  MODE 1: fused final, E via one FMA on the publishing lane.
+template <int W, int K, bool NEAR, int MINB, bool SPLIT, int MODE>
+__global__ void __launch_bounds__(32 * W, MINB) k3v_kernel(const double *in, double *out, int n_steps) {
+    __shared__ __align__(16) double s_K[2][W][W];
+    __shared__ __align__(16) double s_E[2][W + 2];
+    __shared__ double s_dummy;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double l[8], r[8], g[8], x[8];
+    const double *p = in + ((size_t)(blockIdx.x % 64) * 32 * W + tid) * 32;
+    for (int j = 0; j < 8; ++j) { l[j] = p[j]; r[j] = p[8 + j]; g[j] = p[16 + j]; x[j] = p[24 + j]; }
+    const double cf = chunk_product<double, 8>(l), cb = chunk_product<double, 8>(g);
+    const ScanMultipliers sm = scan_multipliers<double>(cf, cb, lane);
+    const Scan2<(K < 5 ? K : 4)> s2 = scan2<(K < 5 ? K : 4)>(cf, cb, lane);
+    // exact table of warp-total products
+    __shared__ double s_T[2][W];
+    if (lane == 31) s_T[0][warp] = sm.tot_f;
+    if (lane == 0) s_T[1][warp] = sm.tot_b;
+    if (tid == 0) { s_E[0][0] = 0.0; s_E[1][W + 1] = 0.0; }
+    __syncthreads();
+    if (tid < W) {
+        double k = 1.0;
+        for (int v = W - 1; v >= 0; --v) { if (v >= tid) s_K[0][tid][v] = 0.0; else { s_K[0][tid][v] = k; k *= s_T[0][v]; } }
+        k = 1.0;
+        for (int v = 0; v < W; ++v) { if (v <= tid) s_K[1][tid][v] = 0.0; else { s_K[1][tid][v] = k; k *= s_T[1][v]; } }
+    }
+    __syncthreads();
+    // s_E[0][1 + v] = forward total of warp v (slot 0 stays zero); s_E[1][1 + v] = backward total of warp v (slot W+1 zero)
+    const unsigned st_f = smem_addr(lane == 31 ? &s_E[0][1 + warp] : &s_dummy);
+    const unsigned st_b = smem_addr(lane == 0 ? &s_E[1][1 + warp] : &s_dummy);
+    const unsigned ld_f = smem_addr(&s_E[0][warp]), ld_b = smem_addr(&s_E[1][warp + 2]);
+    const int keep_f = lane == 0 ? 0 : -1, keep_b = lane == 31 ? 0 : -1;
+#pragma unroll 1
+    for (int n = 0; n < n_steps; ++n) {
+        {   // forward
+            double e;
+            if (SPLIT) {
+                double a = x[0], b = x[4];
+                a = fma(-l[1], a, x[1]); b = fma(-l[5], b, x[5]);
+                a = fma(-l[2], a, x[2]); b = fma(-l[6], b, x[6]);
+                a = fma(-l[3], a, x[3]); b = fma(-l[7], b, x[7]);
+                e = fma((l[4] * l[5]) * (l[6] * l[7]), a, b);  // (a register in the real kernel)
+            } else e = chunk_end_fwd_plain<double, 8>(x, l);
+            double c;
+            if (MODE == 0) {
+                double y = e;
+#pragma unroll
+                for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+                c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
+                if (W > 1) sts_f64(st_f, y);
+            } else {
+                double y = e;
+#pragma unroll
+                for (int s = 0; s < K; ++s) y = fma(s2.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+                const double a = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
+                const double b = __shfl_up_sync(kAllLanes, y, 1 + (1 << K));
+                c = fma(s2.gf, b, a);
+                if (W > 1) sts_f64(st_f, fma(s2.f[0], c, e));  // inclusive total on lane 31 (f[0] = own chunk product)
+            }
+            if (W > 1) {
+                __syncthreads();
+                if (NEAR) c = fma(sm.ex_f, lds_f64(ld_f), c);
+                else {
+                    double cw = 0.0;
+#pragma unroll
+                    for (int v = 0; v < W - 1; ++v) cw = fma(s_K[0][warp][v], s_E[0][1 + v], cw);
+                    c = fma(sm.ex_f, cw, c);
+                }
+            }
+            chunk_apply_fwd_plain<double, 8>(x, l, r, c);
+        }
+        {   // backward
+            double e;
+            if (SPLIT) {
+                double a = x[7], b = x[3];
+                a = fma(-g[6], a, x[6]); b = fma(-g[2], b, x[2]);
+                a = fma(-g[5], a, x[5]); b = fma(-g[1], b, x[1]);
+                a = fma(-g[4], a, x[4]); b = fma(-g[0], b, x[0]);
+                e = fma((g[3] * g[2]) * (g[1] * g[0]), a, b);
+            } else e = chunk_end_bwd_plain<double, 8>(x, g);
+            double c;
+            if (MODE == 0) {
+                double z = e;
+#pragma unroll
+                for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+                c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+                if (W > 1) sts_f64(st_b, z);
+            } else {
+                double z = e;
+#pragma unroll
+                for (int s = 0; s < K; ++s) z = fma(s2.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+                const double a = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+                const double b = __shfl_down_sync(kAllLanes, z, 1 + (1 << K));
+                c = fma(s2.gb, b, a);
+                if (W > 1) sts_f64(st_b, fma(s2.b[0], c, e));
+            }
+            if (W > 1) {
+                __syncthreads();
+                if (NEAR) c = fma(sm.ex_b, lds_f64(ld_b), c);
+                else {
+                    double cw = 0.0;
+#pragma unroll
+                    for (int v = 1; v < W; ++v) cw = fma(s_K[1][warp][v], s_E[1][1 + v], cw);
+                    c = fma(sm.ex_b, cw, c);
+                }
+            }
+            chunk_apply_bwd_plain<double, 8>(x, g, c);
+        }
+    }
+    double *q = out + ((size_t)blockIdx.x * 32 * W + tid) * 8;
+    for (int j = 0; j < 8; ++j) q[j] = x[j];
+}
+
+static double *g_ref = nullptr;
+
+template <int W, int K, bool NEAR, int MINB, bool SPLIT, int MODE>
+void run(const char *name, const double *in, double *out, int n_steps) {
+    auto kern = k3v_kernel<W, K, NEAR, MINB, SPLIT, MODE>;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, 0);
+    const int ctas = occ * 148;
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    kern<<<ctas, 32 * W>>>(in, out, 10);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(a);
+        kern<<<ctas, 32 * W>>>(in, out, n_steps);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms; cudaEventElapsedTime(&ms, a, b);
+        best = ms < best ? ms : best;
+    }
+    // numerics: compare the first 64 CTAs' results after a short run with the first variant's
+    const size_t n = (size_t)64 * 32 * W * 8;
+    kern<<<64, 32 * W>>>(in, out, 50);
+    double *h = (double *)malloc(n * 8);
+    cudaMemcpy(h, out, n * 8, cudaMemcpyDeviceToHost);
+    double err = 0.0, mx = 0.0;
+    if (!g_ref) { g_ref = h; }
+    else { for (size_t i = 0; i < n; ++i) { err = fmax(err, fabs(h[i] - g_ref[i])); mx = fmax(mx, fabs(g_ref[i])); } free(h); }
+    const double cells = (double)ctas * 256 * W;
+    printf("%-46s W=%d K=%d near=%d split=%d occ=%d regs=%3d  %7.3f us/step  %.3e cu/s  C3-equiv %.2f ms  relerr=%.1e %s\n", name, W, K,
+           (int)NEAR, (int)SPLIT, occ, fa.numRegs, best * 1e3 / n_steps, cells * n_steps / (best * 1e-3),
+           2.097152e10 / (cells * n_steps / (best * 1e-3)) * 1e3, mx > 0 ? err / mx : 0.0, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+    const size_t n = (size_t)64 * 512 * 32;
+    double *in, *out; cudaMalloc(&in, n * 8); cudaMalloc(&out, (size_t)2048 * 512 * 8 * 8);
+    double *h = (double *)malloc(n * 8);
+    // per thread: l[8], r[8], g[8], x[8]; multipliers 0.1 .. 0.6 (chunk products ~ 2^-16: a realistic decay)
+    for (size_t i = 0; i < n; ++i) {
+        const double u = ((i * 2654435761u) % 1000) / 1000.0;
+        const int which = (i % 32) / 8;
+        h[i] = which == 1 ? 0.3 + 0.4 * u : which == 3 ? u : 0.1 + 0.5 * u;
+    }
+    cudaMemcpy(in, h, n * 8, cudaMemcpyHostToDevice);
+    const int S = 3000;
+    run<4, 5, false, 4, false, 0>("old: 5 stages + shift, K-table", in, out, S);
+    run<4, 5, true, 4, false, 0>("old scan, near carry", in, out, S);
+    run<4, 4, false, 4, false, 1>("fused K=4 (exact), K-table", in, out, S);
+    run<4, 4, true, 4, false, 1>("fused K=4 (exact in warp), near", in, out, S);
+    run<4, 3, true, 4, false, 1>("fused K=3 (reach 128 cells), near", in, out, S);
+    run<4, 2, true, 4, false, 1>("fused K=2 (reach 64 cells), near", in, out, S);
+    run<4, 4, false, 4, true, 1>("fused K=4, K-table, split chunk end", in, out, S);
+    run<4, 4, true, 4, true, 1>("fused K=4, near, split chunk end", in, out, S);
+    run<4, 3, true, 4, true, 1>("fused K=3, near, split chunk end", in, out, S);
+    run<4, 4, true, 5, false, 1>("fused K=4, near, 5 CTAs/SM", in, out, S);
+    run<4, 3, true, 5, false, 1>("fused K=3, near, 5 CTAs/SM", in, out, S);
+    run<2, 5, false, 8, false, 0>("W=2 old", in, out, S);
+    run<2, 4, false, 8, false, 1>("W=2 fused K=4 exact", in, out, S);
+    run<2, 4, true, 8, false, 1>("W=2 fused K=4 near", in, out, S);
+    run<2, 3, true, 8, false, 1>("W=2 fused K=3 near", in, out, S);
+    run<8, 5, false, 2, false, 0>("W=8 old", in, out, S);
+    run<8, 4, false, 2, false, 1>("W=8 fused K=4 exact", in, out, S);
+    run<8, 4, true, 2, false, 1>("W=8 fused K=4 near", in, out, S);
+    return 0;
+}
