@@ -10,14 +10,19 @@ batch of its own members (weak scaling) and the per-member misfits are all-gathe
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c4|c1]
 
-  value ....... whole-job cell-updates/s, inputs resident in HBM, CUDA events around the three kernels
+  value ....... whole-job cell-updates/s, inputs resident in HBM, CUDA events around the run kernel
   e2e ......... the same through the public API (PDS1D_Ensemble.solve) with HOST arrays in and out
+  parity ...... GATE: the audited members' full snapshots and sampled members' misfits of the
+                TIMED run against the banded C oracle, fp64 gate 1e-10; the run exits non-zero when it fails
   roofline .... K3 alone: 16 B/cell-update (read p^n + write p^{n+1}) / measured launch time vs the
                 measured HBM copy peak (MEASURED_PEAKS.json).  K3 keeps pressure and factors on chip,
-                so this ALGORITHMIC figure can exceed 1: `traffic` is the ncu-measured DRAM bytes.
+                so this ALGORITHMIC figure can exceed 1: `traffic` is the ncu-measured DRAM bytes; the bound
+                that really binds is in roofline.compute: fp64 operations executed / the measured fp64 issue peak
+  other_workloads  c4: BASELINE.json configs[3], the FIXED 1M x 512 x 2000 ensemble split over the N ranks
+                (strong scaling, misfit all-gather and per-rank H2D of the zone values inside e2e); c2 / c5 at N = 1
   cpu_baseline  the banded C oracle (OpenMP over members) on a bounded sample of the same workload
-  --impl reference : the reference's algorithm (dense nx*nx matrix per step + scipy.linalg.solve)
-                restated in oracle/pds_oracle.py, one member per host core, bounded sample per step.
+  --impl reference : the UNMODIFIED reference (fiberis.simulator, byte-identical copy in oracle/_ref made by
+                oracle/make_ref.py; matplotlib stubbed), one member per host core, bounded sample per step.
 """
 from __future__ import annotations
 
@@ -68,12 +73,20 @@ def emit_line(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
-def make_workload(name, world=1):
+C4_TOTAL_MEMBERS = 1_000_000  # BASELINE.json configs[3]
+
+
+def make_workload(name, world=1, strong=False):
     """Synthetic inputs of SURVEY.md 8(d) (C3 recipe; C4 is the same recipe at 512 cells).  With
-    world > 1 the ensemble has world x (members per GPU) members; rank r owns the r-th block."""
+    world > 1 the ensemble has world x (members per GPU) members; rank r owns the r-th block.
+    strong=True (c4 only): the ensemble is BASELINE.json's fixed 1M members whatever the world size."""
     M, nx, n_steps, desc = WORKLOADS[name]
     M_per_gpu = M
     M = M * world
+    if strong:
+        assert name == "c4" and C4_TOTAL_MEMBERS % world == 0
+        M, M_per_gpu = C4_TOTAL_MEMBERS, C4_TOTAL_MEMBERS // world
+        desc = f"C4: 1M models x 512 cells x 2000 steps split over {world} GPU(s) (BASELINE.json configs[3], strong scaling)"
     seed = {"c3": 303, "c4": 404}[name]
     rng = np.random.default_rng(seed)
     mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
@@ -84,10 +97,11 @@ def make_workload(name, world=1):
     return dict(name=name, desc=desc, M=M, M_per_gpu=M_per_gpu, nx=nx, n_steps=n_steps, dt=1.0, mesh=mesh, zones=8, zone=zone,
                 zv=10.0 ** theta, sidx=np.array([nx // 4, 3 * nx // 4]), srcs=srcs,
                 obs_idx=np.linspace(1, nx - 2, 16).astype(np.int64),
-                # 4 audited members (full snapshots every step) in every rank's block
-                audit=[r * M_per_gpu + a for r in range(world)
-                       for a in (0, M_per_gpu // 3, (2 * M_per_gpu) // 3, M_per_gpu - 1)],
-                seed=seed)
+                # audited members (full snapshots every step): 4 in every rank's block; C4 strong: 8 in the whole ensemble
+                audit=([int(v) for v in np.linspace(0, M - 1, 8)] if strong else
+                       [r * M_per_gpu + a for r in range(world)
+                        for a in (0, M_per_gpu // 3, (2 * M_per_gpu) // 3, M_per_gpu - 1)]),
+                seed=seed, strong=strong)
 
 
 def build_ensemble(w):
@@ -261,10 +275,47 @@ def single_step_probe(E, torch, peak):
                           "peak": peak, "unit": "GB/s", "frac": gbs2 / peak, "cell_updates_per_s": M * nx / t2 * 1e3}}
 
 
+def _ref_available():
+    from oracle import _refshim
+    return _refshim.reference_available()
+
+
+def _ref_model(mesh, D, initial, lbc, rbc, sidx, srcs):
+    """A model object of the UNMODIFIED reference (fiberis.simulator.core.pds.PDS1D_MultiSource)."""
+    import contextlib
+    import datetime
+    import io
+
+    from oracle import _refshim
+    R = _refshim.import_reference()
+    p = R.pds.PDS1D_MultiSource()
+    with contextlib.redirect_stdout(io.StringIO()):
+        p.set_mesh(np.asarray(mesh, dtype=float))
+        p.set_source([R.Data1D(data=np.asarray(d, float), taxis=np.asarray(t, float),
+                               start_time=datetime.datetime(2020, 1, 1)) for t, d in srcs])
+        p.set_bcs(lbc, rbc)
+        p.set_initial(np.asarray(initial, dtype=float))
+        p.set_diffusivity(np.asarray(D, dtype=float))
+        p.set_sourceidx([int(v) for v in sidx])
+        p.set_t0(0.0)
+    return p
+
+
 def _ref_member(args):
-    """One member through the reference's algorithm: dense (nx, nx) matrix + scipy.linalg.solve per step."""
+    """One member through the reference: its own PDS1D_MultiSource.solve when oracle/_ref (or the mounted tree) is
+    there, else the reference's algorithm restated in oracle/pds_oracle.py (dense (nx, nx) matrix + scipy.linalg.solve)."""
+    import contextlib
+    import io
+    mesh, D, sidx, srcs, dt, steps, real = args
+    if real:
+        p = _ref_model(mesh, D, np.zeros(len(mesh)), "Neumann", "Neumann", sidx, srcs)
+        t = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            p.solve(dt=dt, t_total=steps * dt)
+        el = time.perf_counter() - t
+        assert p.snapshot.shape == (steps + 1, len(mesh))
+        return el
     from oracle import pds_oracle as O
-    mesh, D, sidx, srcs, dt, steps = args
     t = time.perf_counter()
     O.solve_fixed(mesh, D, np.zeros(len(mesh)), "Neumann", "Neumann", sidx, srcs, 0.0, dt, steps * dt, dense=True,
                   rebuild_every_step=True)
@@ -272,17 +323,19 @@ def _ref_member(args):
 
 
 def run_reference_arm(args):
-    """--impl reference: rank 0 only; every 'step' is a bounded sample (one member per host core,
-    ref_steps time steps each) of the same workload, through the reference's dense algorithm."""
+    """--impl reference: rank 0 only; every 'step' is a bounded sample of the same workload — one member per host
+    core (at most 8: BASELINE.md 4.1), ref_steps time steps each — through the UNMODIFIED reference's own
+    PDS1D_MultiSource.solve (oracle/_ref: byte-identical copies made by oracle/make_ref.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     w = make_workload(args.workload)
     cores = os.cpu_count() or 1
-    procs = max(1, min(cores, 64, w["M"]))
-    ref_steps = 12 if w["nx"] >= 1024 else (40 if w["nx"] >= 512 else w["n_steps"])
-    jobs = [(w["mesh"], w["zv"][m % w["M"]][w["zone"]], w["sidx"], w["srcs"], w["dt"], ref_steps) for m in range(procs)]
+    real = _ref_available()
+    procs = max(1, min(cores, 8 if real else 64, w["M"]))
+    ref_steps = 100 if real else (12 if w["nx"] >= 1024 else 40)
+    jobs = [(w["mesh"], w["zv"][m % w["M"]][w["zone"]], w["sidx"], w["srcs"], w["dt"], ref_steps, real) for m in range(procs)]
     times = []
     with mp.get_context("fork").Pool(procs) as pool:
         for it in range(args.warmup + args.steps):
@@ -293,43 +346,59 @@ def run_reference_arm(args):
     work = procs * ref_steps * w["nx"]
     ms = 1e3 * float(np.mean(times))
     value = work / (ms / 1e3)
-    sample = (f"{procs} members (one per process) x {w['nx']} cells x {ref_steps} steps per step; reference "
-              f"algorithm restated in oracle/pds_oracle.py: dense (nx,nx) A rebuilt every step + scipy.linalg.solve")
+    how = ("the UNMODIFIED reference (fiberis.simulator.core.pds.PDS1D_MultiSource.solve from oracle/_ref, matplotlib stubbed; "
+           f"NumPy {np.__version__})" if real else
+           "reference algorithm restated in oracle/pds_oracle.py (oracle/_ref missing): dense (nx,nx) A rebuilt every step + scipy.linalg.solve")
+    sample = f"{procs} members (one per process) x {w['nx']} cells x {ref_steps} steps per step; {how}"
+    kind = "reference" if real else "port"
     line = {"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["desc"], "seed": w["seed"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit_line(line)
 
 
 def run_single_reference_arm(args):
-    """--impl reference for single-model workloads: C1 goes through the reference's dense algorithm; at 1e5 /
+    """--impl reference for single-model workloads: C1 runs IN FULL through the unmodified reference; at 1e5 /
     1e7 cells the reference cannot run at all (dense nx*nx matrix = 80 GB / 800 TB, matbuilder.py:33), so the
     banded NumPy oracle is timed instead and the line says so."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    import contextlib
+    import io
+
     from oracle import pds_oracle as O
     w = make_single(args.workload)
     dense = w["nx"] <= 4096
+    real = dense and _ref_available()
     ss = w["n_steps"] if dense else max(5, int(2e8 // w["nx"]))
     times = []
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        O.solve_fixed(w["mesh"], w["D"], w["initial"], w["lbc"], w["rbc"], w["sidx"], w["srcs"], 0.0, w["dt"],
-                      ss * w["dt"], dense=dense, rebuild_every_step=dense)
+        if real:
+            p = _ref_model(w["mesh"], w["D"], w["initial"], w["lbc"], w["rbc"], w["sidx"], w["srcs"])
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                p.solve(dt=w["dt"], t_total=ss * w["dt"])
+        else:
+            t0 = time.perf_counter()
+            O.solve_fixed(w["mesh"], w["D"], w["initial"], w["lbc"], w["rbc"], w["sidx"], w["srcs"], 0.0, w["dt"],
+                          ss * w["dt"], dense=dense, rebuild_every_step=dense)
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
     value = w["nx"] * ss / float(np.mean(times))
-    sample = (f"{w['nx']} cells x {ss} steps; " + ("reference algorithm (dense A rebuilt every step + scipy.linalg.solve)"
-              if dense else "reference cannot run at this size (dense nx^2 matrix); banded NumPy oracle (dgttrs per step) timed instead"))
+    sample = (f"{w['nx']} cells x {ss} steps; " + (
+        "the UNMODIFIED reference (PDS1D_MultiSource.solve from oracle/_ref)" if real else
+        "reference algorithm restated (dense A rebuilt every step + scipy.linalg.solve)" if dense else
+        "reference cannot run at this size (dense nx^2 matrix); banded NumPy oracle (dgttrs per step) timed instead"))
     emit_line({"impl": "reference", "metric": "cell-updates/sec (fp64)", "value": value, "unit": "cell-updates/s",
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": {"workload": w["desc"], "seed": w["seed"], "sample": sample},
-                      "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": sample},
+                      "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": 1, "kind": "reference" if real else "port",
+                                       "sample": sample},
                       "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0})
 
@@ -467,8 +536,29 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
                 "d2h_bytes_per_step": int(p.snapshot.nbytes), "api": "PDS1D_MultiSource.solve(host arrays) -> snapshot ndarray"},
         "gpu_launches": int(launches), "clocks": clocks.summary() if sampler else None,
     }
+    # ---- parity gate: the timed run's stored rows against the banded C oracle ----
+    from oracle import c_oracle as CO
+    from oracle import pds_oracle as O
+    t0 = time.perf_counter()
+    budget = 1.2e9  # cell-updates of single-threaded oracle work (~10 s)
+    rows_checked = min(n_steps // every, max(1, int(budget // (nx * every))))
+    ss_par = rows_checked * every
+    ref, _, _ = CO.run(w["mesh"], w["D"], w["initial"], ss_par, dt, w["lbc"], w["rbc"], w["sidx"], table[:ss_par], every=every)
+    got = p.snapshot[1: 1 + rows_checked]
+    rel = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+    num, den = np.linalg.norm(got - ref, axis=1), np.linalg.norm(ref, axis=1)
+    full_axis = np.asarray(O.time_axis(0.0, dt, w["T"]))
+    kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
+    line["parity"] = {"rel_max": rel, "l2_max": float(np.max(num[den > 0] / den[den > 0])), "gate": 1e-10,
+                      "taxis_equal": bool(np.array_equal(p.taxis, full_axis[kept])),
+                      "checked": f"stored rows 1..{rows_checked} of the timed run (time steps 1..{ss_par} of {n_steps}, every "
+                                 f"{every}) against oracle/pds_oracle.c (banded, pivoted, 1 thread)",
+                      "oracle_seconds": time.perf_counter() - t0}
+    line["parity"]["passed"] = bool(rel <= 1e-10 and line["parity"]["l2_max"] <= 1e-10 and line["parity"]["taxis_equal"])
+    if emit and not line["parity"]["passed"]:
+        print("PARITY GATE FAILED: " + json.dumps(line["parity"]), file=sys.stderr)
+        raise SystemExit(3)
     if not args.no_cpu:
-        from oracle import c_oracle as CO
         ss = n_steps if nx * n_steps <= 4e8 else max(10, int(4e8 // nx))
         t0 = time.perf_counter()
         CO.run(w["mesh"], w["D"], w["initial"], ss, dt, w["lbc"], w["rbc"], w["sidx"], table[:ss], every=0)
@@ -481,24 +571,56 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
     return line
 
 
-def run_gpu_arm(args):
+FP64_OPS_PER_STEP_THREAD = {0: 56, 1: 50, 2: 48}  # DFMA + DMUL per time step and thread (8 cells) of K3's step loops, by
+# scan mode (profiles/r02_k3_sass_loops.txt: the SASS instruction mix of run_onchipx_kernel<double,8,4,4,ZONAL>)
+USEFUL_FP64_OPS_PER_CU = 3  # forward FMA, scaling MUL, backward FMA of the two-sweep solve
+
+
+def parity_gate(w, lo, audit_local, snap_gpu, taxis_gpu, misfit_gpu, obs_host, table, check_members, f32):
+    """BASELINE.md 4.3 — the TIMED run against the banded C oracle (oracle/pds_oracle.c, pivoted gttrf/gttrs): full
+    snapshots of the audited members, misfits of sampled members, bit-equal time axis."""
+    from oracle import c_oracle as CO
+    from oracle import pds_oracle as O
+    gate = 1e-5 if f32 else 1e-10
+    nx, n_steps, dt = w["nx"], w["n_steps"], w["dt"]
+    p0 = np.zeros(nx)
+    rel_max = l2_max = 0.0
+    t0 = time.perf_counter()
+    for q, m_local in enumerate(audit_local):
+        D = w["zv"][lo + m_local][w["zone"]]
+        ref, _, _ = CO.run(w["mesh"], D, p0, n_steps, dt, "Neumann", "Neumann", w["sidx"], table, every=1)
+        got = snap_gpu[q][1:]
+        assert got.shape == ref.shape
+        rel_max = max(rel_max, float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+        num, den = np.linalg.norm(got - ref, axis=1), np.linalg.norm(ref, axis=1)
+        ok = den > 0
+        l2_max = max(l2_max, float(np.max(num[ok] / den[ok])))
+    mis_rel = 0.0
+    for m_local in check_members:
+        D = w["zv"][lo + m_local][w["zone"]]
+        _, _, ref = CO.run(w["mesh"], D, p0, n_steps, dt, "Neumann", "Neumann", w["sidx"], table, every=0,
+                           obs_idx=w["obs_idx"], obs=obs_host)
+        mis_rel = max(mis_rel, abs(float(misfit_gpu[m_local]) - ref) / max(abs(ref), 1e-300))
+    taxis_equal = bool(np.array_equal(np.asarray(taxis_gpu), np.asarray(O.time_axis(0.0, dt, n_steps * dt))))
+    misfit_gate = 1e-3 if f32 else 1e-8  # a sum of squared differences of pressures that are each within the gate
+    out = {"rel_max": rel_max, "l2_max": l2_max, "taxis_equal": taxis_equal, "misfit_rel_max": mis_rel, "gate": gate,
+           "misfit_gate": misfit_gate,
+           "checked": f"{len(audit_local)} audited members x ({n_steps + 1}, {nx}) snapshots of the timed run + misfits of "
+                      f"{len(check_members)} sampled members, against oracle/pds_oracle.c (banded, pivoted, 1 thread)",
+           "oracle_seconds": time.perf_counter() - t0}
+    out["passed"] = bool(rel_max <= gate and l2_max <= gate and taxis_equal and mis_rel <= misfit_gate)
+    return out
+
+
+def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, want_probe):
+    """One ensemble workload on this rank's shard: device-resident leg (CUDA events), end-to-end leg through
+    PDS1D_Ensemble.solve (host arrays in and out), parity gate.  Returns the result dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
 
     from fiberis_b200 import _cabi, _engine as E
     from fiberis_b200.simulator.core.ensemble import gather_misfit, shard_bounds
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    _cabi.require_cuda()
-
-    w = make_workload(args.workload, world)
     M, nx, n_steps, dt = w["M_per_gpu"], w["nx"], w["n_steps"], w["dt"]
     lo, hi = shard_bounds(w["M"], world, rank)
     assert hi - lo == M
@@ -517,9 +639,6 @@ def run_gpu_arm(args):
     obs_idx_d, n_obs = E.index_tensor(w["obs_idx"])
     audit_d, n_audit = E.index_tensor(np.asarray(my_audit, dtype=np.int64))
     # observations = member 0's pressure at the observation cells (untimed set-up run on the device)
-    f32 = args.dtype == "f32"  # fp32 MODE of north_star (state and factors in float; gate 1e-5), reported separately
-    # fp64: assembly + factorisation inside the run kernel (fbr_run_zonal_f64); --three-kernels / fp32: K1 + K1b + K3
-    on_chip = not f32 and not args.three_kernels
     if on_chip:  # through the same code path as the timed run: the generating member's misfit is then exactly 0
         snap0, _, _ = E.run(None, p0_d, 1, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1,
                             zonal=(mesh_d, zv0_d, zone_d, dt, None))
@@ -532,8 +651,11 @@ def run_gpu_arm(args):
     obs_host = obs_d.cpu().numpy()
     del snap0
     flags_d = E.zonal_flags(M, mesh_d.device)
-    snap_d = torch.empty((n_audit, n_steps + 1, nx), dtype=torch.float32 if f32 else torch.float64, device=mesh_d.device)
+    snap_d = None
+    if n_audit:
+        snap_d = torch.empty((n_audit, n_steps + 1, nx), dtype=torch.float32 if f32 else torch.float64, device=mesh_d.device)
     misfit_d = torch.empty(M, dtype=torch.float64, device=mesh_d.device)
+    modes_d = torch.full((M,), -1, dtype=torch.int32, device=mesh_d.device)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=mesh_d.device)  # > 126 MB L2
 
     def hot_path(ev=None):
@@ -545,13 +667,13 @@ def run_gpu_arm(args):
             fac, zonal = E.factorize(*diag, check_singular=False), None
         if ev:
             ev[0].record()
-        E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1,
+        E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1 if n_audit else 0,
               snap_models=audit_d, n_snap_models=n_audit, obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d,
               snap_out=snap_d, misfit_out=misfit_d, dtype="float32" if f32 else "float64", zonal=zonal,
-              singular_flags=flags_d if on_chip else None)
+              singular_flags=flags_d if on_chip else None, scan_mode_out=modes_d)
         if ev:
             ev[1].record()
-        return gather_misfit(misfit_d, M * world) if world > 1 else misfit_d
+        return gather_misfit(misfit_d, w["M"]) if world > 1 else misfit_d
 
     def sync_all():
         torch.cuda.synchronize()
@@ -559,7 +681,7 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         flush.zero_()
         hot_path()
     sync_all()
@@ -568,7 +690,7 @@ def run_gpu_arm(args):
     step_ms, k3_ms = [], []
     launches0 = _cabi.launch_count()
     with ClockSampler(local_rank) as clocks:
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush.zero_()  # L2 flush between timed iterations
             sync_all()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -579,23 +701,25 @@ def run_gpu_arm(args):
             sync_all()
             step_ms.append(e0.elapsed_time(e1))
             k3_ms.append(k0.elapsed_time(k1))
-    launches = (_cabi.launch_count() - launches0) // max(args.steps, 1)
+    launches = (_cabi.launch_count() - launches0) // max(steps, 1)
     total_ms = float(np.sum(step_ms))
     t = torch.tensor([total_ms, float(np.sum(k3_ms))], dtype=torch.float64, device=mesh_d.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, k3_total_ms = float(t[0]), float(t[1])
     misfit_resident = misfit_d.cpu().numpy().copy()
+    modes = np.bincount(modes_d.cpu().numpy().clip(min=0), minlength=3)[:3] if not f32 else None
+    snap_resident = snap_d.cpu().numpy() if (snap_d is not None and w["strong"]) else None
 
     # ---- leg 2: end to end through the public API, host arrays in and out ----------------------------
     ens = build_ensemble(w)
     ens.set_observations(w["obs_idx"], obs_host)
-    h2d = (w["mesh"].nbytes + w["zv"].nbytes + w["zone"].nbytes + table.nbytes + obs_host.nbytes + 8 * nx
-           + 8 * len(w["sidx"]) + 8 * len(w["obs_idx"]) + 8 * len(w["audit"]))
-    d2h = 8 * M * world + 8 * n_steps * n_audit * nx
+    h2d = (w["mesh"].nbytes + w["zv"][lo:hi].nbytes + w["zone"].nbytes + table.nbytes + obs_host.nbytes + 8 * nx
+           + 8 * len(w["sidx"]) + 8 * len(w["obs_idx"]) + 8 * len(my_audit))
+    d2h = 8 * w["M"] + 8 * n_steps * n_audit * nx
     del snap_d
     e2e_s = []
-    for it in range(2 + args.steps):
+    for it in range(2 + steps):
         flush.zero_()
         sync_all()
         t0 = time.perf_counter()
@@ -612,46 +736,116 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_total_s = float(t[0])
 
+    # ---- parity gate on the timed run's results (this rank's audited members, sampled members of its shard) ----
+    parity = None
     if rank == 0:
-        peak, peak_src = measured_peak()
-        k3_s = k3_total_ms / 1e3 / args.steps
-        b_alg = B_ALG / 2 if f32 else B_ALG
-        achieved = work * b_alg / k3_s / 1e9
+        sample = sorted({int(v) for v in np.linspace(1, M - 1, 8)})
+        parity = parity_gate(w, lo, my_audit, ens.snapshot if my_audit else [], ens.taxis, misfit_resident, obs_host, table,
+                             sample, f32)
+        if snap_resident is not None and my_audit:
+            parity["resident_equals_e2e_snapshots"] = bool(np.array_equal(snap_resident, ens.snapshot))
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak()
+    k3_s = k3_total_ms / 1e3 / steps
+    b_alg = B_ALG / 2 if f32 else B_ALG
+    achieved = work * b_alg / k3_s / 1e9
+    res = {
+        "value": work * world * steps / (total_ms / 1e3), "ms_per_step": total_ms / steps, "steps": steps,
+        "workload": w["desc"], "members_total": w["M"], "members_per_gpu": M, "n_audit": n_audit, "n_obs": int(n_obs),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(w["name"]) if (on_chip and w["name"] == "c3") else None,
+                     "kernel": ("run_onchipx_kernel<float,16,W> (K3, fp32 mode)" if f32 else
+                                "run_onchipx_kernel<double,8,W,ZONAL> (K3 fp64 x8, on-chip assembly)" if on_chip else
+                                "run_onchipx_kernel<double,8,W> (K3, fp64 x8)"),
+                     "kernel_ms": k3_s * 1e3, "peak_source": peak_src,
+                     "note": "algorithmic 16 B/cell-update (SURVEY 8(d)); K3 keeps pressure + factors on chip for all time "
+                             "steps, so frac > 1 is expected and HBM does not bind (see traffic = ncu DRAM bytes per "
+                             "launch): the binding resource is the fp64 pipe / issue, reported in `compute`"},
+        "e2e": {"value": work * world * steps / e2e_total_s, "unit": "cell-updates/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "PDS1D_Ensemble.solve(host arrays) -> misfit + audit snapshots as numpy"},
+        "gpu_launches": int(launches) * steps, "clocks": clocks.summary(), "parity": parity,
+    }
+    if modes is not None and want_probe:
+        fp64_peak = E.fp64_peak()
+        ops_cu = float(sum(FP64_OPS_PER_STEP_THREAD[k] * int(modes[k]) for k in range(3)) / max(int(modes.sum()), 1) / 8.0)
+        cu_s = work / k3_s
+        res["roofline"]["compute"] = {
+            "bound": "fp64", "peak": fp64_peak, "unit": "lane-level DFMA/s (measured: fbr_probe_fp64_peak, 8 independent "
+            "chains per thread, 16 warps/SM)", "executed_fp64_ops_per_cu": ops_cu, "useful_fp64_ops_per_cu": USEFUL_FP64_OPS_PER_CU,
+            "achieved": cu_s * ops_cu, "frac_of_fp64_peak": cu_s * ops_cu / fp64_peak,
+            "frac_useful": cu_s * USEFUL_FP64_OPS_PER_CU / fp64_peak,
+            "scan_modes": {"exact (5 stages + warp table)": int(modes[0]), "neighbour-warp carry": int(modes[1]),
+                           "neighbour-warp carry + 4 stages": int(modes[2])},
+            "ncu_pipe_fp64_pct": ncu_traffic("c3_pipe_fp64_pct") if w["name"] == "c3" else None}
+    return res
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from fiberis_b200 import _cabi, _engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _cabi.require_cuda()
+
+    f32 = args.dtype == "f32"  # fp32 MODE of north_star (state and factors in float; gate 1e-5), reported separately
+    # fp64: assembly + factorisation inside the run kernel (fbr_run_zonal_f64); --three-kernels / fp32: K1 + K1b + K3
+    on_chip = not f32 and not args.three_kernels
+    strong = args.workload == "c4" and args.strong
+    w = make_workload(args.workload, world, strong=strong)
+    res = ensemble_leg(args, w, world, rank, local_rank, args.steps, max(args.warmup, 3), f32, on_chip, True)
+    del w
+    c4 = None
+    if not args.no_extra and not f32 and args.workload == "c3":
+        # BASELINE.json configs[3] on the driver's clock: the FIXED 1M-member ensemble split over the N ranks
+        torch.cuda.empty_cache()
+        w4 = make_workload("c4", world, strong=True)
+        c4 = ensemble_leg(args, w4, world, rank, local_rank, 2, 1, False, True, False)
+        del w4
+        torch.cuda.empty_cache()
+
+    if rank == 0:
+        n_steps, nx = WORKLOADS[args.workload][2], WORKLOADS[args.workload][1]
         line = {
             "metric": "cell-updates/sec (fp32 mode)" if f32 else "cell-updates/sec (fp64)",
-            "value": work * world * args.steps / (total_ms / 1e3),
-            "unit": "cell-updates/s",
+            "value": res["value"], "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if f32 else "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "seed": w["seed"], "members_per_gpu": M, "cells": nx, "time_steps": n_steps,
-                       "diffusivity": "zonal, 8 zones, 10**U(-1,1)", "sources": 2, "obs_cells": int(n_obs),
-                       "audit_members_with_full_snapshots": n_audit, "bc": "Neumann/Neumann",
+            "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f32" if f32 else "f64", "data": "synthetic",
+            "config": {"workload": res["workload"], "seed": {"c3": 303, "c4": 404}[args.workload],
+                       "members_per_gpu": res["members_per_gpu"], "cells": nx, "time_steps": n_steps,
+                       "diffusivity": "zonal, 8 zones, 10**U(-1,1)", "sources": 2, "obs_cells": res["n_obs"],
+                       "audit_members_with_full_snapshots": res["n_audit"], "bc": "Neumann/Neumann",
                        "l2": "flushed between timed iterations (512 MiB memset)",
                        "timed_kernels": ("K3 run_onchip with on-chip assembly + factorisation (fbr_run_zonal_f64)" if on_chip
                                          else "K1 assemble_zonal + K1b factorize + K3 run_onchip")
                                         + (" + NCCL all-gather of misfits" if world > 1 else "")},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(args.workload) if (on_chip and args.workload == "c3") else None,
-                         "kernel": ("run_onchipx_kernel<float,16,W> (K3, fp32 mode)" if f32 else
-                                    "run_onchipx_kernel<double,8,W,ZONAL> (K3 fp64 x8, on-chip assembly)" if on_chip else
-                                    "run_onchipx_kernel<double,8,W> (K3, fp64 x8)"),
-                         "kernel_ms": k3_s * 1e3, "peak_source": peak_src,
-                         "note": "algorithmic 16 B/cell-update; K3 keeps pressure+factors on chip for all time "
-                                 "steps, so frac > 1 is expected - see traffic (ncu DRAM bytes per launch)"},
-            "e2e": {"value": work * world * args.steps / e2e_total_s, "unit": "cell-updates/s",
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "PDS1D_Ensemble.solve(host arrays) -> misfit + audit snapshots as numpy"},
-            "gpu_launches": int(launches) * args.steps,
-            "clocks": clocks.summary(),
+            "parity": res["parity"], "roofline": res["roofline"], "e2e": res["e2e"],
+            "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
         }
         if world == 1 and not f32:
+            peak, _ = measured_peak()
             line["single_step"] = single_step_probe(E, torch, peak)
+        line["other_workloads"] = {}
+        if c4 is not None:
+            line["other_workloads"]["c4"] = {
+                "workload": c4["workload"], "value": c4["value"], "unit": "cell-updates/s", "ms": c4["ms_per_step"],
+                "scaling": "strong", "members_per_gpu": c4["members_per_gpu"], "e2e": c4["e2e"],
+                "kernel_ms": c4["roofline"]["kernel_ms"], "roofline_frac_16B": c4["roofline"]["frac"], "parity": c4["parity"],
+                "steps": c4["steps"], "gpu_launches": c4["gpu_launches"]}
         if world == 1 and not f32 and not args.no_extra:
             # the single-model configurations of BASELINE.json next to the headline (short runs, same code path
             # as `--workload c2|c5`; full records under profiles/)
             torch.cuda.empty_cache()
-            line["other_workloads"] = {}
             for name in ("c2", "c5"):
                 sub = argparse.Namespace(**{**vars(args), "workload": name, "steps": 3, "no_cpu": True})
                 r = run_single_gpu_arm(sub, emit=False, sampler=False)
@@ -660,9 +854,17 @@ def run_gpu_arm(args):
                     "workload": r["config"]["workload"], "value": r["value"] * r["ms_per_step"] / med, "unit": r["unit"],
                     "ms": med, "ms_each": r["config"]["step_ms_each"],
                     "us_per_time_step": r["config"]["us_per_time_step"], "kernel": r["roofline"]["kernel"],
-                    "roofline_frac_16B": r["roofline"]["frac"], "roofline_frac_32B": 2.0 * r["roofline"]["frac"], "e2e": r["e2e"]["value"], "window_plan": r["config"]["window_plan"]}
+                    "roofline_frac_16B": r["roofline"]["frac"], "roofline_frac_32B": 2.0 * r["roofline"]["frac"], "e2e": r["e2e"]["value"],
+                    "window_plan": r["config"]["window_plan"], "parity": r.get("parity")}
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(w)
+            line["cpu_baseline"] = cpu_baseline(make_workload(args.workload, 1))
+        gates = [line["parity"]] + [v.get("parity") for v in line["other_workloads"].values()]
+        failed = [g for g in gates if g is not None and not g["passed"]]
+        if failed:
+            print("PARITY GATE FAILED: " + json.dumps(failed), file=sys.stderr)
+            if world > 1:
+                dist.destroy_process_group()
+            raise SystemExit(3)
         emit_line(line)
     if world > 1:
         dist.barrier()
@@ -683,6 +885,8 @@ def main():
                     help="ensemble workloads: f32 = the separate fp32 mode (state and factors in float, gate 1e-5)")
     ap.add_argument("--three-kernels", action="store_true",
                     help="ensembles: K1 assemble + K1b factorize + K3 run as separate kernels instead of on-chip assembly")
+    ap.add_argument("--strong", action="store_true",
+                    help="--workload c4: the fixed 1M-member ensemble split over the ranks instead of 125000 members per rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C5 runs appended to the C3 line")
     args = ap.parse_args()

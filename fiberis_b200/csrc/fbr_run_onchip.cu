@@ -498,10 +498,10 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
 //     generic path guarded by one CTA-uniform flag.
 // descriptor: [4:0] overridden cell (31 none)  [12:5] src column (0xFE: constant zero)
 //             [17:13] observed cell (31 none)  [25:18] obs column
-//             [26] the thread's FIRST cell is a boundary row (right-hand side 0)   [27] its LAST cell is one
+//             [26] the thread's FIRST cell is the left boundary row (right-hand side 0, folded into the factors)
 constexpr unsigned kDescNone = 0x1F;  // "no cell" in a descriptor's cell field
 constexpr unsigned kDescObShift = 13, kDescSrcColShift = 5, kDescObColShift = 18;
-constexpr unsigned kDescZeroFirst = 1u << 26, kDescZeroLast = 1u << 27;
+constexpr unsigned kDescZeroFirst = 1u << 26;
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -617,18 +617,14 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 if (a.src_idx[k] == cell) return true;
             return false;
         };
-        // A boundary row that sits in a thread's first / last register (cell 0 always does; cell nx - 1 when nx is a
-        // multiple of the chunk) is zeroed by a mask every thread applies — two instructions, no shared-memory read, no
-        // divergent branch; any other position takes the override path below.
+        // The left boundary row (cell 0, right-hand side 0) is folded into the factors (see the per-model setup) unless a
+        // source sits on it; every other overridden cell takes its value from shared memory.
         const int64_t jl = nx - 1 - cell0;
         if (cell0 == 0 && a.lbc != FBR_BC_NONE) {
             if (!is_source(0)) desc |= kDescZeroFirst;
             else claim(0, kSlotZero);
         }
-        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) {
-            if (jl == CPT - 1 && !is_source(nx - 1)) desc |= kDescZeroLast;
-            else claim((int)jl, kSlotZero);
-        }
+        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) claim((int)jl, kSlotZero);
 #pragma unroll 1
         for (int k = 0; k < a.n_src; ++k) {  // ascending k: later duplicates win
             const int64_t jj = a.src_idx[k] - cell0;
@@ -646,7 +642,10 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
         if (n_ov > 1) { ov_slow = true; desc |= kDescNone; }
         if (n_ob > 1) { ob_slow = true; desc |= kDescNone << kDescObShift; }
     }
-    const bool any_slow = __syncthreads_or(ov_slow || ob_slow);
+    // The common copies of the step loop serve overridden cells in a thread's FIRST or LAST register only (two selects, no
+    // branch: boundary rows, sources on chunk boundaries); any other layout takes the generic copies.
+    const bool mid_ov = (desc & 0x1F) != kDescNone && (desc & 0x1F) != 0 && (desc & 0x1F) != CPT - 1;
+    const bool any_slow = __syncthreads_or(ov_slow || ob_slow || mid_ov);
     // 16-byte loads of a thread's 8 cells when the rows allow it (nx even keeps every member's row aligned)
     const bool vec_ok = (nx % 2 == 0) && cell0 + CPT <= nx && ((reinterpret_cast<uintptr_t>(a.fl) | reinterpret_cast<uintptr_t>(a.fr) |
                          reinterpret_cast<uintptr_t>(a.fg) | reinterpret_cast<uintptr_t>(a.p0)) & 15) == 0 && a.p0_stride % 2 == 0;
@@ -675,7 +674,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     }
     const bool has_ov = (desc & 0x1F) != kDescNone, has_ob = ((desc >> kDescObShift) & 0x1F) != kDescNone;
     const bool ov_zero = ((desc >> kDescSrcColShift) & 0xFF) == kSlotZero;
-    const int keep_first = (desc & kDescZeroFirst) ? 0 : -1, keep_last = (desc & kDescZeroLast) ? 0 : -1;
+    const bool ov_first = (desc & 0x1F) == 0, ov_last = (desc & 0x1F) == CPT - 1;
     // Per-step scalars never travel through a global load inside the sweeps: a load in flight across a sweep
     // shares a scoreboard with its shuffles / shared-memory reads and stalls them (+25 % per step on B200,
     // scratch/ubench_k3.cu), and a load consumed on the spot exposes L2 latency on an in-order warp.  Instead the
@@ -686,7 +685,8 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     //     boundary (samples on the step times, or interpolated onto the observations' own time axis).
     const int blk = a.blk_steps;
     double *s_src = s_dyn;                                  // [2][blk][n_src]
-    double *s_tr = s_src + 2 * blk * a.n_src;               // [2][blk][n_obs]
+    double *s_obs = s_src + 2 * blk * a.n_src;              // [2][blk][n_obs] observation samples the block completes
+    double *s_tr = s_obs + 2 * blk * a.n_obs;               // [2][blk][n_obs] trace of the observed cells
     T *s_patch = reinterpret_cast<T *>(s_tr + 2 * blk * a.n_obs + warp * (32 * 9));  // [W] row-transposition patches (2304 B each)
     const int64_t cs = a.snap_cell_stride;
 
@@ -711,6 +711,10 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             load_row(a.fg + m * nx, 0.0, g);
         }
         load_row(a.p0 + m * a.p0_stride, 0.0, x);
+        // Left boundary row (right-hand side always 0, matbuilder.py:49-55) in a thread's first register: with r_0 := 0 and
+        // l_1 := 0 the stale x_0 never reaches anything (t_0 = r_0 y_0 = 0, y_1 = b_1 - l_1 * 0 = b_1 — the same bits) and
+        // x_0 = -g_0 x_1 comes out of the backward sweep as before: the override costs nothing per step.
+        if (desc & kDescZeroFirst) { r[0] = (T)0; l[1] = (T)0; }
 
         const ScanMultipliersT<T> sm = scan_multipliers<T>(chunk_product<T, CPT>(l), chunk_product<T, CPT>(g), lane);
         if (W > 1) {
@@ -754,51 +758,81 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
         bool far_ok = false;
         if (a.scan_eps > 0.0) far_ok = fabs((double)sm.f[4]) <= a.scan_eps && fabs((double)sm.b[4]) <= a.scan_eps;
         far_ok = __syncthreads_and(far_ok);
-        int scan_mode = kScanExact;
-        if (a.scan_eps > 0.0 && !any_slow) {
-            bool near_ok = true;
-            for (int v = 1; v + 1 < W; ++v)
-                near_ok = near_ok && fabs((double)s_T[0][v]) <= a.scan_eps && fabs((double)s_T[1][v]) <= a.scan_eps;
-            if (near_ok) scan_mode = far_ok ? kScanNear4 : kScanNear;
-        }
+        bool near_ok = a.scan_eps > 0.0 && !any_slow;
+        for (int v = 1; v + 1 < W; ++v)
+            near_ok = near_ok && fabs((double)s_T[0][v]) <= a.scan_eps && fabs((double)s_T[1][v]) <= a.scan_eps;
+        const int scan_mode = near_ok ? (far_ok ? kScanNear4 : kScanNear) : kScanExact;
         if (a.scan_mode && tid == 0) a.scan_mode[m] = scan_mode;
         const long long snap_slot = s_snap_slot;
+        const bool recorded = snap_slot >= 0;
         double acc = 0.0;
 
-        auto stage_block = [&](int b) {  // source values of steps [b blk, ..)
+        // observation samples completed by rows (lo, hi] (for lo == 0 also those that only need the initial state)
+        auto sample_range = [&](int lo, int hi, int &ja, int &jb) {
+            if (a.sample_row) { ja = __ldg(a.row_first_sample + (lo == 0 ? 0 : lo + 1)); jb = __ldg(a.row_first_sample + hi + 1); }
+            else { ja = lo == 0 ? 0 : lo + 1; jb = hi + 1; }
+        };
+        auto stage_block = [&](int b) {  // source values of steps [b blk, ..) and the observations those steps complete
             const int n0 = b * blk;
             const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
             if (rows <= 0) return;
             const int buf = b & 1;
             for (int e = tid; e < rows * a.n_src; e += 32 * W)
                 cp_async8(s_src + buf * blk * a.n_src + e, a.src_table + (int64_t)n0 * a.n_src + e);
+            if (a.n_obs > 0) {  // up to blk samples of the window (denser observations: the rest is read from global memory)
+                int ja, jb;
+                sample_range(n0, n0 + rows, ja, jb);
+                ja = ja < a.first_sample ? a.first_sample : ja;
+                jb = jb > a.last_sample ? a.last_sample : jb;
+                jb = jb > ja + blk ? ja + blk : jb;
+                for (int e = tid; e < (jb - ja) * a.n_obs; e += 32 * W)
+                    cp_async8(s_obs + buf * blk * a.n_obs + e, a.obs + (int64_t)ja * a.n_obs + e);
+            }
         };
         // Residuals of the observation samples whose last needed state lies in rows (lo, hi] — the block just integrated
         // (trace buffer `buf`; row lo itself is s_prev) — plus, for lo == 0, those that only need the initial state.
         auto flush_rows = [&](int lo, int hi, int buf) {
+            if (!a.sample_row) {
+                // observations on the step times: sample j is row j, trace and staged observations share one layout
+                const double *tr = s_tr + buf * blk * a.n_obs, *so = s_obs + buf * blk * a.n_obs;
+                const int n = (hi - lo) * a.n_obs;
+                for (int e = tid; e < n; e += 32 * W) {
+                    const double res = tr[e] - so[e];
+                    const double wgt = a.obs_w ? __ldg(a.obs_w + e % a.n_obs) : 1.0;
+                    acc = fma(wgt * res, res, acc);
+                }
+                return;
+            }
             int ja, jb;
-            if (a.sample_row) { ja = __ldg(a.row_first_sample + (lo == 0 ? 0 : lo + 1)); jb = __ldg(a.row_first_sample + hi + 1); }
-            else { ja = lo == 0 ? 0 : lo + 1; jb = hi + 1; }
+            sample_range(lo, hi, ja, jb);
+            const int n_obs = a.n_obs;
+            const double *tr0 = s_tr + (buf * blk - lo - 1) * n_obs;
             auto sample = [&](int j, int k) -> double {  // simulated channel k at observation sample j
-                const int row = a.sample_row ? __ldg(a.sample_row + j) : j;
-                const double w = a.sample_w ? __ldg(a.sample_w + j) : 0.0;
+                const int row = __ldg(a.sample_row + j);
+                const double w = __ldg(a.sample_w + j);
                 if (row < 0) return __longlong_as_double(0x7ff8000000000000ll);  // outside the simulated time range
-                const double *tr = s_tr + (buf * blk - lo - 1) * a.n_obs + k;
-                const double p_lo = row == lo ? s_prev[k] : tr[row * a.n_obs];
+                const double p_lo = row == lo ? s_prev[k] : tr0[row * n_obs + k];
                 if (w == 0.0) return p_lo;
-                return fma(w, tr[(row + 1) * a.n_obs] - p_lo, p_lo);
+                return fma(w, tr0[(row + 1) * n_obs + k] - p_lo, p_lo);
             };
             if (a.base_sample >= ja && a.base_sample < jb) {  // "initial time calibration" (baseline_model_generator.py:398)
-                for (int k = tid; k < a.n_obs; k += 32 * W) s_base[k] = sample(a.base_sample, k);
+                for (int k = tid; k < n_obs; k += 32 * W) s_base[k] = sample(a.base_sample, k);
                 __syncthreads();
             }
             ja = ja < a.first_sample ? a.first_sample : ja;
             jb = jb > a.last_sample ? a.last_sample : jb;
-            for (int e = tid; e < (jb - ja) * a.n_obs; e += 32 * W) {
-                const int j = ja + e / a.n_obs, k = e % a.n_obs;
-                const double res = (sample(j, k) - s_base[k]) - __ldg(a.obs + (int64_t)j * a.n_obs + k);
+            const int j_staged = ja + blk;  // samples [ja, j_staged) were staged into shared memory with the block
+            const double *so = s_obs + (buf * blk - ja) * n_obs;
+            // (sample, channel) pairs dealt round-robin; j and k advance without a division per pair
+            const int dj = (32 * W) / n_obs, dk = (32 * W) % n_obs;
+            int j = ja + tid / n_obs, k = tid % n_obs;
+            for (; j < jb; j += dj) {
+                const double o = j < j_staged ? so[j * n_obs + k] : __ldg(a.obs + (int64_t)j * n_obs + k);
+                const double res = (sample(j, k) - s_base[k]) - o;
                 const double wgt = a.obs_w ? __ldg(a.obs_w + k) : 1.0;
                 acc = fma(wgt * res, res, acc);
+                k += dk;
+                if (k >= n_obs) { k -= n_obs; ++j; }
             }
         };
         stage_block(0);
@@ -845,12 +879,11 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
 #pragma unroll 1
                 for (int n = n_begin; n < n_end; ++n) {
                     // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
-                    x[0] = and_mask(x[0], keep_first);
-                    x[CPT - 1] = and_mask(x[CPT - 1], keep_last);
-                    if (has_ov) {  // only the threads that own an overridden cell
+                    if (!SLOW) {  // every overridden cell of the team sits in a first / last register
+                        x[0] = ov_first ? v_ov : x[0];
+                        x[CPT - 1] = ov_last ? v_ov : x[CPT - 1];
+                    } else if (has_ov) {  // only the threads that own an overridden cell
                         const int jo = (int)(desc & 0x1F);
-                        // sources that start or end a chunk sit in the first / last register of a thread: one move;
-                        // any other position goes through the compare-and-move chain
                         if (jo == 0) x[0] = v_ov;
                         else if (jo == CPT - 1) x[CPT - 1] = v_ov;
                         else set_at<T, CPT>(x, jo, v_ov);
@@ -927,7 +960,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             using I1 = std::integral_constant<int, kScanNear>;
             using I2 = std::integral_constant<int, kScanNear4>;
             if (scan_mode == kScanExact) {
-                if (snap_slot >= 0) {  // (the copies for unrecorded members carry no snapshot code)
+                if (recorded) {  // (the copies for unrecorded members carry no snapshot code)
                     if (any_slow) steps(I0{}, std::true_type{}, std::true_type{}, done, done + run);
                     else steps(I0{}, std::false_type{}, std::true_type{}, done, done + run);
                 } else {
@@ -935,10 +968,10 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                     else steps(I0{}, std::false_type{}, std::false_type{}, done, done + run);
                 }
             } else if (scan_mode == kScanNear) {
-                if (snap_slot >= 0) steps(I1{}, std::false_type{}, std::true_type{}, done, done + run);
+                if (recorded) steps(I1{}, std::false_type{}, std::true_type{}, done, done + run);
                 else steps(I1{}, std::false_type{}, std::false_type{}, done, done + run);
             } else {
-                if (snap_slot >= 0) steps(I2{}, std::false_type{}, std::true_type{}, done, done + run);
+                if (recorded) steps(I2{}, std::false_type{}, std::true_type{}, done, done + run);
                 else steps(I2{}, std::false_type{}, std::false_type{}, done, done + run);
             }
             done += run;
@@ -1139,10 +1172,12 @@ template <typename T, int CPT, int W, bool ZONAL = false>
 static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
+    // 16 warps per SM (128 registers per thread).  A fifth 4-warp CTA per SM at 96 registers was measured again in round 2
+    // with the leaner loops: 11 spill loads per step, 25.7 against 21.3 ms per C3 sweep.
     constexpr int kFull16 = (16 / W) > 0 ? (16 / W) : 1;
     auto kern = run_onchipx_kernel<T, CPT, W, kFull16, ZONAL>;
     RunArgs b = a;
-    const int cols = a.n_src + a.n_obs;
+    const int cols = a.n_src + 2 * a.n_obs;
     // Time steps per staged block of per-step scalars: the longest block that costs no resident CTA (block boundaries
     // carry three barriers and the residual sums; C3: 64 steps 25.2 ms, 32 steps 25.5 ms, 128 steps lose a CTA: 42.7 ms).
     // The audited side launch of an ensemble must end up with the SAME footprint as the sweep (see ensemble.py): the

@@ -53,6 +53,9 @@ class _Anything:
     def __getattr__(self, name):
         return _Anything()
 
+    def __iter__(self):  # ``fig, ax = plt.subplots()``
+        return iter((_Anything(), _Anything()))
+
 
 def _install_matplotlib_stub() -> None:
     try:
@@ -69,7 +72,8 @@ def _install_matplotlib_stub() -> None:
     ]
     for n in names:
         m = types.ModuleType(n)
-        m.__getattr__ = lambda attr, _n=n: _Anything  # type: ignore[attr-defined]
+        # classes (Axes, Line2D, ...) resolve to the sink class, functions (plt.subplots, ...) to a callable sink object
+        m.__getattr__ = lambda attr, _n=n: _Anything if attr[:1].isupper() else _Anything()  # type: ignore[attr-defined]
         m.__path__ = []  # behave like a package so sub-imports resolve
         sys.modules.setdefault(n, m)
     sys.modules["matplotlib"].use = lambda *a, **k: None  # type: ignore[attr-defined]

@@ -66,9 +66,60 @@ def gauge(rng, T, knots=64, lo=-10, hi=10):
     return np.linspace(0, T, knots), rng.uniform(lo, hi, knots)
 
 
+def misfit_fixture(R):
+    """The history-matching misfit of the reference: ``misfit_calculator``
+    (src/fiberis/moose/templates/baseline_model_generator.py:418-520) run UNMODIFIED on a reference solve and a
+    synthetic observed Data2D with its own, irregular time axis and a later start_time."""
+    from fiberis.moose.templates import baseline_model_generator as B  # type: ignore
+    rng = np.random.default_rng(61)
+    nx = 320
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    D = 10 ** rng.uniform(-1, 1, nx)
+    init = rng.uniform(0, 1, nx)
+    T = 48.0
+    srcs = [gauge(rng, T, 12, 1.0, 10.0) for _ in range(2)]
+    sidx = [80, 240]
+    p = _mk(R, mesh, D, init, "Neumann", "Neumann", sidx, srcs, 0.0, True)
+    with _quiet():
+        p.solve(dt=0.5, t_total=T)
+    conv = 0.3048
+    sim = R.Data2D(data=np.array(p.snapshot).T.copy(), taxis=np.array(p.taxis, float), daxis=mesh * conv, start_time=START,
+                   name="simulated")
+    # observed: 5 channels around cell 121 (3 of them weighted), 41 irregular samples, recorded from 3.5 s after the
+    # simulation's start_time; values = a perturbed copy of another model's response
+    cells = np.arange(119, 124)
+    obs_start = START + datetime.timedelta(seconds=3.5)
+    obs_taxis = np.sort(rng.uniform(0.0, T - 4.0, 41))
+    obs_taxis[0] = 0.0
+    snap = np.array(p.snapshot)
+    obs = np.stack([np.interp(obs_taxis + 3.5, p.taxis, snap[:, c]) for c in cells]) * 0.9 + rng.normal(0, 0.05, (5, 41))
+    obs = obs - obs[:, 1:2]
+    observed = R.Data2D(data=obs, taxis=obs_taxis, daxis=mesh[cells].copy(), start_time=obs_start, name="observed")
+    weights = np.array([0.5, 2.0, 1.0])
+    cwd = os.getcwd()
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp, _quiet():
+        os.chdir(tmp)
+        try:
+            total, per_channel = B.misfit_calculator(weight_matrix=weights, sim_fracture_center_ind=121,
+                                                     observed_data_fracture_center_ind=2, simulated_data=sim,
+                                                     observed_data=observed, save_path=tmp, return_misfit_per_channel=True)
+        finally:
+            os.chdir(cwd)
+    used_cells = np.array([120, 121, 122])  # channels start at observed index 2 - 3 // 2 = 1
+    _save("misfit_reference_320x96", mesh, D, init, "Neumann", "Neumann", sidx, srcs, 0.0, True, p.snapshot, p.taxis,
+          rows=[0, 1, 48, 96], dt=0.5, t_total=T, obs_cells=used_cells, obs=obs[1:4].T.copy(), obs_taxis=obs_taxis,
+          obs_time_offset=3.5, obs_weights=weights, baseline_index=1, window=np.array([1, -1]),
+          sim_channels=snap[:, used_cells].copy(), misfit_total=float(total), misfit_per_channel=np.asarray(per_channel))
+    print("misfit_reference_320x96: total", total, per_channel)
+
+
 def main():
     R = _refshim.import_reference()
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "misfit":
+        misfit_fixture(R)
+        return
 
     # ---- C1 (BASELINE.json configs[0]; SURVEY 8(d) seed 101): fully through the reference
     mesh = np.linspace(0, 199, 200)
@@ -225,6 +276,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "data1d_interp_96.npz"), taxis=gt, data=gd, query=q,
                         value=np.array([g.get_value_by_time(float(t)) for t in q]), **VERS)
     print("data1d_interp_96")
+
+    misfit_fixture(R)
 
 
 if __name__ == "__main__":

@@ -30,8 +30,11 @@ reference's own known-answer tests (``tests/test_simulator_core.py:181-275``,
 and (2) the fixtures in ``tests/golden/`` that ``oracle/gen_golden.py`` produced by running the
 unmodified reference in the build container (NumPy 2.3.5 / SciPy 1.18.1).
 
-The ensemble misfit (``ensemble_misfit``) has NO counterpart in ``fiberis.simulator``: **parity
-unpinned** for that one function; its per-member pressures are pinned by looping the reference.
+The ensemble misfit on the step times (``ensemble_misfit``) has NO counterpart in ``fiberis.simulator``: **parity
+unpinned** for that one function; its per-member pressures are pinned by looping the reference.  The misfit with
+observations on their own time axis (``sampled_misfit``) restates
+``src/fiberis/moose/templates/baseline_model_generator.py:479-490`` and is pinned by
+``tests/golden/misfit_reference_320x96.npz``, produced by the reference's unmodified ``misfit_calculator``.
 """
 from __future__ import annotations
 
@@ -309,3 +312,31 @@ def ensemble_misfit(snapshot, obs_idx, obs, weights=None):
     w = np.ones(len(obs_idx)) if weights is None else np.asarray(weights, dtype=np.float64)
     r = snapshot[1:, obs_idx] - obs[1:]
     return float(np.sum(w[None, :] * r * r))
+
+
+def sampled_misfit(snapshot, taxis, obs_idx, obs, obs_taxis, weights=None, baseline_index=1, window=(1, -1),
+                   time_offset=0.0, per_channel=False):
+    """The reference's history-matching misfit for observations on their OWN time axis
+    (``src/fiberis/moose/templates/baseline_model_generator.py:479-490``):
+
+    * the simulated channel is interpolated onto the observed times — ``Data1D.interpolate``
+      (``src/fiberis/analyzer/Data1D/core1D.py:786-812``): points ``obs_taxis + (obs_start - sim_start)`` in the simulated
+      frame, ``np.interp(..., left=nan, right=nan)``;
+    * "initial time calibration": the sample at ``baseline_index`` (the reference: 1) is subtracted (``:483``);
+    * ``sum((sim[first:last] - obs[first:last]) ** 2)`` with the reference's window ``[1:-1]`` (``:486``), times the
+      channel weight (``:488``), summed over channels.
+
+    ``snapshot (n_t, nx)``, ``taxis (n_t)``; ``obs (n_samples, n_channels)``; ``time_offset`` = observed start_time minus
+    simulated start_time in seconds."""
+    snapshot = np.asarray(snapshot, dtype=np.float64)
+    obs = np.asarray(obs, dtype=np.float64)
+    w = np.ones(len(obs_idx)) if weights is None else np.asarray(weights, dtype=np.float64)
+    points = np.asarray(obs_taxis, dtype=np.float64) + time_offset
+    sl = slice(*window) if window is not None else slice(None)
+    out = []
+    for k, cell in enumerate(obs_idx):
+        sim = np.interp(points, taxis, snapshot[:, cell], left=np.nan, right=np.nan)
+        if baseline_index is not None:
+            sim = sim - sim[baseline_index]
+        out.append(w[k] * np.sum((sim[sl] - obs[sl, k]) ** 2))
+    return np.asarray(out) if per_channel else float(np.sum(out))

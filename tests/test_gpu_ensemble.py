@@ -372,3 +372,157 @@ def test_stiff_and_nearly_explicit_ensembles(nx, dt):
                                     0.0, dt, c["T"])
         assert e.snapshot[k].shape == want.shape
         assert G.rel_max(e.snapshot[k], want) <= 1e-10
+
+
+# ---- observations on their own time axis: the reference's history-matching misfit -------------------------
+def _sampled_ensemble(g, M, rng, dtype_dense=True):
+    """An ensemble whose member 0 is the fixture's model; the others have perturbed diffusivities."""
+    from fiberis_b200.simulator.core.ensemble import PDS1D_Ensemble
+    D = np.tile(g["diffusivity"], (M, 1))
+    D[1:] *= 10 ** rng.uniform(-0.3, 0.3, (M - 1, 1))
+    e = PDS1D_Ensemble()
+    e.set_mesh(g["mesh"])
+    e.set_source(Mo.sources_of(g["sources"]))
+    e.set_sourceidx(g["sourceidx"])
+    e.set_bcs(g["lbc"], g["rbc"])
+    e.set_initial(g["initial"])
+    e.set_diffusivity(D)
+    return e, D
+
+
+def test_fused_misfit_matches_the_reference_misfit_calculator():
+    """Member 0 is the model the reference's UNMODIFIED misfit_calculator was run on (tests/golden/
+    misfit_reference_320x96.npz: irregular observed taxis, observed start_time 3.5 s after the simulation's, baseline
+    sample 1, window [1:-1], channel weights): the misfit K3 fuses into its time loop must reproduce that value."""
+    g = G.load("misfit_reference_320x96")
+    rng = np.random.default_rng(5)
+    M = 9
+    e, D = _sampled_ensemble(g, M, rng)
+    e.set_observations(g["obs_cells"], g["obs"], weights=g["obs_weights"], taxis=g["obs_taxis"] + float(g["obs_time_offset"]),
+                       baseline_index=1, window=(1, -1))
+    mis = e.solve(dt=g["dt"], t_total=g["t_total"], audit_models=[0])
+    assert mis[0] == pytest.approx(float(g["misfit_total"]), rel=1e-10)
+    assert G.rel_max(e.snapshot[0][:, g["obs_cells"]], g["sim_channels"]) <= 1e-10
+    for m in range(1, M):
+        snap, taxis = O.solve_fixed(g["mesh"], D[m], g["initial"], g["lbc"], g["rbc"], g["sourceidx"], g["sources"], g["t0"],
+                                    g["dt"], g["t_total"])
+        want = O.sampled_misfit(snap, taxis, g["obs_cells"], g["obs"], g["obs_taxis"], g["obs_weights"],
+                                time_offset=float(g["obs_time_offset"]))
+        assert mis[m] == pytest.approx(want, rel=1e-10)
+
+
+def test_set_observed_data_aligns_start_times_like_data1d_interpolate():
+    import datetime
+
+    from fiberis_b200.analyzer.Data2D.core2D import Data2D
+    g = G.load("misfit_reference_320x96")
+    e, D = _sampled_ensemble(g, 3, np.random.default_rng(6))
+    observed = Data2D(data=np.ascontiguousarray(g["obs"].T), taxis=g["obs_taxis"], daxis=g["mesh"][g["obs_cells"]],
+                      start_time=Mo.START + datetime.timedelta(seconds=float(g["obs_time_offset"])))
+    e.set_observed_data(observed, g["obs_cells"], weights=g["obs_weights"])  # reference defaults: baseline 1, window [1:-1]
+    mis = e.solve(dt=g["dt"], t_total=g["t_total"])
+    assert mis[0] == pytest.approx(float(g["misfit_total"]), rel=1e-10)
+
+
+@pytest.mark.parametrize("nx,n_steps,n_obs,J,dtype", [
+    (1024, 150, 16, 97, "float64"),    # C3 width, several staged blocks, fewer samples than steps
+    (520, 70, 40, 400, "float64"),     # observations much denser than the steps (more samples per block than staged)
+    (200, 33, 5, 20, "float64"),       # one warp, a partly filled one
+    (24, 40, 3, 30, "float64"),        # short mesh: the call must pick the 64-byte-per-thread kernel by itself
+    (2500, 20, 7, 15, "float64"),      # 10 warps
+    (1024, 130, 9, 60, "float32"),     # fp32 mode
+])
+def test_sampled_misfit_fuzz(nx, n_steps, n_obs, J, dtype):
+    rng = np.random.default_rng(nx + J)
+    M = 6
+    e, c = make_ensemble(3 * nx + J, M, nx, n_steps, dense=(nx == 520))
+    cells = np.sort(rng.choice(np.arange(nx), size=n_obs, replace=False))
+    if n_obs >= 5:
+        cells[1] = cells[0] + 1 if cells[0] + 1 not in cells[2:] else cells[1]  # two observed cells in one thread
+        cells = np.unique(cells)
+        n_obs = len(cells)
+    T = c["T"]
+    obs_taxis = np.sort(rng.uniform(0.0, T, J))
+    obs_taxis[0] = 0.0                      # exactly the initial state
+    obs_taxis[-1] = T                       # exactly the last state
+    obs_taxis[J // 2] = c["dt"] * (n_steps // 2)  # exactly on a step time
+    obs_taxis = np.sort(obs_taxis)
+    obs = rng.normal(0, 1, (J, n_obs))
+    w = rng.uniform(0.5, 2.0, n_obs)
+    for base, window in ((1, (1, -1)), (None, None), (0, (2, J - 3))):
+        e.set_observations(cells, obs, weights=w, taxis=obs_taxis, baseline_index=base, window=window)
+        mis = e.solve(dt=c["dt"], t_total=T, dtype=dtype)
+        for m in range(M):
+            snap, taxis = O.solve_fixed(c["mesh"], c["zv"][m][c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                                        c["srcs"], 0.0, c["dt"], T)
+            want = O.sampled_misfit(snap, taxis, cells, obs, obs_taxis, w, baseline_index=base, window=window)
+            assert mis[m] == pytest.approx(want, rel=1e-9 if dtype == "float64" else 2e-3), (m, base, window)
+
+
+def test_sampled_misfit_outside_the_simulated_range_is_nan_like_the_reference():
+    e, c = make_ensemble(77, 4, 300, 20)
+    cells = np.array([10, 150, 280])
+    obs_taxis = np.array([0.0, 2.5, 7.0, 19.0, 25.0, 30.0])  # the last two lie behind the end of the run (T = 20)
+    obs = np.zeros((6, 3))
+    e.set_observations(cells, obs, taxis=obs_taxis, baseline_index=1, window=(1, -1))  # sample 4 (outside) is inside the window
+    assert np.all(np.isnan(e.solve(dt=c["dt"], t_total=c["T"])))
+    e.set_observations(cells, obs, taxis=obs_taxis, baseline_index=1, window=(1, 4))   # now it is not
+    mis = e.solve(dt=c["dt"], t_total=c["T"])
+    assert np.all(np.isfinite(mis))
+    snap, taxis = O.solve_fixed(c["mesh"], c["zv"][2][c["zone"]], np.zeros(300), "Neumann", "Neumann", c["sidx"], c["srcs"], 0.0,
+                                c["dt"], c["T"])
+    assert mis[2] == pytest.approx(O.sampled_misfit(snap, taxis, cells, obs, obs_taxis, window=(1, 4)), rel=1e-9)
+    e.set_observations(cells, obs, taxis=obs_taxis, baseline_index=3, window=(1, 4))  # a baseline behind the window's start
+    with pytest.raises(ValueError):
+        e.solve(dt=c["dt"], t_total=c["T"])
+
+
+# ---- per-member scan dispatch ------------------------------------------------------------------------------------------
+def test_scan_modes_are_exercised_and_agree_with_the_exact_scans():
+    """C3-shaped members take the truncated scans (neighbour-warp carry; 4 stages when every 16-chunk product is below
+    2^-80); a smooth high-diffusivity mesh keeps the exact ones.  Truncated and exact results agree to rounding."""
+    import torch
+
+    from fiberis_b200 import _engine as E
+    rng = np.random.default_rng(3)
+    M, nx, n_steps = 64, 1024, 40
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    zone = ((np.arange(nx) * 8) // nx).astype(np.int32)
+    zv = 10 ** rng.uniform(-1, 1, (M, 8))
+    zv[0] = 3000.0   # decay horizon far beyond a warp: the exact scans must be kept for this member
+    table = rng.uniform(1, 10, (n_steps, 2))
+    mesh_d, zv_d, zone_d = E.to_device(mesh), E.to_device(zv), E.to_device(zone, np.int32)
+    sidx_d, n_src = E.index_tensor(np.array([256, 768]))
+    table_d, p0_d = E.to_device(table), E.to_device(np.zeros(nx))
+    out = {}
+    for name, eps in (("default", 0.0), ("exact", 1.0)):
+        modes = torch.full((M,), -1, dtype=torch.int32, device=mesh_d.device)
+        snap, _, _ = E.run(None, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=10,
+                           zonal=(mesh_d, zv_d, zone_d, 1.0, None), scan_log2_eps=eps, scan_mode_out=modes)
+        out[name] = (snap.cpu().numpy(), modes.cpu().numpy())
+    m_def, m_ex = out["default"][1], out["exact"][1]
+    assert np.all(m_ex == 0)
+    assert m_def[0] == 0 and set(m_def[1:]) <= {1, 2} and (m_def == 2).sum() > 0 and (m_def == 1).sum() > 0
+    assert G.rel_max(out["default"][0], out["exact"][0]) <= 1e-13
+    want, _ = O.solve_fixed(mesh, zv[5][zone], np.zeros(nx), "Neumann", "Neumann", [256, 768],
+                            [(np.arange(n_steps + 1.0), np.append(table[:, k], table[-1, k])) for k in range(2)], 0.0, 1.0, float(n_steps))
+    assert G.rel_max(out["default"][0][5], want[::10]) <= 1e-10
+
+
+# ---- cell-major snapshots: the (cell, time) layout of Data2D written by the kernel (SURVEY 8(f3)) ---------------------------
+@pytest.mark.parametrize("nx,M", [(1024, 5), (200, 3), (64, 40), (24, 9)])
+def test_cell_major_snapshots_are_the_transpose(nx, M):
+    from fiberis_b200 import _engine as E
+    rng = np.random.default_rng(nx)
+    n_steps = 37
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    D = 10 ** rng.uniform(-1, 1, (M, nx))
+    sidx_d, n_src = E.index_tensor(np.array([nx // 3]))
+    table_d = E.to_device(rng.uniform(1, 10, (n_steps, 1)))
+    p0_d = E.to_device(rng.uniform(0, 1, (M, nx)))
+    fac = E.factorize(*E.assemble(E.to_device(mesh), E.to_device(D), M, nx, 0.5, "Dirichlet", "Neumann", sidx_d, n_src))
+    args = (fac, p0_d, M, nx, n_steps, "Dirichlet", "Neumann", sidx_d, n_src, table_d)
+    rows, _, _ = E.run(*args, snapshot_every=3)
+    cols, _, _ = E.run(*args, snapshot_every=3, cell_major=True)
+    assert cols.shape == (M, nx, rows.shape[1])
+    npt.assert_array_equal(cols.cpu().numpy(), rows.cpu().numpy().transpose(0, 2, 1))
