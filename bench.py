@@ -459,6 +459,14 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
     win = {}
 
     def hot_path(ev=None):
+        if not long_mesh:  # what PDS1D_*.solve does up to 4096 cells: ONE launch (assembly + factorisation inside the run kernel)
+            if ev:
+                ev[0].record()
+            out = E.run(None, p0_d, 1, nx, n_steps, w["lbc"], w["rbc"], sidx_d, n_src, table_d, snapshot_every=every,
+                        zonal=(mesh_d, D_d.reshape(1, nx), None, dt, None))[0]
+            if ev:
+                ev[1].record()
+            return out
         fac = E.factorize(*E.assemble(mesh_d, D_d, 1, nx, dt, w["lbc"], w["rbc"], sidx_d, n_src), check_singular=False)
         if ev:
             ev[0].record()
@@ -515,8 +523,8 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
     peak, peak_src = measured_peak()
     k_s = float(np.mean(k_ms)) / 1e3
     achieved = work * B_ALG / k_s / 1e9
-    kname = ("K3W run_window (time-tiled overlapping windows)" if win else "K3S streaming levels" if streaming
-             else "K3L run_coop" if long_mesh else "K3 run_onchip")
+    kname = ("K3W run_window (time-tiled overlapping windows)" if win else "K3P one pass over HBM per step (exact)" if streaming
+             else "K3L run_coop" if long_mesh else "K3 run_onchip, on-chip assembly (one launch)")
     line = {
         "metric": "cell-updates/sec (fp64)", "value": work / (float(np.mean(step_ms)) / 1e3), "unit": "cell-updates/s",
         "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(np.mean(step_ms)),
@@ -524,11 +532,11 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
         "config": {"workload": w["desc"], "seed": w["seed"], "cells": nx, "time_steps": n_steps, "snapshot_every": every,
                    "us_per_time_step": k_s * 1e6 / n_steps, "step_ms_each": [float(v) for v in step_ms],
                    "l2": "flushed between timed iterations (512 MiB memset)",
-                   "timed_kernels": "K1 assemble + K1b factorize + " + kname, "window_plan": win or None},
+                   "timed_kernels": ("K1 assemble + K1b factorize + " if long_mesh else "") + kname, "window_plan": win or None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(args.workload), "kernel": kname,
                      "frac_32B": 2.0 * achieved / peak,  # SURVEY 8(d) secondary figure: state + 2 coefficient words
-                     "achieved_88B": work * 88.0 / k_s / 1e9 if (streaming and not win) else None,
+                     "achieved_40B": work * 40.0 / k_s / 1e9 if (streaming and not win) else None,
                      "kernel_ms": k_s * 1e3, "peak_source": peak_src,
                      "note": "single latency-bound system: the roofline fraction is quoted, not a target (SURVEY 8(d))"},
         "e2e": {"value": work / float(np.mean(e2e_s)), "unit": "cell-updates/s",
@@ -755,7 +763,8 @@ def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, 
         "workload": w["desc"], "members_total": w["M"], "members_per_gpu": M, "n_audit": n_audit, "n_obs": int(n_obs),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(w["name"]) if (on_chip and w["name"] == "c3") else None,
-                     "kernel": ("run_onchipx_kernel<float,16,W> (K3, fp32 mode)" if f32 else
+                     "kernel": ("run_onchipx_kernel<float,16,W,ZONAL> (K3, fp32 mode, on-chip assembly in fp64)" if (f32 and on_chip) else
+                                "run_onchipx_kernel<float,16,W> (K3, fp32 mode)" if f32 else
                                 "run_onchipx_kernel<double,8,W,ZONAL> (K3 fp64 x8, on-chip assembly)" if on_chip else
                                 "run_onchipx_kernel<double,8,W> (K3, fp64 x8)"),
                      "kernel_ms": k3_s * 1e3, "peak_source": peak_src,
@@ -797,8 +806,8 @@ def run_gpu_arm(args):
     _cabi.require_cuda()
 
     f32 = args.dtype == "f32"  # fp32 MODE of north_star (state and factors in float; gate 1e-5), reported separately
-    # fp64: assembly + factorisation inside the run kernel (fbr_run_zonal_f64); --three-kernels / fp32: K1 + K1b + K3
-    on_chip = not f32 and not args.three_kernels
+    # assembly + factorisation inside the run kernel (fbr_run_zonal_f64 / _f32); --three-kernels: K1 + K1b + K3
+    on_chip = not args.three_kernels
     strong = args.workload == "c4" and args.strong
     w = make_workload(args.workload, world, strong=strong)
     res = ensemble_leg(args, w, world, rank, local_rank, args.steps, max(args.warmup, 3), f32, on_chip, True)

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libf
 FBR_OK, FBR_ERR_BAD_ARG, FBR_ERR_UNSUPPORTED, FBR_ERR_CUDA = 0, -1, -2, -3
 BC_CODES = {"None": 0, "Dirichlet": 1, "Neumann": 2}
 SOLVER_AUTO, SOLVER_THOMAS, SOLVER_PCR, SOLVER_REG = 0, 1, 2, 3
-WS_FACTORIZE, WS_SOLVE, WS_SOLVE_THOMAS, WS_RUN, WS_RUN_LONG, WS_RUN_STREAM, WS_RUN_WINDOW = range(7)
+WS_FACTORIZE, WS_SOLVE, WS_SOLVE_THOMAS, WS_RUN, WS_RUN_LONG, WS_RUN_STREAM, WS_RUN_WINDOW, WS_RUN_PASS = range(8)
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -60,6 +60,7 @@ SIGNATURES = {
     "fbr_last_error": (C.c_char_p, []),
     "fbr_last_launch_count": (_i32, []),
     "fbr_probe_fp64_peak": (_i32, [C.POINTER(_f64), _p, _p]),
+    "fbr_transpose_f64": (_i32, [_p, _i64, _i64, _p, _p]),
     "fbr_device_info": (_i32, [C.POINTER(_i32)] * 3 + [C.POINTER(_i64)] * 3),
     "fbr_assemble_f64": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
     "fbr_assemble_zonal_f64": (_i32, [_p, _p, _i32, _p, _i64, _i64, _f64, _i32, _i32, _p, _i32, _f64, _f64, _p, _p, _p, _p]),
@@ -72,12 +73,16 @@ SIGNATURES = {
                            C.POINTER(RunOpts), _p]),
     "fbr_run_zonal_f64": (_i32, [_p, _p, _i32, _p, _f64, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p,
                                  _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, C.POINTER(RunOpts), _p]),
+    "fbr_run_zonal_f32": (_i32, [_p, _p, _i32, _p, _f64, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p,
+                                 _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, C.POINTER(RunOpts), _p]),
     "fbr_run_max_nx": (_i64, []),
     "fbr_run_long_max_nx": (_i64, []),
     "fbr_run_long_work_bytes": (_i64, [_i64]),
     "fbr_run_long_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "fbr_run_stream_work_bytes": (_i64, [_i64]),
     "fbr_run_stream_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _p, _p]),
+    "fbr_run_pass_work_bytes": (_i64, [_i64]),
+    "fbr_run_pass_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _p, _p]),
     "fbr_decay_horizon_f64": (_i32, [_p, _p, _i64, _f64, _i32, _p, _p, _p]),
     "fbr_run_window_plan": (_i32, [_i64, _i64, _i64, _i64, C.POINTER(_i64)]),
     "fbr_run_window_work_bytes": (_i64, [_i64]),

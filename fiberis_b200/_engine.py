@@ -194,7 +194,7 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
 
     ``factors`` = (fl, fr, fg) from ``factorize``; or ``factors=None`` and ``zonal=(mesh, zone_value (M, n_zones),
     zone_of_cell int32 (nx), dt, sigma | None)``: assembly and factorisation happen inside the kernel
-    (``fbr_run_zonal_f64``, fp64, 128 < nx <= 4096).  Singular members raise ``LinAlgError`` here, unless the
+    (``fbr_run_zonal_f64``: 128 < nx <= 4096; ``fbr_run_zonal_f32``: 512 <= nx <= 4096).  Singular members raise ``LinAlgError`` here, unless the
     caller passes ``singular_flags`` (from ``zonal_flags(M)``) and checks them later with
     ``raise_if_singular_zonal`` — which keeps the launch asynchronous.
 
@@ -210,7 +210,7 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     torch = _torch()
     lib = _cabi.load()
     if zonal is not None:
-        assert factors is None and dtype == "float64"
+        assert factors is None
         z_mesh, z_value, z_of_cell, z_dt, z_sigma = zonal
         dev = z_mesh.device
     else:
@@ -254,8 +254,8 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
             ptr(obs), ptr(obs_w), ptr(misfit), opts, current_stream())
     if zonal is not None:
         flags = zonal_flags(M, dev) if singular_flags is None else singular_flags
-        check(lib.fbr_run_zonal_f64(ptr(z_mesh), ptr(z_value), int(z_value.shape[1]), ptr(z_of_cell), float(z_dt), ptr(z_sigma),
-                                    ptr(flags), *tail))
+        zfn = lib.fbr_run_zonal_f64 if dtype == "float64" else lib.fbr_run_zonal_f32
+        check(zfn(ptr(z_mesh), ptr(z_value), int(z_value.shape[1]), ptr(z_of_cell), float(z_dt), ptr(z_sigma), ptr(flags), *tail))
         if singular_flags is None:
             raise_if_singular_zonal(flags)
     else:
@@ -304,6 +304,15 @@ def sample_plan(taxis, obs_taxis, baseline_index=None, window=None, dev=None):
     return dict(sample_row=to_device(row, np.int32, dev), sample_w=to_device(w, np.float64, dev),
                 row_first_sample=to_device(row_first, np.int32, dev), base_sample=base, first_sample=first,
                 last_sample=last, host=dict(row=row, w=w, done=done))
+
+
+def transpose(src):
+    """(rows, cols) fp64 device matrix -> its transpose (cols, rows) as a new contiguous tensor (fbr_transpose_f64)."""
+    torch = _torch()
+    rows, cols = src.shape
+    dst = torch.empty((cols, rows), dtype=torch.float64, device=src.device)
+    check(_cabi.load().fbr_transpose_f64(ptr(src), rows, cols, ptr(dst), current_stream()))
+    return dst
 
 
 def fp64_peak():
@@ -356,11 +365,14 @@ def run_long(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, s
 
 
 def run_stream(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, want_final=False,
-               with_initial_row=True):
-    """K3S: streaming integration of one very long mesh.  factors / p0: (1, nx).  Returns
-    (snap (1, rows, nx) | None, p_final | None)."""
+               with_initial_row=True, kernel="pass"):
+    """Exact integration of one mesh of any length.  factors / p0: (1, nx).  Returns (snap (1, rows, nx) | None,
+    p_final | None).  ``kernel='pass'``: K3P, one pass over HBM per step (40 B per cell-update, fbr_run_pass_f64);
+    ``'levels'``: K3S, the level hierarchy of round 1 (88 B per cell-update, fbr_run_stream_f64)."""
     torch = _torch()
     lib = _cabi.load()
+    work_fn, run_fn = ((lib.fbr_run_pass_work_bytes, lib.fbr_run_pass_f64) if kernel == "pass" else
+                       (lib.fbr_run_stream_work_bytes, lib.fbr_run_stream_f64))
     fl, fr, fg = factors
     dev = fl.device
     n_rows = n_steps // snapshot_every if snapshot_every else 0
@@ -372,8 +384,8 @@ def run_stream(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, sn
             snap[:, 0, :] = p0
         snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * 8)
     p_final = torch.empty((1, nx), dtype=torch.float64, device=dev) if want_final else None
-    work = torch.empty(int(lib.fbr_run_stream_work_bytes(nx)) // 8, dtype=torch.float64, device=dev)
-    check(lib.fbr_run_stream_f64(ptr(fl), ptr(fr), ptr(fg), ptr(p0), nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
+    work = torch.empty(int(work_fn(nx)) // 8, dtype=torch.float64, device=dev)
+    check(run_fn(ptr(fl), ptr(fr), ptr(fg), ptr(p0), nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
                                  ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), nx, snap_ptr,
                                  ptr(p_final), ptr(work), current_stream()))
     return snap, p_final
@@ -446,6 +458,20 @@ def run_window_to_host(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_t
     snap = torch.empty((n_rows + 1, nx), dtype=torch.float64, device=dev)
     snap[0] = p0.reshape(-1)
     entry = _pool.take(snap.numel() * 8)
+    try:
+        return _run_window_to_host_reserved(entry, snap, factors, nx, n_rows, lbc, rbc, src_idx, n_src, src_table, horizon,
+                                            snapshot_every)
+    except BaseException:
+        _pool.release(entry)
+        raise
+
+
+def _run_window_to_host_reserved(entry, snap, factors, nx, n_rows, lbc, rbc, src_idx, n_src, src_table, horizon, snapshot_every):
+    import weakref
+    torch = _torch()
+    lib = _cabi.load()
+    fl, fr, fg = factors
+    dev = fl.device
     host = entry[0][: snap.numel() * 8].view(torch.float64).view(snap.shape)
     work = torch.empty(int(lib.fbr_run_window_work_bytes(nx)) // 8, dtype=torch.float64, device=dev)
     main, side = torch.cuda.current_stream(), _copy_stream(dev)
@@ -526,9 +552,21 @@ class _PinnedPool:
         self.entries = []  # [pinned uint8 tensor, weakref to the last ndarray handed out]
         self.lock = _threading.Lock()
 
+    @staticmethod
+    def _busy():  # stands in for the weak reference between take() and the caller's entry[1] = weakref.ref(array)
+        return True
+
     def take(self, nbytes):
+        """An entry [buffer, liveness] RESERVED for the caller: the reservation happens under the lock, so two threads
+        never receive the same buffer.  The caller replaces entry[1] by a weak reference to the array it hands out, or
+        calls release(entry) when the copy failed."""
         with self.lock:
-            return self._take(nbytes)
+            entry = self._take(nbytes)
+            entry[1] = self._busy
+            return entry
+
+    def release(self, entry):
+        entry[1] = lambda: None
 
     def _take(self, nbytes):
         torch = _torch()
@@ -565,11 +603,15 @@ def to_host(t, sync=True):
         return t.cpu().numpy()
     import weakref
     entry = _pool.take(max(nbytes, 1))
-    host = entry[0][:nbytes].view(t.dtype).view(t.shape)
-    host.copy_(t, non_blocking=True)
-    if sync:
-        torch.cuda.current_stream().synchronize()
-    arr = host.numpy()
+    try:
+        host = entry[0][:nbytes].view(t.dtype).view(t.shape)
+        host.copy_(t, non_blocking=True)
+        if sync:
+            torch.cuda.current_stream().synchronize()
+        arr = host.numpy()
+    except BaseException:
+        _pool.release(entry)
+        raise
     entry[1] = weakref.ref(arr)
     return arr
 

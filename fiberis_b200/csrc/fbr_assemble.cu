@@ -276,6 +276,7 @@ extern "C" int64_t fbr_workspace_bytes(int what, int64_t M, int64_t nx) {
         case FBR_WS_RUN_LONG: return fbr_run_long_work_bytes(nx);
         case FBR_WS_RUN_STREAM: return fbr_run_stream_work_bytes(nx);
         case FBR_WS_RUN_WINDOW: return fbr_run_window_work_bytes(nx);
+        case FBR_WS_RUN_PASS: return fbr_run_pass_work_bytes(nx);
         default: fail(FBR_ERR_BAD_ARG, "unknown workspace kind %d", what); return -1;
     }
 }
@@ -283,6 +284,37 @@ extern "C" int64_t fbr_workspace_bytes(int what, int64_t M, int64_t nx) {
 extern "C" int fbr_version(void) { return FBR_VERSION; }
 extern "C" const char *fbr_last_error(void) { return last_error_ref().c_str(); }
 extern "C" int fbr_last_launch_count(void) { return launch_count_ref(); }
+
+// (rows, cols) -> (cols, rows), 32 x 32 tiles through shared memory (padded: conflict-free), both sides coalesced.
+// Turns the (time, cell) rows the long-mesh kernels write into the (cell, time) layout of Data2D / pack_result
+// (src/fiberis/simulator/core/pds.py:415) on the device: 1e7 cells x 11 rows in 0.4 ms instead of a host-side transpose.
+__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ src, int64_t rows, int64_t cols,
+                                                        double *__restrict__ dst) {
+    __shared__ double tile[32][33];
+    const int64_t tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    for (int64_t t = blockIdx.x; t < tiles_c * tiles_r; t += gridDim.x) {
+        const int64_t r0 = (t / tiles_c) * 32, c0 = (t % tiles_c) * 32;
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+#pragma unroll
+        for (int k = 0; k < 32; k += 8)
+            if (r0 + ty + k < rows && c0 + tx < cols) tile[ty + k][tx] = src[(r0 + ty + k) * cols + c0 + tx];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 32; k += 8)
+            if (c0 + ty + k < cols && r0 + tx < rows) dst[(c0 + ty + k) * rows + r0 + tx] = tile[tx][ty + k];
+        __syncthreads();
+    }
+}
+
+extern "C" int fbr_transpose_f64(const double *src, int64_t rows, int64_t cols, double *dst, void *stream) {
+    FBR_REQUIRE(src && dst && rows >= 1 && cols >= 1, "NULL pointer or empty matrix");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    const int64_t tiles = ((cols + 31) / 32) * ((rows + 31) / 32);
+    const int64_t cap = (int64_t)f.sm_count * 16;
+    transpose_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 256, 0, as_stream(stream)>>>(src, rows, cols, dst);
+    return check_launch("fbr_transpose_f64");
+}
 
 // fp64 issue peak of this device, measured: every thread runs 8 independent DFMA chains, 16 warps per SM (the
 // residency of K3), so the fp64 pipe — not latency — bounds the loop.  The denominator of bench.py's compute roofline.

@@ -34,7 +34,7 @@
 namespace fbr {
 
 constexpr int kMaxWarps = 16;  // per team
-constexpr int kMaxSrc = 64;
+constexpr int kMaxSrc = 253;  // a source column is one byte of a descriptor (0xFE / 0xFF are reserved)
 constexpr int kMaxObs = 64;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -234,7 +234,7 @@ __device__ __forceinline__ bool next_model(const RunArgs &a, ModelCursor &c, int
     return true;
 }
 
-template <typename T, int CPT, int W>
+template <typename T, int CPT, int W, bool ZONAL>
 __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchip_kernel(const RunArgs a) {
     static_assert(CPT <= 8, "slot bytes are packed into one 64-bit word");
     // cross-warp carry: C_w = sum_v K[dir][w][v] * E[dir][v], K = products of the warp-total
@@ -242,12 +242,22 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
     // E = this step's zero-carry warp-end values
     __shared__ __align__(16) T s_K[2][W][W];
     __shared__ __align__(16) T s_E[2][W];
-    __shared__ T s_T[2][W];
+    __shared__ double s_T[2][W];
     __shared__ double s_red[W];
     __shared__ long long s_snap_slot;
+    __shared__ Mat2 s_zw[ZONAL ? W : 1];
+    __shared__ double s_zc[ZONAL ? W : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nx = a.nx;
     const int64_t cell0 = (int64_t)tid * CPT;
+    unsigned src_rows = 0;  // which of my cells are source rows of the matrix (on-chip assembly mode)
+    if (ZONAL) {
+#pragma unroll 1
+        for (int k = 0; k < a.n_src; ++k) {
+            const int64_t jj = a.src_idx[k] - cell0;
+            if (jj >= 0 && jj < CPT && a.src_idx[k] < nx) src_rows |= 1u << jj;
+        }
+    }
 
     ModelCursor cursor = model_cursor(a);
     int64_t m;
@@ -255,16 +265,37 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
     while (next_model(a, cursor, m, preset)) {
         // ---------------- per-model setup ----------------
         T l[CPT], r[CPT], g[CPT], x[CPT];
+        double ld[CPT], gd[CPT];  // the multipliers in fp64: the scan multipliers are products of these, rounded once
+        if constexpr (ZONAL) {
+            // on-chip assembly (K1's arithmetic, bit-identical diagonals) + factorisation in registers: a single short
+            // model needs ONE launch instead of three (C1: the one-thread factorisation alone took 44 us)
+            double zr[CPT];
+            assemble_zonal_chunk<CPT>(a, m, (int)cell0, src_rows, ld, zr, gd);
+            const int64_t left = nx - cell0;
+            const int bad = factor_rows_in_registers<CPT, W>(ld, zr, gd, (int)cell0, (int)(left < 0 ? 0 : left > CPT ? CPT : left),
+                                                             lane, warp, s_zw, s_zc);
+            if (bad && a.z_singular) atomicMin(a.z_singular + m, bad);
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            const int64_t i = cell0 + j;
-            if (i < nx) {
-                l[j] = (T)__ldg(a.fl + m * nx + i);
-                r[j] = (T)__ldg(a.fr + m * nx + i);
-                g[j] = (T)__ldg(a.fg + m * nx + i);
-                x[j] = (T)__ldg(a.p0 + m * a.p0_stride + i);
-            } else {  // padding cell: identity row, decoupled
-                l[j] = (T)0; r[j] = (T)1; g[j] = (T)0; x[j] = (T)0;
+            for (int j = 0; j < CPT; ++j) {
+                const int64_t i = cell0 + j;
+                l[j] = (T)ld[j]; r[j] = (T)zr[j]; g[j] = (T)gd[j];
+                x[j] = i < nx ? (T)__ldg(a.p0 + m * a.p0_stride + i) : (T)0;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int64_t i = cell0 + j;
+                if (i < nx) {
+                    ld[j] = __ldg(a.fl + m * nx + i);
+                    gd[j] = __ldg(a.fg + m * nx + i);
+                    l[j] = (T)ld[j];
+                    r[j] = (T)__ldg(a.fr + m * nx + i);
+                    g[j] = (T)gd[j];
+                    x[j] = (T)__ldg(a.p0 + m * a.p0_stride + i);
+                } else {  // padding cell: identity row, decoupled
+                    ld[j] = 0.0; gd[j] = 0.0;
+                    l[j] = (T)0; r[j] = (T)1; g[j] = (T)0; x[j] = (T)0;
+                }
             }
         }
         // Which of my cells are overridden in the right-hand side / observed?  The common case — at
@@ -309,42 +340,43 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
         const double ob_w = (ob_j >= 0 && a.obs_w) ? a.obs_w[(obp - a.obs) % a.n_obs] : 1.0;
 
         // scan multipliers (time-invariant): stage products of the chunk multipliers; lanes that a
-        // stage does not touch get a zero multiplier so the time loop needs no predicates
+        // stage does not touch get a zero multiplier so the time loop needs no predicates.  The products are
+        // formed in fp64 from the fp64 factors and rounded ONCE (fp32 mode: a product of up to 256 rounded
+        // multipliers would otherwise carry their accumulated rounding into every carry of every step).
         T PfL[5], PbL[5], PfEx, PbEx;
         {
-            T pf = (T)1, pb = (T)1;
+            double pf = 1.0, pb = 1.0;
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) { pf *= -l[j]; pb *= -g[j]; }
+            for (int j = 0; j < CPT; ++j) { pf *= -ld[j]; pb *= -gd[j]; }
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 const bool fa = lane >= (1 << s), ba = lane + (1 << s) < 32;
-                PfL[s] = fa ? pf : (T)0;
-                PbL[s] = ba ? pb : (T)0;
-                const T upf = __shfl_up_sync(kFull, pf, 1 << s);
-                const T dnb = __shfl_down_sync(kFull, pb, 1 << s);
+                PfL[s] = fa ? (T)pf : (T)0;
+                PbL[s] = ba ? (T)pb : (T)0;
+                const double upf = __shfl_up_sync(kFull, pf, 1 << s);
+                const double dnb = __shfl_down_sync(kFull, pb, 1 << s);
                 if (fa) pf *= upf;
                 if (ba) pb *= dnb;
             }
             // pf = product over lanes 0..lane, pb = product over lanes lane..31
-            PfEx = __shfl_up_sync(kFull, pf, 1);
-            PbEx = __shfl_down_sync(kFull, pb, 1);
-            if (lane == 0) PfEx = (T)1;
-            if (lane == 31) PbEx = (T)1;
+            const double ex_f = __shfl_up_sync(kFull, pf, 1), ex_b = __shfl_down_sync(kFull, pb, 1);
+            PfEx = lane == 0 ? (T)1 : (T)ex_f;
+            PbEx = lane == 31 ? (T)1 : (T)ex_b;
             if (W > 1) {
                 __syncthreads();  // previous model's readers are done with the shared scratch
                 if (lane == 31) s_T[0][warp] = pf;
                 if (lane == 0) s_T[1][warp] = pb;
                 __syncthreads();
                 if (tid < W) {  // row tid of both tables
-                    T k = (T)1;
+                    double k = 1.0;
                     for (int v = W - 1; v >= 0; --v) {  // forward: warps v < tid feed warp tid
                         if (v >= tid) s_K[0][tid][v] = (T)0;
-                        else { s_K[0][tid][v] = k; k *= s_T[0][v]; }
+                        else { s_K[0][tid][v] = (T)k; k *= s_T[0][v]; }
                     }
-                    k = (T)1;
+                    k = 1.0;
                     for (int v = 0; v < W; ++v) {  // backward: warps v > tid feed warp tid
                         if (v <= tid) s_K[1][tid][v] = (T)0;
-                        else { s_K[1][tid][v] = k; k *= s_T[1][v]; }
+                        else { s_K[1][tid][v] = (T)k; k *= s_T[1][v]; }
                     }
                 }
             }
@@ -585,7 +617,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     __shared__ __align__(16) T s_E[2][W + 2];
     __shared__ T s_dummy;
     __shared__ double s_zero, s_trash;  // constant zero source value; where non-observers "record"
-    __shared__ T s_T[2][W];
+    __shared__ double s_T[2][W];
     __shared__ double s_red[W];
     __shared__ long long s_snap_slot;
     __shared__ double s_prev[kMaxObs], s_base[kMaxObs];  // observed cells: last row of the previous block; baseline sample
@@ -649,7 +681,8 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     // 16-byte loads of a thread's 8 cells when the rows allow it (nx even keeps every member's row aligned)
     const bool vec_ok = (nx % 2 == 0) && cell0 + CPT <= nx && ((reinterpret_cast<uintptr_t>(a.fl) | reinterpret_cast<uintptr_t>(a.fr) |
                          reinterpret_cast<uintptr_t>(a.fg) | reinterpret_cast<uintptr_t>(a.p0)) & 15) == 0 && a.p0_stride % 2 == 0;
-    auto load_row = [&](const double *row, double pad, T (&v)[CPT]) {
+    auto load_row = [&](const double *row, double pad, T (&v)[CPT]) -> double {  // returns the fp64 product of the row's chunk
+        double prod = 1.0;
         if (vec_ok) {
             const double2 *q = reinterpret_cast<const double2 *>(row + cell0);
 #pragma unroll
@@ -657,11 +690,17 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 const double2 t = __ldg(q + j);
                 v[2 * j] = (T)t.x;
                 v[2 * j + 1] = (T)t.y;
+                prod *= t.x * t.y;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) v[j] = (T)(cell0 + j < nx ? __ldg(row + cell0 + j) : pad);  // padding cell: identity row
+            for (int j = 0; j < CPT; ++j) {
+                const double t = cell0 + j < nx ? __ldg(row + cell0 + j) : pad;  // padding cell: identity row
+                v[j] = (T)t;
+                prod *= t;
+            }
         }
+        return prod;
     };
 
     unsigned src_rows = 0;  // which of my cells are source rows of the matrix (on-chip assembly mode)
@@ -694,8 +733,36 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     int64_t m;
     long long preset;
     while (next_model(a, cursor, m, preset)) {
+        // observation samples completed by rows (lo, hi] (for lo == 0 also those that only need the initial state)
+        auto sample_range = [&](int lo, int hi, int &ja, int &jb) {
+            if (a.sample_row) { ja = __ldg(a.row_first_sample + (lo == 0 ? 0 : lo + 1)); jb = __ldg(a.row_first_sample + hi + 1); }
+            else { ja = lo == 0 ? 0 : lo + 1; jb = hi + 1; }
+        };
+        auto stage_block = [&](int b) {  // source values of steps [b blk, ..) and the observations those steps complete
+            const int n0 = b * blk;
+            const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
+            if (rows <= 0) return;
+            const int buf = b & 1;
+            for (int e = tid; e < rows * a.n_src; e += 32 * W)
+                cp_async8(s_src + buf * blk * a.n_src + e, a.src_table + (int64_t)n0 * a.n_src + e);
+            if (a.n_obs > 0) {  // up to blk samples of the window (denser observations: the rest is read from global memory)
+                int ja, jb;
+                sample_range(n0, n0 + rows, ja, jb);
+                ja = ja < a.first_sample ? a.first_sample : ja;
+                jb = jb > a.last_sample ? a.last_sample : jb;
+                jb = jb > ja + blk ? ja + blk : jb;
+                for (int e = tid; e < (jb - ja) * a.n_obs; e += 32 * W)
+                    cp_async8(s_obs + buf * blk * a.n_obs + e, a.obs + (int64_t)ja * a.n_obs + e);
+            }
+        };
+        // the first block's scalars start their way into shared memory before anything else of this member is touched:
+        // their latency hides behind the loads of the member's rows (it sat in front of the time loop before: one exposed
+        // global -> shared round trip per member, which the step-at-a-time use pays for every single step)
+        stage_block(0);
+        cp_async_commit_k3();
         // ---------------- per-model setup ----------------
         T l[CPT], r[CPT], g[CPT], x[CPT];
+        double cpf_d = 1.0, cpb_d = 1.0, tot_f_d = 0.0, tot_b_d = 0.0;  // fp64 chunk / warp products (used by the fp32 mode)
         if constexpr (ZONAL) {
             double zl[CPT], zr[CPT], zg[CPT];
             assemble_zonal_chunk<CPT>(a, m, (int)cell0, src_rows, zl, zr, zg);
@@ -704,11 +771,14 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                                                              lane, warp, s_zw, s_zc);
             if (bad && a.z_singular) atomicMin(a.z_singular + m, bad);
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) { l[j] = (T)zl[j]; r[j] = (T)zr[j]; g[j] = (T)zg[j]; }
+            for (int j = 0; j < CPT; ++j) {
+                l[j] = (T)zl[j]; r[j] = (T)zr[j]; g[j] = (T)zg[j];
+                if (sizeof(T) == 4) { cpf_d *= zl[j]; cpb_d *= zg[j]; }
+            }
         } else {
-            load_row(a.fl + m * nx, 0.0, l);
+            cpf_d = load_row(a.fl + m * nx, 0.0, l);
             load_row(a.fr + m * nx, 1.0, r);
-            load_row(a.fg + m * nx, 0.0, g);
+            cpb_d = load_row(a.fg + m * nx, 0.0, g);
         }
         load_row(a.p0 + m * a.p0_stride, 0.0, x);
         // Left boundary row (right-hand side always 0, matbuilder.py:49-55) in a thread's first register: with r_0 := 0 and
@@ -716,22 +786,32 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
         // x_0 = -g_0 x_1 comes out of the backward sweep as before: the override costs nothing per step.
         if (desc & kDescZeroFirst) { r[0] = (T)0; l[1] = (T)0; }
 
-        const ScanMultipliersT<T> sm = scan_multipliers<T>(chunk_product<T, CPT>(l), chunk_product<T, CPT>(g), lane);
-        if (W > 1) {
-            __syncthreads();  // previous model's readers are done with the shared scratch
-            if (lane == 31) s_T[0][warp] = sm.tot_f;
-            if (lane == 0) s_T[1][warp] = sm.tot_b;
+        // scan multipliers: products of the chunk multipliers over runs of lanes / warps.  In the fp32 mode they are formed
+        // in fp64 from the fp64 factors and rounded ONCE — a product of up to 512 rounded multipliers would otherwise carry
+        // their accumulated rounding into every carry of every step.
+        ScanMultipliersT<T> sm;
+        if constexpr (sizeof(T) == 8) sm = scan_multipliers<T>(chunk_product<T, CPT>(l), chunk_product<T, CPT>(g), lane);
+        else {
+            const ScanMultipliersT<double> smd = scan_multipliers<double>(cpf_d, cpb_d, lane);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { sm.f[q] = (T)smd.f[q]; sm.b[q] = (T)smd.b[q]; }
+            sm.ex_f = (T)smd.ex_f; sm.ex_b = (T)smd.ex_b; sm.tot_f = (T)smd.tot_f; sm.tot_b = (T)smd.tot_b;
+            tot_f_d = smd.tot_f; tot_b_d = smd.tot_b;
+        }
+        if (W > 1) {  // (the barrier that ends every member protects the shared scratch of the previous one)
+            if (lane == 31) s_T[0][warp] = sizeof(T) == 8 ? (double)sm.tot_f : tot_f_d;
+            if (lane == 0) s_T[1][warp] = sizeof(T) == 8 ? (double)sm.tot_b : tot_b_d;
             __syncthreads();
             if (tid < W) {  // row tid of both tables
-                T k = (T)1;
+                double k = 1.0;
                 for (int v = W - 1; v >= 0; --v) {  // forward: warps v < tid feed warp tid
                     if (v >= tid) s_K[0][tid][v] = (T)0;
-                    else { s_K[0][tid][v] = k; k *= s_T[0][v]; }
+                    else { s_K[0][tid][v] = (T)k; k *= s_T[0][v]; }
                 }
-                k = (T)1;
+                k = 1.0;
                 for (int v = 0; v < W; ++v) {  // backward: warps v > tid feed warp tid
                     if (v <= tid) s_K[1][tid][v] = (T)0;
-                    else { s_K[1][tid][v] = k; k *= s_T[1][v]; }
+                    else { s_K[1][tid][v] = (T)k; k *= s_T[1][v]; }
                 }
             }
         }
@@ -767,28 +847,6 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
         const bool recorded = snap_slot >= 0;
         double acc = 0.0;
 
-        // observation samples completed by rows (lo, hi] (for lo == 0 also those that only need the initial state)
-        auto sample_range = [&](int lo, int hi, int &ja, int &jb) {
-            if (a.sample_row) { ja = __ldg(a.row_first_sample + (lo == 0 ? 0 : lo + 1)); jb = __ldg(a.row_first_sample + hi + 1); }
-            else { ja = lo == 0 ? 0 : lo + 1; jb = hi + 1; }
-        };
-        auto stage_block = [&](int b) {  // source values of steps [b blk, ..) and the observations those steps complete
-            const int n0 = b * blk;
-            const int rows = n_steps - n0 < blk ? n_steps - n0 : blk;
-            if (rows <= 0) return;
-            const int buf = b & 1;
-            for (int e = tid; e < rows * a.n_src; e += 32 * W)
-                cp_async8(s_src + buf * blk * a.n_src + e, a.src_table + (int64_t)n0 * a.n_src + e);
-            if (a.n_obs > 0) {  // up to blk samples of the window (denser observations: the rest is read from global memory)
-                int ja, jb;
-                sample_range(n0, n0 + rows, ja, jb);
-                ja = ja < a.first_sample ? a.first_sample : ja;
-                jb = jb > a.last_sample ? a.last_sample : jb;
-                jb = jb > ja + blk ? ja + blk : jb;
-                for (int e = tid; e < (jb - ja) * a.n_obs; e += 32 * W)
-                    cp_async8(s_obs + buf * blk * a.n_obs + e, a.obs + (int64_t)ja * a.n_obs + e);
-            }
-        };
         // Residuals of the observation samples whose last needed state lies in rows (lo, hi] — the block just integrated
         // (trace buffer `buf`; row lo itself is s_prev) — plus, for lo == 0, those that only need the initial state.
         auto flush_rows = [&](int lo, int hi, int buf) {
@@ -835,8 +893,6 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 if (k >= n_obs) { k -= n_obs; ++j; }
             }
         };
-        stage_block(0);
-        cp_async_commit_k3();
         unsigned src_addr = smem_addr(&s_zero), tr_addr = smem_addr(&s_trash);
         const unsigned src_inc = (has_ov && !ov_zero) ? 8u * a.n_src : 0u, tr_inc = has_ob ? 8u * a.n_obs : 0u;
 
@@ -1215,14 +1271,12 @@ template <typename T>
 static int launch_x(const RunArgs &a, cudaStream_t stream) {
     constexpr int CPT = 64 / sizeof(T);
     const int64_t threads = (a.nx + CPT - 1) / CPT;
-    if constexpr (sizeof(T) == 8) {
-        if (a.z_mesh) {  // on-chip assembly + factorisation (fbr_run_zonal_f64)
-            if (threads <= 32) return launch_onchipx<T, CPT, 1, true>(a, stream);
-            if (threads <= 64) return launch_onchipx<T, CPT, 2, true>(a, stream);
-            if (threads <= 128) return launch_onchipx<T, CPT, 4, true>(a, stream);
-            if (threads <= 256) return launch_onchipx<T, CPT, 8, true>(a, stream);
-            return launch_onchipx<T, CPT, 16, true>(a, stream);
-        }
+    if (a.z_mesh) {  // on-chip assembly + factorisation (fbr_run_zonal_f64 / _f32: assembled and factorised in fp64)
+        if (threads <= 32) return launch_onchipx<T, CPT, 1, true>(a, stream);
+        if (threads <= 64) return launch_onchipx<T, CPT, 2, true>(a, stream);
+        if (threads <= 128) return launch_onchipx<T, CPT, 4, true>(a, stream);
+        if (threads <= 256) return launch_onchipx<T, CPT, 8, true>(a, stream);
+        return launch_onchipx<T, CPT, 16, true>(a, stream);
     }
     if (threads <= 32) return launch_onchipx<T, CPT, 1>(a, stream);
     if (threads <= 64) return launch_onchipx<T, CPT, 2>(a, stream);
@@ -1231,11 +1285,11 @@ static int launch_x(const RunArgs &a, cudaStream_t stream) {
     return launch_onchipx<T, CPT, 16>(a, stream);
 }
 
-template <typename T, int CPT, int W>
+template <typename T, int CPT, int W, bool ZONAL>
 static int launch_onchip(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
-    auto kern = run_onchip_kernel<T, CPT, W>;
+    auto kern = run_onchip_kernel<T, CPT, W, ZONAL>;
     int occ = 0;
     FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, 0));
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d)", 32 * W);
@@ -1245,14 +1299,15 @@ static int launch_onchip(const RunArgs &a, cudaStream_t stream) {
     return check_launch("fbr_run (on-chip)");
 }
 
-template <typename T, int CPT>
+template <typename T, int CPT, bool ZONAL = false>
 static int launch_cpt(const RunArgs &a, cudaStream_t stream) {
     const int64_t threads = (a.nx + CPT - 1) / CPT;
-    if (threads <= 32) return launch_onchip<T, CPT, 1>(a, stream);
-    if (threads <= 64) return launch_onchip<T, CPT, 2>(a, stream);
-    if (threads <= 128) return launch_onchip<T, CPT, 4>(a, stream);
-    if (threads <= 256) return launch_onchip<T, CPT, 8>(a, stream);
-    return launch_onchip<T, CPT, 16>(a, stream);
+    if (threads <= 32) return launch_onchip<T, CPT, 1, ZONAL>(a, stream);
+    if (threads <= 64) return launch_onchip<T, CPT, 2, ZONAL>(a, stream);
+    if (threads <= 128) return launch_onchip<T, CPT, 4, ZONAL>(a, stream);
+    if (ZONAL) return fail(FBR_ERR_UNSUPPORTED, "on-chip assembly of short models covers up to 128 threads");
+    if (threads <= 256) return launch_onchip<T, CPT, 8, false>(a, stream);
+    return launch_onchip<T, CPT, 16, false>(a, stream);
 }
 
 template <typename T>
@@ -1294,7 +1349,17 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     const int64_t x_min = min_env ? atoll(min_env) : (sizeof(T) == 8 ? 129 : 512);
     // (a handful of members below 256 cells is a latency problem, not a throughput one: the generic kernel's shorter
     // chains over more threads win there — C1, one 200-cell model: 0.50 against 0.75 us per step)
-    const bool few_short = sizeof(T) == 8 && a.nx < 256 && a.M < 32 && !a.z_mesh && !min_env;
+    const bool few_short = sizeof(T) == 8 && a.nx < 256 && a.M < 32 && !min_env;
+    if constexpr (sizeof(T) == 8) {
+        if (few_short && a.z_mesh && a.n_samples == 0) {  // one launch for a short single model (on-chip assembly, fp64)
+            switch (cpt) {
+                case 1: return launch_cpt<T, 1, true>(a, stream);
+                case 2: return launch_cpt<T, 2, true>(a, stream);
+                case 4: return launch_cpt<T, 4, true>(a, stream);
+                default: return launch_cpt<T, 8, true>(a, stream);
+            }
+        }
+    }
     // observations on their own time axis are evaluated by the 64-byte-per-thread kernel only
     const bool needs_x = a.n_samples > 0;
     if (needs_x || (a.nx >= x_min && !few_short && !getenv("FBR_K3_GENERIC"))) return launch_x<T>(a, stream);
@@ -1390,9 +1455,28 @@ extern "C" int fbr_run_zonal_f64(const double *mesh, const double *zone_value, i
     FBR_FILL_ARGS();
     FBR_REQUIRE(mesh && zone_value && n_zones >= 1, "NULL mesh / zone arguments");
     FBR_REQUIRE(zone_of_cell || n_zones == nx, "zone_of_cell == NULL means one diffusivity per cell: n_zones must equal nx");
-    FBR_REQUIRE(nx > 128 && nx <= fbr_run_max_nx(), "on-chip assembly covers 128 < nx <= %lld (got %lld)",
-                (long long)fbr_run_max_nx(), (long long)nx);
+    FBR_REQUIRE((nx > 128 || (M < 32 && nx >= 2)) && nx <= fbr_run_max_nx(),
+                "on-chip assembly covers 128 < nx <= %lld (a few short models: 2 <= nx), got nx = %lld, M = %lld",
+                (long long)fbr_run_max_nx(), (long long)nx, (long long)M);
     a.z_mesh = mesh; a.z_value = zone_value; a.z_of_cell = zone_of_cell; a.z_n = n_zones; a.z_dt = dt; a.z_sigma = sigma;
     a.z_singular = singular;
     return run_dispatch<double>(a, as_stream(stream));
+}
+
+extern "C" int fbr_run_zonal_f32(const double *mesh, const double *zone_value, int n_zones, const int32_t *zone_of_cell,
+                                 double dt, const double *sigma, int32_t *singular, const double *p0, int64_t p0_stride,
+                                 int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                                 const double *src_table, int64_t snapshot_every, const int64_t *snap_models,
+                                 int64_t n_snap_models, int64_t snap_row_stride, int64_t snap_model_stride, float *snap,
+                                 float *p_final, const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
+                                 double *misfit, const fbr_run_opts *opts, void *stream) {
+    const double *fl = nullptr, *fr = nullptr, *fg = nullptr;
+    FBR_FILL_ARGS();
+    FBR_REQUIRE(mesh && zone_value && n_zones >= 1, "NULL mesh / zone arguments");
+    FBR_REQUIRE(zone_of_cell || n_zones == nx, "zone_of_cell == NULL means one diffusivity per cell: n_zones must equal nx");
+    FBR_REQUIRE(nx >= 512 && nx <= fbr_run_max_nx(), "fp32 on-chip assembly covers 512 <= nx <= %lld (got %lld)",
+                (long long)fbr_run_max_nx(), (long long)nx);
+    a.z_mesh = mesh; a.z_value = zone_value; a.z_of_cell = zone_of_cell; a.z_n = n_zones; a.z_dt = dt; a.z_sigma = sigma;
+    a.z_singular = singular;
+    return run_dispatch<float>(a, as_stream(stream));
 }

@@ -1,0 +1,368 @@
+// K3P  exact time integration of meshes of ANY length in ONE pass over HBM per step: 40 B per cell-update
+// (three factors + p^n in, p^{n+1} out).  Replaces the level hierarchy of K3S (88 B per cell-update) as the
+// exact fallback behind the windowed kernel K3W — stiff long meshes, whose decay horizon is too long for windows.
+//
+// The mesh is cut into tiles of 2048 cells; a CTA of 8 warps solves a tile in registers with the sweeps of K3
+// (8 cells per thread, warp scans, exact carry table across the warps).  What couples the tiles is one number per
+// tile and sweep direction — the carry — and both carries are obtained without a second pass over the data:
+//   * forward carry: y at the last cell of the tile on the left.  It depends only on p^n, which the previous launch
+//     finished: every tile leaves, next to p^{n+1}, the zero-carry end value of ITS forward sweep for the NEXT step
+//     (Ef) — the next launch folds the Ef of the tiles on its left with the time-invariant tile products Mf
+//     (exact: the fold stops when the running product underflows to exactly 0, or at tile 0);
+//   * backward carry: x at the first cell of the tile on the right.  It depends on this step's forward results, so it
+//     is resolved inside the launch by a decoupled look-back: tiles are handed out right to left (atomic ticket), a
+//     tile publishes its zero-carry aggregate as soon as its own forward sweep is done, its right-hand neighbours
+//     already run, and the inclusive value follows (status word: epoch * 4 + {1 local, 2 inclusive}; release /
+//     acquire on the word, no reset between launches).
+// One launch per time step; snapshot rows are written in place and read back as the next step's input.
+// Latency is what this pipeline fights (a tile is ~2.5 us of dependent work, two CTAs per SM): the next tile's four rows
+// stream into shared memory (cp.async, 64 KB) while the current one is solved, its ticket is drawn a tile ahead, the
+// forward fold is issued before the rows are touched, and a tile's aggregate travels with its status in ONE 16-byte
+// word (one store to publish, one load to poll — no fence, no second round trip).
+#include "fbr_common.cuh"
+#include "fbr_sweep.cuh"
+
+namespace fbr {
+
+constexpr int kPW = 8;              // warps per tile
+constexpr int kPTile = 256 * kPW;   // cells per tile
+
+struct PassArgs {
+    const double *fl, *fr, *fg;
+    const double *p_in;
+    double *p_out;
+    int64_t nx, n_tiles;
+    int lbc, rbc;
+    const int64_t *src_idx;
+    int n_src;
+    const double *src_now, *src_next;  // (n_src) values overriding the right-hand side of this / the next step (next: NULL at the end)
+    double *Mf, *Mb;                   // (n_tiles) products of the multipliers over each tile (written by the setup pass)
+    const double *Ef_now;              // (n_tiles) zero-carry forward end value of every tile for THIS step
+    double *Ef_next;                   // (n_tiles) the same for the next step
+    double2 *Lw, *Iw;                  // (n_tiles) backward aggregates of this launch as (value, epoch * 4 + status) words:
+                                       // Lw = zero-carry (local) aggregate, status 1; Iw = inclusive value, status 2
+    unsigned *ticket;                  // one counter, never reset: every launch adds n_tiles + gridDim.x to it (each CTA's last,
+    unsigned ticket_base;              // failing draw included), so launch e starts at e * (n_tiles + grid) = ticket_base
+    unsigned epoch;                    // launch number, from 1 (0 = the setup launch)
+};
+
+// (value, tag) in one naturally aligned 16-byte word: written and read by single 128-bit accesses that bypass L1
+__device__ __forceinline__ void st_word(double2 *p, double v, unsigned tag) {
+    asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(__hiloint2double(0, (int)tag)) : "memory");
+}
+__device__ __forceinline__ unsigned ld_word(const double2 *p, double &v) {
+    double t;
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "l"(p) : "memory");
+    return (unsigned)__double2loint(t);
+}
+__device__ __forceinline__ void cp_async16_pass(unsigned smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// b = p with this step's overrides on my 8 cells (matbuilder.py:45-76: boundary rows first, sources in list order).
+// tile_has_src: some source lies in this CTA's tile (almost never: the scan over the source list is skipped otherwise)
+__device__ __forceinline__ void apply_overrides(double (&x)[8], int64_t cell0, int64_t nx, int lbc, int rbc,
+                                                const int64_t *__restrict__ src_idx, int n_src, const double *__restrict__ src_val,
+                                                bool tile_has_src) {
+    if (cell0 == 0 && lbc != FBR_BC_NONE) x[0] = 0.0;
+    const int64_t jl = nx - 1 - cell0;
+    if (jl >= 0 && jl < 8 && rbc != FBR_BC_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j == jl) x[j] = 0.0;
+    }
+    if (!tile_has_src) return;
+#pragma unroll 1
+    for (int k = 0; k < n_src; ++k) {
+        const int64_t jj = __ldg(src_idx + k) - cell0;
+        if (jj >= 0 && jj < 8 && __ldg(src_idx + k) < nx) {
+            const double v = __ldg(src_val + k);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j == jj) x[j] = v;
+        }
+    }
+}
+
+// SETUP: only the tile products and the forward aggregates of step 0 are produced (p_out, look-back untouched).
+template <bool SETUP>
+__global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
+    constexpr int W = kPW;
+    __shared__ double s_E[2][W];        // zero-carry warp totals of the current sweep
+    __shared__ double s_T[2][W];        // products of the multipliers over each warp
+    __shared__ double s_carry[2];       // carries into the tile: forward (from the left), backward (from the right)
+    __shared__ unsigned s_ticket[2];
+    extern __shared__ __align__(16) double s_stage[];  // [4 arrays][4 pieces][256 threads] x 16 bytes: the NEXT tile's rows
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned base = a.ticket_base;
+    const int64_t nx = a.nx;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.fl) | reinterpret_cast<uintptr_t>(a.fr) | reinterpret_cast<uintptr_t>(a.fg) |
+                           reinterpret_cast<uintptr_t>(a.p_in)) & 15) == 0;
+    const unsigned stage0 = smem_addr(s_stage) + 16u * tid;
+    // rows of tile `t` -> shared memory, each thread its own 8 cells, piece j of array q at [(q * 4 + j) * 256 + tid]
+    // (conflict-free for the copy and for the 16-byte reads); only whole, aligned tiles are staged
+    auto staged = [&](int64_t t) { return !SETUP && aligned && t >= 0 && (t + 1) * kPTile <= nx; };
+    // (one array per call, spread over the tile's computation: sixteen copies per thread back to back overflow the
+    //  load / store queue — 22 % of the stall samples of the first version)
+    auto stage_rows = [&](int64_t t, int q) {
+        if (!staged(t)) return;
+        const int64_t c0 = t * kPTile + (int64_t)tid * 8;
+        const double *src = (q == 0 ? a.fl : q == 1 ? a.fr : q == 2 ? a.fg : a.p_in) + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cp_async16_pass(stage0 + 16u * 256u * (q * 4 + j), src + 2 * j);
+    };
+    auto stage_tile = [&](int64_t t) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) stage_rows(t, q);
+    };
+    // the source cells, once per CTA: which tiles hold one is then a shared-memory question
+    __shared__ int64_t s_src[256];
+    for (int k = tid; k < a.n_src && k < 256; k += 32 * W) s_src[k] = __ldg(a.src_idx + k);
+
+    if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1u) - base;
+    __syncthreads();
+    if (s_ticket[0] < (unsigned)a.n_tiles) stage_tile(a.n_tiles - 1 - (int64_t)s_ticket[0]);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int it = 0;; ++it) {
+        const unsigned ticket = s_ticket[it & 1];
+        if (ticket >= (unsigned)a.n_tiles) break;
+        if (tid == 0) s_ticket[(it & 1) ^ 1] = atomicAdd(a.ticket, 1u) - base;  // the next tile's ticket, a tile ahead
+        const int64_t tile = a.n_tiles - 1 - (int64_t)ticket;  // right to left
+        const int64_t cell0 = tile * kPTile + (int64_t)tid * 8;
+
+        // ---- forward carry into the tile: fold the finished aggregates of the tiles on the left (issued first: its
+        //      loads fly while the rows arrive) ----
+        if (!SETUP && warp == 0) {
+            double c = 0.0, prod = 1.0;
+            for (int64_t j0 = tile - 1; j0 >= 0 && prod != 0.0; j0 -= 32) {
+                const int64_t j = j0 - lane;  // lane 0 = nearest tile
+                double acc = j >= 0 ? __ldg(a.Ef_now + j) : 0.0;  // value carried out of the nearest tile by lanes 0 .. lane
+                double pm = j >= 0 ? __ldg(a.Mf + j) : 0.0;       // product of the multipliers of lanes 0 .. lane
+#pragma unroll
+                for (int s = 1; s < 32; s <<= 1) {  // affine maps composed nearest-first
+                    const double up_acc = __shfl_up_sync(kAllLanes, acc, s), up_pm = __shfl_up_sync(kAllLanes, pm, s);
+                    if (lane >= s) { acc = fma(up_pm, acc, up_acc); pm *= up_pm; }
+                }
+                c = fma(prod, __shfl_sync(kAllLanes, acc, 31), c);
+                prod *= __shfl_sync(kAllLanes, pm, 31);
+            }
+            if (lane == 0) s_carry[0] = c;
+        }
+
+        // ---- my 8 cells: factors and state (identity rows behind the mesh) ----
+        double l[8], r[8], g[8], x[8];
+        if (staged(tile)) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");  // my own copies: no barrier needed to read them back
+            auto take = [&](int q, double (&v)[8]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 t = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(s_stage) +
+                                                                         16 * (256 * (q * 4 + j) + tid));
+                    v[2 * j] = t.x;
+                    v[2 * j + 1] = t.y;
+                }
+            };
+            take(0, l); take(1, r); take(2, g); take(3, x);
+        } else {
+            auto load8 = [&](const double *src, double pad, double (&v)[8], bool ro) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = cell0 + j < nx ? (ro ? __ldg(src + cell0 + j) : src[cell0 + j]) : pad;
+            };
+            load8(a.fl, 0.0, l, true);
+            load8(a.fr, 1.0, r, true);
+            load8(a.fg, 0.0, g, true);
+            load8(a.p_in, 0.0, x, false);  // written by the previous launch: plain (coherent) loads
+        }
+        // the next ticket is visible; everybody has taken its rows out of the staging buffer; does a source lie in this tile?
+        bool src_here = false;
+        for (int k = tid; k < a.n_src; k += 32 * W) {
+            const int64_t i = k < 256 ? s_src[k] : __ldg(a.src_idx + k);
+            src_here = src_here || (i >= tile * kPTile && i < (tile + 1) * kPTile);
+        }
+        const bool tile_has_src = __syncthreads_or(src_here);
+        const unsigned nt = s_ticket[(it & 1) ^ 1];
+        const int64_t next_tile = nt < (unsigned)a.n_tiles ? a.n_tiles - 1 - (int64_t)nt : -1;
+        stage_rows(next_tile, 0);
+        const ScanMultipliers sm = scan_multipliers<double>(chunk_product<double, 8>(l), chunk_product<double, 8>(g), lane);
+        if (lane == 31) s_T[0][warp] = sm.tot_f;
+        if (lane == 0) s_T[1][warp] = sm.tot_b;
+
+        // zero-carry forward sweep of the tile for right-hand side b: the warp-inclusive chunk-end values
+        auto forward_ends = [&](const double (&b)[8]) {
+            double y = chunk_end_fwd_plain<double, 8>(b, l);
+#pragma unroll
+            for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+            return y;
+        };
+        // value at the tile's last cell from the warps' zero-carry totals E (and a carry c into the tile)
+        auto tile_forward_end = [&](double c) {
+            double v = c;
+            for (int w = 0; w < W; ++w) v = fma(s_T[0][w], v, s_E[0][w]);
+            return v;
+        };
+
+        if (SETUP) {
+            apply_overrides(x, cell0, nx, a.lbc, a.rbc, a.src_idx, a.n_src, a.src_now, tile_has_src);
+            const double y = forward_ends(x);
+            if (lane == 31) s_E[0][warp] = y;
+            __syncthreads();
+            if (tid == 0) {
+                double mf = 1.0, mb = 1.0;
+                for (int w = 0; w < W; ++w) { mf *= s_T[0][w]; mb *= s_T[1][w]; }
+                a.Mf[tile] = mf;
+                a.Mb[tile] = mb;
+                a.Ef_next[tile] = tile_forward_end(0.0);
+            }
+            __syncthreads();  // the shared scratch is reused by the next tile
+            continue;
+        }
+
+        apply_overrides(x, cell0, nx, a.lbc, a.rbc, a.src_idx, a.n_src, a.src_now, tile_has_src);
+        // ---- forward sweep: y_i = b_i - l_i y_{i-1}, t_i = r_i y_i ----
+        {
+            const double y = forward_ends(x);
+            double c = and_mask(__shfl_up_sync(kAllLanes, y, 1), lane == 0 ? 0 : -1);
+            if (lane == 31) s_E[0][warp] = y;
+            __syncthreads();
+            double cw = s_carry[0];  // y in front of my warp: the tile's carry folded through the warps on my left
+            for (int w = 0; w < warp; ++w) cw = fma(s_T[0][w], cw, s_E[0][w]);
+            c = fma(sm.ex_f, cw, c);
+            chunk_apply_fwd_plain<double, 8>(x, l, r, c);
+        }
+        if (!SETUP) stage_rows(next_tile, 1);
+        // ---- backward sweep, zero carry from the right: publish the tile's aggregate, look back, apply ----
+        {
+            double z = chunk_end_bwd_plain<double, 8>(x, g);
+#pragma unroll
+            for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+            double c = and_mask(__shfl_down_sync(kAllLanes, z, 1), lane == 31 ? 0 : -1);
+            if (lane == 0) s_E[1][warp] = z;
+            stage_rows(next_tile, 2);
+            __syncthreads();
+            if (tid == 0) {
+                double loc = 0.0, mb = 1.0;  // value at the tile's first cell for a zero carry from the right
+                for (int w = W - 1; w >= 0; --w) { loc = fma(s_T[1][w], loc, s_E[1][w]); mb *= s_T[1][w]; }
+                st_word(a.Lw + tile, loc, a.epoch * 4u + 1u);
+                double cb = 0.0, prod = 1.0;
+                for (int64_t j = tile + 1; j < a.n_tiles && prod != 0.0; ++j) {
+                    const double mbj = __ldg(a.Mb + j);
+                    for (;;) {  // the neighbour's inclusive value ends the walk; its local aggregate continues it
+                        double vi, vl;
+                        const unsigned ti = ld_word(a.Iw + j, vi), tl = ld_word(a.Lw + j, vl);  // (both in flight together)
+                        if (ti == a.epoch * 4u + 2u) { cb = fma(prod, vi, cb); prod = 0.0; break; }
+                        if (tl == a.epoch * 4u + 1u) { cb = fma(prod, vl, cb); prod *= mbj; break; }
+                    }
+                }
+                st_word(a.Iw + tile, fma(mb, cb, loc), a.epoch * 4u + 2u);
+                s_carry[1] = cb;
+            }
+            __syncthreads();
+            double cw = s_carry[1];  // x behind my warp: the tile's carry folded through the warps on my right
+            for (int w = W - 1; w > warp; --w) cw = fma(s_T[1][w], cw, s_E[1][w]);
+            c = fma(sm.ex_b, cw, c);
+            chunk_apply_bwd_plain<double, 8>(x, g, c);
+        }
+        stage_rows(next_tile, 3);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // ---- p^{n+1} out ----
+        if (cell0 + 8 <= nx && (reinterpret_cast<uintptr_t>(a.p_out + cell0) & 15) == 0) {
+            double2 *q = reinterpret_cast<double2 *>(a.p_out + cell0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) q[j] = make_double2(x[2 * j], x[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (cell0 + j < nx) a.p_out[cell0 + j] = x[j];
+        }
+        // ---- the next step's forward aggregate of this tile (its right-hand side is p^{n+1} with that step's overrides) ----
+        if (a.src_next || a.n_src == 0) {
+            apply_overrides(x, cell0, nx, a.lbc, a.rbc, a.src_idx, a.n_src, a.src_next, tile_has_src);
+            const double y = forward_ends(x);
+            if (lane == 31) s_E[0][warp] = y;  // (this step's forward totals were last read before the previous barrier)
+            __syncthreads();
+            if (tid == 0) a.Ef_next[tile] = tile_forward_end(0.0);
+        }
+        __syncthreads();  // the shared scratch is reused by the next tile
+    }
+}
+
+constexpr int64_t kPassTileWords = 8;  // Mf, Mb, Ef[2], two 16-byte status words per tile
+
+}  // namespace fbr
+
+using namespace fbr;
+
+extern "C" int64_t fbr_run_pass_work_bytes(int64_t nx) {
+    const int64_t tiles = (nx + kPTile - 1) / kPTile;
+    return (2 * nx + kPassTileWords * tiles + 16) * (int64_t)sizeof(double);
+}
+
+extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
+                                int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                                const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
+                                double *snap, double *p_final, double *work, void *stream) {
+    FBR_REQUIRE(nx >= 1 && n_steps >= 0, "bad nx / n_steps");
+    FBR_REQUIRE(fl && fr && fg && p0 && work, "NULL factor / initial-state / work pointer");
+    FBR_REQUIRE(lbc >= 0 && lbc <= 2 && rbc >= 0 && rbc <= 2, "bad boundary code");
+    FBR_REQUIRE(n_src >= 0 && (n_src == 0 || (src_idx && src_table)), "sources given without src_idx / src_table");
+    FBR_REQUIRE(!snap || (snapshot_every >= 1 && snap_row_stride >= nx), "bad snapshot layout");
+    FBR_REQUIRE(n_steps < (1 << 29), "n_steps per call is limited to 2^29 - 1");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    cudaStream_t st = as_stream(stream);
+    const int64_t tiles = (nx + kPTile - 1) / kPTile;
+    FBR_REQUIRE((tiles + 4096) * (n_steps + 2) < 0xffffffffll, "tiles x steps overflows the ticket counter: split the run");
+    // ---- carve the workspace ----
+    double *w = work;
+    double *buf[2] = {w, w + nx};
+    w += 2 * nx;
+    double *Mf = w; w += tiles;
+    double *Mb = w; w += tiles;
+    double *Ef[2] = {w, w + tiles};
+    w += 2 * tiles;
+    if ((reinterpret_cast<uintptr_t>(w) & 15) != 0) ++w;  // 16-byte words
+    double2 *Lw = reinterpret_cast<double2 *>(w); w += 2 * tiles;
+    double2 *Iw = reinterpret_cast<double2 *>(w); w += 2 * tiles;
+    unsigned *ticket = reinterpret_cast<unsigned *>(w);
+    FBR_CUDA(cudaMemsetAsync(Lw, 0, (size_t)tiles * 32 + 16, st));  // status words and the ticket counter
+    const size_t smem = 4 * (size_t)kPTile * sizeof(double);  // staging of one tile's four rows
+    FBR_CUDA(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBR_CUDA(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel<false>, 32 * kPW, smem));
+    if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "pass kernel does not fit on an SM");
+    int64_t grid = (int64_t)occ * f.sm_count;
+    if (grid > tiles) grid = tiles;
+
+    PassArgs a;
+    a.fl = fl; a.fr = fr; a.fg = fg; a.nx = nx; a.n_tiles = tiles; a.lbc = lbc; a.rbc = rbc; a.src_idx = src_idx; a.n_src = n_src;
+    a.Mf = Mf; a.Mb = Mb; a.Lw = Lw; a.Iw = Iw; a.ticket = ticket;
+    // setup launch (epoch 0): tile products and the forward aggregates of step 0
+    a.p_in = p0; a.p_out = nullptr; a.src_now = src_table; a.src_next = nullptr; a.Ef_now = nullptr; a.Ef_next = Ef[0]; a.epoch = 0;
+    a.ticket_base = 0;
+    if (n_steps > 0) {
+        pass_kernel<true><<<(unsigned)grid, 32 * kPW, smem, st>>>(a);
+        if (int rc = check_launch("fbr_run_pass (setup)")) return rc;
+    }
+    const double *cur = p0;
+    int64_t snap_row = 0;
+    for (int64_t n = 0; n < n_steps; ++n) {
+        const bool row_due = snap && (n + 1) % snapshot_every == 0;
+        const bool last = n + 1 == n_steps;
+        double *out = row_due ? snap + snap_row * snap_row_stride : (last && p_final) ? p_final : buf[n & 1];
+        if (out == cur) out = buf[(n & 1) ^ 1];  // (never the case: rows and work buffers alternate) keep in != out
+        a.p_in = cur; a.p_out = out;
+        a.src_now = n_src ? src_table + n * n_src : nullptr;
+        a.src_next = (n_src && !last) ? src_table + (n + 1) * n_src : nullptr;
+        a.Ef_now = Ef[n & 1]; a.Ef_next = Ef[(n & 1) ^ 1];
+        a.epoch = (unsigned)(n + 1);
+        a.ticket_base = (unsigned)((n + 1) * (tiles + grid));
+        pass_kernel<false><<<(unsigned)grid, 32 * kPW, smem, st>>>(a);
+        if (int rc = check_launch("fbr_run_pass")) return rc;
+        if (row_due) ++snap_row;
+        cur = out;
+    }
+    if (p_final && cur != p_final)
+        FBR_CUDA(cudaMemcpyAsync(p_final, cur, (size_t)nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return FBR_OK;
+}

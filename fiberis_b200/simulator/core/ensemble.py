@@ -168,11 +168,15 @@ class PDS1D_Ensemble:
 
     # -- solve ------------------------------------------------------------------------------------
     def solve(self, dt, t_total=None, audit_models=(), snapshot_every=1, dtype="float64", models=None,
-              process_group=None, gather=True, split_audit=True, on_chip_assembly=True, scan_log2_eps=0.0):
+              process_group=None, gather=True, split_audit=True, on_chip_assembly=True, scan_log2_eps=0.0,
+              result_layout="time_major"):
         """Integrate every member with a fixed ``dt``.
 
         Ensembles in fp64 with 129..4096 cells assemble and factorise their matrices inside the run
         kernel (``fbr_run_zonal_f64``; ``on_chip_assembly=False`` selects the three-kernel path K1 + K1b + K3).
+
+        ``result_layout='cell_major'``: the audited members' snapshots are written by the kernel as ``(member, cell,
+        time)`` — ``Data2D``'s layout; ``snapshot`` stays ``(member, time, cell)`` as a transposed view of that array.
 
         ``scan_log2_eps``: threshold below which a member's far scan terms are skipped (``fbr_run_opts``; default
         2^-80, a positive value keeps every member's scans exact).
@@ -193,8 +197,20 @@ class PDS1D_Ensemble:
         dist = _dist(process_group)
         if models is None and dist is not None:
             models = shard_bounds(M_all, dist.get_world_size(process_group), dist.get_rank(process_group))
+        sharded = models is None and dist is not None
         lo, hi = (0, M_all) if models is None else models
         M = hi - lo
+        if dist is not None and gather and not sharded and (lo, hi) != shard_bounds(
+                M_all, dist.get_world_size(process_group), dist.get_rank(process_group)):
+            raise ValueError("gather=True assembles the misfits of the ranks' own shards (shard_bounds); with an explicit "
+                             "`models` block that is not this rank's shard pass gather=False.")
+        if M == 0:  # more ranks than members: nothing to integrate here, but the collective still needs this rank
+            import torch
+            self.taxis = np.array(taxis)
+            self.snapshot, self.audit_models = None, []
+            empty = torch.empty(0, dtype=torch.float64, device=_engine.device())
+            self.misfit = (gather_misfit(empty, M_all, process_group) if (dist is not None and gather) else empty).cpu().numpy()
+            return self.misfit
 
         proto = PDS1D_MultiSource()
         proto.source, proto.t0 = self.source, self.t0
@@ -203,9 +219,10 @@ class PDS1D_Ensemble:
         mesh_d = _engine.to_device(self.mesh)
         sidx_d, n_src = _engine.index_tensor(self.sourceidx)
         # fp64 ensembles on a shared mesh: the matrices are assembled and factorised inside the run kernel
-        # (fbr_run_zonal_f64), no (M, nx) coefficient array exists.  The fp32 mode / short meshes: K1 + K1b + K3.
+        # (fbr_run_zonal_f64 / _f32), no (M, nx) coefficient array exists.  Short meshes: K1 + K1b + K3.
         zonal = flags_d = None
-        on_chip = dtype == "float64" and 128 < nx <= _engine.run_max_nx() and on_chip_assembly and (nx >= 256 or M >= 32)
+        on_chip = on_chip_assembly and nx <= _engine.run_max_nx() and (
+            (dtype == "float64" and nx > 128 and (nx >= 256 or M >= 32)) or (dtype == "float32" and nx >= 512))
         if on_chip:
             if self.diffusivity is None:
                 zonal = (mesh_d, _engine.to_device(self.zone_value[lo:hi]), _engine.to_device(self.zone_of_cell, np.int32),
@@ -244,8 +261,11 @@ class PDS1D_Ensemble:
             obs_d = _engine.to_device(self.obs)
             w_d = None if self.obs_weights is None else _engine.to_device(self.obs_weights)
 
+        if result_layout not in ("time_major", "cell_major"):
+            raise ValueError("result_layout must be 'time_major' or 'cell_major'.")
+        cell_major = result_layout == "cell_major"
         run_kw = dict(obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, obs_w=w_d, dtype=dtype, sampling=sampling,
-                      scan_log2_eps=scan_log2_eps)
+                      scan_log2_eps=scan_log2_eps, cell_major=cell_major)
         n_rows = n_steps // snapshot_every if n_audit else 0
         host_snap = None
         if n_rows and M >= 8 * n_audit and M >= 512 and split_audit:
@@ -296,6 +316,8 @@ class PDS1D_Ensemble:
                 self.snapshot = _engine.to_host(_engine.as_f64(snap_d))  # fp32 mode: widened on the device, not on the host
             if len(audit_unique) != len(audit) or np.any(audit_slot != np.arange(len(audit))):
                 self.snapshot = self.snapshot[audit_slot]  # back to the order (and repeats) the caller listed
+            if cell_major:  # the array is (member, cell, time): expose the reference's (time, cell) order as a view
+                self.snapshot = np.transpose(self.snapshot, (0, 2, 1))
         elif n_audit:  # snapshot_every > n_steps: only the initial state is kept, as in the single-model path
             rows = np.asarray(self.initial, dtype=np.float64)
             self.snapshot = np.stack([(rows if rows.ndim == 1 else rows[a]).copy() for a in audit])[:, None, :]

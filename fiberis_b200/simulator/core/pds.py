@@ -82,6 +82,9 @@ def fixed_time_axis(t0, dt, t_total):
     taxis[0] = t0
     return taxis
 
+_K3_MAX_SOURCES = 253  # fbr_run_*: a source column is one descriptor byte
+
+
 class PDS1D_SingleSource:
     """One mesh, one pressure source pinned at ``sourceidx`` (a Dirichlet-in-time row)."""
 
@@ -295,8 +298,13 @@ class PDS1D_SingleSource:
         mode = kwargs.get("mode", "implicit")
         dtype = kwargs.get("dtype", "float64")
         every = int(kwargs.get("snapshot_every", 1))
+        layout = kwargs.get("result_layout", "time_major")
         if dtype not in ("float64", "float32"):
             raise ValueError("dtype must be 'float64' or 'float32'.")
+        if layout not in ("time_major", "cell_major"):
+            raise ValueError("result_layout must be 'time_major' or 'cell_major'.")
+        cell_major = layout == "cell_major" and mode == "implicit"
+        self._data_cell_major = None
         if every < 1:
             raise ValueError("snapshot_every must be >= 1.")
         # exact replica of the reference's time axis (fp64 accumulation decides the step count)
@@ -310,19 +318,63 @@ class PDS1D_SingleSource:
             return
         nx, mesh_d, diff_d, sidx_d, n_src, pml, smax, p0_d = self._device_model(kwargs, initial[None, :])
         table = self._source_table(taxis[:-1])
+        one_launch = (mode == "implicit" and dtype == "float64" and 2 <= nx <= _engine.run_max_nx()
+                      and n_src <= _K3_MAX_SOURCES and kwargs.get("on_chip_assembly", True))
+        if one_launch:
+            # the whole solve is ONE kernel: the matrix is assembled (K1's arithmetic) and factorised in registers by the
+            # run kernel itself (fbr_run_zonal_f64 with one diffusivity per cell) — no (nx) coefficient arrays, no
+            # separate assembly / factorisation launches (C1: 3 launches and a 44 us one-thread factorisation before)
+            sigma_d = _engine.pml_sigma(mesh_d, pml, smax) if pml != 0.0 else None
+            table_d = _engine.to_device(table)
+            snap_d, _, _ = _engine.run(None, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                       snapshot_every=every, cell_major=cell_major,
+                                       zonal=(mesh_d, diff_d.reshape(1, nx), None, dt, sigma_d))
+            if cell_major and snap_d is not None:
+                snap_d = _CellMajor(snap_d[0])
+            if snap_d is None:
+                self.snapshot = initial[None, :].copy()
+            elif isinstance(snap_d, _CellMajor):
+                self._data_cell_major = _engine.to_host(snap_d.t)
+                self.snapshot = self._data_cell_major.T
+            else:
+                self.snapshot = _engine.to_host(snap_d[0])
+            kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
+            self.taxis = np.array(taxis)[kept] if every > 1 else np.array(taxis)
+            self.record_log(f"{n_steps} full steps solved on device (dt={dt}, mode={mode}, dtype={dtype}). "
+                            f"taxis[-1]=", taxis[-1])
+            if kwargs.get("print_progress"):
+                for n in range(n_steps):
+                    vals = table[n].tolist()
+                    print("Time:", taxis[n + 1], "Source term:", vals if self._multi else vals[0])
+            return
         dl, d, du = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
         if mode == "implicit":
             factors = _engine.factorize(dl, d, du)
             table_d = _engine.to_device(table)
-            if nx <= _engine.run_max_nx():  # K3: one CTA keeps the whole model in registers
+            if nx <= _engine.run_max_nx() and n_src > _K3_MAX_SOURCES:
+                # more sources than the on-chip kernel's descriptors hold (the reference takes any number): one
+                # right-hand side + one register-resident solve per step (fbr_rhs_f64 + fbr_solve_tridiag_f64)
+                snap_d = self._step_loop(dl, d, du, p0_d, sidx_d, n_src, table_d, n_steps, every)
+            elif nx <= _engine.run_max_nx():  # K3: one CTA keeps the whole model in registers
                 snap_d, _, _ = _engine.run(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                           snapshot_every=every, dtype=dtype)
+                                           snapshot_every=every, dtype=dtype, cell_major=cell_major)
+                if cell_major and snap_d is not None:  # (1, nx, rows + 1): the kernel wrote Data2D's layout
+                    snap_d = _CellMajor(snap_d[0])
             else:
                 if dtype != "float64":
                     raise NotImplementedError("the long-mesh kernels are fp64 only")
+                if cell_major:  # keep the rows on the device: they are transposed there, then copied home once
+                    kwargs = dict(kwargs, stream_rows=False)
                 snap_d = self._run_long_mesh(factors, p0_d, nx, n_steps, sidx_d, n_src, table_d, every, kwargs)
+            if cell_major and snap_d is not None and not isinstance(snap_d, _CellMajor):
+                snap_d = _CellMajor(_engine.transpose(_engine.as_f64(snap_d[0])))  # (rows + 1, nx) -> (nx, rows + 1) on the device
             if snap_d is None:  # snapshot_every > n_steps: only the initial state is kept
                 self.snapshot = initial[None, :].copy()
+            elif isinstance(snap_d, _CellMajor):
+                # result_layout='cell_major': the host array IS Data2D's (cell, time) matrix; `snapshot` stays the
+                # reference's (time, cell) object as a transposed view of it (no copy either way)
+                self._data_cell_major = _engine.to_host(_engine.as_f64(snap_d.t))
+                self.snapshot = self._data_cell_major.T
             elif isinstance(snap_d, np.ndarray):  # rows already streamed to the host
                 self.snapshot = snap_d
             else:  # (1, rows + 1, nx) with row 0 = initial, written in place by the kernel
@@ -368,11 +420,23 @@ class PDS1D_SingleSource:
             self.long_mesh_path = dict(kernel="K3L")  # tiled over one cooperative grid
             snap_d, _ = _engine.run_long(factors, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
                                          table_d, snapshot_every=every)
-        else:  # state and factors stream from HBM every step
-            self.long_mesh_path = dict(kernel="K3S")
+        else:  # state and factors stream from HBM every step: one pass per step (K3P; 'levels' = K3S of round 1)
+            which_exact = kwargs.get("_exact_kernel", "pass")
+            self.long_mesh_path = dict(kernel="K3P" if which_exact == "pass" else "K3S")
             snap_d, _ = _engine.run_stream(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                           snapshot_every=every)
+                                           snapshot_every=every, kernel=which_exact)
         return snap_d
+
+    def _step_loop(self, dl, d, du, p_d, sidx_d, n_src, table_d, n_steps, every):
+        """Fixed-dt loop with one library call pair per step (models with more than 253 sources)."""
+        import torch
+        rows = [p_d[0]]
+        for n in range(n_steps):
+            b = _engine.rhs(p_d, self.lbc, self.rbc, sidx_d, n_src, table_d[n])
+            p_d = _engine.solve_tridiag(dl, d, du, b)
+            if (n + 1) % every == 0:
+                rows.append(p_d[0])
+        return torch.stack(rows)[None] if len(rows) > 1 else None
 
     def _jacobi_loop(self, dl, d, du, p_d, sidx_d, n_src, table, n_steps, every):
         """mode != 'implicit': one Jacobi solve per step (reference pds.py:296-300)."""
@@ -398,6 +462,10 @@ class PDS1D_SingleSource:
         limit, PML runs, ``print_progress`` and duck-typed sources use the host-driven loop below,
         which keeps the states on the device and moves one 8-byte error per iteration."""
         nx = len(self.mesh)
+        if kwargs.get("mode", "implicit") != "implicit":
+            # the reference solves the FULL step of every iteration with Jacobi in this mode (pds.py:296-300, 562-569;
+            # the two half steps stay implicit): host-driven loop, Jacobi kernel for the full step
+            return self._solve_adaptive_host(dt_init, t_total, kwargs)
         device_loop = (nx <= _engine.adaptive_max_nx() and not kwargs.get("print_progress")
                        and float(kwargs.get("pml_thickness", 0.0)) == 0.0
                        and all(_uses_stock_interp(s) for s in self._sources())
@@ -470,8 +538,13 @@ class PDS1D_SingleSource:
             self.record_log("Time:", self.taxis[-1], "Source term:", vals if self._multi else vals[0])
             vals_d = _engine.to_device(np.asarray(vals, dtype=np.float64))
             bc = (self.lbc, self.rbc, sidx_d, n_src, vals_d)  # fbr_step_f64: rhs overrides fused into the solve
-            full = _engine.step(*_engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax),
-                                p_d, *bc)
+            full_sys = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
+            if kwargs.get("mode", "implicit") == "implicit":
+                full = _engine.step(*full_sys, p_d, *bc)
+            else:  # reference pds.py:296-300: anything but 'implicit' is the Jacobi solver (warns when it does not converge)
+                full, iters = _engine.jacobi(*full_sys, _engine.rhs(p_d, self.lbc, self.rbc, sidx_d, n_src, vals_d))
+                if int((iters <= 0).sum().item()):
+                    print("Warning: Maximum iterations reached without convergence.")
             half_sys = _engine.assemble(mesh_d, diff_d, 1, nx, dt / 2, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
             mid = _engine.step(*half_sys, p_d, *bc)
             half = _engine.step(*half_sys, mid, *bc)
@@ -502,8 +575,15 @@ class PDS1D_SingleSource:
     def get_val_at_source_idx(self):
         return self.snapshot[:, self.sourceidx]
 
-    def get_val_at_idx(self, idx):
-        return self.snapshot[:, idx]
+    def get_val_at_idx(self, idx, as_data1d=False):
+        """Pressure history of cell ``idx`` (reference pds.py:364-366: the raw column).  ``as_data1d=True`` returns it
+        as a ``Data1D`` channel (taxis of the run, the source's start_time) — the object the analyzer side works with."""
+        if not as_data1d:
+            return self.snapshot[:, idx]
+        from fiberis_b200.analyzer.Data1D.core1D import Data1D
+        first = self.source[0] if isinstance(self.source, list) else self.source
+        return Data1D(data=np.array(self.snapshot[:, idx], dtype=np.float64), taxis=np.asarray(self.taxis, dtype=float).copy(),
+                      start_time=getattr(first, "start_time", None), name=f"cell {int(idx)}")
 
     def get_val_at_time(self, time):
         k = np.argmin(np.abs(self.taxis - time))
@@ -543,6 +623,7 @@ class PDS1D_SingleSource:
         """The result as a ``Data2D`` object without the npz round trip (additive helper)."""
         from fiberis_b200.analyzer.Data2D.core2D import Data2D
         first = self.source[0] if isinstance(self.source, list) else self.source
+        # after solve(result_layout='cell_major') snapshot.T is the C-contiguous array the kernel wrote: no copy here
         return Data2D(data=np.ascontiguousarray(self.snapshot.T), taxis=np.asarray(self.taxis, dtype=float),
                       daxis=np.asarray(self.mesh, dtype=float), start_time=getattr(first, "start_time", None),
                       name=name)
@@ -550,7 +631,15 @@ class PDS1D_SingleSource:
     def reset(self):
         self.taxis = None
         self.snapshot = None
+        self._data_cell_major = None
         self.history = []
+
+
+class _CellMajor:
+    """Marks a device tensor that already has the (cell, time) layout."""
+
+    def __init__(self, t):
+        self.t = t
 
 
 class _DeviceRow:

@@ -56,6 +56,12 @@ enum {
 int fbr_version(void);
 const char *fbr_last_error(void);
 
+/* dst (cols, rows) = transpose of src (rows, cols), both row-major fp64.  Turns the (time, cell) rows written by the
+ * long-mesh run kernels into the (cell, time) array Data2D / pack_result hold (src/fiberis/simulator/core/pds.py:415,
+ * src/fiberis/analyzer/Data2D/core2D.py:27) without a host-side transpose; the on-chip kernels write that layout
+ * directly (fbr_run_opts.snap_cell_stride). */
+int fbr_transpose_f64(const double *src, int64_t rows, int64_t cols, double *dst, void *stream);
+
 /* Measurement aid: the fp64 issue peak of the current device in lane-level DFMA per second (8 independent chains per
  * thread, 16 warps per SM, timed with CUDA events on `stream`; synchronous).  bench.py's compute-side roofline divides
  * the fp64 operations K3 executes by this figure.  h_dfma_per_s: host; d_sink: 8 bytes of device scratch. */
@@ -138,7 +144,7 @@ int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64
  *                 With opts->n_samples > 0 the observations have their OWN time axis (see fbr_run_opts).
  *   opts        : NULL (all defaults) or a pointer to a struct fbr_run_opts in host memory, read during the call
  * The _f32 variant keeps state and factors in float (fp32 mode of north_star, gated at 1e-5).
- * Limits of this on-chip variant: nx <= fbr_run_max_nx(), n_src <= 64, n_obs <= 64.
+ * Limits of this on-chip variant: nx <= fbr_run_max_nx(), n_src <= 253, n_obs <= 64.
  * ------------------------------------------------------------------------------------------ */
 
 /* Options of fbr_run_f64 / fbr_run_f32 / fbr_run_zonal_f64.  A zero-filled struct (with struct_bytes set) means
@@ -216,6 +222,17 @@ int fbr_run_zonal_f64(const double *mesh, const double *zone_value, int n_zones,
                       const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
                       double *misfit, const fbr_run_opts *opts, void *stream);
 
+/* The same with state and factors kept in float (fp32 mode): the matrices are still assembled and factorised in
+ * fp64 on chip and rounded once.  512 <= nx <= fbr_run_max_nx(). */
+int fbr_run_zonal_f32(const double *mesh, const double *zone_value, int n_zones,
+                      const int32_t *zone_of_cell, double dt, const double *sigma, int32_t *singular,
+                      const double *p0, int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc,
+                      int rbc, const int64_t *src_idx, int n_src, const double *src_table,
+                      int64_t snapshot_every, const int64_t *snap_models, int64_t n_snap_models,
+                      int64_t snap_row_stride, int64_t snap_model_stride, float *snap, float *p_final,
+                      const int64_t *obs_idx, int n_obs, const double *obs, const double *obs_w,
+                      double *misfit, const fbr_run_opts *opts, void *stream);
+
 int64_t fbr_run_max_nx(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -249,6 +266,20 @@ int fbr_run_stream_f64(const double *fl, const double *fr, const double *fg, con
                        int n_src, const double *src_table, int64_t snapshot_every,
                        int64_t snap_row_stride, double *snap, double *p_final, double *work,
                        void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3P the exact long-mesh integration in ONE pass over HBM per step (40 B per cell-update: three factors and p^n
+ * in, p^{n+1} out; csrc/fbr_run_pass.cu) — any nx.  Tiles of 2048 cells are solved in registers; the forward carry
+ * between tiles comes from aggregates the previous launch left behind, the backward carry from a decoupled look-back
+ * inside the launch.  Same arguments as fbr_run_stream_f64; work: fbr_run_pass_work_bytes(nx) bytes; one launch per
+ * time step plus one setup launch.  Takes the place of K3S behind PDS1D_*.solve for meshes whose decay horizon is too
+ * long for the windowed kernel.
+ * ------------------------------------------------------------------------------------------ */
+int64_t fbr_run_pass_work_bytes(int64_t nx);
+int fbr_run_pass_f64(const double *fl, const double *fr, const double *fg, const double *p0,
+                     int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                     const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
+                     double *snap, double *p_final, double *work, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3W the same integration for ONE long mesh through overlapping on-chip WINDOWS with time blocking
@@ -364,7 +395,7 @@ int fbr_misfit_f64(const double *snap, int64_t n_models, int64_t n_rows, int64_t
  * named by `what` needs for M models of nx cells (0 = none); < 0 on an unknown kind. */
 enum {
     FBR_WS_FACTORIZE = 0, FBR_WS_SOLVE = 1, FBR_WS_SOLVE_THOMAS = 2, FBR_WS_RUN = 3, FBR_WS_RUN_LONG = 4,
-    FBR_WS_RUN_STREAM = 5, FBR_WS_RUN_WINDOW = 6
+    FBR_WS_RUN_STREAM = 5, FBR_WS_RUN_WINDOW = 6, FBR_WS_RUN_PASS = 7
 };
 int64_t fbr_workspace_bytes(int what, int64_t M, int64_t nx);
 

@@ -252,14 +252,15 @@ def adjust_dt(dt, error, safety_factor=0.9, p=2, max_dt=40, min_dt=1e-4, tol=1e-
 
 
 def solve_adaptive(mesh, diffusivity, initial, lbc, rbc, sourceidx, sources, t0, dt_init, t_total,
-                   tol=1e-3, max_iter=None, **adjust_kwargs):
+                   tol=1e-3, max_iter=None, mode="implicit", **adjust_kwargs):
     """pds.py:312-336 + tso.py:4-33 for optimizer=True.
 
     Quirks preserved: the user's ``tol`` is used for accept/reject only and is NOT forwarded to
     ``adjust_dt`` (tso.py:4,21 — it binds to the positional parameter); both half steps use the
     source value at the START of the step (taxis is not advanced, matbuilder.py:73); the accepted
     state is the FULL-step solution (tso.py:26).  ``max_iter`` bounds the loop (the reference can
-    spin forever when err is nan).
+    spin forever when err is nan).  ``mode`` other than ``'implicit'``: the FULL step of every iteration is
+    solved with Jacobi, the two half steps stay implicit (pds.py:296-300 against :319,325).
     Returns (snapshot, taxis, n_iterations).
     """
     sidx = np.atleast_1d(np.asarray(sourceidx)).astype(np.int64)
@@ -275,7 +276,10 @@ def solve_adaptive(mesh, diffusivity, initial, lbc, rbc, sourceidx, sources, t0,
         it += 1
         sv = [np.interp(float(taxis[-1] - t0), st, sd) for st, sd in sources]
         b = assemble_rhs(snaps[-1], lbc, rbc, sidx, sv)
-        full = solve_tridiag(*assemble_tridiag(mesh, diffusivity, dt, lbc, rbc, sidx), b)
+        if mode == "implicit":
+            full = solve_tridiag(*assemble_tridiag(mesh, diffusivity, dt, lbc, rbc, sidx), b)
+        else:
+            full = jacobi(*assemble_tridiag(mesh, diffusivity, dt, lbc, rbc, sidx), b)
         fh = _Factor(*assemble_tridiag(mesh, diffusivity, dt / 2, lbc, rbc, sidx))
         mid = fh.solve(b)
         half = fh.solve(assemble_rhs(mid, lbc, rbc, sidx, sv))

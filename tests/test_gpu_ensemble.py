@@ -63,11 +63,15 @@ def test_ensemble_member_equals_single_model_api():
     e, c = make_ensemble(3, 5, 300, 30)
     e.solve(dt=1.0, t_total=c["T"], audit_models=[2], on_chip_assembly=False)
     p = e.member(2)
-    p.solve(dt=1.0, t_total=c["T"])
-    npt.assert_array_equal(e.snapshot[0], p.snapshot)  # same kernels, same arithmetic: bit-equal
-    # default: the matrices are assembled and factorised inside the run kernel (scan-based pivots: last-bit differences)
+    p.solve(dt=1.0, t_total=c["T"], on_chip_assembly=False)
+    npt.assert_array_equal(e.snapshot[0], p.snapshot)  # same kernels (K1 + K1b + K3), same arithmetic: bit-equal
+    # default, both APIs: the matrices are assembled and factorised inside the run kernel (scan-based pivots:
+    # last-bit differences against the sequential factorisation)
     e.solve(dt=1.0, t_total=c["T"], audit_models=[2])
     assert G.rel_max(e.snapshot[0], p.snapshot) <= 1e-13
+    q = e.member(2)
+    q.solve(dt=1.0, t_total=c["T"])
+    assert G.rel_max(q.snapshot, p.snapshot) <= 1e-13
 
 
 @pytest.mark.parametrize("nx,lbc,rbc", [(256, "Neumann", "Neumann"), (300, "Dirichlet", "Neumann"), (777, "Neumann", "Dirichlet"),
@@ -526,3 +530,13 @@ def test_cell_major_snapshots_are_the_transpose(nx, M):
     cols, _, _ = E.run(*args, snapshot_every=3, cell_major=True)
     assert cols.shape == (M, nx, rows.shape[1])
     npt.assert_array_equal(cols.cpu().numpy(), rows.cpu().numpy().transpose(0, 2, 1))
+
+
+def test_ensemble_cell_major_audit_snapshots():
+    e, c = make_ensemble(21, 600, 512, 40)
+    e.solve(dt=c["dt"], t_total=c["T"], audit_models=[3, 599, 3])
+    ref = e.snapshot.copy()
+    e.solve(dt=c["dt"], t_total=c["T"], audit_models=[3, 599, 3], result_layout="cell_major")
+    assert e.snapshot.shape == ref.shape
+    npt.assert_array_equal(e.snapshot, ref)
+    assert np.transpose(e.snapshot, (0, 2, 1)).flags["C_CONTIGUOUS"]

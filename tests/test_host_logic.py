@@ -336,6 +336,25 @@ def test_pinned_pool_drops_unused_buffers_by_identity():
         for n in sizes:
             e = pool.take(n)
             assert e[0].numel() >= n
+            pool.release(e)  # (what the death of the array that aliased the buffer amounts to)
         assert len(pool.entries) <= 8
+        # a reservation holds until the caller installs its weak reference or releases: the same buffer is never handed
+        # out twice, also not to a second thread that asks between take() and the caller's bookkeeping
+        a, b = pool.take(5000), pool.take(5000)
+        assert a is not b and a[0].data_ptr() != b[0].data_ptr()
+        pool.release(a)
+        assert pool.take(5000) is a
+        import threading
+        got, lock = [], threading.Lock()
+
+        def grab():
+            for _ in range(200):
+                e = pool.take(4096)
+                with lock:
+                    got.append(id(e))
+        ts = [threading.Thread(target=grab) for _ in range(4)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert len(set(got)) == len(got) == 800
     finally:
         torch.empty = real_empty
