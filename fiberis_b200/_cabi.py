@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libf
 
 FBR_OK, FBR_ERR_BAD_ARG, FBR_ERR_UNSUPPORTED, FBR_ERR_CUDA = 0, -1, -2, -3
 BC_CODES = {"None": 0, "Dirichlet": 1, "Neumann": 2}
-SOLVER_AUTO, SOLVER_THOMAS, SOLVER_PCR, SOLVER_REG = 0, 1, 2, 3
+SOLVER_AUTO, SOLVER_THOMAS, SOLVER_PCR, SOLVER_REG, SOLVER_PIVOT = 0, 1, 2, 3, 4
 WS_FACTORIZE, WS_SOLVE, WS_SOLVE_THOMAS, WS_RUN, WS_RUN_LONG, WS_RUN_STREAM, WS_RUN_WINDOW, WS_RUN_PASS = range(8)
 
 _p = C.c_void_p
@@ -92,6 +92,7 @@ SIGNATURES = {
                                     _p, _f64, _f64, _f64, _f64, _f64, _f64, _i64, _i64, _p, _p, _p, _i64, _p, _p]),
     "fbr_solve_tridiag_work_bytes": (_i64, [_i64, _i64, _i32]),
     "fbr_solve_tridiag_f64": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p]),
+    "fbr_solve_dense_f64": (_i32, [_p, _i64, _p, _p, _p]),
     "fbr_step_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i32, _p, _p, _p]),
     "fbr_misfit_f64": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i32, _p, _p, _i64, _p, _p]),
     "fbr_workspace_bytes": (_i64, [_i32, _i64, _i64]),

@@ -640,14 +640,33 @@ def solve_tridiag(dl, d, du, b, variant=_cabi.SOLVER_AUTO, check_singular=True):
     work = None
     if variant == _cabi.SOLVER_THOMAS or (variant == _cabi.SOLVER_AUTO and nx > 4096):
         work = torch.empty((M, nx), dtype=torch.float64, device=d.device)
+    elif variant == _cabi.SOLVER_PIVOT:
+        work = torch.empty((4, M, nx), dtype=torch.float64, device=d.device)
     check(lib.fbr_solve_tridiag_f64(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(x), M, nx, int(variant), ptr(work),
                                     ptr(flags), current_stream()))
-    if check_singular:
-        if variant == _cabi.SOLVER_AUTO and nx <= 4096 and bool(flags.any()):
+    if check_singular and bool(flags.any()):
+        if variant == _cabi.SOLVER_AUTO and nx <= 4096:
             # the register-resident variant also flags systems whose leading minors leave the fp64 range between two
             # rescalings (rows scaled by ~1e77 and more): the elimination without products of pivots decides
             return solve_tridiag(dl, d, du, b, _cabi.SOLVER_THOMAS, True)
+        if variant != _cabi.SOLVER_PIVOT:
+            # a zero pivot WITHOUT row interchanges: the reference's LAPACK solve pivots (PDESolver_IMP.py:27-28) and
+            # only a truly singular matrix raises there — same here (DGTSV algorithm, fbr_solve_tridiag_f64 PIVOT)
+            return solve_tridiag(dl, d, du, b, _cabi.SOLVER_PIVOT, True)
         raise_if_singular(flags, "system")
+    return x
+
+
+def solve_dense(A, b):
+    """General dense solve with partial pivoting (fbr_solve_dense_f64; API completeness of ``solver_implicit``)."""
+    torch = _torch()
+    n = A.shape[0]
+    Ab = torch.cat([A, b.reshape(n, 1)], dim=1).contiguous()
+    x = torch.empty(n, dtype=torch.float64, device=A.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=A.device)
+    check(_cabi.load().fbr_solve_dense_f64(ptr(Ab), n, ptr(x), ptr(flag), current_stream()))
+    if int(flag):
+        raise np.linalg.LinAlgError("Matrix is singular.")
     return x
 
 

@@ -234,14 +234,19 @@ __device__ __forceinline__ bool next_model(const RunArgs &a, ModelCursor &c, int
     return true;
 }
 
-template <typename T, int CPT, int W, bool ZONAL>
+// WIDE (fp32 mode, a few short models): the state is kept and written in float, but factors and arithmetic stay in
+// fp64 — ONE model has no throughput reason to round its factors, and on a uniform mesh every cell's l, r, g round to
+// fp32 the same way: the bias of the conserved mean is then systematic (C1, 1000 steps: 1.04e-5 with float factors
+// whatever the chunking; the fp32-rounded STATE alone stays near 1e-6).
+template <typename T, int CPT, int W, bool ZONAL, bool WIDE>
 __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchip_kernel(const RunArgs a) {
     static_assert(CPT <= 8, "slot bytes are packed into one 64-bit word");
+    using A = typename std::conditional<WIDE, double, T>::type;  // arithmetic / factor type
     // cross-warp carry: C_w = sum_v K[dir][w][v] * E[dir][v], K = products of the warp-total
     // multipliers between warp v and warp w (time-invariant, zero where warp v does not feed warp w),
     // E = this step's zero-carry warp-end values
-    __shared__ __align__(16) T s_K[2][W][W];
-    __shared__ __align__(16) T s_E[2][W];
+    __shared__ __align__(16) A s_K[2][W][W];
+    __shared__ __align__(16) A s_E[2][W];
     __shared__ double s_T[2][W];
     __shared__ double s_red[W];
     __shared__ long long s_snap_slot;
@@ -264,7 +269,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
     long long preset;
     while (next_model(a, cursor, m, preset)) {
         // ---------------- per-model setup ----------------
-        T l[CPT], r[CPT], g[CPT], x[CPT];
+        A l[CPT], r[CPT], g[CPT], x[CPT];
         double ld[CPT], gd[CPT];  // the multipliers in fp64: the scan multipliers are products of these, rounded once
         if constexpr (ZONAL) {
             // on-chip assembly (K1's arithmetic, bit-identical diagonals) + factorisation in registers: a single short
@@ -278,8 +283,8 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int64_t i = cell0 + j;
-                l[j] = (T)ld[j]; r[j] = (T)zr[j]; g[j] = (T)gd[j];
-                x[j] = i < nx ? (T)__ldg(a.p0 + m * a.p0_stride + i) : (T)0;
+                l[j] = (A)ld[j]; r[j] = (A)zr[j]; g[j] = (A)gd[j];
+                x[j] = i < nx ? (A)__ldg(a.p0 + m * a.p0_stride + i) : (A)0;
             }
         } else {
 #pragma unroll
@@ -288,13 +293,13 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 if (i < nx) {
                     ld[j] = __ldg(a.fl + m * nx + i);
                     gd[j] = __ldg(a.fg + m * nx + i);
-                    l[j] = (T)ld[j];
-                    r[j] = (T)__ldg(a.fr + m * nx + i);
-                    g[j] = (T)gd[j];
-                    x[j] = (T)__ldg(a.p0 + m * a.p0_stride + i);
+                    l[j] = (A)ld[j];
+                    r[j] = (A)__ldg(a.fr + m * nx + i);
+                    g[j] = (A)gd[j];
+                    x[j] = (A)__ldg(a.p0 + m * a.p0_stride + i);
                 } else {  // padding cell: identity row, decoupled
                     ld[j] = 0.0; gd[j] = 0.0;
-                    l[j] = (T)0; r[j] = (T)1; g[j] = (T)0; x[j] = (T)0;
+                    l[j] = (A)0; r[j] = (A)1; g[j] = (A)0; x[j] = (A)0;
                 }
             }
         }
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
         // stage does not touch get a zero multiplier so the time loop needs no predicates.  The products are
         // formed in fp64 from the fp64 factors and rounded ONCE (fp32 mode: a product of up to 256 rounded
         // multipliers would otherwise carry their accumulated rounding into every carry of every step).
-        T PfL[5], PbL[5], PfEx, PbEx;
+        A PfL[5], PbL[5], PfEx, PbEx;
         {
             double pf = 1.0, pb = 1.0;
 #pragma unroll
@@ -351,8 +356,8 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 const bool fa = lane >= (1 << s), ba = lane + (1 << s) < 32;
-                PfL[s] = fa ? (T)pf : (T)0;
-                PbL[s] = ba ? (T)pb : (T)0;
+                PfL[s] = fa ? (A)pf : (A)0;
+                PbL[s] = ba ? (A)pb : (A)0;
                 const double upf = __shfl_up_sync(kFull, pf, 1 << s);
                 const double dnb = __shfl_down_sync(kFull, pb, 1 << s);
                 if (fa) pf *= upf;
@@ -360,8 +365,8 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
             }
             // pf = product over lanes 0..lane, pb = product over lanes lane..31
             const double ex_f = __shfl_up_sync(kFull, pf, 1), ex_b = __shfl_down_sync(kFull, pb, 1);
-            PfEx = lane == 0 ? (T)1 : (T)ex_f;
-            PbEx = lane == 31 ? (T)1 : (T)ex_b;
+            PfEx = lane == 0 ? (A)1 : (A)ex_f;
+            PbEx = lane == 31 ? (A)1 : (A)ex_b;
             if (W > 1) {
                 __syncthreads();  // previous model's readers are done with the shared scratch
                 if (lane == 31) s_T[0][warp] = pf;
@@ -370,13 +375,13 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 if (tid < W) {  // row tid of both tables
                     double k = 1.0;
                     for (int v = W - 1; v >= 0; --v) {  // forward: warps v < tid feed warp tid
-                        if (v >= tid) s_K[0][tid][v] = (T)0;
-                        else { s_K[0][tid][v] = (T)k; k *= s_T[0][v]; }
+                        if (v >= tid) s_K[0][tid][v] = (A)0;
+                        else { s_K[0][tid][v] = (A)k; k *= s_T[0][v]; }
                     }
                     k = 1.0;
                     for (int v = 0; v < W; ++v) {  // backward: warps v > tid feed warp tid
-                        if (v <= tid) s_K[1][tid][v] = (T)0;
-                        else { s_K[1][tid][v] = (T)k; k *= s_T[1][v]; }
+                        if (v <= tid) s_K[1][tid][v] = (A)0;
+                        else { s_K[1][tid][v] = (A)k; k *= s_T[1][v]; }
                     }
                 }
             }
@@ -412,65 +417,65 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
             const double ov_next = __ldg(ovp), ob_next = __ldg(obp);
 
             // right-hand side: b = p^n with boundary / source overrides (matbuilder.py:45-76)
-            if (ov_j >= 0) set_at<T, CPT>(x, ov_j, (T)ov_val);
+            if (ov_j >= 0) set_at<A, CPT>(x, ov_j, (A)ov_val);
             if (ov_slow) {  // several overridden cells in this thread: re-derive them (rare, slow)
                 const int64_t n = a.n_steps - left;
-                if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (T)0;
+                if (cell0 == 0 && a.lbc != FBR_BC_NONE) x[0] = (A)0;
                 const int64_t jl = nx - 1 - cell0;
-                if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) set_at<T, CPT>(x, (int)jl, (T)0);
+                if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) set_at<A, CPT>(x, (int)jl, (A)0);
 #pragma unroll 1
                 for (int k = 0; k < a.n_src; ++k) {
                     const int64_t jj = a.src_idx[k] - cell0;
-                    if (jj >= 0 && jj < CPT) set_at<T, CPT>(x, (int)jj, (T)__ldg(a.src_table + n * a.n_src + k));
+                    if (jj >= 0 && jj < CPT) set_at<A, CPT>(x, (int)jj, (A)__ldg(a.src_table + n * a.n_src + k));
                 }
             }
             // ---- forward sweep: y_i = b_i - l_i y_{i-1} ----
-            T y = (T)0;
+            A y = (A)0;
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) y = fma_t<T>(-l[j], y, x[j]);
+            for (int j = 0; j < CPT; ++j) y = fma_t<A>(-l[j], y, x[j]);
 #pragma unroll
-            for (int s = 0; s < 5; ++s) y = fma_t<T>(PfL[s], __shfl_up_sync(kFull, y, 1 << s), y);
-            T carry = __shfl_up_sync(kFull, y, 1);
-            if (lane == 0) carry = (T)0;
+            for (int s = 0; s < 5; ++s) y = fma_t<A>(PfL[s], __shfl_up_sync(kFull, y, 1 << s), y);
+            A carry = __shfl_up_sync(kFull, y, 1);
+            if (lane == 0) carry = (A)0;
             if (W > 1) {
                 if (lane == 31) s_E[0][warp] = y;
                 __syncthreads();
-                T c = (T)0;
+                A c = (A)0;
 #pragma unroll
-                for (int v = 0; v < W - 1; ++v) c = fma_t<T>(s_K[0][warp][v], s_E[0][v], c);
-                carry = fma_t<T>(PfEx, c, carry);
+                for (int v = 0; v < W - 1; ++v) c = fma_t<A>(s_K[0][warp][v], s_E[0][v], c);
+                carry = fma_t<A>(PfEx, c, carry);
             }
             y = carry;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                y = fma_t<T>(-l[j], y, x[j]);
+                y = fma_t<A>(-l[j], y, x[j]);
                 x[j] = r[j] * y;  // t_j = r_j y_j
             }
             // ---- backward sweep: x_i = t_i - g_i x_{i+1} ----
-            T z = (T)0;
+            A z = (A)0;
 #pragma unroll
-            for (int j = CPT - 1; j >= 0; --j) z = fma_t<T>(-g[j], z, x[j]);
+            for (int j = CPT - 1; j >= 0; --j) z = fma_t<A>(-g[j], z, x[j]);
 #pragma unroll
-            for (int s = 0; s < 5; ++s) z = fma_t<T>(PbL[s], __shfl_down_sync(kFull, z, 1 << s), z);
+            for (int s = 0; s < 5; ++s) z = fma_t<A>(PbL[s], __shfl_down_sync(kFull, z, 1 << s), z);
             carry = __shfl_down_sync(kFull, z, 1);
-            if (lane == 31) carry = (T)0;
+            if (lane == 31) carry = (A)0;
             if (W > 1) {
                 if (lane == 0) s_E[1][warp] = z;
                 __syncthreads();
-                T c = (T)0;
+                A c = (A)0;
 #pragma unroll
-                for (int v = 1; v < W; ++v) c = fma_t<T>(s_K[1][warp][v], s_E[1][v], c);
-                carry = fma_t<T>(PbEx, c, carry);
+                for (int v = 1; v < W; ++v) c = fma_t<A>(s_K[1][warp][v], s_E[1][v], c);
+                carry = fma_t<A>(PbEx, c, carry);
             }
             z = carry;
 #pragma unroll
             for (int j = CPT - 1; j >= 0; --j) {
-                z = fma_t<T>(-g[j], z, x[j]);
-                x[j] = z;
+                z = fma_t<A>(-g[j], z, x[j]);
+                x[j] = WIDE ? (A)(T)z : z;  // (the recurrence itself continues unrounded: z is not the stored state)
             }
             // ---- fused objective ----
             if (ob_j >= 0) {  // one observed cell: its weight is applied once, after the loop
-                const double res = (double)get_at<T, CPT>(x, ob_j) - ob_val;
+                const double res = (double)get_at<A, CPT>(x, ob_j) - ob_val;
                 acc = fma(res, res, acc);
             }
             if (ob_slow) {
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 for (int k = 0; k < a.n_obs; ++k) {
                     const int64_t jj = a.obs_idx[k] - cell0;
                     if (jj >= 0 && jj < CPT) {
-                        const double res = (double)get_at<T, CPT>(x, (int)jj) - __ldg(a.obs + (n + 1) * a.n_obs + k);
+                        const double res = (double)get_at<A, CPT>(x, (int)jj) - __ldg(a.obs + (n + 1) * a.n_obs + k);
                         acc = fma((a.obs_w ? a.obs_w[k] : 1.0) * res, res, acc);
                     }
                 }
@@ -489,7 +494,7 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
                 snap_countdown = snap_every;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j)
-                    if (cell0 + j < nx) snap_dst[j * a.snap_cell_stride] = x[j];
+                    if (cell0 + j < nx) snap_dst[j * a.snap_cell_stride] = (T)x[j];
                 snap_dst += snap_stride;
             }
             ov_val = ov_next;
@@ -1285,11 +1290,11 @@ static int launch_x(const RunArgs &a, cudaStream_t stream) {
     return launch_onchipx<T, CPT, 16>(a, stream);
 }
 
-template <typename T, int CPT, int W, bool ZONAL>
+template <typename T, int CPT, int W, bool ZONAL, bool WIDE>
 static int launch_onchip(const RunArgs &a, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
-    auto kern = run_onchip_kernel<T, CPT, W, ZONAL>;
+    auto kern = run_onchip_kernel<T, CPT, W, ZONAL, WIDE>;
     int occ = 0;
     FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, 0));
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "run kernel does not fit on an SM (threads=%d)", 32 * W);
@@ -1299,15 +1304,15 @@ static int launch_onchip(const RunArgs &a, cudaStream_t stream) {
     return check_launch("fbr_run (on-chip)");
 }
 
-template <typename T, int CPT, bool ZONAL = false>
+template <typename T, int CPT, bool ZONAL = false, bool WIDE = false>
 static int launch_cpt(const RunArgs &a, cudaStream_t stream) {
     const int64_t threads = (a.nx + CPT - 1) / CPT;
-    if (threads <= 32) return launch_onchip<T, CPT, 1, ZONAL>(a, stream);
-    if (threads <= 64) return launch_onchip<T, CPT, 2, ZONAL>(a, stream);
-    if (threads <= 128) return launch_onchip<T, CPT, 4, ZONAL>(a, stream);
+    if (threads <= 32) return launch_onchip<T, CPT, 1, ZONAL, WIDE>(a, stream);
+    if (threads <= 64) return launch_onchip<T, CPT, 2, ZONAL, WIDE>(a, stream);
+    if (threads <= 128) return launch_onchip<T, CPT, 4, ZONAL, WIDE>(a, stream);
     if (ZONAL) return fail(FBR_ERR_UNSUPPORTED, "on-chip assembly of short models covers up to 128 threads");
-    if (threads <= 256) return launch_onchip<T, CPT, 8, false>(a, stream);
-    return launch_onchip<T, CPT, 16, false>(a, stream);
+    if (threads <= 256) return launch_onchip<T, CPT, 8, false, WIDE>(a, stream);
+    return launch_onchip<T, CPT, 16, false, WIDE>(a, stream);
 }
 
 template <typename T>
@@ -1368,6 +1373,16 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
         if (a.nx <= 16) return launch_group<T, 2>(a, stream);
         if (a.nx <= 32) return launch_group<T, 4>(a, stream);
         return a.nx <= 64 ? launch_group<T, 8>(a, stream) : launch_group<T, 16>(a, stream);
+    }
+    if constexpr (sizeof(T) == 4) {
+        if (a.M < 32) {  // fp32 mode, a few short models: float state, fp64 factors and arithmetic (see run_onchip_kernel)
+            switch (cpt) {
+                case 1: return launch_cpt<T, 1, false, true>(a, stream);
+                case 2: return launch_cpt<T, 2, false, true>(a, stream);
+                case 4: return launch_cpt<T, 4, false, true>(a, stream);
+                default: return launch_cpt<T, 8, false, true>(a, stream);
+            }
+        }
     }
     switch (cpt) {
         case 1: return launch_cpt<T, 1>(a, stream);

@@ -11,12 +11,16 @@
 //     (exact: the fold stops when the running product underflows to exactly 0, or at tile 0);
 //   * backward carry: x at the first cell of the tile on the right.  It depends on this step's forward results, so it
 //     is resolved inside the launch by a decoupled look-back: tiles are handed out right to left (atomic ticket), a
-//     tile publishes its zero-carry aggregate as soon as its own forward sweep is done, its right-hand neighbours
-//     already run, and the inclusive value follows (status word: epoch * 4 + {1 local, 2 inclusive}; release /
-//     acquire on the word, no reset between launches).
+//     tile publishes its zero-carry aggregate as soon as its own forward sweep is done (its right-hand neighbours
+//     hold earlier tickets: they run or are done) and folds the aggregates on its right exactly like the forward ones
+//     — always the same association, so the result does not depend on the schedule (value and epoch-tagged status in
+//     one 16-byte word, no reset between launches).
 // One launch per time step; snapshot rows are written in place and read back as the next step's input.
 // Latency is what this pipeline fights (a tile is ~2.5 us of dependent work, two CTAs per SM): the next tile's four rows
-// stream into shared memory (cp.async, 64 KB) while the current one is solved, its ticket is drawn a tile ahead, the
+// stream into shared memory while the current one is solved — four 16 KB BULK copies (cp.async.bulk, the 1-D TMA path,
+// completion on an mbarrier) issued by one thread: 16-byte cp.async by every thread (16 per thread and tile) topped out
+// at 4.0 TB/s in isolation against 6.9 TB/s for the bulk copies, conflicting shared-memory reads of the linear rows
+// included (scratch/ubench_bulk.cu, profiles/r02_ubench_bulk_copy.txt) —, its ticket is drawn a tile ahead, the
 // forward fold is issued before the rows are touched, and a tile's aggregate travels with its status in ONE 16-byte
 // word (one store to publish, one load to poll — no fence, no second round trip).
 #include "fbr_common.cuh"
@@ -39,8 +43,7 @@ struct PassArgs {
     double *Mf, *Mb;                   // (n_tiles) products of the multipliers over each tile (written by the setup pass)
     const double *Ef_now;              // (n_tiles) zero-carry forward end value of every tile for THIS step
     double *Ef_next;                   // (n_tiles) the same for the next step
-    double2 *Lw, *Iw;                  // (n_tiles) backward aggregates of this launch as (value, epoch * 4 + status) words:
-                                       // Lw = zero-carry (local) aggregate, status 1; Iw = inclusive value, status 2
+    double2 *Lw;                       // (n_tiles) zero-carry backward aggregates of this launch as (value, epoch * 4 + 1) words
     unsigned *ticket;                  // one counter, never reset: every launch adds n_tiles + gridDim.x to it (each CTA's last,
     unsigned ticket_base;              // failing draw included), so launch e starts at e * (n_tiles + grid) = ticket_base
     unsigned epoch;                    // launch number, from 1 (0 = the setup launch)
@@ -55,8 +58,16 @@ __device__ __forceinline__ unsigned ld_word(const double2 *p, double &v) {
     asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "l"(p) : "memory");
     return (unsigned)__double2loint(t);
 }
-__device__ __forceinline__ void cp_async16_pass(unsigned smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+// bulk copy global -> shared (1-D TMA) whose bytes complete on an mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
 }
 
 // b = p with this step's overrides on my 8 cells (matbuilder.py:45-76: boundary rows first, sources in list order).
@@ -92,37 +103,38 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
     __shared__ double s_T[2][W];        // products of the multipliers over each warp
     __shared__ double s_carry[2];       // carries into the tile: forward (from the left), backward (from the right)
     __shared__ unsigned s_ticket[2];
-    extern __shared__ __align__(16) double s_stage[];  // [4 arrays][4 pieces][256 threads] x 16 bytes: the NEXT tile's rows
+    extern __shared__ __align__(128) double s_stage[];  // [4 rows][2048] doubles: the NEXT tile's rows (bulk copies)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned base = a.ticket_base;
     const int64_t nx = a.nx;
     const bool aligned = ((reinterpret_cast<uintptr_t>(a.fl) | reinterpret_cast<uintptr_t>(a.fr) | reinterpret_cast<uintptr_t>(a.fg) |
                            reinterpret_cast<uintptr_t>(a.p_in)) & 15) == 0;
-    const unsigned stage0 = smem_addr(s_stage) + 16u * tid;
-    // rows of tile `t` -> shared memory, each thread its own 8 cells, piece j of array q at [(q * 4 + j) * 256 + tid]
-    // (conflict-free for the copy and for the 16-byte reads); only whole, aligned tiles are staged
+    // rows of tile `t` -> shared memory, linear (row q at s_stage + q * 2048 doubles): only whole, aligned tiles are staged
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned bar = smem_addr(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     auto staged = [&](int64_t t) { return !SETUP && aligned && t >= 0 && (t + 1) * kPTile <= nx; };
-    // (one array per call, spread over the tile's computation: sixteen copies per thread back to back overflow the
-    //  load / store queue — 22 % of the stall samples of the first version)
-    auto stage_rows = [&](int64_t t, int q) {
+    auto stage_tile = [&](int64_t t) {  // thread 0, after everybody has read the previous tile out of the buffer
         if (!staged(t)) return;
-        const int64_t c0 = t * kPTile + (int64_t)tid * 8;
-        const double *src = (q == 0 ? a.fl : q == 1 ? a.fr : q == 2 ? a.fg : a.p_in) + c0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cp_async16_pass(stage0 + 16u * 256u * (q * 4 + j), src + 2 * j);
+        const int64_t c0 = t * kPTile;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before async-proxy writes
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * kPTile * 8u) : "memory");
+        bulk_g2s(smem_addr(s_stage) + 0 * kPTile * 8, a.fl + c0, kPTile * 8, bar);
+        bulk_g2s(smem_addr(s_stage) + 1 * kPTile * 8, a.fr + c0, kPTile * 8, bar);
+        bulk_g2s(smem_addr(s_stage) + 2 * kPTile * 8, a.fg + c0, kPTile * 8, bar);
+        bulk_g2s(smem_addr(s_stage) + 3 * kPTile * 8, a.p_in + c0, kPTile * 8, bar);
     };
-    auto stage_tile = [&](int64_t t) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) stage_rows(t, q);
-    };
+    unsigned n_staged = 0;  // staged tiles consumed so far: the mbarrier's phase
     // the source cells, once per CTA: which tiles hold one is then a shared-memory question
     __shared__ int64_t s_src[256];
     for (int k = tid; k < a.n_src && k < 256; k += 32 * W) s_src[k] = __ldg(a.src_idx + k);
 
     if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1u) - base;
     __syncthreads();
-    if (s_ticket[0] < (unsigned)a.n_tiles) stage_tile(a.n_tiles - 1 - (int64_t)s_ticket[0]);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid == 0 && s_ticket[0] < (unsigned)a.n_tiles) stage_tile(a.n_tiles - 1 - (int64_t)s_ticket[0]);
     for (int it = 0;; ++it) {
         const unsigned ticket = s_ticket[it & 1];
         if (ticket >= (unsigned)a.n_tiles) break;
@@ -152,12 +164,12 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
         // ---- my 8 cells: factors and state (identity rows behind the mesh) ----
         double l[8], r[8], g[8], x[8];
         if (staged(tile)) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");  // my own copies: no barrier needed to read them back
-            auto take = [&](int q, double (&v)[8]) {
+            mbar_wait(bar, n_staged & 1u);
+            ++n_staged;
+            auto take = [&](int q, double (&v)[8]) {  // my 64 bytes of row q (16-byte loads 64 bytes apart: 4-way conflicts, paid)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double2 t = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(s_stage) +
-                                                                         16 * (256 * (q * 4 + j) + tid));
+                    const double2 t = *reinterpret_cast<const double2 *>(s_stage + q * kPTile + tid * 8 + 2 * j);
                     v[2 * j] = t.x;
                     v[2 * j + 1] = t.y;
                 }
@@ -182,7 +194,7 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
         const bool tile_has_src = __syncthreads_or(src_here);
         const unsigned nt = s_ticket[(it & 1) ^ 1];
         const int64_t next_tile = nt < (unsigned)a.n_tiles ? a.n_tiles - 1 - (int64_t)nt : -1;
-        stage_rows(next_tile, 0);
+        if (tid == 0) stage_tile(next_tile);  // (everybody passed the barrier above: the buffer is free)
         const ScanMultipliers sm = scan_multipliers<double>(chunk_product<double, 8>(l), chunk_product<double, 8>(g), lane);
         if (lane == 31) s_T[0][warp] = sm.tot_f;
         if (lane == 0) s_T[1][warp] = sm.tot_b;
@@ -229,7 +241,6 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
             c = fma(sm.ex_f, cw, c);
             chunk_apply_fwd_plain<double, 8>(x, l, r, c);
         }
-        if (!SETUP) stage_rows(next_tile, 1);
         // ---- backward sweep, zero carry from the right: publish the tile's aggregate, look back, apply ----
         {
             double z = chunk_end_bwd_plain<double, 8>(x, g);
@@ -237,24 +248,50 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
             for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
             double c = and_mask(__shfl_down_sync(kAllLanes, z, 1), lane == 31 ? 0 : -1);
             if (lane == 0) s_E[1][warp] = z;
-            stage_rows(next_tile, 2);
             __syncthreads();
-            if (tid == 0) {
-                double loc = 0.0, mb = 1.0;  // value at the tile's first cell for a zero carry from the right
-                for (int w = W - 1; w >= 0; --w) { loc = fma(s_T[1][w], loc, s_E[1][w]); mb *= s_T[1][w]; }
-                st_word(a.Lw + tile, loc, a.epoch * 4u + 1u);
-                double cb = 0.0, prod = 1.0;
-                for (int64_t j = tile + 1; j < a.n_tiles && prod != 0.0; ++j) {
-                    const double mbj = __ldg(a.Mb + j);
-                    for (;;) {  // the neighbour's inclusive value ends the walk; its local aggregate continues it
-                        double vi, vl;
-                        const unsigned ti = ld_word(a.Iw + j, vi), tl = ld_word(a.Lw + j, vl);  // (both in flight together)
-                        if (ti == a.epoch * 4u + 2u) { cb = fma(prod, vi, cb); prod = 0.0; break; }
-                        if (tl == a.epoch * 4u + 1u) { cb = fma(prod, vl, cb); prod *= mbj; break; }
-                    }
+            if (warp == 0) {
+                if (lane == 0) {
+                    double loc = 0.0;  // value at the tile's first cell for a zero carry from the right
+                    for (int w = W - 1; w >= 0; --w) loc = fma(s_T[1][w], loc, s_E[1][w]);
+                    st_word(a.Lw + tile, loc, a.epoch * 4u + 1u);
                 }
-                st_word(a.Iw + tile, fma(mb, cb, loc), a.epoch * 4u + 2u);
-                s_carry[1] = cb;
+                // Carry from the right: fold the zero-carry aggregates of the tiles on the right, nearest first, 32 per
+                // iteration, until the running product of the tile multipliers is exactly 0 (one tile on ordinary meshes) or
+                // the mesh ends.  Always the same association — the result does not depend on which tiles happen to be done
+                // (an inclusive value picked up when available would make the last bits a matter of timing).  The tiles on
+                // the right hold earlier tickets: they are running or done, and publish before they wait for anybody.
+                double cb = 0.0, prod = 1.0;
+                if (tile + 1 < a.n_tiles) {  // the nearest tile by itself: on ordinary meshes its product already ends the fold
+                    double v = 0.0;
+                    if (lane == 0)
+                        while (ld_word(a.Lw + tile + 1, v) != a.epoch * 4u + 1u) { }
+                    cb = __shfl_sync(kAllLanes, v, 0);
+                    prod = __ldg(a.Mb + tile + 1);
+                }
+                for (int64_t j0 = tile + 2; j0 < a.n_tiles && prod != 0.0; j0 += 32) {
+                    const int64_t j = j0 + lane;  // lane 0 = nearest tile
+                    double pm = j < a.n_tiles ? __ldg(a.Mb + j) : 0.0;  // product of the multipliers of lanes 0 .. lane (after the scan)
+                    // does anything reach me?  (the exclusive product of the nearer tiles, known without waiting for anybody)
+                    double reach = pm;
+#pragma unroll
+                    for (int s = 1; s < 32; s <<= 1) {
+                        const double up = __shfl_up_sync(kAllLanes, reach, s);
+                        if (lane >= s) reach *= up;
+                    }
+                    double before = __shfl_up_sync(kAllLanes, reach, 1);
+                    if (lane == 0) before = 1.0;
+                    double acc = 0.0;
+                    if (j < a.n_tiles && prod * before != 0.0)
+                        while (ld_word(a.Lw + j, acc) != a.epoch * 4u + 1u) { }
+#pragma unroll
+                    for (int s = 1; s < 32; s <<= 1) {  // affine maps composed nearest-first
+                        const double up_acc = __shfl_up_sync(kAllLanes, acc, s), up_pm = __shfl_up_sync(kAllLanes, pm, s);
+                        if (lane >= s) { acc = fma(up_pm, acc, up_acc); pm *= up_pm; }
+                    }
+                    cb = fma(prod, __shfl_sync(kAllLanes, acc, 31), cb);
+                    prod *= __shfl_sync(kAllLanes, pm, 31);
+                }
+                if (lane == 0) s_carry[1] = cb;
             }
             __syncthreads();
             double cw = s_carry[1];  // x behind my warp: the tile's carry folded through the warps on my right
@@ -262,8 +299,6 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
             c = fma(sm.ex_b, cw, c);
             chunk_apply_bwd_plain<double, 8>(x, g, c);
         }
-        stage_rows(next_tile, 3);
-        asm volatile("cp.async.commit_group;" ::: "memory");
         // ---- p^{n+1} out ----
         if (cell0 + 8 <= nx && (reinterpret_cast<uintptr_t>(a.p_out + cell0) & 15) == 0) {
             double2 *q = reinterpret_cast<double2 *>(a.p_out + cell0);
@@ -322,9 +357,8 @@ extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double
     w += 2 * tiles;
     if ((reinterpret_cast<uintptr_t>(w) & 15) != 0) ++w;  // 16-byte words
     double2 *Lw = reinterpret_cast<double2 *>(w); w += 2 * tiles;
-    double2 *Iw = reinterpret_cast<double2 *>(w); w += 2 * tiles;
     unsigned *ticket = reinterpret_cast<unsigned *>(w);
-    FBR_CUDA(cudaMemsetAsync(Lw, 0, (size_t)tiles * 32 + 16, st));  // status words and the ticket counter
+    FBR_CUDA(cudaMemsetAsync(Lw, 0, (size_t)tiles * 16 + 16, st));  // status words and the ticket counter
     const size_t smem = 4 * (size_t)kPTile * sizeof(double);  // staging of one tile's four rows
     FBR_CUDA(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FBR_CUDA(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -332,11 +366,15 @@ extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double
     FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel<false>, 32 * kPW, smem));
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "pass kernel does not fit on an SM");
     int64_t grid = (int64_t)occ * f.sm_count;
+    if (const char *e = getenv("FBR_PASS_GRID")) {  // testing aid: other interleavings of the look-back (never more CTAs than fit)
+        const int64_t v = atoll(e);
+        if (v >= 1 && v < grid) grid = v;
+    }
     if (grid > tiles) grid = tiles;
 
     PassArgs a;
     a.fl = fl; a.fr = fr; a.fg = fg; a.nx = nx; a.n_tiles = tiles; a.lbc = lbc; a.rbc = rbc; a.src_idx = src_idx; a.n_src = n_src;
-    a.Mf = Mf; a.Mb = Mb; a.Lw = Lw; a.Iw = Iw; a.ticket = ticket;
+    a.Mf = Mf; a.Mb = Mb; a.Lw = Lw; a.ticket = ticket;
     // setup launch (epoch 0): tile products and the forward aggregates of step 0
     a.p_in = p0; a.p_out = nullptr; a.src_now = src_table; a.src_next = nullptr; a.Ef_now = nullptr; a.Ef_next = Ef[0]; a.epoch = 0;
     a.ticket_base = 0;

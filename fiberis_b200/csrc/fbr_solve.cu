@@ -246,16 +246,131 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const double *__restrict__
 using namespace fbr;
 
 extern "C" int64_t fbr_solve_tridiag_work_bytes(int64_t M, int64_t nx, int variant) {
+    if (variant == FBR_SOLVER_PIVOT) return 4 * M * nx * (int64_t)sizeof(double);
     if (variant == FBR_SOLVER_PCR || variant == FBR_SOLVER_REG) return 0;
     if (variant == FBR_SOLVER_AUTO && nx <= kSolveRegMaxNx) return 0;
     return M * nx * (int64_t)sizeof(double);
+}
+
+// ---- partial pivoting, where the reference has it --------------------------------------------------------------------
+// The reference solves with scipy.linalg.solve -> LAPACK (src/fiberis/simulator/solver/PDESolver_IMP.py:27-28): Gaussian
+// elimination with PARTIAL PIVOTING.  The simulator's own matrices never need the row swaps, so every hot kernel eliminates
+// without them; a regular matrix whose un-pivoted elimination meets a zero pivot (PML on a Neumann row with dt * sigma = 1:
+// diagonal -1 + 1 = 0) takes this path instead: the published DGTSV algorithm, one thread per system — row i is swapped
+// with row i + 1 when |dl_{i+1}| > |d_i|, the swap's fill-in goes to a second super-diagonal.  work: 4 * M * nx doubles
+// (copies of d, du, the fill-in du2 and the right-hand side); singular[m] = 1 + row of an exactly zero pivot.
+__global__ void __launch_bounds__(64) gtsv_pivot_kernel(const double *__restrict__ dl, const double *__restrict__ d,
+                                                        const double *__restrict__ du, const double *__restrict__ b,
+                                                        double *__restrict__ x, int64_t M, int64_t nx, double *__restrict__ work,
+                                                        int32_t *__restrict__ singular) {
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double *sub = dl + m * nx;  // sub[i] = A[i, i-1]
+    double *dd = work + (0 * M + m) * nx, *u1 = work + (1 * M + m) * nx, *u2 = work + (2 * M + m) * nx, *rhs = work + (3 * M + m) * nx;
+    for (int64_t i = 0; i < nx; ++i) { dd[i] = d[m * nx + i]; u1[i] = du[m * nx + i]; u2[i] = 0.0; rhs[i] = b[m * nx + i]; }
+    int bad = 0;
+    double below = nx > 1 ? sub[1] : 0.0;  // the (possibly updated) entry below the current pivot
+    for (int64_t i = 0; i + 1 < nx; ++i) {
+        const double next_below = i + 2 < nx ? sub[i + 2] : 0.0;
+        if (fabs(dd[i]) >= fabs(below)) {  // no row interchange
+            if (dd[i] == 0.0) { if (!bad) bad = (int)i + 1; break; }
+            const double fact = below / dd[i];
+            dd[i + 1] -= fact * u1[i];
+            rhs[i + 1] -= fact * rhs[i];
+        } else {  // interchange rows i and i + 1
+            const double fact = dd[i] / below;
+            dd[i] = below;
+            const double t = dd[i + 1];
+            dd[i + 1] = u1[i] - fact * t;
+            if (i + 2 < nx) { u2[i] = u1[i + 1]; u1[i + 1] = -fact * u2[i]; }
+            u1[i] = t;
+            const double tb = rhs[i];
+            rhs[i] = rhs[i + 1];
+            rhs[i + 1] = tb - fact * rhs[i + 1];
+        }
+        below = next_below;
+    }
+    if (!bad && dd[nx - 1] == 0.0) bad = (int)nx;
+    if (singular) singular[m] = bad;
+    if (bad) return;
+    double *out = x + m * nx;
+    out[nx - 1] = rhs[nx - 1] / dd[nx - 1];
+    if (nx > 1) out[nx - 2] = (rhs[nx - 2] - u1[nx - 2] * out[nx - 1]) / dd[nx - 2];
+    for (int64_t i = nx - 3; i >= 0; --i) out[i] = (rhs[i] - u1[i] * out[i + 1] - u2[i] * out[i + 2]) / dd[i];
+}
+
+// A general dense system (API completeness of solver_implicit: the simulator itself never builds one): Gaussian elimination
+// with partial pivoting by ONE CTA on a working copy [A | b] of n x (n + 1) doubles in global memory.
+__global__ void __launch_bounds__(256) dense_pivot_kernel(double *__restrict__ Ab, int n, double *__restrict__ x, int32_t *singular) {
+    __shared__ int s_piv;
+    __shared__ double s_red_v[256];
+    __shared__ int s_red_i[256];
+    const int tid = threadIdx.x, ld = n + 1;
+    for (int k = 0; k < n; ++k) {
+        double best = -1.0;
+        int row = k;
+        for (int i = k + tid; i < n; i += blockDim.x) {
+            const double v = fabs(Ab[(int64_t)i * ld + k]);
+            if (v > best) { best = v; row = i; }
+        }
+        s_red_v[tid] = best; s_red_i[tid] = row;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (tid < s && (s_red_v[tid + s] > s_red_v[tid] || (s_red_v[tid + s] == s_red_v[tid] && s_red_i[tid + s] < s_red_i[tid]))) {
+                s_red_v[tid] = s_red_v[tid + s]; s_red_i[tid] = s_red_i[tid + s];
+            }
+            __syncthreads();
+        }
+        if (tid == 0) s_piv = s_red_i[0];
+        __syncthreads();
+        if (s_red_v[0] == 0.0) { if (tid == 0 && singular) *singular = k + 1; return; }
+        const int p = s_piv;
+        if (p != k)
+            for (int j = k + tid; j < ld; j += blockDim.x) {
+                const double t = Ab[(int64_t)k * ld + j];
+                Ab[(int64_t)k * ld + j] = Ab[(int64_t)p * ld + j];
+                Ab[(int64_t)p * ld + j] = t;
+            }
+        __syncthreads();
+        const double piv = Ab[(int64_t)k * ld + k];
+        for (int i = k + 1 + (tid >> 5); i < n; i += blockDim.x >> 5) {  // a warp per row
+            const double f = Ab[(int64_t)i * ld + k] / piv;
+            __syncwarp();  // (everybody has read column k of this row before lane 0's columns overwrite it)
+            for (int j = k + 1 + (tid & 31); j < ld; j += 32) Ab[(int64_t)i * ld + j] -= f * Ab[(int64_t)k * ld + j];
+        }
+        __syncthreads();
+    }
+    for (int i = n - 1; i >= 0; --i) {  // back substitution, one row at a time
+        double part = 0.0;
+        for (int j = i + 1 + tid; j < n; j += blockDim.x) part += Ab[(int64_t)i * ld + j] * x[j];
+        s_red_v[tid] = part;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (tid < s) s_red_v[tid] += s_red_v[tid + s];
+            __syncthreads();
+        }
+        if (tid == 0) x[i] = (Ab[(int64_t)i * ld + n] - s_red_v[0]) / Ab[(int64_t)i * ld + i];
+        __syncthreads();
+    }
+    if (tid == 0 && singular) *singular = 0;
+}
+
+extern "C" int fbr_solve_dense_f64(double *Ab, int64_t n, double *x, int32_t *singular, void *stream) {
+    FBR_REQUIRE(Ab && x && n >= 1 && n <= 16384, "bad argument (1 <= n <= 16384)");
+    dense_pivot_kernel<<<1, 256, 0, as_stream(stream)>>>(Ab, (int)n, x, singular);
+    return check_launch("fbr_solve_dense_f64");
 }
 
 extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, const double *b,
                                      double *x, int64_t M, int64_t nx, int variant, double *work,
                                      int32_t *singular, void *stream) {
     FBR_REQUIRE(M >= 1 && nx >= 1 && dl && d && du && b && x, "bad argument");
-    FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_REG, "unknown solver variant %d", variant);
+    FBR_REQUIRE(variant >= FBR_SOLVER_AUTO && variant <= FBR_SOLVER_PIVOT, "unknown solver variant %d", variant);
+    if (variant == FBR_SOLVER_PIVOT) {
+        FBR_REQUIRE(work, "the PIVOT variant needs a work array of fbr_solve_tridiag_work_bytes()");
+        gtsv_pivot_kernel<<<(unsigned)((M + 63) / 64), 64, 0, as_stream(stream)>>>(dl, d, du, b, x, M, nx, work, singular);
+        return check_launch("fbr_solve_tridiag_f64 (pivoted)");
+    }
     if (variant == FBR_SOLVER_AUTO)
         // measured on B200 (scratch/k2_bench.py, profiles/r01_k2_bare_solve.txt): the register-resident variant
         // wins at every shape it covers; beyond 4096 cells the tile-transposed Thomas walk

@@ -25,7 +25,7 @@ from datetime import datetime
 
 import numpy as np
 
-from fiberis_b200 import _engine
+from fiberis_b200 import _cabi, _engine
 from fiberis_b200.simulator.optimizer import tso
 
 _ALLOWED_BC = ["Dirichlet", "Neumann", "None"]
@@ -326,11 +326,20 @@ class PDS1D_SingleSource:
             # separate assembly / factorisation launches (C1: 3 launches and a 44 us one-thread factorisation before)
             sigma_d = _engine.pml_sigma(mesh_d, pml, smax) if pml != 0.0 else None
             table_d = _engine.to_device(table)
-            snap_d, _, _ = _engine.run(None, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                       snapshot_every=every, cell_major=cell_major,
-                                       zonal=(mesh_d, diff_d.reshape(1, nx), None, dt, sigma_d))
-            if cell_major and snap_d is not None:
-                snap_d = _CellMajor(snap_d[0])
+            try:
+                snap_d, _, _ = _engine.run(None, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
+                                           snapshot_every=every, cell_major=cell_major,
+                                           zonal=(mesh_d, diff_d.reshape(1, nx), None, dt, sigma_d))
+                if cell_major and snap_d is not None:
+                    snap_d = _CellMajor(snap_d[0])
+            except np.linalg.LinAlgError:
+                # a zero pivot WITHOUT row interchanges (PML on a Neumann row with dt * sigma = 1 ...): the reference's
+                # LAPACK solve pivots (PDESolver_IMP.py:27-28) — so does this fallback, one pivoted solve per step
+                # (DGTSV algorithm); a truly singular matrix raises LinAlgError from there, as in the reference
+                diag = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
+                snap_d = self._step_loop(*diag, p0_d, sidx_d, n_src, table_d, n_steps, every, variant=_cabi.SOLVER_PIVOT)
+                if cell_major and snap_d is not None:
+                    snap_d = _CellMajor(_engine.transpose(snap_d[0]))
             if snap_d is None:
                 self.snapshot = initial[None, :].copy()
             elif isinstance(snap_d, _CellMajor):
@@ -349,9 +358,18 @@ class PDS1D_SingleSource:
             return
         dl, d, du = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
         if mode == "implicit":
-            factors = _engine.factorize(dl, d, du)
             table_d = _engine.to_device(table)
-            if nx <= _engine.run_max_nx() and n_src > _K3_MAX_SOURCES:
+            try:
+                factors = _engine.factorize(dl, d, du)
+            except np.linalg.LinAlgError:
+                if nx > (1 << 22):
+                    raise
+                factors = None  # zero pivot without row interchanges: pivoted solve per step, as above
+            if factors is None:
+                snap_d = self._step_loop(dl, d, du, p0_d, sidx_d, n_src, table_d, n_steps, every, variant=_cabi.SOLVER_PIVOT)
+                if dtype == "float32" and snap_d is not None:
+                    snap_d = snap_d.float()
+            elif nx <= _engine.run_max_nx() and n_src > _K3_MAX_SOURCES:
                 # more sources than the on-chip kernel's descriptors hold (the reference takes any number): one
                 # right-hand side + one register-resident solve per step (fbr_rhs_f64 + fbr_solve_tridiag_f64)
                 snap_d = self._step_loop(dl, d, du, p0_d, sidx_d, n_src, table_d, n_steps, every)
@@ -427,13 +445,14 @@ class PDS1D_SingleSource:
                                            snapshot_every=every, kernel=which_exact)
         return snap_d
 
-    def _step_loop(self, dl, d, du, p_d, sidx_d, n_src, table_d, n_steps, every):
-        """Fixed-dt loop with one library call pair per step (models with more than 253 sources)."""
+    def _step_loop(self, dl, d, du, p_d, sidx_d, n_src, table_d, n_steps, every, variant=_cabi.SOLVER_AUTO):
+        """Fixed-dt loop with one library call pair per step (models with more than 253 sources; matrices that need the
+        row interchanges of the reference's LAPACK solve: ``variant=SOLVER_PIVOT``)."""
         import torch
         rows = [p_d[0]]
         for n in range(n_steps):
             b = _engine.rhs(p_d, self.lbc, self.rbc, sidx_d, n_src, table_d[n])
-            p_d = _engine.solve_tridiag(dl, d, du, b)
+            p_d = _engine.solve_tridiag(dl, d, du, b, variant)
             if (n + 1) % every == 0:
                 rows.append(p_d[0])
         return torch.stack(rows)[None] if len(rows) > 1 else None

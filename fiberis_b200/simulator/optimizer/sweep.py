@@ -1,12 +1,15 @@
 """Parameter sweeps over ensembles of diffusion models.
 
-NEW capability, parity unpinned: ``fiberis.simulator.optimizer`` holds only the adaptive time-step
-controller (``tso.py``); the closest thing to a sweep in the reference is the scripted MOOSE
-pipeline with its ``misfit_calculator``
-(src/fiberis/moose/templates/baseline_model_generator.py:335-404).  What is here is deliberately
-small: candidate generators on the host, one ensemble solve per batch of candidates on the GPU(s)
-with the misfit fused into the run kernel (``PDS1D_Ensemble``), and a shrinking-box random search on
-top.  Candidates are per-zone log10 diffusivities ``theta`` (M, n_zones); D = 10 ** theta.
+NEW capability: ``fiberis.simulator.optimizer`` holds only the adaptive time-step controller
+(``tso.py``); the closest thing to a sweep in the reference is the scripted MOOSE pipeline with its
+``misfit_calculator`` (src/fiberis/moose/templates/baseline_model_generator.py:418-520).  What is here is
+deliberately small: candidate generators on the host, one ensemble solve per batch of candidates on the
+GPU(s) with the misfit fused into the run kernel (``PDS1D_Ensemble``), and a shrinking-box random search on
+top.  The objective is whatever the ensemble's observations define: with
+``set_observations(..., taxis=...)`` / ``set_observed_data`` it is the reference's ``misfit_calculator``
+(observed channels on their own time axis, baseline sample, window, channel weights — pinned by
+tests/golden/misfit_reference_320x96.npz); candidates whose misfit is NaN (observed times outside the
+simulated range) sort last.  Candidates are per-zone log10 diffusivities ``theta`` (M, n_zones); D = 10 ** theta.
 """
 from __future__ import annotations
 

@@ -3,10 +3,10 @@
 
 ``A`` arrives as the dense matrix the reference's ``matbuilder`` produces.  A tridiagonal ``A`` (the
 only kind the simulator builds) is solved by the CUDA batched tridiagonal kernel K2
-(``fbr_solve_tridiag_f64``: register-resident elimination without pivoting).  Any other dense ``A`` —
-and a tridiagonal one whose un-pivoted elimination meets a zero pivot although the matrix is regular,
-which LAPACK's partial pivoting in the reference's ``scipy.linalg.solve`` copes with — is handed to
-cuSOLVER through ``torch.linalg.solve`` on the device, a plain library solve outside the hot path.
+(``fbr_solve_tridiag_f64``: register-resident elimination without pivoting; a zero pivot of a regular
+matrix falls through to the pivoted variant — LAPACK's DGTSV algorithm, what the reference's
+``scipy.linalg.solve`` does).  Any other dense ``A`` goes to ``fbr_solve_dense_f64`` (Gaussian elimination
+with partial pivoting by one CTA) — no library solve is left behind this API.
 All three ``solver`` names of the reference select the same device path; an unknown name raises ``ValueError('Invalid solver type.')`` like the reference.
 """
 import numpy as np
@@ -36,18 +36,7 @@ def solver_implicit(A, b, **kwargs):
     b = np.asarray(b, dtype=np.float64)
     tri = split_tridiagonal(A)
 
-    def dense_pivoted():
-        import torch
-        A_d = _engine.to_device(np.asarray(A, dtype=np.float64))
-        try:
-            return torch.linalg.solve(A_d, _engine.to_device(b)).cpu().numpy()
-        except RuntimeError as exc:  # torch reports singular matrices as RuntimeError
-            raise np.linalg.LinAlgError(str(exc)) from exc
-
     if tri is None or len(b) < 2:
-        return dense_pivoted()
+        return _engine.solve_dense(_engine.to_device(np.asarray(A, dtype=np.float64)), _engine.to_device(b)).cpu().numpy()
     dl, d, du = (_engine.to_device(v[None, :]) for v in tri)
-    try:
-        return _engine.solve_tridiag(dl, d, du, _engine.to_device(b[None, :]))[0].cpu().numpy()
-    except np.linalg.LinAlgError:
-        return dense_pivoted()  # zero pivot without pivoting: regular matrices still have a solution
+    return _engine.solve_tridiag(dl, d, du, _engine.to_device(b[None, :]))[0].cpu().numpy()

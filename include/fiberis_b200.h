@@ -48,9 +48,12 @@ enum {
     FBR_SOLVER_THOMAS = 1, /* one thread per system, tiles transposed in shared memory so that
                               global traffic is coalesced (many small systems)        */
     FBR_SOLVER_PCR = 2,    /* one CTA per system, shared-memory parallel cyclic reduction */
-    FBR_SOLVER_REG = 3     /* register-resident: a thread owns 8 consecutive cells, pivots from a scan of
+    FBR_SOLVER_REG = 3,    /* register-resident: a thread owns 8 consecutive cells, pivots from a scan of
                               2x2 Moebius matrices, the two sweeps as warp scans; one pass over HBM
                               (40 B per unknown), no work array; 1 <= nx <= 4096 (AUTO's choice there) */
+    FBR_SOLVER_PIVOT = 4   /* partial pivoting as in the reference's LAPACK solve (the DGTSV algorithm, one thread
+                              per system): the fallback for regular matrices whose un-pivoted elimination meets
+                              a zero pivot; work: 4 * M * nx doubles */
 };
 
 int fbr_version(void);
@@ -331,6 +334,12 @@ int64_t fbr_solve_tridiag_work_bytes(int64_t M, int64_t nx, int variant);
 int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, const double *b,
                           double *x, int64_t M, int64_t nx, int variant, double *work,
                           int32_t *singular, void *stream);
+
+/* A general dense system A x = b (API completeness of solver_implicit, src/fiberis/simulator/solver/PDESolver_IMP.py:9-34;
+ * the simulator itself only builds tridiagonal matrices): Gaussian elimination with partial pivoting by one CTA.
+ * Ab: device working copy of the augmented matrix [A | b], row-major n x (n + 1), destroyed; x: (n);
+ * singular: NULL or one int32 that receives 1 + the column of an exactly zero pivot column (0: regular). */
+int fbr_solve_dense_f64(double *Ab, int64_t n, double *x, int32_t *singular, void *stream);
 
 /* One implicit step, batched (SURVEY 8(b) "fbr_step_*"): p_next = A^-1 rhs(p) with the diagonals of
  * A(dt) from fbr_assemble_*; rhs = p with the boundary / source overrides of

@@ -119,8 +119,8 @@ def run_misc_case(rng):
     with contextlib.redirect_stdout(io.StringIO()):
         if kind == "pml":
             L, smax = float(rng.uniform(1.0, 0.3 * (mesh[-1] - mesh[0]))), float(rng.choice([0.5, 3.0, 10.0]))
-            # (dt * sigma_max = 1 on a Neumann row makes its diagonal -1 + dt sigma exactly zero: the un-pivoted
-            #  elimination of the GPU path stops there with LinAlgError, LAPACK would swap rows — DESIGN.md, known gaps)
+            # (dt * sigma_max = 1 on a Neumann row makes its diagonal -1 + dt sigma exactly zero: the un-pivoted elimination
+            #  flags it and solve() falls back to the pivoted variant — round 2, tests/test_gpu_parity.py)
             p.solve(dt=0.5, t_total=T, pml_thickness=L, sigma_max=smax)
             want, taxis = O.solve_fixed(mesh, D, init, lbc, rbc, sidx, srcs, 0.0, 0.5, T, pml_thickness=L, sigma_max=smax)
             gate = 1e-10

@@ -540,3 +540,28 @@ def test_ensemble_cell_major_audit_snapshots():
     assert e.snapshot.shape == ref.shape
     npt.assert_array_equal(e.snapshot, ref)
     assert np.transpose(e.snapshot, (0, 2, 1)).flags["C_CONTIGUOUS"]
+
+
+def test_sweep_with_observations_on_their_own_time_axis():
+    """The sweep driver on the reference's misfit: gauge channels recorded on an irregular time axis (offset from the
+    simulation's), baseline sample 1, window [1:-1].  The generating candidate has the smallest misfit — not 0: the
+    observed samples are interpolated values of ITS states, which the kernel reproduces to rounding."""
+    from fiberis_b200.simulator.optimizer import sweep
+    M, nx, n_steps = 48, 512, 80
+    e, c = make_ensemble(91, M, nx, n_steps, zones=3, n_obs=4)
+    truth = np.array([0.2, -0.3, 0.4])
+    want, taxis = O.solve_fixed(c["mesh"], (10.0 ** truth)[c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                                c["srcs"], 0.0, c["dt"], c["T"])
+    rng = np.random.default_rng(2)
+    obs_taxis = np.sort(rng.uniform(0.5, c["T"] - 0.5, 33))
+    obs = np.stack([np.interp(obs_taxis, taxis, want[:, i]) for i in c["obs_idx"]], axis=1)
+    obs = obs - obs[1]
+    e.set_observations(c["obs_idx"], obs, taxis=obs_taxis, baseline_index=1, window=(1, -1))
+    theta = sweep.random_candidates(M, [-1, -1, -1], [1, 1, 1], seed=4)
+    theta[5] = truth
+    out = sweep.run_sweep(e, theta, c["zone"], c["dt"], c["T"])
+    assert out["best"] == 5 and out["best_misfit"] < 1e-20
+    for m in (0, 11, 47):
+        snap, _ = O.solve_fixed(c["mesh"], (10.0 ** theta[m])[c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                                c["srcs"], 0.0, c["dt"], c["T"])
+        assert out["misfit"][m] == pytest.approx(O.sampled_misfit(snap, taxis, c["obs_idx"], obs, obs_taxis), rel=1e-9)
