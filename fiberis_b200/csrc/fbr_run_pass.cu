@@ -135,31 +135,36 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
     if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1u) - base;
     __syncthreads();
     if (tid == 0 && s_ticket[0] < (unsigned)a.n_tiles) stage_tile(a.n_tiles - 1 - (int64_t)s_ticket[0]);
+    // Forward carry into tile t: fold the finished aggregates of the tiles on its left (exact: it stops at tile 0 or when
+    // the running product underflows to 0).  One warp's job — warp 1 does it for the NEXT tile while warp 0 looks back for
+    // the current one, so nobody waits for it (at the head of a tile it was 17 % of the stall samples).
+    auto forward_fold = [&](int64_t t) {
+        double c = 0.0, prod = 1.0;
+        for (int64_t j0 = t - 1; j0 >= 0 && prod != 0.0; j0 -= 32) {
+            const int64_t j = j0 - lane;  // lane 0 = nearest tile
+            double acc = j >= 0 ? __ldg(a.Ef_now + j) : 0.0;  // value carried out of the nearest tile by lanes 0 .. lane
+            double pm = j >= 0 ? __ldg(a.Mf + j) : 0.0;       // product of the multipliers of lanes 0 .. lane
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {  // affine maps composed nearest-first
+                const double up_acc = __shfl_up_sync(kAllLanes, acc, s), up_pm = __shfl_up_sync(kAllLanes, pm, s);
+                if (lane >= s) { acc = fma(up_pm, acc, up_acc); pm *= up_pm; }
+            }
+            c = fma(prod, __shfl_sync(kAllLanes, acc, 31), c);
+            prod *= __shfl_sync(kAllLanes, pm, 31);
+        }
+        return c;
+    };
+    __shared__ double s_cf[2];  // forward carry of the current / the next tile
+    if (!SETUP && warp == 1 && s_ticket[0] < (unsigned)a.n_tiles) {
+        const double c = forward_fold(a.n_tiles - 1 - (int64_t)s_ticket[0]);
+        if (lane == 0) s_cf[0] = c;
+    }
     for (int it = 0;; ++it) {
         const unsigned ticket = s_ticket[it & 1];
         if (ticket >= (unsigned)a.n_tiles) break;
         if (tid == 0) s_ticket[(it & 1) ^ 1] = atomicAdd(a.ticket, 1u) - base;  // the next tile's ticket, a tile ahead
         const int64_t tile = a.n_tiles - 1 - (int64_t)ticket;  // right to left
         const int64_t cell0 = tile * kPTile + (int64_t)tid * 8;
-
-        // ---- forward carry into the tile: fold the finished aggregates of the tiles on the left (issued first: its
-        //      loads fly while the rows arrive) ----
-        if (!SETUP && warp == 0) {
-            double c = 0.0, prod = 1.0;
-            for (int64_t j0 = tile - 1; j0 >= 0 && prod != 0.0; j0 -= 32) {
-                const int64_t j = j0 - lane;  // lane 0 = nearest tile
-                double acc = j >= 0 ? __ldg(a.Ef_now + j) : 0.0;  // value carried out of the nearest tile by lanes 0 .. lane
-                double pm = j >= 0 ? __ldg(a.Mf + j) : 0.0;       // product of the multipliers of lanes 0 .. lane
-#pragma unroll
-                for (int s = 1; s < 32; s <<= 1) {  // affine maps composed nearest-first
-                    const double up_acc = __shfl_up_sync(kAllLanes, acc, s), up_pm = __shfl_up_sync(kAllLanes, pm, s);
-                    if (lane >= s) { acc = fma(up_pm, acc, up_acc); pm *= up_pm; }
-                }
-                c = fma(prod, __shfl_sync(kAllLanes, acc, 31), c);
-                prod *= __shfl_sync(kAllLanes, pm, 31);
-            }
-            if (lane == 0) s_carry[0] = c;
-        }
 
         // ---- my 8 cells: factors and state (identity rows behind the mesh) ----
         double l[8], r[8], g[8], x[8];
@@ -236,7 +241,7 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
             double c = and_mask(__shfl_up_sync(kAllLanes, y, 1), lane == 0 ? 0 : -1);
             if (lane == 31) s_E[0][warp] = y;
             __syncthreads();
-            double cw = s_carry[0];  // y in front of my warp: the tile's carry folded through the warps on my left
+            double cw = s_cf[it & 1];  // y in front of my warp: the tile's carry folded through the warps on my left
             for (int w = 0; w < warp; ++w) cw = fma(s_T[0][w], cw, s_E[0][w]);
             c = fma(sm.ex_f, cw, c);
             chunk_apply_fwd_plain<double, 8>(x, l, r, c);
@@ -292,6 +297,9 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
                     prod *= __shfl_sync(kAllLanes, pm, 31);
                 }
                 if (lane == 0) s_carry[1] = cb;
+            } else if (warp == 1 && next_tile >= 0) {  // meanwhile: the NEXT tile's forward carry
+                const double c = forward_fold(next_tile);
+                if (lane == 0) s_cf[(it & 1) ^ 1] = c;
             }
             __syncthreads();
             double cw = s_carry[1];  // x behind my warp: the tile's carry folded through the warps on my right
