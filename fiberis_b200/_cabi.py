@@ -59,6 +59,7 @@ SIGNATURES = {
     "fbr_version": (_i32, []),
     "fbr_last_error": (C.c_char_p, []),
     "fbr_last_launch_count": (_i32, []),
+    "fbr_nccl_allgather_f64": (_i32, [_p, _p, _i64, _p, _p]),
     "fbr_probe_fp64_peak": (_i32, [C.POINTER(_f64), _p, _p]),
     "fbr_transpose_f64": (_i32, [_p, _i64, _i64, _p, _p]),
     "fbr_device_info": (_i32, [C.POINTER(_i32)] * 3 + [C.POINTER(_i64)] * 3),

@@ -2,6 +2,8 @@
 // All bandwidth-trivial one-off kernels (they run once per dt, the time loop is in fbr_run_onchip.cu).
 #include <stdarg.h>
 
+#include <dlfcn.h>
+
 #include "fbr_common.cuh"
 
 namespace fbr {
@@ -356,6 +358,27 @@ extern "C" int fbr_probe_fp64_peak(double *h_dfma_per_s, double *d_sink, void *s
     cudaEventDestroy(e1);
     if (int rc = check_launch("fbr_probe_fp64_peak")) return rc;
     *h_dfma_per_s = (double)f.sm_count * 512.0 * iters * 64.0 / (best * 1e-3);  // lane-level DFMA per second
+    return FBR_OK;
+}
+
+// The one collective of the path — the all-gather of per-member misfits over the ranks' contiguous shards —
+// for callers that bring their own communicator: the library does not link NCCL, it resolves ncclAllGather from the NCCL
+// the process already has loaded (or can load) at first use.
+extern "C" int fbr_nccl_allgather_f64(const double *send, double *recv, int64_t count, void *nccl_comm, void *stream) {
+    FBR_REQUIRE(send && recv && count >= 0 && nccl_comm, "NULL buffer / communicator");
+    typedef int (*allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+    static allgather_fn fn = nullptr;
+    if (!fn) {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return fail(FBR_ERR_UNSUPPORTED, "NCCL is not available in this process (%s)", dlerror());
+        fn = reinterpret_cast<allgather_fn>(dlsym(h, "ncclAllGather"));
+        if (!fn) return fail(FBR_ERR_UNSUPPORTED, "ncclAllGather not found in the loaded NCCL");
+    }
+    const int kNcclFloat64 = 8;  // ncclDataType_t: ncclFloat64 / ncclDouble
+    const int rc = fn(send, recv, (size_t)count, kNcclFloat64, nccl_comm, as_stream(stream));
+    if (rc != 0) return fail(FBR_ERR_CUDA, "ncclAllGather failed with ncclResult_t %d", rc);
     return FBR_OK;
 }
 

@@ -65,6 +65,12 @@ const char *fbr_last_error(void);
  * directly (fbr_run_opts.snap_cell_stride). */
 int fbr_transpose_f64(const double *src, int64_t rows, int64_t cols, double *dst, void *stream);
 
+/* The path's only collective: all-gather of the ranks' per-member misfit blocks (`count` doubles each, equal
+ * on every rank: pad the last block) with a communicator the CALLER created (ncclComm_t passed as void*), asynchronous on
+ * `stream`.  The library links no NCCL: ncclAllGather is resolved at first use from the NCCL loaded in the process
+ * (FBR_ERR_UNSUPPORTED when there is none).  PDS1D_Ensemble itself gathers through torch.distributed (NCCL backend). */
+int fbr_nccl_allgather_f64(const double *send, double *recv, int64_t count, void *nccl_comm, void *stream);
+
 /* Measurement aid: the fp64 issue peak of the current device in lane-level DFMA per second (8 independent chains per
  * thread, 16 warps per SM, timed with CUDA events on `stream`; synchronous).  bench.py's compute-side roofline divides
  * the fp64 operations K3 executes by this figure.  h_dfma_per_s: host; d_sink: 8 bytes of device scratch. */
