@@ -35,13 +35,15 @@ def _worker(rank, world, id_file, out_dir):
     if rank == 0:
         assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
         with open(id_file + ".tmp", "wb") as f:
-            f.write(bytes(uid.internal))
+            f.write(C.string_at(C.addressof(uid), 128))  # (the id contains NUL bytes: not bytes(uid.internal))
         os.rename(id_file + ".tmp", id_file)
     else:
         import time
         while not os.path.exists(id_file):
             time.sleep(0.05)
-        C.memmove(C.byref(uid), open(id_file, "rb").read(), 128)
+        raw = open(id_file, "rb").read()
+        assert len(raw) == 128
+        C.memmove(C.addressof(uid), raw, 128)
     comm = C.c_void_p()
     nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _UniqueId, C.c_int]
     assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
