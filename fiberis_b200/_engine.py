@@ -635,6 +635,19 @@ def solve_tridiag(dl, d, du, b, variant=_cabi.SOLVER_AUTO, check_singular=True):
     torch = _torch()
     lib = _cabi.load()
     M, nx = d.shape
+    if variant == _cabi.SOLVER_AUTO and nx > 4096 and M <= 4:
+        # a few LONG systems: the Thomas walk is one thread per system.  Parallel along the mesh instead: the tile-parallel
+        # factorisation (K1b) and ONE pass of K3P with the right-hand side as "state" and nothing overridden
+        # (fbr_run_pass_f64, n_steps = 1) — 1e7 unknowns in ~0.5 ms
+        try:
+            rows = []
+            for m in range(M):
+                fac = factorize(dl[m:m + 1], d[m:m + 1], du[m:m + 1], check_singular=check_singular, parallel=True)
+                rows.append(run_stream(fac, b[m:m + 1], nx, 1, "None", "None", None, 0, None, snapshot_every=0,
+                                       want_final=True, kernel="pass")[1])
+            return torch.cat(rows, dim=0)
+        except np.linalg.LinAlgError:  # zero pivot without row interchanges: the pivoted variant decides
+            return solve_tridiag(dl, d, du, b, _cabi.SOLVER_PIVOT, True)
     x = torch.empty_like(b)
     flags = torch.zeros(M, dtype=torch.int32, device=d.device)
     work = None

@@ -550,11 +550,19 @@ __device__ __forceinline__ void cp_async_wait_all_k3() { asm volatile("cp.async.
 // v = x[j] for a run-time j (any CPT): a chain of selects, no dynamic register indexing
 template <typename T, int CPT>
 __device__ __forceinline__ T pick_at(const T (&x)[CPT], int j) {
-    if (CPT <= 8) return get_at<T, CPT>(x, j);
-    T v = x[0];
+    if constexpr (CPT <= 8) return get_at<T, CPT>(x, j);
+    else {  // 16 cells (fp32 mode): a select tree on the four bits of j — 15 selects on 4 predicates instead of a chain of
+            // 15 compare-and-select pairs
+        static_assert(CPT == 16, "select tree for 16 cells");
+        const bool b0 = j & 1, b1 = j & 2, b2 = j & 4, b3 = j & 8;
+        T a[8], c[4];
 #pragma unroll
-    for (int k = 1; k < CPT; ++k) v = (j == k) ? x[k] : v;
-    return v;
+        for (int k = 0; k < 8; ++k) a[k] = b0 ? x[2 * k + 1] : x[2 * k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = b1 ? a[2 * k + 1] : a[2 * k];
+        const T d0 = b2 ? c[1] : c[0], d1 = b2 ? c[3] : c[2];
+        return b3 ? d1 : d0;
+    }
 }
 
 // A thread's 64 bytes straight to global memory (16-byte stores when aligned).
@@ -688,7 +696,8 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                          reinterpret_cast<uintptr_t>(a.fg) | reinterpret_cast<uintptr_t>(a.p0)) & 15) == 0 && a.p0_stride % 2 == 0;
     auto load_row = [&](const double *row, double pad, T (&v)[CPT]) -> double {  // returns the fp64 product of the row's chunk
         double prod = 1.0;
-        if (vec_ok) {
+        const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(row + cell0) & 15);
+        if (vec_ok || (cell0 + CPT <= nx && mis == 0)) {
             const double2 *q = reinterpret_cast<const double2 *>(row + cell0);
 #pragma unroll
             for (int j = 0; j < CPT / 2; ++j) {
@@ -697,6 +706,20 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 v[2 * j + 1] = (T)t.y;
                 prod *= t.x * t.y;
             }
+        } else if (cell0 + CPT <= nx && mis == 8) {
+            // a full chunk starting on an odd element (odd nx: every other member's row): 8-byte load, 16-byte loads, 8-byte load
+            const double first = __ldg(row + cell0), last = __ldg(row + cell0 + CPT - 1);
+            v[0] = (T)first;
+            prod = first * last;
+            const double2 *q = reinterpret_cast<const double2 *>(row + cell0 + 1);
+#pragma unroll
+            for (int j = 0; j < CPT / 2 - 1; ++j) {
+                const double2 t = __ldg(q + j);
+                v[2 * j + 1] = (T)t.x;
+                v[2 * j + 2] = (T)t.y;
+                prod *= t.x * t.y;
+            }
+            v[CPT - 1] = (T)last;
         } else {
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
