@@ -619,7 +619,10 @@ __device__ __forceinline__ void store_row_coalesced(T *__restrict__ row, int64_t
 // loops (scratch/ubench_k3v.cu) — the table costs 6 shared loads and 3 dependent FMAs behind every barrier.
 constexpr int kScanExact = 0, kScanNear = 1, kScanNear4 = 2;
 
-template <typename T, int CPT, int W, int MINB, bool ZONAL>
+// LEAN: the instantiation for launches that record nothing (no snapshots) — the step-at-a-time use, where the per-member
+// prologue is all that counts: without the copies of the step loop that carry snapshot code the register allocator leaves
+// far fewer spills on that path (W = 2: 192 -> see the ptxas log).
+template <typename T, int CPT, int W, int MINB, bool ZONAL, bool LEAN = false>
 __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs a) {
     __shared__ Mat2 s_zw[ZONAL ? W : 1];
     __shared__ double s_zc[ZONAL ? W : 1];
@@ -1043,7 +1046,13 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             using I0 = std::integral_constant<int, kScanExact>;
             using I1 = std::integral_constant<int, kScanNear>;
             using I2 = std::integral_constant<int, kScanNear4>;
-            if (scan_mode == kScanExact) {
+            if constexpr (LEAN) {  // nothing is recorded in this instantiation (the launcher checked)
+                if (scan_mode == kScanExact) {
+                    if (any_slow) steps(I0{}, std::true_type{}, std::false_type{}, done, done + run);
+                    else steps(I0{}, std::false_type{}, std::false_type{}, done, done + run);
+                } else if (scan_mode == kScanNear) steps(I1{}, std::false_type{}, std::false_type{}, done, done + run);
+                else steps(I2{}, std::false_type{}, std::false_type{}, done, done + run);
+            } else if (scan_mode == kScanExact) {
                 if (recorded) {  // (the copies for unrecorded members carry no snapshot code)
                     if (any_slow) steps(I0{}, std::true_type{}, std::true_type{}, done, done + run);
                     else steps(I0{}, std::false_type{}, std::true_type{}, done, done + run);
@@ -1259,7 +1268,10 @@ static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     // 16 warps per SM (128 registers per thread).  A fifth 4-warp CTA per SM at 96 registers was measured again in round 2
     // with the leaner loops: 11 spill loads per step, 25.7 against 21.3 ms per C3 sweep.
     constexpr int kFull16 = (16 / W) > 0 ? (16 / W) : 1;
-    auto kern = run_onchipx_kernel<T, CPT, W, kFull16, ZONAL>;
+    void (*kern)(const RunArgs) = run_onchipx_kernel<T, CPT, W, kFull16, ZONAL>;
+    if constexpr (!ZONAL && sizeof(T) == 8) {
+        if (!a.snap && !getenv("FBR_K3_NO_LEAN")) kern = run_onchipx_kernel<T, CPT, W, kFull16, ZONAL, true>;
+    }
     RunArgs b = a;
     const int cols = a.n_src + 2 * a.n_obs;
     // Time steps per staged block of per-step scalars: the longest block that costs no resident CTA (block boundaries
