@@ -534,7 +534,7 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
                    "l2": "flushed between timed iterations (512 MiB memset)",
                    "timed_kernels": ("K1 assemble + K1b factorize + " if long_mesh else "") + kname, "window_plan": win or None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(args.workload), "kernel": kname,
+                     "traffic": ncu_traffic("c5_exact" if (streaming and not win) else args.workload), "kernel": kname,
                      "frac_32B": 2.0 * achieved / peak,  # SURVEY 8(d) secondary figure: state + 2 coefficient words
                      "achieved_40B": work * 40.0 / k_s / 1e9 if (streaming and not win) else None,
                      "kernel_ms": k_s * 1e3, "peak_source": peak_src,
@@ -855,8 +855,10 @@ def run_gpu_arm(args):
             # the single-model configurations of BASELINE.json next to the headline (short runs, same code path
             # as `--workload c2|c5`; full records under profiles/)
             torch.cuda.empty_cache()
-            for name in ("c2", "c5"):
-                sub = argparse.Namespace(**{**vars(args), "workload": name, "steps": 3, "no_cpu": True})
+            for name, long_mesh in (("c2", args.long_mesh), ("c5", args.long_mesh), ("c5_exact", "exact")):
+                # (c5_exact: C5's mesh forced onto the exact long-mesh path — K3P, one pass over HBM per step)
+                sub = argparse.Namespace(**{**vars(args), "workload": name.split("_")[0], "steps": 3, "no_cpu": True,
+                                            "long_mesh": long_mesh})
                 r = run_single_gpu_arm(sub, emit=False, sampler=False)
                 med = float(np.median(r["config"]["step_ms_each"]))  # launch-heavy: the median shrugs off host jitter
                 line["other_workloads"][name] = {
@@ -864,7 +866,8 @@ def run_gpu_arm(args):
                     "ms": med, "ms_each": r["config"]["step_ms_each"],
                     "us_per_time_step": r["config"]["us_per_time_step"], "kernel": r["roofline"]["kernel"],
                     "roofline_frac_16B": r["roofline"]["frac"], "roofline_frac_32B": 2.0 * r["roofline"]["frac"], "e2e": r["e2e"]["value"],
-                    "window_plan": r["config"]["window_plan"], "parity": r.get("parity")}
+                    "window_plan": r["config"]["window_plan"], "parity": r.get("parity"),
+                    "achieved_GBs_40B": r["roofline"].get("achieved_40B")}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(make_workload(args.workload, 1))
         gates = [line["parity"]] + [v.get("parity") for v in line["other_workloads"].values()]

@@ -426,8 +426,11 @@ class PDS1D_SingleSource:
                 raise NotImplementedError(f"decay horizon {horizon} is too long for the windowed path")
             if plan is not None:
                 self.long_mesh_path = dict(kernel="K3W", horizon=horizon, **plan)
-                # rows of >= 8 MB: stream them to the host while later blocks are integrated
-                if nx * 8 >= (8 << 20) and kwargs.get("stream_rows", True):
+                # rows of >= 8 MB — or >= 512 KB each when the stored rows add up to >= 32 MB (C2: 101 rows of 0.8 MB, whose
+                # 80 MB copy otherwise trails the 7.7 ms run by 3 ms): stream them to the host while later blocks are integrated
+                n_rows = n_steps // every if every else 0
+                big_rows = nx * 8 >= (8 << 20) or (nx * 8 >= (512 << 10) and n_rows * nx * 8 >= (32 << 20))
+                if big_rows and kwargs.get("stream_rows", True):
                     self.long_mesh_path["rows"] = "streamed to host"
                     return _engine.run_window_to_host(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
                                                       table_d, horizon, snapshot_every=every)
