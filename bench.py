@@ -576,6 +576,8 @@ def run_single_gpu_arm(args, emit=True, sampler=True):
                                           f"sequential: 1 thread), {el:.1f} s"}
     if emit:
         emit_line(line)
+    else:
+        line["_snapshot"] = p.snapshot  # (for the caller's cross-checks; never serialised)
     return line
 
 
@@ -855,6 +857,7 @@ def run_gpu_arm(args):
             # the single-model configurations of BASELINE.json next to the headline (short runs, same code path
             # as `--workload c2|c5`; full records under profiles/)
             torch.cuda.empty_cache()
+            snaps = {}
             for name, long_mesh in (("c2", args.long_mesh), ("c5", args.long_mesh), ("c5_exact", "exact")):
                 # (c5_exact: C5's mesh forced onto the exact long-mesh path — K3P, one pass over HBM per step)
                 sub = argparse.Namespace(**{**vars(args), "workload": name.split("_")[0], "steps": 3, "no_cpu": True,
@@ -868,6 +871,16 @@ def run_gpu_arm(args):
                     "roofline_frac_16B": r["roofline"]["frac"], "roofline_frac_32B": 2.0 * r["roofline"]["frac"], "e2e": r["e2e"]["value"],
                     "window_plan": r["config"]["window_plan"], "parity": r.get("parity"),
                     "achieved_GBs_40B": r["roofline"].get("achieved_40B")}
+                snaps[name] = r.pop("_snapshot")
+            # the FULL-LENGTH check of the truncated windows (K3W drops influence below 2^-80): all stored rows of the timed
+            # 1000-step C5 run against the exact one-pass kernel (K3P), which the oracle pins row by row where it is affordable
+            a5, b5 = snaps.pop("c5"), snaps.pop("c5_exact")
+            rel5 = float(np.max(np.abs(a5 - b5)) / np.max(np.abs(b5)))
+            par5 = line["other_workloads"]["c5"]["parity"]
+            par5["windowed_vs_exact_rel_max"] = rel5
+            par5["checked"] += f"; all {a5.shape[0] - 1} stored rows (1000 steps) against the exact kernel K3P on the device"
+            par5["passed"] = bool(par5["passed"] and rel5 <= 1e-10)
+            del a5, b5, snaps
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(make_workload(args.workload, 1))
         gates = [line["parity"]] + [v.get("parity") for v in line["other_workloads"].values()]
