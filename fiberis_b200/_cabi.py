@@ -88,6 +88,9 @@ SIGNATURES = {
     "fbr_run_window_plan": (_i32, [_i64, _i64, _i64, _i64, C.POINTER(_i64)]),
     "fbr_run_window_work_bytes": (_i64, [_i64]),
     "fbr_run_window_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
+    "fbr_run_window_plan_f32": (_i32, [_i64, _i64, _i64, _i64, C.POINTER(_i64)]),
+    "fbr_run_window_f32_work_bytes": (_i64, [_i64]),
+    "fbr_run_window_f32": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _i64, _i64, _p, _p]),
     "fbr_run_adaptive_max_nx": (_i64, []),
     "fbr_run_adaptive_f64": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _p, _p, _i32, _f64, _f64,
                                     _p, _f64, _f64, _f64, _f64, _f64, _f64, _i64, _i64, _p, _p, _p, _i64, _p, _p]),

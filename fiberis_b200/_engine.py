@@ -406,12 +406,17 @@ def decay_horizon(factors, log2_eps=-80.0, cap=2048):
     return hf, hb
 
 
-def window_plan(nx, horizon, snapshot_every=0):
+def window_plan(nx, horizon, snapshot_every=0, dtype="float64", cap=2048):
     """What K3W would use for this mesh: dict(warps, steps_per_block, owned, windows), or None when
-    the horizons are too long for windows to pay."""
+    the horizons are too long for windows to pay.  ``cap``: the cap decay_horizon ran with — a horizon of
+    cap + 1 means "not established within cap cells" and is never a usable halo (the fp32 mode's 8192-cell
+    windows would otherwise accept it)."""
+    if max(int(horizon[0]), int(horizon[1])) > cap:
+        return None
     lib = _cabi.load()
     out = (_cabi.C.c_int64 * 4)()
-    rc = lib.fbr_run_window_plan(int(nx), int(horizon[0]), int(horizon[1]), int(snapshot_every), out)
+    fn = lib.fbr_run_window_plan if dtype == "float64" else lib.fbr_run_window_plan_f32
+    rc = fn(int(nx), int(horizon[0]), int(horizon[1]), int(snapshot_every), out)
     if rc == _cabi.FBR_ERR_UNSUPPORTED:
         return None
     check(rc)
@@ -419,26 +424,31 @@ def window_plan(nx, horizon, snapshot_every=0):
 
 
 def run_window(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, horizon, snapshot_every=1,
-               want_final=False, with_initial_row=True):
-    """K3W: time-tiled overlapping windows for one long mesh.  factors / p0: (1, nx).  Returns
-    (snap (1, rows, nx) | None, p_final | None)."""
+               want_final=False, with_initial_row=True, dtype="float64"):
+    """K3W: time-tiled overlapping windows for one long mesh.  factors / p0: (1, nx), fp64.  Returns
+    (snap (1, rows, nx) | None, p_final | None) — float tensors in the fp32 mode (``dtype='float32'``:
+    fbr_run_window_f32, 16 cells per thread on the fp32 pipe)."""
     torch = _torch()
     lib = _cabi.load()
     fl, fr, fg = factors
     dev = fl.device
+    f32 = dtype == "float32"
+    tdt, esz = (torch.float32, 4) if f32 else (torch.float64, 8)
     n_rows = n_steps // snapshot_every if snapshot_every else 0
     snap = snap_ptr = None
     lead = 1 if with_initial_row else 0
     if n_rows > 0:
-        snap = torch.empty((1, n_rows + lead, nx), dtype=torch.float64, device=dev)
+        snap = torch.empty((1, n_rows + lead, nx), dtype=tdt, device=dev)
         if lead:
             snap[:, 0, :] = p0
-        snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * 8)
-    p_final = torch.empty((1, nx), dtype=torch.float64, device=dev) if want_final else None
-    work = torch.empty(int(lib.fbr_run_window_work_bytes(nx)) // 8, dtype=torch.float64, device=dev)
-    check(lib.fbr_run_window_f64(ptr(fl), ptr(fr), ptr(fg), ptr(p0), nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
-                                 ptr(src_idx), n_src, ptr(src_table), int(snapshot_every) if snap is not None else 0, nx, snap_ptr,
-                                 ptr(p_final), int(horizon[0]), int(horizon[1]), ptr(work), current_stream()))
+        snap_ptr = _cabi.C.c_void_p(snap.data_ptr() + lead * nx * esz)
+    p_final = torch.empty((1, nx), dtype=tdt, device=dev) if want_final else None
+    work_bytes = int((lib.fbr_run_window_f32_work_bytes if f32 else lib.fbr_run_window_work_bytes)(nx))
+    work = torch.empty(work_bytes // 8 + 1, dtype=torch.float64, device=dev)
+    fn = lib.fbr_run_window_f32 if f32 else lib.fbr_run_window_f64
+    check(fn(ptr(fl), ptr(fr), ptr(fg), ptr(p0), nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
+             ptr(src_idx), n_src, ptr(src_table), int(snapshot_every) if snap is not None else 0, nx, snap_ptr,
+             ptr(p_final), int(horizon[0]), int(horizon[1]), ptr(work), current_stream()))
     return snap, p_final
 
 

@@ -27,10 +27,13 @@ constexpr unsigned kFullW = 0xffffffffu;
 constexpr int kWinCPT = 8;
 constexpr int kWinList = 64;  // sources per window kept in shared memory (more: global scan)
 
-struct WinArgs {
-    const double *fl, *fr, *fg;  // (nx) factors
-    const double *p_in;          // (nx) state at the start of the block
-    double *p_out;               // (nx) state at the end of the block (owned cells of every window)
+// T = double (8 cells per thread) or float (the fp32 mode: 16 cells per thread, the same 64 bytes — a window holds
+// twice the cells, the halos stay the same number of cells, and the sweeps run on the fp32 pipe)
+template <typename T>
+struct WinArgsT {
+    const T *fl, *fr, *fg;  // (nx) factors
+    const T *p_in;          // (nx) state at the start of the block
+    T *p_out;               // (nx) state at the end of the block (owned cells of every window)
     int64_t nx;
     int64_t own, lead;  // owned cells per window; window k starts at cell k * own - lead
     int n_steps;        // steps in this block
@@ -42,6 +45,7 @@ struct WinArgs {
     int n_src;
     const double *src_table;  // (n_steps, n_src) rows of this block
 };
+using WinArgs = WinArgsT<double>;
 
 __device__ const double kZeroWin = 0.0;
 
@@ -70,6 +74,34 @@ __device__ __forceinline__ void load8(const double *__restrict__ base, int64_t c
     }
 }
 
+__device__ __forceinline__ void mov_if_eq_w(float &dst, float v, int j, int k) {
+    asm volatile("{ .reg .pred p; setp.eq.s32 p, %2, %3; @p mov.f32 %0, %1; }" : "+f"(dst) : "f"(v), "r"(j), "r"(k));
+}
+// fp32 mode: 16 consecutive cells
+__device__ __forceinline__ void load8(const float *__restrict__ base, int64_t cell0, int64_t nx, float pad, float (&v)[16]) {
+    const float *p = base + cell0;
+    if (cell0 >= 0 && cell0 + 16 <= nx && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        const float4 *q = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldg(q + j);
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int64_t i = cell0 + j;
+            v[j] = (i >= 0 && i < nx) ? __ldg(base + i) : pad;
+        }
+    }
+}
+__device__ __forceinline__ float lds_any(unsigned addr, float) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_any(unsigned addr, double) { return lds_f64(addr); }
+
 // 16-byte asynchronous copy global -> shared (no register staging; completion via cp.async groups)
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -86,8 +118,8 @@ __device__ __forceinline__ int swz_piece(int row, int piece) { return row * 4 + 
 
 // issue the copies of one array of window [win0, win0 + T*8): piece p (16 B) is fetched by thread
 // p % T — fully coalesced 512-byte warp requests — and lands in its consumer's swizzled row
-template <int T>
-__device__ __forceinline__ void stage_array(double *sm, const double *__restrict__ base, int64_t win0, int tid) {
+template <int T, typename V>
+__device__ __forceinline__ void stage_array(V *sm, const V *__restrict__ base, int64_t win0, int tid) {
     const double2 *src = reinterpret_cast<const double2 *>(base + win0);
     double2 *dst = reinterpret_cast<double2 *>(sm);
 #pragma unroll
@@ -105,22 +137,32 @@ __device__ __forceinline__ void unstage8(const double *sm, int tid, double (&v)[
         v[2 * j + 1] = t.y;
     }
 }
+__device__ __forceinline__ void unstage8(const float *sm, int tid, float (&v)[16]) {
+    const float4 *src = reinterpret_cast<const float4 *>(sm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 t = src[swz_piece(tid, j)];
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+}
 
 // Persistent CTAs: CTA b integrates windows b, b + gridDim.x, ...; while it advances one window
 // through the time block, the next window's pressure and factors stream into shared memory
 // (cp.async), so HBM latency is hidden behind the sweeps.
 // NS = scan stages (5: exact; 3 / 4 when the horizon is <= 64 / 128 cells); NEAR: the horizon fits
 // one warp (256 cells), so a warp's carry comes from its immediate neighbour only.
-template <int W, int NS, bool NEAR>
-__global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(const WinArgs a) {
-    constexpr int CPT = kWinCPT;
+template <typename R, int W, int NS, bool NEAR>
+__global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(const WinArgsT<R> a) {
+    constexpr bool F64 = sizeof(R) == 8;
+    constexpr int CPT = 64 / (int)sizeof(R);
     constexpr int T = 32 * W;
     constexpr int WC = T * CPT;  // cells per window
-    extern __shared__ __align__(128) double s_stage[];  // [4][WC]: l, r, g, p of the NEXT window
-    __shared__ __align__(16) double s_K[2][W][W];
-    __shared__ __align__(16) double s_Ef[W + 1];  // s_Ef[w + 1] = zero-carry end value of warp w; s_Ef[0] = 0
-    __shared__ __align__(16) double s_Eb[W + 1];  // s_Eb[w] = zero-carry first value of warp w; s_Eb[W] = 0
-    __shared__ double s_dummy;                    // where lanes that have nothing to publish store
+    extern __shared__ __align__(128) double s_stage_raw[];  // [4][WC] of R: l, r, g, p of the NEXT window
+    R *const s_stage = reinterpret_cast<R *>(s_stage_raw);
+    __shared__ __align__(16) R s_K[2][W][W];
+    __shared__ __align__(16) R s_Ef[W + 1];  // s_Ef[w + 1] = zero-carry end value of warp w; s_Ef[0] = 0
+    __shared__ __align__(16) R s_Eb[W + 1];  // s_Eb[w] = zero-carry first value of warp w; s_Eb[W] = 0
+    __shared__ R s_dummy;                    // where lanes that have nothing to publish store
     __shared__ double s_T[2][W];
     __shared__ int s_list_n;
     __shared__ int s_list_k[kWinList];    // sources that fall into this window: slot ...
@@ -153,7 +195,7 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     // Everything up to the grid-dependency wait reads only time-invariant inputs, so under
     // programmatic dependent launch the first window's setup overlaps the previous time block.
     if (tid == 0) s_list_n = 0;
-    double l[CPT], r[CPT], g[CPT], x[CPT];
+    R l[CPT], r[CPT], g[CPT], x[CPT];
     if (staged) {
         cp_async_wait_all();
         __syncthreads();
@@ -162,9 +204,9 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         unstage8(s_stage + 2 * WC, tid, g);
         if (!first) unstage8(s_stage + 3 * WC, tid, x);
     } else {
-        load8(a.fl, cell0, nx, 0.0, l);
-        load8(a.fr, cell0, nx, 1.0, r);
-        load8(a.fg, cell0, nx, 0.0, g);
+        load8(a.fl, cell0, nx, (R)0, l);
+        load8(a.fr, cell0, nx, (R)1, r);
+        load8(a.fg, cell0, nx, (R)0, g);
     }
     __syncthreads();
     for (int q = tid; q < a.n_src; q += T) {  // one parallel pass over the source rows
@@ -183,16 +225,30 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     const double *ovp = &kZeroWin;
     if (cell0 < nx && cell0 + CPT > 0) {
         constexpr unsigned kNoSlot = 0xFF, kZeroSlot = 0xFE;
-        uint64_t ov = ~0ull;
-        if (cell0 <= 0 && a.lbc != FBR_BC_NONE) ov = (ov & ~(0xFFull << (8 * (-cell0)))) | ((uint64_t)kZeroSlot << (8 * (-cell0)));
+        uint64_t ov[CPT / 8];  // one byte per cell: the slot that overrides it
+#pragma unroll
+        for (int q = 0; q < CPT / 8; ++q) ov[q] = ~0ull;
+        auto slot_of = [&](int j) {
+            uint64_t w = ov[0];
+#pragma unroll
+            for (int q = 1; q < CPT / 8; ++q)
+                if (q == (j >> 3)) w = ov[q];
+            return (unsigned)(w >> (8 * (j & 7))) & 0xFF;
+        };
+        auto put = [&](int j, unsigned v) {
+#pragma unroll
+            for (int q = 0; q < CPT / 8; ++q)
+                if (q == (j >> 3)) ov[q] = (ov[q] & ~(0xFFull << (8 * (j & 7)))) | ((uint64_t)v << (8 * (j & 7)));
+        };
+        if (cell0 <= 0 && a.lbc != FBR_BC_NONE) put((int)(-cell0), kZeroSlot);
         const int64_t jl = nx - 1 - cell0;
-        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) ov = (ov & ~(0xFFull << (8 * jl))) | ((uint64_t)kZeroSlot << (8 * jl));
+        if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) put((int)jl, kZeroSlot);
         bool wide = list_n > kWinList;
         // later duplicates win (matbuilder.py:156-161): the list is unordered, so keep the largest slot
         auto claim = [&](int q, int jj) {
             if (q >= 0xFE) wide = true;
-            const unsigned cur = (unsigned)(ov >> (8 * jj)) & 0xFF;
-            if (cur >= 0xFE || (unsigned)q > cur) ov = (ov & ~(0xFFull << (8 * jj))) | ((uint64_t)(q & 0xFF) << (8 * jj));
+            const unsigned cur = slot_of(jj);
+            if (cur >= 0xFE || (unsigned)q > cur) put(jj, (unsigned)(q & 0xFF));
         };
         if (list_n <= kWinList) {
             for (int q = 0; q < list_n; ++q) {
@@ -210,7 +266,7 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         int n_ov = 0;
 #pragma unroll 1
         for (int j = 0; j < CPT; ++j) {
-            const unsigned so = (unsigned)(ov >> (8 * j)) & 0xFF;
+            const unsigned so = slot_of(j);
             if (so != kNoSlot) {
                 ++n_ov; ov_j = j;
                 if (so != kZeroSlot) { ovp = a.src_table + so; ov_stride = a.n_src; }
@@ -221,11 +277,22 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     }
 
     // scan multipliers (time-invariant within the block)
-    const HalfProducts hf = half_products_fwd(l), hb = half_products_bwd(g);
-    const ScanMultipliers sm = scan_multipliers(hf.a * hf.b, hb.a * hb.b, lane);
-    double Pf[NS], Pb[NS];
+    // (fp32 mode: products of up to 512 multipliers — formed in fp64 from the multipliers the sweeps use, rounded once)
+    HalfProducts hf = {1.0, 1.0}, hb = {1.0, 1.0};
+    double chunk_f, chunk_b;
+    if constexpr (F64) {
+        hf = half_products_fwd(l); hb = half_products_bwd(g);
+        chunk_f = hf.a * hf.b; chunk_b = hb.a * hb.b;
+    } else {
+        chunk_f = 1.0; chunk_b = 1.0;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) { Pf[s] = sm.f[s]; Pb[s] = sm.b[s]; }
+        for (int j = 0; j < CPT; ++j) { chunk_f *= (double)l[j]; chunk_b *= (double)g[j]; }
+    }
+    const ScanMultipliers sm = scan_multipliers(chunk_f, chunk_b, lane);
+    R Pf[NS], Pb[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { Pf[s] = (R)sm.f[s]; Pb[s] = (R)sm.b[s]; }
+    const R ex_f = (R)sm.ex_f, ex_b = (R)sm.ex_b;
     if (!NEAR) {
         if (lane == 31) s_T[0][warp] = sm.tot_f;
         if (lane == 0) s_T[1][warp] = sm.tot_b;
@@ -233,23 +300,23 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         if (tid < W) {
             double kk = 1.0;
             for (int v = W - 1; v >= 0; --v) {
-                if (v >= tid) s_K[0][tid][v] = 0.0;
-                else { s_K[0][tid][v] = kk; kk *= s_T[0][v]; }
+                if (v >= tid) s_K[0][tid][v] = (R)0;
+                else { s_K[0][tid][v] = (R)kk; kk *= s_T[0][v]; }
             }
             kk = 1.0;
             for (int v = 0; v < W; ++v) {
-                if (v <= tid) s_K[1][tid][v] = 0.0;
-                else { s_K[1][tid][v] = kk; kk *= s_T[1][v]; }
+                if (v <= tid) s_K[1][tid][v] = (R)0;
+                else { s_K[1][tid][v] = (R)kk; kk *= s_T[1][v]; }
             }
         }
     }
-    if (tid == 0) { s_Ef[0] = 0.0; s_Eb[W] = 0.0; }
+    if (tid == 0) { s_Ef[0] = (R)0; s_Eb[W] = (R)0; }
     const bool any_slow = __syncthreads_or(ov_slow);
     if (first) {  // ---- the previous time block's output is needed from here on ----
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;");
     }
-    if (!staged || first) load8(a.p_in, cell0, nx, 0.0, x);
+    if (!staged || first) load8(a.p_in, cell0, nx, (R)0, x);
     first = false;
     __syncthreads();  // everybody has emptied the staging buffer: stream the next window in
     {
@@ -275,15 +342,20 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
 #pragma unroll 1
     for (int left = a.n_steps; left > 0; --left) {
         if (ov_j >= 0) {  // only the threads that own an overridden cell come here
-            switch (ov_j) {
-                case 0: x[0] = ov_val; break;
-                case 1: x[1] = ov_val; break;
-                case 2: x[2] = ov_val; break;
-                case 3: x[3] = ov_val; break;
-                case 4: x[4] = ov_val; break;
-                case 5: x[5] = ov_val; break;
-                case 6: x[6] = ov_val; break;
-                default: x[7] = ov_val; break;
+            if constexpr (F64) {
+                switch (ov_j) {
+                    case 0: x[0] = ov_val; break;
+                    case 1: x[1] = ov_val; break;
+                    case 2: x[2] = ov_val; break;
+                    case 3: x[3] = ov_val; break;
+                    case 4: x[4] = ov_val; break;
+                    case 5: x[5] = ov_val; break;
+                    case 6: x[6] = ov_val; break;
+                    default: x[7] = ov_val; break;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) mov_if_eq_w(x[q], (R)ov_val, ov_j, q);
             }
             if (left == 1) ov_stride = 0;
             ovp += ov_stride;
@@ -294,19 +366,19 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
                 const int64_t n = a.n_steps - left;
                 if (cell0 <= 0 && cell0 + CPT > 0 && a.lbc != FBR_BC_NONE) {
 #pragma unroll
-                    for (int q = 0; q < CPT; ++q) mov_if_eq_w(x[q], 0.0, (int)(-cell0), q);
+                    for (int q = 0; q < CPT; ++q) mov_if_eq_w(x[q], (R)0, (int)(-cell0), q);
                 }
                 const int64_t jl = nx - 1 - cell0;
                 if (jl >= 0 && jl < CPT && a.rbc != FBR_BC_NONE) {
 #pragma unroll
-                    for (int q = 0; q < CPT; ++q) mov_if_eq_w(x[q], 0.0, (int)jl, q);
+                    for (int q = 0; q < CPT; ++q) mov_if_eq_w(x[q], (R)0, (int)jl, q);
                 }
 #pragma unroll 1
                 for (int q = 0; q < a.n_src; ++q) {
                     const int64_t s = a.src_idx[q];
                     const int64_t jj = s - cell0;
                     if (jj >= 0 && jj < CPT && s >= 0 && s < nx) {
-                        const double v = __ldg(a.src_table + n * a.n_src + q);
+                        const R v = (R)__ldg(a.src_table + n * a.n_src + q);
 #pragma unroll
                         for (int u = 0; u < CPT; ++u) mov_if_eq_w(x[u], v, (int)jj, u);
                     }
@@ -315,48 +387,60 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         }
         // ---- forward sweep: y_i = b_i - l_i y_{i-1}, then t_i = r_i y_i ----
         {
-            double ya;
-            double y = chunk_end_fwd(x, l, hf.b, ya);
+            [[maybe_unused]] double ya;
+            R y;
+            if constexpr (F64) y = chunk_end_fwd(x, l, hf.b, ya);
+            else y = chunk_end_fwd_plain<R, CPT>(x, l);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) y = fma(Pf[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
-            const double carry = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
-            sts_f64(st_f, y);
+            for (int s = 0; s < NS; ++s) y = fma_any<R>(Pf[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+            const R carry = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
+            sts_any(st_f, y);
             __syncthreads();
-            double c;
+            R c;
             if (NEAR) {
-                c = lds_f64(ld_f);
+                c = lds_any(ld_f, R());
             } else {
-                c = 0.0;
-                for (int v = vf0; v < warp; ++v) c = fma(s_K[0][warp][v], s_Ef[v + 1], c);
+                c = (R)0;
+                for (int v = vf0; v < warp; ++v) c = fma_any<R>(s_K[0][warp][v], s_Ef[v + 1], c);
             }
-            chunk_apply_fwd(x, l, r, hf.a, ya, fma(sm.ex_f, c, carry));
+            if constexpr (F64) chunk_apply_fwd(x, l, r, hf.a, ya, fma(ex_f, c, carry));
+            else chunk_apply_fwd_plain<R, CPT>(x, l, r, fma_any<R>(ex_f, c, carry));
         }
         // ---- backward sweep: x_i = t_i - g_i x_{i+1} ----
         {
-            double za;
-            double z = chunk_end_bwd(x, g, hb.b, za);
+            [[maybe_unused]] double za;
+            R z;
+            if constexpr (F64) z = chunk_end_bwd(x, g, hb.b, za);
+            else z = chunk_end_bwd_plain<R, CPT>(x, g);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) z = fma(Pb[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
-            const double carry = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
-            sts_f64(st_b, z);
+            for (int s = 0; s < NS; ++s) z = fma_any<R>(Pb[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+            const R carry = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+            sts_any(st_b, z);
             __syncthreads();
-            double c;
+            R c;
             if (NEAR) {
-                c = lds_f64(ld_b);
+                c = lds_any(ld_b, R());
             } else {
-                c = 0.0;
-                for (int v = vb1; v > warp; --v) c = fma(s_K[1][warp][v], s_Eb[v], c);
+                c = (R)0;
+                for (int v = vb1; v > warp; --v) c = fma_any<R>(s_K[1][warp][v], s_Eb[v], c);
             }
-            chunk_apply_bwd(x, g, hb.a, za, fma(sm.ex_b, c, carry));
+            if constexpr (F64) chunk_apply_bwd(x, g, hb.a, za, fma(ex_b, c, carry));
+            else chunk_apply_bwd_plain<R, CPT>(x, g, fma_any<R>(ex_b, c, carry));
         }
     }
 
     // ---------------- write back the owned cells ----------------
-    double *dst = a.p_out + cell0;
+    R *dst = a.p_out + cell0;
     if (cell0 >= own0 && cell0 + CPT <= own1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        double2 *q = reinterpret_cast<double2 *>(dst);
+        if constexpr (F64) {
+            double2 *q = reinterpret_cast<double2 *>(dst);
 #pragma unroll
-        for (int j = 0; j < CPT / 2; ++j) q[j] = make_double2(x[2 * j], x[2 * j + 1]);
+            for (int j = 0; j < CPT / 2; ++j) q[j] = make_double2(x[2 * j], x[2 * j + 1]);
+        } else {
+            float4 *q = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+            for (int j = 0; j < CPT / 4; ++j) q[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
@@ -475,7 +559,7 @@ static inline int64_t round_up8(int64_t v) { return (v + 7) / 8 * 8; }
 // Pick (W, s): a block of s steps costs  waves * (t_fixed + s * t_step) + t_launch  with
 // waves = windows / resident CTAs; minimise the cost per step.  max_s caps the block length
 // (snapshot interval).  Constants are measured orders of magnitude on a B200, not tuned per run.
-static bool plan_window(int64_t nx, int64_t Hf, int64_t Hb, int64_t max_s, int sm_count, WinPlan *best) {
+static bool plan_window(int64_t nx, int64_t Hf, int64_t Hb, int64_t max_s, int sm_count, WinPlan *best, int cpt = kWinCPT) {
     const int64_t hf = round_up8(Hf > 0 ? Hf : 1), hb = round_up8(Hb > 0 ? Hb : 1);
     int force_w = 0;
     int64_t force_s = 0;
@@ -485,7 +569,7 @@ static bool plan_window(int64_t nx, int64_t Hf, int64_t Hb, int64_t max_s, int s
     bool found = false;
     for (int W : {8, 16}) {
         if (force_w && W != force_w) continue;
-        const int64_t wc = 32 * (int64_t)W * kWinCPT;
+        const int64_t wc = 32 * (int64_t)W * cpt;
         const int resident = (W >= 16 ? 1 : 2) * sm_count;
         // us per window: fixed (load / setup / store) + per time step; measured on B200 (C2 / C5 sweeps,
         // profiles/r01_k3w_sweep.txt).  Dependent launches hide the launch gap.
@@ -540,14 +624,46 @@ extern "C" int fbr_run_window_plan(int64_t nx, int64_t horizon_fwd, int64_t hori
     return FBR_OK;
 }
 
-extern "C" int64_t fbr_run_window_work_bytes(int64_t nx) { return 2 * nx * (int64_t)sizeof(double); }
+extern "C" int fbr_run_window_plan_f32(int64_t nx, int64_t horizon_fwd, int64_t horizon_bwd, int64_t snapshot_every,
+                                       int64_t *plan4) {
+    FBR_REQUIRE(nx >= 1 && horizon_fwd >= 0 && horizon_bwd >= 0 && plan4, "bad window-plan arguments");
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    WinPlan pl;
+    const int64_t max_s = snapshot_every >= 1 ? (snapshot_every < 4096 ? snapshot_every : 4096) : 4096;
+    if (!plan_window(nx, horizon_fwd, horizon_bwd, max_s, f.sm_count, &pl, 16))
+        return fail(FBR_ERR_UNSUPPORTED, "decay horizon (%lld, %lld) is too long for the windowed path",
+                    (long long)horizon_fwd, (long long)horizon_bwd);
+    plan4[0] = pl.W; plan4[1] = pl.s; plan4[2] = pl.own; plan4[3] = pl.n_win;
+    return FBR_OK;
+}
 
-extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
+extern "C" int64_t fbr_run_window_work_bytes(int64_t nx) { return 2 * nx * (int64_t)sizeof(double); }
+// fp32 mode: the three factors and the initial state narrowed once + two state buffers, each padded to 16 bytes
+static inline int64_t pitch_f32(int64_t nx) { return (nx + 3) / 4 * 4; }
+extern "C" int64_t fbr_run_window_f32_work_bytes(int64_t nx) { return 6 * pitch_f32(nx) * (int64_t)sizeof(float); }
+
+namespace fbr {
+__global__ void narrow4_kernel(const double *__restrict__ a, const double *__restrict__ b, const double *__restrict__ c,
+                               const double *__restrict__ d, float *__restrict__ out, int64_t nx, int64_t pitch) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (int64_t)gridDim.x * blockDim.x) {
+        out[i] = (float)__ldg(a + i);
+        out[pitch + i] = (float)__ldg(b + i);
+        out[2 * pitch + i] = (float)__ldg(c + i);
+        out[3 * pitch + i] = (float)__ldg(d + i);
+    }
+}
+}  // namespace fbr
+
+// fl, fr, fg, p0, the two state buffers: arrays of R (fp32 mode: narrowed by the caller below)
+template <typename R>
+static int run_window_impl(const R *fl, const R *fr, const R *fg, const R *p0, int64_t nx,
                                   int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
-                                  const double *src_table, int64_t snapshot_every, int64_t snap_row_stride, double *snap,
-                                  double *p_final, int64_t horizon_fwd, int64_t horizon_bwd, double *work, void *stream) {
+                                  const double *src_table, int64_t snapshot_every, int64_t snap_row_stride, R *snap,
+                                  R *p_final, int64_t horizon_fwd, int64_t horizon_bwd, R *buf0, R *buf1, void *stream) {
+    constexpr int kCPT = 64 / (int)sizeof(R);
     FBR_REQUIRE(nx >= 1 && n_steps >= 0, "bad nx / n_steps");
-    FBR_REQUIRE(fl && fr && fg && p0 && work, "NULL factor / initial-state / work pointer");
+    FBR_REQUIRE(fl && fr && fg && p0 && buf0 && buf1, "NULL factor / initial-state / work pointer");
     FBR_REQUIRE(lbc >= 0 && lbc <= 2 && rbc >= 0 && rbc <= 2, "bad boundary code");
     FBR_REQUIRE(n_src >= 0 && (n_src == 0 || (src_idx && src_table)), "sources given without src_idx / src_table");
     FBR_REQUIRE(snapshot_every >= 0 && (!snap || (snapshot_every >= 1 && snap_row_stride >= nx)), "bad snapshot layout");
@@ -560,7 +676,7 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
     // rows out itself, one call per interval, then gets the same window geometry — the same bits — as
     // the single-call path); 0 = no cap
     const int64_t max_s = snapshot_every >= 1 ? (snapshot_every < 4096 ? snapshot_every : 4096) : 4096;
-    if (!plan_window(nx, horizon_fwd, horizon_bwd, max_s, f.sm_count, &pl))
+    if (!plan_window(nx, horizon_fwd, horizon_bwd, max_s, f.sm_count, &pl, kCPT))
         return fail(FBR_ERR_UNSUPPORTED, "decay horizon (%lld, %lld) is too long for the windowed path",
                     (long long)horizon_fwd, (long long)horizon_bwd);
     // equalise the blocks inside one snapshot interval
@@ -569,28 +685,29 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
         const int64_t nblk = (snapshot_every + s_blk - 1) / s_blk;
         s_blk = (snapshot_every + nblk - 1) / nblk;
     }
-    const int64_t warp_span = 32 * kWinCPT;
-    WinArgs a;
+    const int64_t warp_span = 32 * kCPT;
+    WinArgsT<R> a;
     a.fl = fl; a.fr = fr; a.fg = fg; a.nx = nx; a.own = pl.own; a.lead = pl.lead; a.lbc = lbc; a.rbc = rbc;
     a.src_idx = src_idx; a.n_src = n_src;
     a.nbf = (int)((horizon_fwd + warp_span - 1) / warp_span); if (a.nbf < 1) a.nbf = 1;
     a.nbb = (int)((horizon_bwd + warp_span - 1) / warp_span); if (a.nbb < 1) a.nbb = 1;
     const bool no_pdl = getenv("FBR_WIN_NO_PDL") != nullptr;  // tuning aid
     a.n_win = pl.n_win;
-    const size_t smem = 4 * (size_t)(32 * pl.W * kWinCPT) * sizeof(double);  // staging: l, r, g, p of one window
+    const size_t smem = 4 * (size_t)(32 * pl.W) * 64;  // staging: l, r, g, p of one window, 64 bytes per thread each
     // kernel variant: how many scan stages the horizon needs, and whether carries stop at the neighbouring warp
     const int64_t hmax = horizon_fwd > horizon_bwd ? horizon_fwd : horizon_bwd;
     const bool near = a.nbf == 1 && a.nbb == 1 && !getenv("FBR_WIN_GENERAL");
-    const int ns = !near ? 5 : hmax <= 64 ? 3 : hmax <= 128 ? 4 : 5;
-    void (*kern)(const WinArgs) = nullptr;
-    if (pl.W >= 16) kern = !near ? run_window_kernel<16, 5, false> : ns == 3 ? run_window_kernel<16, 3, true>
-                           : ns == 4 ? run_window_kernel<16, 4, true> : run_window_kernel<16, 5, true>;
-    else kern = !near ? run_window_kernel<8, 5, false> : ns == 3 ? run_window_kernel<8, 3, true>
-                : ns == 4 ? run_window_kernel<8, 4, true> : run_window_kernel<8, 5, true>;
+    // (2^ns lanes of kCPT cells each must span the horizon: 64 / 128 cells in fp64, 128 / 256 in the fp32 mode)
+    const int ns = !near ? 5 : hmax <= 8 * kCPT ? 3 : hmax <= 16 * kCPT ? 4 : 5;
+    void (*kern)(const WinArgsT<R>) = nullptr;
+    if (pl.W >= 16) kern = !near ? run_window_kernel<R, 16, 5, false> : ns == 3 ? run_window_kernel<R, 16, 3, true>
+                           : ns == 4 ? run_window_kernel<R, 16, 4, true> : run_window_kernel<R, 16, 5, true>;
+    else kern = !near ? run_window_kernel<R, 8, 5, false> : ns == 3 ? run_window_kernel<R, 8, 3, true>
+                : ns == 4 ? run_window_kernel<R, 8, 4, true> : run_window_kernel<R, 8, 5, true>;
     FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t resident = (int64_t)(pl.W >= 16 ? 1 : 2) * f.sm_count;  // persistent CTAs, one wave
-    double *buf[2] = {work, work + nx};
-    const double *cur = p0;
+    R *buf[2] = {buf0, buf1};
+    const R *cur = p0;
     int64_t n = 0, snap_row = 0;
     int which = 0;
     while (n < n_steps) {
@@ -602,7 +719,7 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
         if (len > n_steps - n) len = n_steps - n;
         const bool at_snap = snap && (n + len) % snapshot_every == 0;
         const bool at_end = n + len == n_steps;
-        double *out;
+        R *out;
         if (at_snap) out = snap + snap_row * snap_row_stride;
         else if (at_end && p_final) out = p_final;
         else { out = buf[which]; which ^= 1; }
@@ -627,10 +744,37 @@ extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const doub
         if (int rc = check_launch("fbr_run_window_f64")) return rc;
         if (at_snap) ++snap_row;
         if (at_end && at_snap && p_final)
-            FBR_CUDA(cudaMemcpyAsync(p_final, out, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            FBR_CUDA(cudaMemcpyAsync(p_final, out, nx * sizeof(R), cudaMemcpyDeviceToDevice, st));
         cur = out;
         n += len;
     }
-    if (n_steps == 0 && p_final) FBR_CUDA(cudaMemcpyAsync(p_final, p0, nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (n_steps == 0 && p_final) FBR_CUDA(cudaMemcpyAsync(p_final, p0, nx * sizeof(R), cudaMemcpyDeviceToDevice, st));
     return FBR_OK;
+}
+
+extern "C" int fbr_run_window_f64(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
+                                  int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                                  const double *src_table, int64_t snapshot_every, int64_t snap_row_stride, double *snap,
+                                  double *p_final, int64_t horizon_fwd, int64_t horizon_bwd, double *work, void *stream) {
+    FBR_REQUIRE(nx >= 1 && work, "bad nx / NULL work pointer");
+    return run_window_impl<double>(fl, fr, fg, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every,
+                                   snap_row_stride, snap, p_final, horizon_fwd, horizon_bwd, work, work + nx, stream);
+}
+
+extern "C" int fbr_run_window_f32(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
+                                  int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                                  const double *src_table, int64_t snapshot_every, int64_t snap_row_stride, float *snap,
+                                  float *p_final, int64_t horizon_fwd, int64_t horizon_bwd, void *work, void *stream) {
+    FBR_REQUIRE(nx >= 1 && fl && fr && fg && p0 && work, "bad nx / NULL factor / initial-state / work pointer");
+    FBR_REQUIRE((reinterpret_cast<uintptr_t>(work) & 15) == 0, "work must be 16-byte aligned");
+    const int64_t pitch = pitch_f32(nx);
+    float *w = static_cast<float *>(work);
+    DeviceFacts f;
+    if (int rc = device_facts(&f)) return rc;
+    const int64_t want = (nx + 255) / 256, cap = (int64_t)f.sm_count * 16;
+    narrow4_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(fl, fr, fg, p0, w, nx, pitch);
+    if (int rc = check_launch("fbr_run_window_f32 (narrow)")) return rc;
+    return run_window_impl<float>(w, w + pitch, w + 2 * pitch, w + 3 * pitch, nx, n_steps, lbc, rbc, src_idx, n_src, src_table,
+                                  snapshot_every, snap_row_stride, snap, p_final, horizon_fwd, horizon_bwd, w + 4 * pitch,
+                                  w + 5 * pitch, stream);
 }

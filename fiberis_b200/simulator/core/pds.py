@@ -379,11 +379,13 @@ class PDS1D_SingleSource:
                 if cell_major and snap_d is not None:  # (1, nx, rows + 1): the kernel wrote Data2D's layout
                     snap_d = _CellMajor(snap_d[0])
             else:
-                if dtype != "float64":
-                    raise NotImplementedError("the long-mesh kernels are fp64 only")
-                if cell_major:  # keep the rows on the device: they are transposed there, then copied home once
+                if cell_major or dtype == "float32":  # keep the rows on the device: they are transposed there, then copied home once
                     kwargs = dict(kwargs, stream_rows=False)
                 snap_d = self._run_long_mesh(factors, p0_d, nx, n_steps, sidx_d, n_src, table_d, every, kwargs)
+                if dtype == "float32" and snap_d is not None and snap_d.dtype.itemsize == 8:
+                    # stiff long meshes in the fp32 mode: the exact kernels integrate in fp64, the stored rows are rounded
+                    self.long_mesh_path["arithmetic"] = "fp64, rows rounded to fp32"
+                    snap_d = snap_d.float()
             if cell_major and snap_d is not None and not isinstance(snap_d, _CellMajor):
                 snap_d = _CellMajor(_engine.transpose(_engine.as_f64(snap_d[0])))  # (rows + 1, nx) -> (nx, rows + 1) on the device
             if snap_d is None:  # snapshot_every > n_steps: only the initial state is kept
@@ -414,14 +416,16 @@ class PDS1D_SingleSource:
         time-tiled window kernel K3W when the measured decay horizon of the factors makes it pay,
         else the exact kernels; 'windowed' insists on K3W (NotImplementedError when the horizon is too
         long); 'exact' uses only the exact kernels — K3L (cooperative, register-resident) up to its
-        capacity, K3S (streaming) beyond."""
+        capacity, K3P (one pass over HBM per step) beyond.  ``dtype='float32'``: K3W's fp32 instantiation
+        (16 cells per thread); the exact kernels stay fp64 and their rows are rounded."""
         which = kwargs.get("long_mesh", "auto")
         if which not in ("auto", "windowed", "exact"):
             raise ValueError("long_mesh must be 'auto', 'windowed' or 'exact'.")
         self.long_mesh_path = None
         if which != "exact":
             horizon = _engine.decay_horizon(factors, log2_eps=float(kwargs.get("window_log2_eps", -80.0)))
-            plan = _engine.window_plan(nx, horizon, every)
+            f32 = kwargs.get("dtype", "float64") == "float32"
+            plan = _engine.window_plan(nx, horizon, every, dtype="float32" if f32 else "float64")
             if plan is None and which == "windowed":
                 raise NotImplementedError(f"decay horizon {horizon} is too long for the windowed path")
             if plan is not None:
@@ -435,7 +439,7 @@ class PDS1D_SingleSource:
                     return _engine.run_window_to_host(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
                                                       table_d, horizon, snapshot_every=every)
                 snap_d, _ = _engine.run_window(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src,
-                                               table_d, horizon, snapshot_every=every)
+                                               table_d, horizon, snapshot_every=every, dtype="float32" if f32 else "float64")
                 return snap_d
         if nx <= min(_engine.run_long_max_nx(), int(kwargs.get("_stream_above", 1 << 62))):
             self.long_mesh_path = dict(kernel="K3L")  # tiled over one cooperative grid

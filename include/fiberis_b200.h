@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FBR_VERSION 200 /* 0.2.0: fbr_run_opts */
+#define FBR_VERSION 201 /* 0.2.1: the fp32 windowed kernel; 0.2.0: the options struct of the run entries */
 
 typedef enum {
     FBR_OK = 0,
@@ -322,6 +322,19 @@ int fbr_run_window_f64(const double *fl, const double *fr, const double *fg, con
                        int n_src, const double *src_table, int64_t snapshot_every,
                        int64_t snap_row_stride, double *snap, double *p_final,
                        int64_t horizon_fwd, int64_t horizon_bwd, double *work, void *stream);
+/* fp32 mode of K3W (the reference has no single-precision path: this is the `dtype='float32'` option of this
+ * package's solve(), to 1e-5 of the fp64 result).  Same arguments; factors and initial state are the fp64 arrays
+ * of fbr_factorize_f64 and are narrowed once into `work`, 16-byte aligned,
+ * fbr_run_window_f32_work_bytes(nx) bytes; snapshots and the final state are float.  A thread holds 16 cells, so
+ * a window is 4096 / 8192 cells with the same halos: fbr_run_window_plan_f32 reports the geometry. */
+int fbr_run_window_plan_f32(int64_t nx, int64_t horizon_fwd, int64_t horizon_bwd,
+                            int64_t snapshot_every, int64_t *plan4);
+int64_t fbr_run_window_f32_work_bytes(int64_t nx);
+int fbr_run_window_f32(const double *fl, const double *fr, const double *fg, const double *p0,
+                       int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx,
+                       int n_src, const double *src_table, int64_t snapshot_every,
+                       int64_t snap_row_stride, float *snap, float *p_final,
+                       int64_t horizon_fwd, int64_t horizon_bwd, void *work, void *stream);
 
 /* Running count of kernels this thread has launched through the library (bench.py's
  * gpu_launches is a difference of two readings). */

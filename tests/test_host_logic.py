@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_cabi.SIGNATURES), "ctypes signatures out of sync with the header"
-    assert lib.fbr_version() == 200 and lib.fbr_run_max_nx() >= 4096
+    assert lib.fbr_version() == 201 and lib.fbr_run_max_nx() >= 4096
 
 
 def test_no_cpu_fallback():
