@@ -97,6 +97,7 @@ SIGNATURES = {
     "fbr_solve_tridiag_work_bytes": (_i64, [_i64, _i64, _i32]),
     "fbr_solve_tridiag_f64": (_i32, [_p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p]),
     "fbr_solve_dense_f64": (_i32, [_p, _i64, _p, _p, _p]),
+    "fbr_jacobi_dense_f64": (_i32, [_p, _p, _p, _i64, _f64, _i32, _p, _p, _p]),
     "fbr_step_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p, _i32, _p, _p, _p]),
     "fbr_misfit_f64": (_i32, [_p, _i64, _i64, _i64, _i64, _i64, _p, _i32, _p, _p, _i64, _p, _p]),
     "fbr_workspace_bytes": (_i64, [_i32, _i64, _i64]),

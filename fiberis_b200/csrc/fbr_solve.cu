@@ -361,6 +361,56 @@ extern "C" int fbr_solve_dense_f64(double *Ab, int64_t n, double *x, int32_t *si
     return check_launch("fbr_solve_dense_f64");
 }
 
+// Jacobi iteration on a general dense system (API completeness of solver_explicit, PDESolver_EXP.py:5-39: x starts at 0,
+// x_new = (b - R x) / diag(A), stop when max |x_new - x| < tol).  ONE CTA of 32 warps: a warp per row (coalesced reads of
+// the row, the diagonal term left out of the sum as the reference's R = A - diag(A) does), iterates ping-pong between x
+// and work; iters = iterations used, or -max_iter when the tolerance was not met.
+__global__ void __launch_bounds__(1024) jacobi_dense_kernel(const double *__restrict__ A, const double *__restrict__ b, double *x,
+                                                            double *work, int n, double tol, int max_iter, int *iters) {
+    __shared__ double s_max[32];
+    __shared__ int s_done;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, warps = blockDim.x >> 5;
+    double *cur = x, *nxt = work;
+    for (int i = tid; i < n; i += blockDim.x) cur[i] = 0.0;
+    __syncthreads();
+    int used = -max_iter;
+    for (int it = 0; it < max_iter; ++it) {
+        double worst = 0.0;
+        for (int i = warp; i < n; i += warps) {
+            const double *row = A + (int64_t)i * n;
+            double sum = 0.0;
+            for (int j = lane; j < n; j += 32)
+                if (j != i) sum = fma(row[j], cur[j], sum);
+            for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+            const double v = (b[i] - sum) / row[i];
+            if (lane == 0) nxt[i] = v;
+            const double diff = fabs(v - cur[i]);
+            if (!(diff <= worst)) worst = diff;  // NaN propagates: never "converged"
+        }
+        if (lane == 0) s_max[warp] = worst;
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            for (int w = 0; w < warps; ++w)
+                if (!(s_max[w] <= m)) m = s_max[w];
+            s_done = m < tol;
+        }
+        __syncthreads();
+        double *t = cur; cur = nxt; nxt = t;
+        if (s_done) { used = it + 1; break; }
+    }
+    if (cur != x)
+        for (int i = tid; i < n; i += blockDim.x) x[i] = cur[i];
+    if (tid == 0 && iters) *iters = used;
+}
+
+extern "C" int fbr_jacobi_dense_f64(const double *A, const double *b, double *x, int64_t n, double tol, int max_iter,
+                                    int32_t *iters, double *work, void *stream) {
+    FBR_REQUIRE(A && b && x && work && n >= 1 && n <= 16384 && max_iter >= 0, "bad argument (1 <= n <= 16384)");
+    jacobi_dense_kernel<<<1, 1024, 0, as_stream(stream)>>>(A, b, x, work, (int)n, tol, max_iter, iters);
+    return check_launch("fbr_jacobi_dense_f64");
+}
+
 extern "C" int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, const double *b,
                                      double *x, int64_t M, int64_t nx, int variant, double *work,
                                      int32_t *singular, void *stream) {

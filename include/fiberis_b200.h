@@ -359,6 +359,12 @@ int fbr_solve_tridiag_f64(const double *dl, const double *d, const double *du, c
  * Ab: device working copy of the augmented matrix [A | b], row-major n x (n + 1), destroyed; x: (n);
  * singular: NULL or one int32 that receives 1 + the column of an exactly zero pivot column (0: regular). */
 int fbr_solve_dense_f64(double *Ab, int64_t n, double *x, int32_t *singular, void *stream);
+/* Jacobi iteration on a general dense system (API completeness of solver_explicit,
+ * src/fiberis/simulator/solver/PDESolver_EXP.py:5-39: x starts at 0, x_new = (b - R x) / diag(A) with
+ * R = A - diag(A), stop when max|x_new - x| < tol).  A: row-major n x n; work: n doubles;
+ * iters: iterations used, or -max_iter when the tolerance was not met (x = the last iterate). */
+int fbr_jacobi_dense_f64(const double *A, const double *b, double *x, int64_t n, double tol, int max_iter,
+                         int32_t *iters, double *work, void *stream);
 
 /* One implicit step, batched (SURVEY 8(b) "fbr_step_*"): p_next = A^-1 rhs(p) with the diagonals of
  * A(dt) from fbr_assemble_*; rhs = p with the boundary / source overrides of
