@@ -349,6 +349,7 @@ class PDS1D_SingleSource:
                 self.snapshot = _engine.to_host(snap_d[0])
             kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
             self.taxis = np.array(taxis)[kept] if every > 1 else np.array(taxis)
+            self._log_steps(taxis, table, kwargs)
             self.record_log(f"{n_steps} full steps solved on device (dt={dt}, mode={mode}, dtype={dtype}). "
                             f"taxis[-1]=", taxis[-1])
             if kwargs.get("print_progress"):
@@ -404,12 +405,25 @@ class PDS1D_SingleSource:
             self.snapshot = np.concatenate([initial[None, :], rows], axis=0)
         kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
         self.taxis = np.array(taxis)[kept] if every > 1 else np.array(taxis)
+        self._log_steps(taxis, table, kwargs)
         self.record_log(f"{n_steps} full steps solved on device (dt={dt}, mode={mode}, dtype={dtype}). "
                         f"taxis[-1]=", taxis[-1])
         if kwargs.get("print_progress"):
             for n in range(n_steps):
                 vals = table[n].tolist()
                 print("Time:", taxis[n + 1], "Source term:", vals if self._multi else vals[0])
+
+    def _log_steps(self, taxis, table, kwargs):
+        """``log_steps=True`` (additive kwarg): the two ``history`` lines per time step the reference records inside its
+        loop (pds.py:290,310 / 556,575) — "Time: t Source term: v" and "Full step solution done. taxis[-1]= t'".  Off by
+        default: the device integrates all steps in one launch, and 2 x n_steps strings cost more host time than C1's
+        whole solve; one summary line is recorded instead."""
+        if not kwargs.get("log_steps"):
+            return
+        for n in range(len(taxis) - 1):
+            vals = table[n].tolist()
+            self.record_log("Time:", taxis[n], "Source term:", vals if self._multi else vals[0])
+            self.record_log("Full step solution done. taxis[-1]=", taxis[n + 1])
 
     def _run_long_mesh(self, factors, p0_d, nx, n_steps, sidx_d, n_src, table_d, every, kwargs):
         """Meshes that do not fit one CTA.  ``long_mesh`` (additive kwarg): 'auto' (default) takes the
