@@ -84,6 +84,7 @@ SIGNATURES = {
     "fbr_run_stream_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _p, _p]),
     "fbr_run_pass_work_bytes": (_i64, [_i64]),
     "fbr_run_pass_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _p, _p]),
+    "fbr_run_pass_tiled_f64": (_i32, [_p, _p, _p, _p, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _i64, _p, _p, _i32, _p, _p]),
     "fbr_decay_horizon_f64": (_i32, [_p, _p, _i64, _f64, _i32, _p, _p, _p]),
     "fbr_run_window_plan": (_i32, [_i64, _i64, _i64, _i64, C.POINTER(_i64)]),
     "fbr_run_window_work_bytes": (_i64, [_i64]),

@@ -373,15 +373,25 @@ def run_long(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, s
 
 
 def run_stream(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, want_final=False,
-               with_initial_row=True, kernel="pass"):
+               with_initial_row=True, kernel="pass", horizon=None, tile_warps=None):
     """Exact integration of one mesh of any length.  factors / p0: (1, nx).  Returns (snap (1, rows, nx) | None,
-    p_final | None).  ``kernel='pass'``: K3P, one pass over HBM per step (40 B per cell-update, fbr_run_pass_f64);
-    ``'levels'``: K3S, the level hierarchy of round 1 (88 B per cell-update, fbr_run_stream_f64)."""
+    p_final | None).  ``kernel='pass'``: K3P, one pass over HBM per step (40 B per cell-update, fbr_run_pass_tiled_f64);
+    ``'levels'``: K3S, the level hierarchy of round 1 (88 B per cell-update, fbr_run_stream_f64).
+    K3P's tile width follows the decay horizon of the factors (``horizon``: what decay_horizon returned, measured here
+    with a small cap when not given and the run is long enough to pay for the 16-byte read): narrow tiles when the
+    coupling ends at the neighbouring tile, wide ones on stiff meshes; ``tile_warps`` = 2 | 4 | 8 overrides."""
     torch = _torch()
     lib = _cabi.load()
-    work_fn, run_fn = ((lib.fbr_run_pass_work_bytes, lib.fbr_run_pass_f64) if kernel == "pass" else
-                       (lib.fbr_run_stream_work_bytes, lib.fbr_run_stream_f64))
     fl, fr, fg = factors
+    if kernel == "pass":
+        if tile_warps is None:
+            tile_warps = pass_tile_warps(factors, n_steps, horizon)
+        work_fn = lib.fbr_run_pass_work_bytes
+
+        def run_fn(*args):
+            return lib.fbr_run_pass_tiled_f64(*args[:-2], int(tile_warps), *args[-2:])
+    else:
+        work_fn, run_fn = lib.fbr_run_stream_work_bytes, lib.fbr_run_stream_f64
     dev = fl.device
     n_rows = n_steps // snapshot_every if snapshot_every else 0
     snap = snap_ptr = None
@@ -397,6 +407,15 @@ def run_stream(factors, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, sn
                                  ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), nx, snap_ptr,
                                  ptr(p_final), ptr(work), current_stream()))
     return snap, p_final
+
+
+def pass_tile_warps(factors, n_steps, horizon=None):
+    """Tile width (warps of 256 cells) K3P should use for this factorisation: 2 when the decay horizon (``horizon``, or
+    measured here — one 16-byte read, only for runs long enough to pay for it) is below ~100 cells, so that the coupling
+    between tiles ends at the neighbouring tile; 8 on stiff meshes, whose carries fold over tens of tiles."""
+    if horizon is None and n_steps >= 16:
+        horizon = decay_horizon(factors, cap=512)
+    return 2 if horizon is not None and max(horizon) <= 96 else 8
 
 
 def decay_horizon(factors, log2_eps=-80.0, cap=2048):

@@ -2,8 +2,8 @@
 // (three factors + p^n in, p^{n+1} out).  Replaces the level hierarchy of K3S (88 B per cell-update) as the
 // exact fallback behind the windowed kernel K3W — stiff long meshes, whose decay horizon is too long for windows.
 //
-// The mesh is cut into tiles of 2048 cells; a CTA of 8 warps solves a tile in registers with the sweeps of K3
-// (8 cells per thread, warp scans, exact carry table across the warps).  What couples the tiles is one number per
+// The mesh is cut into tiles of 256 W cells (W = 2, 4 or 8, see kPWMin); a CTA of W warps solves a tile in registers with
+// the sweeps of K3 (8 cells per thread, warp scans, exact carry table across the warps).  What couples the tiles is one number per
 // tile and sweep direction — the carry — and both carries are obtained without a second pass over the data:
 //   * forward carry: y at the last cell of the tile on the left.  It depends only on p^n, which the previous launch
 //     finished: every tile leaves, next to p^{n+1}, the zero-carry end value of ITS forward sweep for the NEXT step
@@ -16,7 +16,7 @@
 //     — always the same association, so the result does not depend on the schedule (value and epoch-tagged status in
 //     one 16-byte word, no reset between launches).
 // One launch per time step; snapshot rows are written in place and read back as the next step's input.
-// Latency is what this pipeline fights (a tile is ~2.5 us of dependent work, two CTAs per SM): the next tile's four rows
+// Latency is what this pipeline fights (a tile is ~2.5 us of dependent work, 16 warps per SM): the next tile's four rows
 // stream into shared memory while the current one is solved — four 16 KB BULK copies (cp.async.bulk, the 1-D TMA path,
 // completion on an mbarrier) issued by one thread: 16-byte cp.async by every thread (16 per thread and tile) topped out
 // at 4.0 TB/s in isolation against 6.9 TB/s for the bulk copies, conflicting shared-memory reads of the linear rows
@@ -28,8 +28,11 @@
 
 namespace fbr {
 
-constexpr int kPW = 8;              // warps per tile
-constexpr int kPTile = 256 * kPW;   // cells per tile
+// Warps per tile W (a tile = 256 W cells, 16 / W CTAs per SM): what couples the tiles costs per TILE, what a tile costs
+// grows with its width.  Ordinary meshes (the fold ends at the neighbouring tile): narrow tiles win — C5's mesh 89 / 92 /
+// 101 us per step for W = 2 / 4 / 8; stiff meshes (K3P's own domain: the fold spans tens of tiles) want few, wide tiles —
+// 4e6 cells at alpha ~ 3e4: 154 / 102 / 88 us.  The caller says which (fbr_run_pass_tiled_f64); default 8.
+constexpr int kPWMin = 2;  // narrowest tile: sizes the workspace
 
 struct PassArgs {
     const double *fl, *fr, *fg;
@@ -96,9 +99,9 @@ __device__ __forceinline__ void apply_overrides(double (&x)[8], int64_t cell0, i
 }
 
 // SETUP: only the tile products and the forward aggregates of step 0 are produced (p_out, look-back untouched).
-template <bool SETUP>
-__global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
-    constexpr int W = kPW;
+template <bool SETUP, int W>
+__global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) {
+    constexpr int kPTile = 256 * W;  // cells per tile
     __shared__ double s_E[2][W];        // zero-carry warp totals of the current sweep
     __shared__ double s_T[2][W];        // products of the multipliers over each warp
     __shared__ double s_carry[2];       // carries into the tile: forward (from the left), backward (from the right)
@@ -171,12 +174,26 @@ __global__ void __launch_bounds__(32 * kPW, 2) pass_kernel(const PassArgs a) {
         if (staged(tile)) {
             mbar_wait(bar, n_staged & 1u);
             ++n_staged;
-            auto take = [&](int q, double (&v)[8]) {  // my 64 bytes of row q (16-byte loads 64 bytes apart: 4-way conflicts, paid)
+            // my 64 bytes of row q.  The bulk copies leave the rows linear, so the same 16-byte piece of every thread would
+            // hit 2 of the 8 bank groups (4-way conflicts: 16 wavefronts per load — with 16 warps per SM a third of a tile's
+            // time on the shared-memory pipe, which the sweeps' shuffles share).  Thread t therefore starts with piece
+            // (t / 2) % 4 — every quarter warp then covers all 8 groups — and rotates the four pieces back into place with two
+            // select stages (128 selects per tile on idle ALUs): 113 -> 95 us per step on C5's mesh.
+            const int rot = (tid >> 1) & 3;
+            auto take = [&](int q, double (&v)[8]) {
+                double2 ld[4], mid[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double2 t = *reinterpret_cast<const double2 *>(s_stage + q * kPTile + tid * 8 + 2 * j);
-                    v[2 * j] = t.x;
-                    v[2 * j + 1] = t.y;
+                for (int j = 0; j < 4; ++j)
+                    ld[j] = *reinterpret_cast<const double2 *>(s_stage + q * kPTile + tid * 8 + 2 * ((j + rot) & 3));
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {  // ld[j] holds piece (j + rot) % 4
+                    mid[p].x = (rot & 1) ? ld[(p + 3) & 3].x : ld[p].x;
+                    mid[p].y = (rot & 1) ? ld[(p + 3) & 3].y : ld[p].y;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    v[2 * p] = (rot & 2) ? mid[(p + 2) & 3].x : mid[p].x;
+                    v[2 * p + 1] = (rot & 2) ? mid[(p + 2) & 3].y : mid[p].y;
                 }
             };
             take(0, l); take(1, r); take(2, g); take(3, x);
@@ -336,20 +353,16 @@ constexpr int64_t kPassTileWords = 8;  // Mf, Mb, Ef[2], two 16-byte status word
 using namespace fbr;
 
 extern "C" int64_t fbr_run_pass_work_bytes(int64_t nx) {
-    const int64_t tiles = (nx + kPTile - 1) / kPTile;
+    const int64_t tiles = (nx + 256 * kPWMin - 1) / (256 * kPWMin);
     return (2 * nx + kPassTileWords * tiles + 16) * (int64_t)sizeof(double);
 }
 
-extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
-                                int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
-                                const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
-                                double *snap, double *p_final, double *work, void *stream) {
-    FBR_REQUIRE(nx >= 1 && n_steps >= 0, "bad nx / n_steps");
-    FBR_REQUIRE(fl && fr && fg && p0 && work, "NULL factor / initial-state / work pointer");
-    FBR_REQUIRE(lbc >= 0 && lbc <= 2 && rbc >= 0 && rbc <= 2, "bad boundary code");
-    FBR_REQUIRE(n_src >= 0 && (n_src == 0 || (src_idx && src_table)), "sources given without src_idx / src_table");
-    FBR_REQUIRE(!snap || (snapshot_every >= 1 && snap_row_stride >= nx), "bad snapshot layout");
-    FBR_REQUIRE(n_steps < (1 << 29), "n_steps per call is limited to 2^29 - 1");
+template <int W>
+static int run_pass_impl(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
+                         int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                         const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
+                         double *snap, double *p_final, double *work, void *stream) {
+    constexpr int kPTile = 256 * W;
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
     cudaStream_t st = as_stream(stream);
@@ -368,10 +381,10 @@ extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double
     unsigned *ticket = reinterpret_cast<unsigned *>(w);
     FBR_CUDA(cudaMemsetAsync(Lw, 0, (size_t)tiles * 16 + 16, st));  // status words and the ticket counter
     const size_t smem = 4 * (size_t)kPTile * sizeof(double);  // staging of one tile's four rows
-    FBR_CUDA(cudaFuncSetAttribute(pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FBR_CUDA(cudaFuncSetAttribute(pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBR_CUDA(cudaFuncSetAttribute(pass_kernel<false, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FBR_CUDA(cudaFuncSetAttribute(pass_kernel<true, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel<false>, 32 * kPW, smem));
+    FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_kernel<false, W>, 32 * W, smem));
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "pass kernel does not fit on an SM");
     int64_t grid = (int64_t)occ * f.sm_count;
     if (const char *e = getenv("FBR_PASS_GRID")) {  // testing aid: other interleavings of the look-back (never more CTAs than fit)
@@ -387,7 +400,7 @@ extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double
     a.p_in = p0; a.p_out = nullptr; a.src_now = src_table; a.src_next = nullptr; a.Ef_now = nullptr; a.Ef_next = Ef[0]; a.epoch = 0;
     a.ticket_base = 0;
     if (n_steps > 0) {
-        pass_kernel<true><<<(unsigned)grid, 32 * kPW, smem, st>>>(a);
+        pass_kernel<true, W><<<(unsigned)grid, 32 * W, smem, st>>>(a);
         if (int rc = check_launch("fbr_run_pass (setup)")) return rc;
     }
     const double *cur = p0;
@@ -403,7 +416,7 @@ extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double
         a.Ef_now = Ef[n & 1]; a.Ef_next = Ef[(n & 1) ^ 1];
         a.epoch = (unsigned)(n + 1);
         a.ticket_base = (unsigned)((n + 1) * (tiles + grid));
-        pass_kernel<false><<<(unsigned)grid, 32 * kPW, smem, st>>>(a);
+        pass_kernel<false, W><<<(unsigned)grid, 32 * W, smem, st>>>(a);
         if (int rc = check_launch("fbr_run_pass")) return rc;
         if (row_due) ++snap_row;
         cur = out;
@@ -411,4 +424,37 @@ extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double
     if (p_final && cur != p_final)
         FBR_CUDA(cudaMemcpyAsync(p_final, cur, (size_t)nx * sizeof(double), cudaMemcpyDeviceToDevice, st));
     return FBR_OK;
+}
+
+extern "C" int fbr_run_pass_tiled_f64(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
+                                      int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                                      const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
+                                      double *snap, double *p_final, int tile_warps, double *work, void *stream) {
+    FBR_REQUIRE(nx >= 1 && n_steps >= 0, "bad nx / n_steps");
+    FBR_REQUIRE(fl && fr && fg && p0 && work, "NULL factor / initial-state / work pointer");
+    FBR_REQUIRE(lbc >= 0 && lbc <= 2 && rbc >= 0 && rbc <= 2, "bad boundary code");
+    FBR_REQUIRE(n_src >= 0 && (n_src == 0 || (src_idx && src_table)), "sources given without src_idx / src_table");
+    FBR_REQUIRE(!snap || (snapshot_every >= 1 && snap_row_stride >= nx), "bad snapshot layout");
+    FBR_REQUIRE(n_steps < (1 << 29), "n_steps per call is limited to 2^29 - 1");
+    FBR_REQUIRE(tile_warps == 0 || tile_warps == 2 || tile_warps == 4 || tile_warps == 8, "tile_warps must be 0 (default), 2, 4 or 8");
+    if (const char *e = getenv("FBR_PASS_WARPS")) {  // tuning aid
+        const int v = atoi(e);
+        if (v == 2 || v == 4 || v == 8) tile_warps = v;
+    }
+    switch (tile_warps) {
+        case 2: return run_pass_impl<2>(fl, fr, fg, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every,
+                                        snap_row_stride, snap, p_final, work, stream);
+        case 4: return run_pass_impl<4>(fl, fr, fg, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every,
+                                        snap_row_stride, snap, p_final, work, stream);
+        default: return run_pass_impl<8>(fl, fr, fg, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every,
+                                         snap_row_stride, snap, p_final, work, stream);
+    }
+}
+
+extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double *fg, const double *p0, int64_t nx,
+                                int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                                const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
+                                double *snap, double *p_final, double *work, void *stream) {
+    return fbr_run_pass_tiled_f64(fl, fr, fg, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every, snap_row_stride,
+                                  snap, p_final, 0, work, stream);
 }

@@ -462,8 +462,13 @@ class PDS1D_SingleSource:
         else:  # state and factors stream from HBM every step: one pass per step (K3P; 'levels' = K3S of round 1)
             which_exact = kwargs.get("_exact_kernel", "pass")
             self.long_mesh_path = dict(kernel="K3P" if which_exact == "pass" else "K3S")
+            tile_warps = None
+            if which_exact == "pass":  # narrow tiles on ordinary meshes, wide ones on stiff meshes (K3P's own domain)
+                tile_warps = kwargs.get("_tile_warps") or _engine.pass_tile_warps(factors, n_steps,
+                                                                                  horizon if which != "exact" else None)
+                self.long_mesh_path["tile_warps"] = tile_warps
             snap_d, _ = _engine.run_stream(factors, p0_d, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                           snapshot_every=every, kernel=which_exact)
+                                           snapshot_every=every, kernel=which_exact, tile_warps=tile_warps)
         return snap_d
 
     def _step_loop(self, dl, d, du, p_d, sidx_d, n_src, table_d, n_steps, every, variant=_cabi.SOLVER_AUTO):

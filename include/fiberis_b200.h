@@ -278,7 +278,7 @@ int fbr_run_stream_f64(const double *fl, const double *fr, const double *fg, con
 
 /* ------------------------------------------------------------------------------------------
  * K3P the exact long-mesh integration in ONE pass over HBM per step (40 B per cell-update: three factors and p^n
- * in, p^{n+1} out; csrc/fbr_run_pass.cu) — any nx.  Tiles of 2048 cells are solved in registers; the forward carry
+ * in, p^{n+1} out; csrc/fbr_run_pass.cu) — any nx.  Tiles of 512 .. 2048 cells are solved in registers; the forward carry
  * between tiles comes from aggregates the previous launch left behind, the backward carry from a decoupled look-back
  * inside the launch.  Same arguments as fbr_run_stream_f64; work: fbr_run_pass_work_bytes(nx) bytes; one launch per
  * time step plus one setup launch.  Takes the place of K3S behind PDS1D_*.solve for meshes whose decay horizon is too
@@ -289,6 +289,15 @@ int fbr_run_pass_f64(const double *fl, const double *fr, const double *fg, const
                      int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
                      const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
                      double *snap, double *p_final, double *work, void *stream);
+/* The same with the tile width chosen by the caller: tile_warps = 2, 4 or 8 warps of 256 cells (0 = 8, what
+ * fbr_run_pass_f64 uses).  What couples the tiles costs per tile, a tile's own latency grows with its width: narrow
+ * tiles (2) when the decay horizon of the factors (fbr_decay_horizon_f64) is below ~100 cells — the coupling then ends
+ * at the neighbouring tile: 1e7 cells in 89 us per step, 4.5 TB/s —, wide tiles (8) on stiff meshes, where the carries
+ * fold over tens of tiles.  Results do not depend on the width beyond rounding. */
+int fbr_run_pass_tiled_f64(const double *fl, const double *fr, const double *fg, const double *p0,
+                           int64_t nx, int64_t n_steps, int lbc, int rbc, const int64_t *src_idx, int n_src,
+                           const double *src_table, int64_t snapshot_every, int64_t snap_row_stride,
+                           double *snap, double *p_final, int tile_warps, double *work, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3W the same integration for ONE long mesh through overlapping on-chip WINDOWS with time blocking
