@@ -34,6 +34,13 @@ namespace fbr {
 // 4e6 cells at alpha ~ 3e4: 154 / 102 / 88 us.  The caller says which (fbr_run_pass_tiled_f64); default 8.
 constexpr int kPWMin = 2;  // narrowest tile: sizes the workspace
 
+#ifdef FBR_K3P_PROF  // debug build: clock64 stamps of a tile's phases for a few CTAs (scratch/k3p_prof.py reads them)
+__device__ long long g_k3p_prof[8 * 24 * 8];
+#define K3P_STAMP(k) do { if (tid == 0 && blockIdx.x % 37 == 0 && blockIdx.x / 37 < 8 && it < 24) g_k3p_prof[((blockIdx.x / 37) * 24 + it) * 8 + (k)] = clock64(); } while (0)
+#else
+#define K3P_STAMP(k) do { } while (0)
+#endif
+
 struct PassArgs {
     const double *fl, *fr, *fg;
     const double *p_in;
@@ -169,10 +176,15 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
         const int64_t tile = a.n_tiles - 1 - (int64_t)ticket;  // right to left
         const int64_t cell0 = tile * kPTile + (int64_t)tid * 8;
 
+        // (warp 0) products of the multipliers over each of the 32 tiles on my right: time-invariant, needed by the look-back
+        double pm_near = 0.0;
+        if (!SETUP && warp == 0 && tile + 1 + lane < a.n_tiles) pm_near = __ldg(a.Mb + tile + 1 + lane);
         // ---- my 8 cells: factors and state (identity rows behind the mesh) ----
         double l[8], r[8], g[8], x[8];
+        K3P_STAMP(0);
         if (staged(tile)) {
             mbar_wait(bar, n_staged & 1u);
+            K3P_STAMP(1);
             ++n_staged;
             // my 64 bytes of row q.  The bulk copies leave the rows linear, so the same 16-byte piece of every thread would
             // hit 2 of the 8 bank groups (4-way conflicts: 16 wavefronts per load — with 16 warps per SM a third of a tile's
@@ -217,6 +229,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
         const unsigned nt = s_ticket[(it & 1) ^ 1];
         const int64_t next_tile = nt < (unsigned)a.n_tiles ? a.n_tiles - 1 - (int64_t)nt : -1;
         if (tid == 0) stage_tile(next_tile);  // (everybody passed the barrier above: the buffer is free)
+        K3P_STAMP(2);
         const ScanMultipliers sm = scan_multipliers<double>(chunk_product<double, 8>(l), chunk_product<double, 8>(g), lane);
         if (lane == 31) s_T[0][warp] = sm.tot_f;
         if (lane == 0) s_T[1][warp] = sm.tot_b;
@@ -263,6 +276,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
             c = fma(sm.ex_f, cw, c);
             chunk_apply_fwd_plain<double, 8>(x, l, r, c);
         }
+        K3P_STAMP(3);
         // ---- backward sweep, zero carry from the right: publish the tile's aggregate, look back, apply ----
         {
             double z = chunk_end_bwd_plain<double, 8>(x, g);
@@ -277,23 +291,62 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
                     for (int w = W - 1; w >= 0; --w) loc = fma(s_T[1][w], loc, s_E[1][w]);
                     st_word(a.Lw + tile, loc, a.epoch * 4u + 1u);
                 }
+                K3P_STAMP(4);
                 // Carry from the right: fold the zero-carry aggregates of the tiles on the right, nearest first, 32 per
                 // iteration, until the running product of the tile multipliers is exactly 0 (one tile on ordinary meshes) or
                 // the mesh ends.  Always the same association — the result does not depend on which tiles happen to be done
                 // (an inclusive value picked up when available would make the last bits a matter of timing).  The tiles on
                 // the right hold earlier tickets: they are running or done, and publish before they wait for anybody.
                 double cb = 0.0, prod = 1.0;
-                if (tile + 1 < a.n_tiles) {  // the nearest tile by itself: on ordinary meshes its product already ends the fold
-                    double v = 0.0;
-                    if (lane == 0)
-                        while (ld_word(a.Lw + tile + 1, v) != a.epoch * 4u + 1u) { }
-                    cb = __shfl_sync(kAllLanes, v, 0);
-                    prod = __ldg(a.Mb + tile + 1);
+                if (tile + 1 < a.n_tiles) {
+                    const unsigned want = a.epoch * 4u + 1u;
+                    if (__shfl_sync(kAllLanes, pm_near, 0) == 0.0) {
+                        // ordinary mesh, wide tile: the product over the nearest tile is already 0 — its aggregate is the carry
+                        double v = 0.0;
+                        if (lane == 0)
+                            while (ld_word(a.Lw + tile + 1, v) != want) { }
+                        cb = __shfl_sync(kAllLanes, v, 0);
+                        prod = 0.0;
+                    } else {
+                        // the 32 nearest tiles at once: every lane polls its tile's word FIRST (one round trip for all of them),
+                        // the time-invariant products — loaded at the head of the tile — say meanwhile which lanes matter
+                        const int64_t j = tile + 1 + lane;  // lane 0 = nearest tile
+                        const bool in = j < a.n_tiles;
+                        double acc = 0.0, pm = pm_near;
+                        unsigned tag = in ? ld_word(a.Lw + j, acc) : want;
+                        double reach = pm;  // product of the multipliers of lanes 0 .. lane
+#pragma unroll
+                        for (int s = 1; s < 32; s <<= 1) {
+                            const double up = __shfl_up_sync(kAllLanes, reach, s);
+                            if (lane >= s) reach *= up;
+                        }
+                        double before = __shfl_up_sync(kAllLanes, reach, 1);
+                        if (lane == 0) before = 1.0;
+                        // something of a tile reaches me: wait for it.  ONE lane spins at a time (the nearest tile still
+                        // missing), the others look again when it has arrived: 32 lanes of every CTA hammering the words the
+                        // publishers are writing slowed everybody down on stiff meshes (4e6 cells, alpha ~ 3e4: 87 -> 110 us)
+                        const bool need = in && before != 0.0;
+                        unsigned waiting = __ballot_sync(kAllLanes, need && tag != want);
+                        while (waiting) {
+                            if (lane == __ffs(waiting) - 1)
+                                while (tag != want) tag = ld_word(a.Lw + j, acc);
+                            __syncwarp();
+                            if (need && tag != want) tag = ld_word(a.Lw + j, acc);
+                            waiting = __ballot_sync(kAllLanes, need && tag != want);
+                        }
+                        if (!need) acc = 0.0;
+#pragma unroll
+                        for (int s = 1; s < 32; s <<= 1) {  // affine maps composed nearest-first
+                            const double up_acc = __shfl_up_sync(kAllLanes, acc, s), up_pm = __shfl_up_sync(kAllLanes, pm, s);
+                            if (lane >= s) { acc = fma(up_pm, acc, up_acc); pm *= up_pm; }
+                        }
+                        cb = __shfl_sync(kAllLanes, acc, 31);
+                        prod = __shfl_sync(kAllLanes, pm, 31);
+                    }
                 }
-                for (int64_t j0 = tile + 2; j0 < a.n_tiles && prod != 0.0; j0 += 32) {
-                    const int64_t j = j0 + lane;  // lane 0 = nearest tile
-                    double pm = j < a.n_tiles ? __ldg(a.Mb + j) : 0.0;  // product of the multipliers of lanes 0 .. lane (after the scan)
-                    // does anything reach me?  (the exclusive product of the nearer tiles, known without waiting for anybody)
+                for (int64_t j0 = tile + 33; j0 < a.n_tiles && prod != 0.0; j0 += 32) {  // very stiff meshes: further blocks of 32
+                    const int64_t j = j0 + lane;
+                    double pm = j < a.n_tiles ? __ldg(a.Mb + j) : 0.0;
                     double reach = pm;
 #pragma unroll
                     for (int s = 1; s < 32; s <<= 1) {
@@ -302,11 +355,12 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
                     }
                     double before = __shfl_up_sync(kAllLanes, reach, 1);
                     if (lane == 0) before = 1.0;
-                    double acc = 0.0;
+                    double acc = 0.0;  // (these tiles published long ago: a plain spin per lane; restructuring this loop like the
+                    // block above made the whole kernel slower — 57 -> 82 us on a mesh that never enters it — and was dropped)
                     if (j < a.n_tiles && prod * before != 0.0)
                         while (ld_word(a.Lw + j, acc) != a.epoch * 4u + 1u) { }
 #pragma unroll
-                    for (int s = 1; s < 32; s <<= 1) {  // affine maps composed nearest-first
+                    for (int s = 1; s < 32; s <<= 1) {
                         const double up_acc = __shfl_up_sync(kAllLanes, acc, s), up_pm = __shfl_up_sync(kAllLanes, pm, s);
                         if (lane >= s) { acc = fma(up_pm, acc, up_acc); pm *= up_pm; }
                     }
@@ -314,6 +368,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
                     prod *= __shfl_sync(kAllLanes, pm, 31);
                 }
                 if (lane == 0) s_carry[1] = cb;
+                K3P_STAMP(5);
             } else if (warp == 1 && next_tile >= 0) {  // meanwhile: the NEXT tile's forward carry
                 const double c = forward_fold(next_tile);
                 if (lane == 0) s_cf[(it & 1) ^ 1] = c;
@@ -334,6 +389,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
             for (int j = 0; j < 8; ++j)
                 if (cell0 + j < nx) a.p_out[cell0 + j] = x[j];
         }
+        K3P_STAMP(6);
         // ---- the next step's forward aggregate of this tile (its right-hand side is p^{n+1} with that step's overrides) ----
         if (a.src_next || a.n_src == 0) {
             apply_overrides(x, cell0, nx, a.lbc, a.rbc, a.src_idx, a.n_src, a.src_next, tile_has_src);
@@ -343,6 +399,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
             if (tid == 0) a.Ef_next[tile] = tile_forward_end(0.0);
         }
         __syncthreads();  // the shared scratch is reused by the next tile
+        K3P_STAMP(7);
     }
 }
 
@@ -458,3 +515,9 @@ extern "C" int fbr_run_pass_f64(const double *fl, const double *fr, const double
     return fbr_run_pass_tiled_f64(fl, fr, fg, p0, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every, snap_row_stride,
                                   snap, p_final, 0, work, stream);
 }
+
+#ifdef FBR_K3P_PROF
+extern "C" int fbr_debug_pass_prof(long long *host) {
+    return (int)cudaMemcpyFromSymbol(host, fbr::g_k3p_prof, sizeof(fbr::g_k3p_prof));
+}
+#endif

@@ -20,7 +20,8 @@ for dx, label in ((0.03, "alpha ~ 5e2"), (0.004, "alpha ~ 3e4"), (0.0004, "alpha
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        out = E.run_stream(fac, p0, nx, n_steps, "Neumann", "Dirichlet", sidx, n_src, table, snapshot_every=n_steps)[0]
+        out = E.run_stream(fac, p0, nx, n_steps, "Neumann", "Dirichlet", sidx, n_src, table, snapshot_every=n_steps,
+                           tile_warps=int(os.environ.get("K3P_W", "8")))[0]
         b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3 / n_steps)
     print(f"{label}: {min(ts[1:]):.1f} us per step  ({nx * 40.0 / min(ts[1:]) / 1e6:.2f} TB/s at 40 B)  checksum {float(out.sum()):.6e}")
