@@ -35,8 +35,8 @@ namespace fbr {
 constexpr int kPWMin = 2;  // narrowest tile: sizes the workspace
 
 #ifdef FBR_K3P_PROF  // debug build: clock64 stamps of a tile's phases for a few CTAs (scratch/k3p_prof.py reads them)
-__device__ long long g_k3p_prof[8 * 24 * 8];
-#define K3P_STAMP(k) do { if (tid == 0 && blockIdx.x % 37 == 0 && blockIdx.x / 37 < 8 && it < 24) g_k3p_prof[((blockIdx.x / 37) * 24 + it) * 8 + (k)] = clock64(); } while (0)
+__device__ long long g_k3p_prof[8 * 24 * 12];
+#define K3P_STAMP(k) do { if (tid == 0 && blockIdx.x % 37 == 0 && blockIdx.x / 37 < 8 && it < 24) g_k3p_prof[((blockIdx.x / 37) * 24 + it) * 12 + (k)] = clock64(); } while (0)
 #else
 #define K3P_STAMP(k) do { } while (0)
 #endif
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
             load8(a.fg, 0.0, g, true);
             load8(a.p_in, 0.0, x, false);  // written by the previous launch: plain (coherent) loads
         }
+        K3P_STAMP(8);
         // the next ticket is visible; everybody has taken its rows out of the staging buffer; does a source lie in this tile?
         bool src_here = false;
         for (int k = tid; k < a.n_src; k += 32 * W) {
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
             src_here = src_here || (i >= tile * kPTile && i < (tile + 1) * kPTile);
         }
         const bool tile_has_src = __syncthreads_or(src_here);
+        K3P_STAMP(9);
         const unsigned nt = s_ticket[(it & 1) ^ 1];
         const int64_t next_tile = nt < (unsigned)a.n_tiles ? a.n_tiles - 1 - (int64_t)nt : -1;
         if (tid == 0) stage_tile(next_tile);  // (everybody passed the barrier above: the buffer is free)
