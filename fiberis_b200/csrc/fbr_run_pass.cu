@@ -68,18 +68,6 @@ __device__ __forceinline__ unsigned ld_word(const double2 *p, double &v) {
     asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v), "=d"(t) : "l"(p) : "memory");
     return (unsigned)__double2loint(t);
 }
-// bulk copy global -> shared (1-D TMA) whose bytes complete on an mbarrier
-__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned ok = 0;
-    while (!ok)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-}
-
 // b = p with this step's overrides on my 8 cells (matbuilder.py:45-76: boundary rows first, sources in list order).
 // tile_has_src: some source lies in this CTA's tile (almost never: the scan over the source list is skipped otherwise)
 __device__ __forceinline__ void apply_overrides(double (&x)[8], int64_t cell0, int64_t nx, int lbc, int rbc,

@@ -29,6 +29,13 @@ constexpr int kWinList = 64;  // sources per window kept in shared memory (more:
 
 // T = double (8 cells per thread) or float (the fp32 mode: 16 cells per thread, the same 64 bytes — a window holds
 // twice the cells, the halos stay the same number of cells, and the sweeps run on the fp32 pipe)
+#ifdef FBR_K3W_PROF  // debug build: clock64 stamps of a window's phases for a few CTAs (scratch/k3w_prof.py reads them)
+__device__ long long g_k3w_prof[8 * 8 * 8];
+#define K3W_STAMP(n) do { if (threadIdx.x == 0 && blockIdx.x % 17 == 0 && blockIdx.x / 17 < 8 && wi < 8) g_k3w_prof[((blockIdx.x / 17) * 8 + wi) * 8 + (n)] = clock64(); } while (0)
+#else
+#define K3W_STAMP(n) do { } while (0)
+#endif
+
 template <typename T>
 struct WinArgsT {
     const T *fl, *fr, *fg;  // (nx) factors
@@ -102,53 +109,43 @@ __device__ __forceinline__ float lds_any(unsigned addr, float) {
 }
 __device__ __forceinline__ double lds_any(unsigned addr, double) { return lds_f64(addr); }
 
-// 16-byte asynchronous copy global -> shared (no register staging; completion via cp.async groups)
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// Staging layout of one per-cell array of a window in shared memory: thread t's 8 cells are the
-// 64-byte row t; inside a row the four 16-byte pieces are XOR-swizzled with (t >> 1) & 3, so that a
-// quarter-warp reading "piece j" of its eight rows touches eight different 16-byte bank groups
-// (rows are 64 B apart: unswizzled, LDS.128 would be 4-way bank conflicted).
-__device__ __forceinline__ int swz_piece(int row, int piece) { return row * 4 + (piece ^ ((row >> 1) & 3)); }
-
-// issue the copies of one array of window [win0, win0 + T*8): piece p (16 B) is fetched by thread
-// p % T — fully coalesced 512-byte warp requests — and lands in its consumer's swizzled row
-template <int T, typename V>
-__device__ __forceinline__ void stage_array(V *sm, const V *__restrict__ base, int64_t win0, int tid) {
-    const double2 *src = reinterpret_cast<const double2 *>(base + win0);
-    double2 *dst = reinterpret_cast<double2 *>(sm);
+// Staging of a window's rows in shared memory: BULK copies (cp.async.bulk, the 1-D TMA path) issued by four threads, one per
+// array, completing on an mbarrier — round 1 had every thread issue sixteen 16-byte cp.async into XOR-swizzled rows, which
+// cost 1 300 cycles of issue per window (scratch/k3w_prof.py).  The rows land LINEAR: thread t's 64 bytes of an array sit
+// at byte 64 t, so the same 16-byte piece of every thread would hit 2 of the 8 bank groups.  Thread t therefore starts with
+// piece (t / 2) % 4 — a quarter warp then covers all 8 groups — and rotates the four pieces back with two select stages.
+template <typename R, int CPT>
+__device__ __forceinline__ void unstage_row(const R *row, int tid, R (&v)[CPT]) {
+    const int rot = (tid >> 1) & 3;
+    const char *base = reinterpret_cast<const char *>(row) + tid * 64;
+    int4 ld[4], mid[4], out[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int piece = i * T + tid;
-        cp_async16(dst + swz_piece(piece >> 2, piece & 3), src + piece);
+    for (int j = 0; j < 4; ++j) ld[j] = *reinterpret_cast<const int4 *>(base + 16 * ((j + rot) & 3));  // piece (j + rot) % 4
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int4 a = ld[(p + 3) & 3], b = ld[p];
+        mid[p] = (rot & 1) ? a : b;
     }
-}
-__device__ __forceinline__ void unstage8(const double *sm, int tid, double (&v)[kWinCPT]) {
-    const double2 *src = reinterpret_cast<const double2 *>(sm);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const double2 t = src[swz_piece(tid, j)];
-        v[2 * j] = t.x;
-        v[2 * j + 1] = t.y;
+    for (int p = 0; p < 4; ++p) {
+        const int4 a = mid[(p + 2) & 3], b = mid[p];
+        out[p] = (rot & 2) ? a : b;
     }
-}
-__device__ __forceinline__ void unstage8(const float *sm, int tid, float (&v)[16]) {
-    const float4 *src = reinterpret_cast<const float4 *>(sm);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float4 t = src[swz_piece(tid, j)];
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    for (int p = 0; p < 4; ++p) {
+        if constexpr (sizeof(R) == 8) {
+            v[2 * p] = __hiloint2double(out[p].y, out[p].x);
+            v[2 * p + 1] = __hiloint2double(out[p].w, out[p].z);
+        } else {
+            v[4 * p] = __int_as_float(out[p].x); v[4 * p + 1] = __int_as_float(out[p].y);
+            v[4 * p + 2] = __int_as_float(out[p].z); v[4 * p + 3] = __int_as_float(out[p].w);
+        }
     }
 }
 
 // Persistent CTAs: CTA b integrates windows b, b + gridDim.x, ...; while it advances one window
 // through the time block, the next window's pressure and factors stream into shared memory
-// (cp.async), so HBM latency is hidden behind the sweeps.
+// (bulk copies), so HBM latency is hidden behind the sweeps.
 // NS = scan stages (5: exact; 3 / 4 when the horizon is <= 64 / 128 cells); NEAR: the horizon fits
 // one warp (256 cells), so a warp's carry comes from its immediate neighbour only.
 template <typename R, int W, int NS, bool NEAR>
@@ -174,18 +171,38 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         const int64_t w0 = k * a.own - a.lead;
         return a.aligned && w0 >= 0 && w0 + WC <= nx;
     };
+    __shared__ __align__(8) unsigned long long s_bar;
+    const unsigned bar = smem_addr(&s_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr unsigned kRowBytes = (unsigned)(WC * sizeof(R));
+    // rows of window `kw` -> shared memory (factors, and the state when with_p): lane 0 of warps 0 .. 3 issues one copy each
+    // (callers: after a barrier behind the last read of the buffer)
+    auto stage_window = [&](int64_t kw, bool with_p) {
+        const int64_t w0 = kw * a.own - a.lead;
+        if (lane != 0 || warp >= (with_p ? 4 : 3)) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before async-proxy writes
+        if (warp == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((with_p ? 4u : 3u) * kRowBytes) : "memory");
+        const R *src = warp == 0 ? a.fl : warp == 1 ? a.fr : warp == 2 ? a.fg : a.p_in;
+        bulk_g2s(smem_addr(s_stage) + warp * kRowBytes, src + w0, kRowBytes, bar);
+    };
+    unsigned n_staged = 0;  // staged windows consumed so far: the mbarrier's phase
     int64_t k = blockIdx.x;
     bool staged = k < a.n_win && stageable(k);
     bool first = true;
-    if (staged) {  // time-invariant inputs of my first window: may run ahead of the previous time block
-        const int64_t w0 = k * a.own - a.lead;
-        stage_array<T>(s_stage, a.fl, w0, tid);
-        stage_array<T>(s_stage + WC, a.fr, w0, tid);
-        stage_array<T>(s_stage + 2 * WC, a.fg, w0, tid);
-        cp_async_commit();
-    }
+    if (staged) stage_window(k, false);  // time-invariant inputs of my first window: may run ahead of the previous time block
 
+    // my source row (window-independent: read once, off every window's path — it was an exposed L2 round trip per window)
+    const int64_t src_mine = tid < a.n_src ? __ldg(a.src_idx + tid) : -1;
+
+    [[maybe_unused]] int wi = -1;
     for (; k < a.n_win; k += gridDim.x) {
+    ++wi;
+    K3W_STAMP(0);
     const int64_t own0 = k * a.own;
     const int64_t own1 = own0 + a.own < nx ? own0 + a.own : nx;
     const int64_t win0 = own0 - a.lead;
@@ -197,20 +214,21 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     if (tid == 0) s_list_n = 0;
     R l[CPT], r[CPT], g[CPT], x[CPT];
     if (staged) {
-        cp_async_wait_all();
-        __syncthreads();
-        unstage8(s_stage, tid, l);
-        unstage8(s_stage + WC, tid, r);
-        unstage8(s_stage + 2 * WC, tid, g);
-        if (!first) unstage8(s_stage + 3 * WC, tid, x);
+        mbar_wait(bar, n_staged & 1u);
+        ++n_staged;
+        unstage_row<R, CPT>(s_stage, tid, l);
+        unstage_row<R, CPT>(s_stage + WC, tid, r);
+        unstage_row<R, CPT>(s_stage + 2 * WC, tid, g);
+        if (!first) unstage_row<R, CPT>(s_stage + 3 * WC, tid, x);
     } else {
         load8(a.fl, cell0, nx, (R)0, l);
         load8(a.fr, cell0, nx, (R)1, r);
         load8(a.fg, cell0, nx, (R)0, g);
     }
     __syncthreads();
+    K3W_STAMP(1);
     for (int q = tid; q < a.n_src; q += T) {  // one parallel pass over the source rows
-        const int64_t s = a.src_idx[q];
+        const int64_t s = q == tid ? src_mine : a.src_idx[q];
         if (s >= 0 && s < nx && s >= win0 && s < win0 + WC) {
             const int pos = atomicAdd(&s_list_n, 1);
             if (pos < kWinList) { s_list_k[pos] = q; s_list_off[pos] = (int)(s - win0); }
@@ -218,12 +236,14 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     }
     __syncthreads();
     const int list_n = s_list_n;
+    // most windows of a long mesh hold neither a source nor a boundary row: nothing to work out for them
+    const bool plain_window = list_n == 0 && !(win0 <= 0 && a.lbc != FBR_BC_NONE) && !(win0 + WC >= nx && a.rbc != FBR_BC_NONE);
 
     // right-hand-side overrides owned by this thread (same scheme as fbr_run_onchip.cu), by GLOBAL cell
     int ov_j = -1, ov_stride = 0;
     bool ov_slow = false;
     const double *ovp = &kZeroWin;
-    if (cell0 < nx && cell0 + CPT > 0) {
+    if (!plain_window && cell0 < nx && cell0 + CPT > 0) {
         constexpr unsigned kNoSlot = 0xFF, kZeroSlot = 0xFE;
         uint64_t ov[CPT / 8];  // one byte per cell: the slot that overrides it
 #pragma unroll
@@ -276,6 +296,7 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         if (n_ov > 1 || wide) { ov_slow = true; ov_j = -1; ovp = &kZeroWin; ov_stride = 0; }
     }
 
+    K3W_STAMP(2);
     // scan multipliers (time-invariant within the block)
     // (fp32 mode: products of up to 512 multipliers — formed in fp64 from the multipliers the sweeps use, rounded once)
     HalfProducts hf = {1.0, 1.0}, hb = {1.0, 1.0};
@@ -312,25 +333,21 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     }
     if (tid == 0) { s_Ef[0] = (R)0; s_Eb[W] = (R)0; }
     const bool any_slow = __syncthreads_or(ov_slow);
+    K3W_STAMP(3);
     if (first) {  // ---- the previous time block's output is needed from here on ----
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;");
     }
     if (!staged || first) load8(a.p_in, cell0, nx, (R)0, x);
     first = false;
+    K3W_STAMP(4);
     __syncthreads();  // everybody has emptied the staging buffer: stream the next window in
     {
         const int64_t kn = k + gridDim.x;
         staged = kn < a.n_win && stageable(kn);
-        if (staged) {
-            const int64_t w0 = kn * a.own - a.lead;
-            stage_array<T>(s_stage, a.fl, w0, tid);
-            stage_array<T>(s_stage + WC, a.fr, w0, tid);
-            stage_array<T>(s_stage + 2 * WC, a.fg, w0, tid);
-            stage_array<T>(s_stage + 3 * WC, a.p_in, w0, tid);
-            cp_async_commit();
-        }
+        if (staged) stage_window(kn, true);
     }
+    K3W_STAMP(5);
     const int vf0 = warp - a.nbf > 0 ? warp - a.nbf : 0;          // forward carry: warps vf0 .. warp-1
     const int vb1 = warp + a.nbb < W - 1 ? warp + a.nbb : W - 1;  // backward carry: warps warp+1 .. vb1
     const unsigned st_f = smem_addr(lane == 31 ? &s_Ef[warp + 1] : &s_dummy), ld_f = smem_addr(&s_Ef[warp]);
@@ -429,6 +446,7 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
         }
     }
 
+    K3W_STAMP(6);
     // ---------------- write back the owned cells ----------------
     R *dst = a.p_out + cell0;
     if (cell0 >= own0 && cell0 + CPT <= own1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
@@ -448,6 +466,7 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
             if (i >= own0 && i < own1) dst[j] = x[j];
         }
     }
+    K3W_STAMP(7);
     }  // windows of this CTA
 }
 
@@ -778,3 +797,9 @@ extern "C" int fbr_run_window_f32(const double *fl, const double *fr, const doub
                                   snapshot_every, snap_row_stride, snap, p_final, horizon_fwd, horizon_bwd, w + 4 * pitch,
                                   w + 5 * pitch, stream);
 }
+
+#ifdef FBR_K3W_PROF
+extern "C" int fbr_debug_window_prof(long long *host) {
+    return (int)cudaMemcpyFromSymbol(host, fbr::g_k3w_prof, sizeof(fbr::g_k3w_prof));
+}
+#endif

@@ -31,6 +31,18 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
     return v;
 }
+// bulk copy global -> shared (1-D TMA) whose bytes complete on an mbarrier
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void *gsrc, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+
 // v with all bits cleared when keep == 0 (keep is 0 or -1): a select without a predicate
 __device__ __forceinline__ double and_mask(double v, int keep) {
     const long long b = __double_as_longlong(v) & (long long)keep;
