@@ -592,12 +592,16 @@ static bool plan_window(int64_t nx, int64_t Hf, int64_t Hb, int64_t max_s, int s
         const int resident = (W >= 16 ? 1 : 2) * sm_count;
         // us per window: fixed (load / setup / store) + per time step; measured on B200 (C2 / C5 sweeps,
         // profiles/r01_k3w_sweep.txt).  Dependent launches hide the launch gap.
-        const double t_step = W >= 16 ? 0.58 : 0.46, t_fixed = W >= 16 ? 3.6 : 3.0, t_launch = 0.3;
+        // (round 2, after the bulk-copy staging, fitted to the (W, s) sweeps of C2 and C5 — profiles/r02_k3w_sweep_v2.txt: a
+        // window costs 2.9 / 1.5 us + 0.57 / 0.52 us per step (16 / 8 warps); two 8-warp CTAs sharing an SM step in 0.64 us
+        // each, so C2 prefers 143 windows on 148 SMs to 241 on 296 slots)
+        const double t_fixed = W >= 16 ? 2.9 : 1.5, t_launch = 0.3;
         for (int64_t s = 1; s <= max_s; ++s) {
             if (force_s && s != force_s) continue;
             const int64_t own = wc - s * (hf + hb);
             if (own < wc / 8) break;
             const int64_t n_win = (nx + own - 1) / own;
+            const double t_step = W >= 16 ? 0.57 : n_win <= sm_count ? 0.52 : 0.64;
             const double waves = (double)((n_win + resident - 1) / resident);
             // a partially filled last wave still costs a full one; long runs of waves pipeline well
             const double cost = (waves * (t_fixed + s * t_step) + t_launch) / s;

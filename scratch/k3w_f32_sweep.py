@@ -18,7 +18,7 @@ table_d = E.to_device(table)
 fac = E.factorize(*E.assemble(mesh_d, D_d, 1, nx, dt, w["lbc"], w["rbc"], sidx_d, n_src), check_singular=False)
 horizon = E.decay_horizon(fac)
 print(wl, dt_name, "horizon", horizon)
-combos = [(None, None)] + [(W, S) for W in (8, 16) for S in (6, 9, 12, 16, 20, 25, 33, 50)]
+combos = [(None, None)] + [(W, S) for W in (8, 16) for S in (6, 8, 10, 12, 14, 17, 20, 25, 33, 50)]
 for W, S in combos:
     for k, v in (("FBR_WIN_W", W), ("FBR_WIN_S", S)):
         if v is None:
