@@ -523,6 +523,13 @@ __global__ void __launch_bounds__(32 * W, (16 / W) > 0 ? (16 / W) : 1) run_onchi
     }
 }
 
+#ifdef FBR_K3_PROF  // debug build: where a member's time goes in run_onchipx_kernel (scratch/k3_prof.py reads it)
+__device__ long long g_k3_prof[8 * 8 * 4];  // [CTA slot][member of that CTA][prologue, block boundaries, step runs, epilogue]
+#define K3_CLK() clock64()
+#else
+#define K3_CLK() 0ll
+#endif
+
 // ---- fp64, 8 cells per thread: the time loop built from the half-chain sweep blocks ---------------
 // Same algorithm and results as run_onchip_kernel<double, 8, W> (the cross-warp carry stays EXACT:
 // ensemble members are not required to have a short decay horizon), on a register diet so that the
@@ -765,6 +772,8 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     long long preset;
     while (next_model(a, cursor, m, preset)) {
         // observation samples completed by rows (lo, hi] (for lo == 0 also those that only need the initial state)
+        [[maybe_unused]] const long long k3t0 = K3_CLK();
+        [[maybe_unused]] long long k3_bnd = 0, k3_run = 0;
         auto sample_range = [&](int lo, int hi, int &ja, int &jb) {
             if (a.sample_row) { ja = __ldg(a.row_first_sample + (lo == 0 ? 0 : lo + 1)); jb = __ldg(a.row_first_sample + hi + 1); }
             else { ja = lo == 0 ? 0 : lo + 1; jb = hi + 1; }
@@ -936,8 +945,10 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
         // takes the transposing, fully coalesced path
         const bool direct_rows = gridDim.x <= 64;
         int done = 0;
+        [[maybe_unused]] const long long k3t1 = K3_CLK();
         while (done < n_steps) {
             const int b = done / blk;
+            [[maybe_unused]] const long long k3ta = K3_CLK();
             if (done % blk == 0) {  // entering block b (CTA-uniform)
                 cp_async_wait_all_k3();
                 __syncthreads();  // block b's inputs have landed; everybody is done with block b - 1
@@ -954,6 +965,7 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             }
             int run = blk - done % blk;
             if (run > n_steps - done) run = n_steps - done;
+            [[maybe_unused]] const long long k3tb = K3_CLK();
             // several copies of the step loop: the common ones carry no code for threads that own several
             // overridden / observed cells, nor for snapshots, and only the scan stages their mode needs
             auto steps = [&](auto mode_tag, auto slow_tag, auto rec_tag, int n_begin, int n_end) {
@@ -1068,7 +1080,11 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 else steps(I2{}, std::false_type{}, std::false_type{}, done, done + run);
             }
             done += run;
+#ifdef FBR_K3_PROF
+            { const long long k3tc = K3_CLK(); k3_bnd += k3tb - k3ta; k3_run += k3tc - k3tb; }
+#endif
         }
+        [[maybe_unused]] const long long k3t2 = K3_CLK();
         cp_async_wait_all_k3();
         __syncthreads();
         if (n_steps > 0 && a.n_obs > 0) {
@@ -1090,6 +1106,15 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
             }
         }
         __syncthreads();  // shared scratch is reused by the next model
+#ifdef FBR_K3_PROF
+        if (tid == 0 && blockIdx.x % 71 == 0 && blockIdx.x / 71 < 8) {
+            static_assert(true, "");
+            long long *q = g_k3_prof + (blockIdx.x / 71) * 32;
+            int slot = 0;
+            while (slot < 8 && q[slot * 4 + 2] != 0) ++slot;
+            if (slot < 8) { q[slot * 4] = k3t1 - k3t0; q[slot * 4 + 1] = k3_bnd; q[slot * 4 + 2] = k3_run; q[slot * 4 + 3] = K3_CLK() - k3t2; }
+        }
+#endif
     }
 }
 
@@ -1530,3 +1555,10 @@ extern "C" int fbr_run_zonal_f32(const double *mesh, const double *zone_value, i
     a.z_singular = singular;
     return run_dispatch<float>(a, as_stream(stream));
 }
+
+#ifdef FBR_K3_PROF
+extern "C" int fbr_debug_k3_prof(long long *host, int reset) {
+    if (reset) { long long z[8 * 8 * 4] = {0}; return (int)cudaMemcpyToSymbol(fbr::g_k3_prof, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(host, fbr::g_k3_prof, sizeof(fbr::g_k3_prof));
+}
+#endif
