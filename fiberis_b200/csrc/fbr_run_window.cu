@@ -143,6 +143,31 @@ __device__ __forceinline__ void unstage_row(const R *row, int tid, R (&v)[CPT]) 
     }
 }
 
+// the reverse: thread t's 64 bytes into byte 64 t of a linear row, conflict-free (piece (j + rot) % 4 goes out j-th)
+template <typename R, int CPT>
+__device__ __forceinline__ void stage_row_out(R *row, int tid, const R (&v)[CPT]) {
+    const int rot = (tid >> 1) & 3;
+    char *base = reinterpret_cast<char *>(row) + tid * 64;
+    int4 in[4], mid[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if constexpr (sizeof(R) == 8)
+            in[p] = make_int4(__double2loint(v[2 * p]), __double2hiint(v[2 * p]), __double2loint(v[2 * p + 1]), __double2hiint(v[2 * p + 1]));
+        else
+            in[p] = make_int4(__float_as_int(v[4 * p]), __float_as_int(v[4 * p + 1]), __float_as_int(v[4 * p + 2]), __float_as_int(v[4 * p + 3]));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int4 a = in[(j + 1) & 3], b = in[j];
+        mid[j] = (rot & 1) ? a : b;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // out-th piece = in[(j + rot) % 4]
+        const int4 a = mid[(j + 2) & 3], b = mid[j];
+        *reinterpret_cast<int4 *>(base + 16 * ((j + rot) & 3)) = (rot & 2) ? a : b;
+    }
+}
+
 // Persistent CTAs: CTA b integrates windows b, b + gridDim.x, ...; while it advances one window
 // through the time block, the next window's pressure and factors stream into shared memory
 // (bulk copies), so HBM latency is hidden behind the sweeps.
@@ -154,8 +179,9 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     constexpr int CPT = 64 / (int)sizeof(R);
     constexpr int T = 32 * W;
     constexpr int WC = T * CPT;  // cells per window
-    extern __shared__ __align__(128) double s_stage_raw[];  // [4][WC] of R: l, r, g, p of the NEXT window
+    extern __shared__ __align__(128) double s_stage_raw[];  // [4][WC] of R: l, r, g, p of the NEXT window; [WC]: the state going out
     R *const s_stage = reinterpret_cast<R *>(s_stage_raw);
+    R *const s_out = s_stage + 4 * WC;
     __shared__ __align__(16) R s_K[2][W][W];
     __shared__ __align__(16) R s_Ef[W + 1];  // s_Ef[w + 1] = zero-carry end value of warp w; s_Ef[0] = 0
     __shared__ __align__(16) R s_Eb[W + 1];  // s_Eb[w] = zero-carry first value of warp w; s_Eb[W] = 0
@@ -448,8 +474,24 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
 
     K3W_STAMP(6);
     // ---------------- write back the owned cells ----------------
+    // Whole windows inside the mesh leave through shared memory and ONE bulk store (cp.async.bulk shared -> global) of the
+    // owned range: 512 threads issuing four 16-byte stores each held the window for 1 400 cycles (scratch/k3w_prof.py);
+    // the bulk store drains while the next window is being set up.
     R *dst = a.p_out + cell0;
-    if (cell0 >= own0 && cell0 + CPT <= own1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const bool bulk_out = a.aligned && win0 >= 0 && win0 + WC <= nx && own1 - own0 == a.own &&
+                          (reinterpret_cast<uintptr_t>(a.p_out + own0) & 15) == 0 && (a.own * sizeof(R)) % 16 == 0;
+    if (bulk_out) {  // (CTA-uniform)
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous window's store has read s_out
+        __syncthreads();
+        stage_row_out<R, CPT>(s_out, tid, x);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic-proxy writes -> visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.p_out + own0),
+                         "r"(smem_addr(s_out + (own0 - win0))), "r"((unsigned)(a.own * sizeof(R))) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    } else if (cell0 >= own0 && cell0 + CPT <= own1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         if constexpr (F64) {
             double2 *q = reinterpret_cast<double2 *>(dst);
 #pragma unroll
@@ -468,6 +510,7 @@ __global__ void __launch_bounds__(32 * W, W >= 16 ? 1 : 2) run_window_kernel(con
     }
     K3W_STAMP(7);
     }  // windows of this CTA
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // my bulk stores are complete before the CTA retires
 }
 
 // ---- decay horizon of the factors ----------------------------------------------------------------
@@ -716,7 +759,7 @@ static int run_window_impl(const R *fl, const R *fr, const R *fg, const R *p0, i
     a.nbb = (int)((horizon_bwd + warp_span - 1) / warp_span); if (a.nbb < 1) a.nbb = 1;
     const bool no_pdl = getenv("FBR_WIN_NO_PDL") != nullptr;  // tuning aid
     a.n_win = pl.n_win;
-    const size_t smem = 4 * (size_t)(32 * pl.W) * 64;  // staging: l, r, g, p of one window, 64 bytes per thread each
+    const size_t smem = 5 * (size_t)(32 * pl.W) * 64;  // staging: l, r, g, p of the next window + the state going out, 64 bytes per thread each
     // kernel variant: how many scan stages the horizon needs, and whether carries stop at the neighbouring warp
     const int64_t hmax = horizon_fwd > horizon_bwd ? horizon_fwd : horizon_bwd;
     const bool near = a.nbf == 1 && a.nbb == 1 && !getenv("FBR_WIN_GENERAL");
