@@ -677,6 +677,9 @@ def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, 
     if n_audit:
         snap_d = torch.empty((n_audit, n_steps + 1, nx), dtype=torch.float32 if f32 else torch.float64, device=mesh_d.device)
     misfit_d = torch.empty(M, dtype=torch.float64, device=mesh_d.device)
+    split_audit = bool(n_audit) and M >= 8 * n_audit and M >= 512 and not getattr(args, "inline_audit", False)
+    zv_audit_d = zv_d.index_select(0, audit_d).contiguous() if split_audit else None
+    flags_audit_d = E.zonal_flags(max(n_audit, 1), mesh_d.device)
     modes_d = torch.full((M,), -1, dtype=torch.int32, device=mesh_d.device)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=mesh_d.device)  # > 126 MB L2
 
@@ -689,10 +692,28 @@ def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, 
             fac, zonal = E.factorize(*diag, check_singular=False), None
         if ev:
             ev[0].record()
-        E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1 if n_audit else 0,
-              snap_models=audit_d, n_snap_models=n_audit, obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d,
-              snap_out=snap_d, misfit_out=misfit_d, dtype="float32" if f32 else "float64", zonal=zonal,
-              singular_flags=flags_d if on_chip else None, scan_mode_out=modes_d)
+        kw = dict(obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, dtype="float32" if f32 else "float64")
+        if split_audit:
+            # what PDS1D_Ensemble.solve does for a large sweep with a few audited members (ensemble.py): the audited members
+            # (a snapshot row every step) are their own small launch on a side stream, the sweep records nothing and leaves
+            # their CTA slots free — inline they are the slowest members of their CTAs and the sweep's tail
+            main, side = torch.cuda.current_stream(), E._copy_stream(mesh_d.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                if on_chip:
+                    fac_a, zon_a = None, (mesh_d, zv_audit_d, zone_d, dt, None)
+                else:
+                    fac_a, zon_a = tuple(f_.index_select(0, audit_d).contiguous() for f_ in fac), None
+                E.run(fac_a, p0_d, n_audit, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1,
+                      snap_out=snap_d, zonal=zon_a, singular_flags=flags_audit_d if on_chip else None, **kw)
+            E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=0,
+                  misfit_out=misfit_d, zonal=zonal, singular_flags=flags_d if on_chip else None, scan_mode_out=modes_d,
+                  reserve_ctas=n_audit, **kw)
+            main.wait_stream(side)
+        else:
+            E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1 if n_audit else 0,
+                  snap_models=audit_d, n_snap_models=n_audit, snap_out=snap_d, misfit_out=misfit_d, zonal=zonal,
+                  singular_flags=flags_d if on_chip else None, scan_mode_out=modes_d, **kw)
         if ev:
             ev[1].record()
         return gather_misfit(misfit_d, w["M"]) if world > 1 else misfit_d
@@ -789,6 +810,9 @@ def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, 
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "PDS1D_Ensemble.solve(host arrays) -> misfit + audit snapshots as numpy"},
         "gpu_launches": int(launches) * steps, "clocks": clocks.summary(), "parity": parity,
+        "audit_launch": ("the audited members are their own small launch on a side stream next to the sweep, which records nothing "
+                         "and leaves their CTA slots free — what PDS1D_Ensemble.solve does (they are integrated twice: +0.1 % of "
+                         "work, not counted)" if split_audit else "audited members inside the sweep's launch"),
     }
     if modes is not None and want_probe:
         fp64_peak = E.fp64_peak()
@@ -847,7 +871,8 @@ def run_gpu_arm(args):
             "config": {"workload": res["workload"], "seed": {"c3": 303, "c4": 404}[args.workload],
                        "members_per_gpu": res["members_per_gpu"], "cells": nx, "time_steps": n_steps,
                        "diffusivity": "zonal, 8 zones, 10**U(-1,1)", "sources": 2, "obs_cells": res["n_obs"],
-                       "audit_members_with_full_snapshots": res["n_audit"], "bc": "Neumann/Neumann",
+                       "audit_members_with_full_snapshots": res["n_audit"], "audit_launch": res["audit_launch"],
+                       "bc": "Neumann/Neumann",
                        "l2": "flushed between timed iterations (512 MiB memset)",
                        "timed_kernels": ("K3 run_onchip with on-chip assembly + factorisation (fbr_run_zonal_f64)" if on_chip
                                          else "K1 assemble_zonal + K1b factorize + K3 run_onchip")
@@ -926,6 +951,8 @@ def main():
                     help="--workload c4: the fixed 1M-member ensemble split over the ranks instead of 125000 members per rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C2 / C5 runs appended to the C3 line")
+    ap.add_argument("--inline-audit", action="store_true",
+                    help="device-resident leg: audited members inside the sweep's launch (round 1) instead of their own side launch")
     args = ap.parse_args()
     if args.workload in SINGLE:
         if args.impl == "reference":
