@@ -8,7 +8,7 @@ from tests._fuzz import run_case
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 dtype = sys.argv[3] if len(sys.argv) > 3 else "float64"
-gate = 1e-10 if dtype == "float64" else 2e-5
+gate = 1e-10 if dtype == "float64" else 1e-5
 worst, fails, t_start = 0.0, 0, time.time()
 for case in range(n_cases):
     try:

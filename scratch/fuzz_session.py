@@ -48,5 +48,5 @@ for case in range(n_cases):
         if len(keep) > 3: keep.pop(0)
     except Exception as ex:
         fails += 1
-        print("FAIL", kind, type(ex).__name__, str(ex)[:300])
+        print("FAIL", kind, type(ex).__name__, str(ex)[:900].replace("\n", " | "))
 print(f"{n_cases} mixed cases, {fails} failures, {time.time() - t0:.0f} s")
