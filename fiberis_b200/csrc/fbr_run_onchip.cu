@@ -59,6 +59,7 @@ struct RunArgs {
     const double *obs_w;  // (n_obs) or NULL
     double *misfit;       // (M)
     int blk_steps;        // fp64 x8 kernel: time steps per staged block of per-step scalars
+    int prefetch_rows;    // fp64 x8 kernel, short runs: the NEXT member's four rows stream into shared memory (bulk copies)
     // on-chip assembly mode (fbr_run_zonal_f64): no factor arrays, the members' matrices are assembled (K1 arithmetic)
     // and factorised in registers from the shared mesh and n_zones diffusivities per member
     const double *z_mesh;        // (nx)
@@ -765,11 +766,64 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
     double *s_obs = s_src + 2 * blk * a.n_src;              // [2][blk][n_obs] observation samples the block completes
     double *s_tr = s_obs + 2 * blk * a.n_obs;               // [2][blk][n_obs] trace of the observed cells
     T *s_patch = reinterpret_cast<T *>(s_tr + 2 * blk * a.n_obs + warp * (32 * 9));  // [W] row-transposition patches (2304 B each)
+    // Short runs (the step-at-a-time use: n_steps = 1 .. 16) live on the latency of loading a member's four rows: while a
+    // member is integrated the NEXT one's rows arrive in shared memory by four bulk copies (cp.async.bulk + mbarrier) and are
+    // read with the rotated start piece that keeps linear 64-byte rows conflict-free (csrc/fbr_run_pass.cu).  Round 2's first
+    // two attempts at this (16-byte cp.async; bulk copies read with 4-way conflicts) were slower than no prefetch at all.
+    [[maybe_unused]] double *s_rows = s_tr + 2 * blk * a.n_obs + W * (32 * 9);  // (behind the patches; fp64 instantiation only)
+    [[maybe_unused]] const int64_t row_pitch = (int64_t)W * 32 * CPT;  // doubles per staged row (the team's width)
+    __shared__ __align__(8) unsigned long long s_rbar;
+    [[maybe_unused]] const unsigned rbar = smem_addr(&s_rbar);
+    [[maybe_unused]] unsigned n_rows_taken = 0;
+    constexpr bool kCanPrefetch = LEAN && !ZONAL && sizeof(T) == 8;
+    const bool prefetch = kCanPrefetch && a.prefetch_rows;
+    if (kCanPrefetch && prefetch) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    [[maybe_unused]] auto stage_member = [&](int64_t mm) {  // lane 0 of warps 0 .. min(W, 4) - 1 (W = 1: lane 0 issues all four)
+        if (lane != 0) return;
+        const unsigned bytes = (unsigned)(nx * sizeof(double));
+        const double *src[4] = {a.fl + mm * nx, a.fr + mm * nx, a.fg + mm * nx, a.p0 + mm * a.p0_stride};
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (warp == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar), "r"(4u * bytes) : "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (warp == (W >= 4 ? q : W >= 2 ? (q & 1) : 0)) bulk_g2s(smem_addr(s_rows + q * row_pitch), src[q], bytes, rbar);
+    };
+    [[maybe_unused]] auto take_row = [&](int q, double pad, T (&v)[CPT]) {  // my 64 bytes of staged row q
+        if constexpr (sizeof(T) == 8) {
+            const double *row = s_rows + q * row_pitch;
+            if (cell0 + CPT <= nx) {
+                const int rot = (tid >> 1) & 3;
+                double2 ld[4], mid[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ld[j] = *reinterpret_cast<const double2 *>(row + cell0 + 2 * ((j + rot) & 3));
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    mid[pp].x = (rot & 1) ? ld[(pp + 3) & 3].x : ld[pp].x;
+                    mid[pp].y = (rot & 1) ? ld[(pp + 3) & 3].y : ld[pp].y;
+                }
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    v[2 * pp] = (rot & 2) ? mid[(pp + 2) & 3].x : mid[pp].x;
+                    v[2 * pp + 1] = (rot & 2) ? mid[(pp + 2) & 3].y : mid[pp].y;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) v[j] = cell0 + j < nx ? row[cell0 + j] : pad;
+            }
+        }
+    };
     const int64_t cs = a.snap_cell_stride;
 
     ModelCursor cursor = model_cursor(a);
     int64_t m;
     long long preset;
+    if (kCanPrefetch && prefetch && cursor.k < a.M) stage_member(cursor.k);  // (LEAN: nothing is recorded, members are k, k + G, ..)
     while (next_model(a, cursor, m, preset)) {
         // observation samples completed by rows (lo, hi] (for lo == 0 also those that only need the initial state)
         [[maybe_unused]] const long long k3t0 = K3_CLK();
@@ -815,12 +869,18 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                 l[j] = (T)zl[j]; r[j] = (T)zr[j]; g[j] = (T)zg[j];
                 if (sizeof(T) == 4) { cpf_d *= zl[j]; cpb_d *= zg[j]; }
             }
+        } else if (kCanPrefetch && prefetch) {
+            mbar_wait(rbar, n_rows_taken & 1u);
+            ++n_rows_taken;
+            take_row(0, 0.0, l); take_row(1, 1.0, r); take_row(2, 0.0, g); take_row(3, 0.0, x);
+            __syncthreads();  // everybody has its rows: the buffer is free for the next member's
+            if (cursor.k < a.M) stage_member(cursor.k);
         } else {
             cpf_d = load_row(a.fl + m * nx, 0.0, l);
             load_row(a.fr + m * nx, 1.0, r);
             cpb_d = load_row(a.fg + m * nx, 0.0, g);
         }
-        load_row(a.p0 + m * a.p0_stride, 0.0, x);
+        if (!(kCanPrefetch && prefetch)) load_row(a.p0 + m * a.p0_stride, 0.0, x);
         // Left boundary row (right-hand side always 0, matbuilder.py:49-55) in a thread's first register: with r_0 := 0 and
         // l_1 := 0 the stale x_0 never reaches anything (t_0 = r_0 y_0 = 0, y_1 = b_1 - l_1 * 0 = b_1 — the same bits) and
         // x_0 = -g_0 x_1 comes out of the backward sweep as before: the override costs nothing per step.
@@ -1299,13 +1359,22 @@ static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     }
     RunArgs b = a;
     const int cols = a.n_src + 2 * a.n_obs;
+    // short runs without records (the step-at-a-time use): prefetch the next member's rows through shared memory
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    bool prefetch = false;
+    if constexpr (!ZONAL && sizeof(T) == 8)
+        prefetch = !a.snap && !getenv("FBR_K3_NO_LEAN") && !getenv("FBR_K3_NO_PREFETCH") && a.n_steps <= 16 && a.nx % 2 == 0 &&
+                   a.p0_stride % 2 == 0 && al16(a.fl) && al16(a.fr) && al16(a.fg) && al16(a.p0) && a.M > 1;
+    b.prefetch_rows = prefetch;
+    const size_t rows_bytes = prefetch ? 4 * (size_t)W * 32 * CPT * sizeof(double) : 0;
     // Time steps per staged block of per-step scalars: the longest block that costs no resident CTA (block boundaries
     // carry three barriers and the residual sums; C3: 64 steps 25.2 ms, 32 steps 25.5 ms, 128 steps lose a CTA: 42.7 ms).
     // The audited side launch of an ensemble must end up with the SAME footprint as the sweep (see ensemble.py): the
     // choice depends only on the column count and the team width, not on M.
-    auto smem_for = [&](int blk) { return (2 * (size_t)blk * (size_t)cols + (size_t)W * 32 * 9) * sizeof(double); };
+    auto smem_for = [&](int blk) { return (2 * (size_t)blk * (size_t)cols + (size_t)W * 32 * 9) * sizeof(double) + rows_bytes; };
     int occ = 0, occ_ref = 0;
     size_t smem = smem_for(8);
+    if (smem > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ref, kern, 32 * W, smem));
     b.blk_steps = 8;
     occ = occ_ref;
@@ -1492,7 +1561,7 @@ extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
     a.src_table = src_table; a.snapshot_every = snapshot_every; a.snap_models = snap_models;              \
     a.n_snap_models = n_snap_models; a.snap_row_stride = snap_row_stride;                                  \
     a.snap_model_stride = snap_model_stride; a.snap = snap; a.p_final = p_final; a.obs_idx = obs_idx;             \
-    a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit; a.blk_steps = 0;     \
+    a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit; a.blk_steps = 0; a.prefetch_rows = 0;     \
     a.z_mesh = nullptr; a.z_value = nullptr; a.z_of_cell = nullptr; a.z_n = 0; a.z_dt = 0.0;              \
     a.z_sigma = nullptr; a.z_singular = nullptr;                                                         \
     if (int rc_opts = apply_opts(a, opts)) return rc_opts;
