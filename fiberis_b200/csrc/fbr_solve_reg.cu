@@ -107,7 +107,7 @@ template <int CPT, int W, int S, int L>
 __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kernel(const double *__restrict__ dl, const double *__restrict__ d,
                                                                const double *__restrict__ du, const double *b, double *x,
                                                                int64_t M, int64_t nx, int32_t *__restrict__ singular,
-                                                               const StepOverrides ov) {
+                                                               const StepOverrides ov, const int prefetch) {
     static_assert(S == 1 || W == 1, "several systems per CTA only for single-warp systems");
     static_assert(CPT % 2 == 0, "16-byte accesses and sign-free chunk products need an even chunk");
     static_assert(L == 32 || W == 1, "sub-warp groups only for single-warp systems");
@@ -126,6 +126,56 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(dl) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(du) |
                           reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
     const int64_t stride = (int64_t)gridDim.x * S * GPW;
+    // Whole-warp systems of 8-cell threads: while a system is solved, the NEXT one's four rows arrive in shared memory by
+    // four bulk copies on an mbarrier and are read with the rotated, conflict-free start piece (as in fbr_run_onchip.cu's
+    // step-at-a-time path and fbr_run_pass.cu): the solve lives on the latency of loading its rows.
+    constexpr bool kCanPrefetch = CPT == 8 && S == 1 && L == 32;
+    extern __shared__ __align__(128) double s_rows[];  // [4][32 W CPT]
+    constexpr int kPitch = 32 * W * CPT;
+    __shared__ __align__(8) unsigned long long s_rbar;
+    [[maybe_unused]] const unsigned rbar = smem_addr(&s_rbar);
+    [[maybe_unused]] unsigned n_taken = 0;
+    const bool pf = kCanPrefetch && prefetch;
+    [[maybe_unused]] auto stage_system = [&](int64_t mm) {  // lane 0 of warps 0 .. min(W, 4) - 1
+        if (lane != 0) return;
+        const unsigned bytes = (unsigned)(nx * sizeof(double));
+        const double *src[4] = {dl + mm * nx, d + mm * nx, du + mm * nx, b + mm * nx};
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (warp == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rbar), "r"(4u * bytes) : "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (warp == (W >= 4 ? q : W >= 2 ? (q & 1) : 0)) bulk_g2s(smem_addr(s_rows + q * kPitch), src[q], bytes, rbar);
+    };
+    [[maybe_unused]] auto take_row = [&](int q, double pad, double (&v)[CPT]) {
+        const double *row = s_rows + q * kPitch;
+        if (nvalid == CPT) {
+            const int rot = (tid >> 1) & 3;
+            double2 ld[4], mid[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ld[j] = *reinterpret_cast<const double2 *>(row + cell0 + 2 * ((j + rot) & 3));
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                mid[pp].x = (rot & 1) ? ld[(pp + 3) & 3].x : ld[pp].x;
+                mid[pp].y = (rot & 1) ? ld[(pp + 3) & 3].y : ld[pp].y;
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                v[(2 * pp) % CPT] = (rot & 2) ? mid[(pp + 2) & 3].x : mid[pp].x;
+                v[(2 * pp + 1) % CPT] = (rot & 2) ? mid[(pp + 2) & 3].y : mid[pp].y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) v[j] = j < nvalid ? row[cell0 + j] : pad;
+        }
+    };
+    if (kCanPrefetch && pf) {
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(rbar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if ((int64_t)blockIdx.x < M) stage_system(blockIdx.x);
+    }
     // which of my rows get an overridden right-hand side: one byte per row (0xFF none, 0xFE zero, else source column);
     // later claims win (sources over boundary rows, later duplicates over earlier ones)
     uint64_t slots = ~0ull;
@@ -147,13 +197,25 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
         double l[CPT], dd[CPT], g[CPT], v[CPT];
         const bool vec = nvalid == CPT && ptr_ok && ((o + cell0) & 1) == 0;
         const bool odd = nvalid == CPT && ptr_ok && !vec;
-        load_chunk<CPT>(dl + o + cell0, nvalid, vec, 0.0, l, odd);
-        load_chunk<CPT>(d + o + cell0, nvalid, vec, 1.0, dd, odd);
-        load_chunk<CPT>(du + o + cell0, nvalid, vec, 0.0, g, odd);
-        load_chunk<CPT>(b + o + cell0, nvalid, vec, 0.0, v, odd);
         // super-diagonal entry in front of a warp's first chunk (the first padding row has none)
         double c_first = 0.0;
-        if (W > 1 && lane == 0 && cell0 > 0 && cell0 < nxi) c_first = __ldg(du + o + cell0 - 1);
+        if constexpr (kCanPrefetch) {
+            if (pf) {  // (S == 1, L == 32: m_raw = blockIdx.x + k gridDim.x, always < M)
+                mbar_wait(rbar, n_taken & 1u);
+                ++n_taken;
+                if constexpr (CPT == 8) { take_row(0, 0.0, l); take_row(1, 1.0, dd); take_row(2, 0.0, g); take_row(3, 0.0, v); }
+                if (W > 1 && lane == 0 && cell0 > 0 && cell0 < nxi) c_first = s_rows[2 * kPitch + cell0 - 1];
+                __syncthreads();  // everybody has its rows: the buffer is free for the next system's
+                if (m_raw + stride < M) stage_system(m_raw + stride);
+            }
+        }
+        if (!pf) {
+            load_chunk<CPT>(dl + o + cell0, nvalid, vec, 0.0, l, odd);
+            load_chunk<CPT>(d + o + cell0, nvalid, vec, 1.0, dd, odd);
+            load_chunk<CPT>(du + o + cell0, nvalid, vec, 0.0, g, odd);
+            load_chunk<CPT>(b + o + cell0, nvalid, vec, 0.0, v, odd);
+            if (W > 1 && lane == 0 && cell0 > 0 && cell0 < nxi) c_first = __ldg(du + o + cell0 - 1);
+        }
         if ((unsigned)jlast < (unsigned)CPT) {
 #pragma unroll
             for (int j = 0; j < CPT; ++j)
@@ -330,7 +392,11 @@ static int launch_reg(const double *dl, const double *d, const double *du, const
     if (int rc = device_facts(&f)) return rc;
     auto kern = solve_reg_kernel<CPT, W, S, L>;
     constexpr int NT = 32 * W * S;
-    const size_t smem = 0;
+    auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const int prefetch = CPT == 8 && S == 1 && L == 32 && nx % 2 == 0 && al16(dl) && al16(d) && al16(du) && al16(b) && M > 1 &&
+                         !getenv("FBR_K2_NO_PREFETCH");
+    const size_t smem = prefetch ? 4 * (size_t)(32 * W * CPT) * sizeof(double) : 0;
+    if (smem > 48 * 1024) FBR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     FBR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
     if (occ < 1) return fail(FBR_ERR_UNSUPPORTED, "REG solve kernel does not fit on an SM (threads=%d)", NT);
@@ -338,7 +404,7 @@ static int launch_reg(const double *dl, const double *d, const double *du, const
     const int64_t per_cta = S * (32 / L);
     const int64_t groups = (M + per_cta - 1) / per_cta;
     if (grid > groups) grid = groups;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(dl, d, du, b, x, M, nx, singular, ov);
+    kern<<<(unsigned)grid, NT, smem, stream>>>(dl, d, du, b, x, M, nx, singular, ov, prefetch);
     return check_launch("fbr_solve_tridiag_f64 (REG)");
 }
 
