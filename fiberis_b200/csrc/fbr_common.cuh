@@ -53,6 +53,8 @@ int device_facts(DeviceFacts *out);
 
 // K2 REG (fbr_solve_reg.cu): register-resident bare solve, 1 <= nx <= kSolveRegMaxNx
 constexpr int kSolveRegMaxNx = 4096;
+int step_factors_dispatch(const double *fl, const double *fr, const double *fg, const double *p, double *p_next, int64_t M, int64_t nx,
+                          int lbc, int rbc, const int64_t *src_idx, int n_src, const double *src_val, cudaStream_t stream);
 int solve_reg_dispatch(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
                        int32_t *singular, cudaStream_t stream);
 

@@ -1469,6 +1469,16 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
     if (a.nx > fbr_run_max_nx())
         return fail(FBR_ERR_UNSUPPORTED, "nx=%lld exceeds the on-chip run kernel limit %lld", (long long)a.nx,
                     (long long)fbr_run_max_nx());
+    // ONE step with reused factors, nothing recorded but the new state (the step-at-a-time use): the persistent kernel's
+    // per-member set-up (scan-mode detection, staging of per-step scalars, 12 loop copies) buys nothing here — K2's
+    // register-resident kernel in its FACTORS mode does the two sweeps straight from the rows it prefetches
+    // (65536 x 512: 0.25 -> 0.22 ms).
+    if constexpr (sizeof(T) == 8) {
+        if (a.n_steps == 1 && !a.snap && a.n_obs == 0 && a.p_final && !a.z_mesh && a.p0_stride == a.nx && a.nx > 256 &&
+            a.nx <= kSolveRegMaxNx && a.n_samples == 0 && !a.scan_mode && !getenv("FBR_K3_NO_STEP_KERNEL"))
+            return step_factors_dispatch(a.fl, a.fr, a.fg, a.p0, reinterpret_cast<double *>(a.p_final), a.M, a.nx, a.lbc, a.rbc,
+                                         a.src_idx, a.n_src, a.src_table, stream);
+    }
     int cpt = a.nx >= 256 ? 8 : a.nx >= 128 ? 4 : a.nx >= 64 ? 2 : 1;
     // a few members of 128..255 cells (C1: one model of 200 cells) are a latency problem: shorter chains over more warps
     // (2 cells per thread, 4 warps: 0.48 us per step against 0.52 with 4 cells per thread and 0.58 with 8)

@@ -103,7 +103,10 @@ struct StepOverrides {
 
 // W warps per system, S warps of single-warp systems per CTA (S > 1 only with W == 1: no CTA barrier inside the loop
 // then), L lanes per system (L < 32 only with W == 1: 32 / L small systems share a warp, shuffles stay inside a group)
-template <int CPT, int W, int S, int L>
+// FACTORS: (dl, d, du) are the time-invariant factors (l, r = 1 / u, g) of fbr_factorize_f64 instead of the diagonals — the
+// pivots are not recomputed, the sweeps are K3's (y_i = b_i - l_i y_{i-1}, t_i = r_i y_i, x_i = t_i - g_i x_{i+1}): ONE
+// implicit step with reused factors (fbr_run_f64 with n_steps = 1 takes this kernel).
+template <int CPT, int W, int S, int L, bool FACTORS = false>
 __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kernel(const double *__restrict__ dl, const double *__restrict__ d,
                                                                const double *__restrict__ du, const double *b, double *x,
                                                                int64_t M, int64_t nx, int32_t *__restrict__ singular,
@@ -233,6 +236,8 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
         double c_prev = __shfl_up_sync(kAll, g[CPT - 1], 1, L);
         if (sub == 0) c_prev = c_first;
 
+        int bad = 0;
+        if constexpr (!FACTORS) {
         // ---- 1. pivots ----
         double ee[CPT];  // e_j = -dl_j du_{j-1}
         {
@@ -297,7 +302,6 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
                 p1 *= s; p2 *= s;
             }
         }
-        int bad = 0;
         if (nanacc != nanacc) {  // a zero (or non-finite) pivot makes its quotient non-finite: find the first such row
 #pragma unroll
             for (int j = CPT - 1; j >= 0; --j)
@@ -309,6 +313,7 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
             l[j] *= r[j];
             g[j] *= r[j];
             v[j] *= r[j];
+        }
         }
         const GroupMultipliers<L> sm = group_multipliers<L>(chunk_product<double, CPT>(l), chunk_product<double, CPT>(g), sub);
         constexpr int NS = GroupMultipliers<L>::NS;
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 yy = fma(-l[j], yy, v[j]);
-                v[j] = yy;
+                v[j] = FACTORS ? dd[j] * yy : yy;  // (FACTORS: dd holds r = 1 / u)
             }
         }
         {
@@ -385,12 +390,12 @@ __global__ void __launch_bounds__(32 * W * S, 512 / (32 * W * S)) solve_reg_kern
     }
 }
 
-template <int CPT, int W, int S, int L>
+template <int CPT, int W, int S, int L, bool FACTORS = false>
 static int launch_reg(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,
                       int32_t *singular, const StepOverrides &ov, cudaStream_t stream) {
     DeviceFacts f;
     if (int rc = device_facts(&f)) return rc;
-    auto kern = solve_reg_kernel<CPT, W, S, L>;
+    auto kern = solve_reg_kernel<CPT, W, S, L, FACTORS>;
     constexpr int NT = 32 * W * S;
     auto al16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const int prefetch = CPT == 8 && S == 1 && L == 32 && nx % 2 == 0 && al16(dl) && al16(d) && al16(du) && al16(b) && M > 1 &&
@@ -421,6 +426,16 @@ static int reg_dispatch(const double *dl, const double *d, const double *du, con
     if (nx <= 1024) return launch_reg<8, 4, 1, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
     if (nx <= 2048) return launch_reg<8, 8, 1, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
     return launch_reg<8, 16, 1, 32>(dl, d, du, b, x, M, nx, singular, ov, stream);
+}
+
+// one implicit step with reused factors (fl, fr, fg): right-hand side overrides + K3's two sweeps, 129 <= nx <= 4096
+int step_factors_dispatch(const double *fl, const double *fr, const double *fg, const double *p, double *p_next, int64_t M, int64_t nx,
+                          int lbc, int rbc, const int64_t *src_idx, int n_src, const double *src_val, cudaStream_t stream) {
+    StepOverrides ov{1, lbc, rbc, n_src, src_idx, src_val, 0};
+    if (nx <= 512) return launch_reg<8, 2, 1, 32, true>(fl, fr, fg, p, p_next, M, nx, nullptr, ov, stream);
+    if (nx <= 1024) return launch_reg<8, 4, 1, 32, true>(fl, fr, fg, p, p_next, M, nx, nullptr, ov, stream);
+    if (nx <= 2048) return launch_reg<8, 8, 1, 32, true>(fl, fr, fg, p, p_next, M, nx, nullptr, ov, stream);
+    return launch_reg<8, 16, 1, 32, true>(fl, fr, fg, p, p_next, M, nx, nullptr, ov, stream);
 }
 
 int solve_reg_dispatch(const double *dl, const double *d, const double *du, const double *b, double *x, int64_t M, int64_t nx,

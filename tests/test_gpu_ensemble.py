@@ -565,3 +565,32 @@ def test_sweep_with_observations_on_their_own_time_axis():
         snap, _ = O.solve_fixed(c["mesh"], (10.0 ** theta[m])[c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
                                 c["srcs"], 0.0, c["dt"], c["T"])
         assert out["misfit"][m] == pytest.approx(O.sampled_misfit(snap, taxis, c["obs_idx"], obs, obs_taxis), rel=1e-9)
+
+
+@pytest.mark.parametrize("M,nx", [(5, 257), (40, 512), (33, 1000), (3, 4096), (17, 2047)])
+@pytest.mark.parametrize("lbc,rbc", [("Neumann", "Dirichlet"), ("Dirichlet", "Neumann")])
+def test_one_step_with_reused_factors_takes_the_register_resident_step_kernel(M, nx, lbc, rbc, monkeypatch):
+    """fbr_run_f64 with n_steps = 1 and nothing recorded but the new state (the step-at-a-time use) is served by K2's
+    kernel in its FACTORS mode (csrc/fbr_solve_reg.cu): same answer as the persistent kernel and as the oracle's step,
+    with sources on a boundary row, next to each other and listed twice."""
+    from fiberis_b200 import _engine as E
+    from oracle import pds_oracle as O
+    rng = np.random.default_rng(M * 7919 + nx)
+    mesh = np.cumsum(rng.uniform(0.5, 2.0, nx))
+    D = 10 ** rng.uniform(-1, 1, (M, nx))
+    p = rng.uniform(-1, 1, (M, nx))
+    sidx = np.array([0, 5, 6, nx // 2, nx // 2, nx - 1])
+    vals = rng.uniform(-10, 10, (1, len(sidx)))
+    mesh_d, D_d, p_d = E.to_device(mesh), E.to_device(D), E.to_device(p)
+    sidx_d, n_src = E.index_tensor(sidx)
+    fac = E.factorize(*E.assemble(mesh_d, D_d, M, nx, 0.5, lbc, rbc, sidx_d, n_src))
+    table_d = E.to_device(vals)
+    _, fin, _ = E.run(fac, p_d, M, nx, 1, lbc, rbc, sidx_d, n_src, table_d, snapshot_every=0, want_final=True)
+    got = fin.cpu().numpy()
+    monkeypatch.setenv("FBR_K3_NO_STEP_KERNEL", "1")
+    _, fin2, _ = E.run(fac, p_d, M, nx, 1, lbc, rbc, sidx_d, n_src, table_d, snapshot_every=0, want_final=True)
+    assert np.max(np.abs(got - fin2.cpu().numpy())) <= 1e-13 * np.max(np.abs(got))
+    for m in (0, M - 1):
+        b = O.assemble_rhs(p[m], lbc, rbc, sidx, vals[0])
+        want = O.solve_tridiag(*O.assemble_tridiag(mesh, D[m], 0.5, lbc, rbc, sidx), b)
+        assert np.max(np.abs(got[m] - want)) <= 1e-12 * np.max(np.abs(want))
