@@ -153,6 +153,9 @@ int fbr_factorize_f64(const double *dl, const double *d, const double *du, int64
  *                 With opts->n_samples > 0 the observations have their OWN time axis (see fbr_run_opts).
  *   opts        : NULL (all defaults) or a pointer to a struct fbr_run_opts in host memory, read during the call
  * The _f32 variant keeps state and factors in float (fp32 mode of north_star, gated at 1e-5).
+ * Step-at-a-time use (n_steps = 1, snap = NULL, no observations, p_final given, 256 < nx <= 4096, p0_stride = nx): served
+ * by the register-resident solve kernel with the factors as its rows (csrc/fbr_solve_reg.cu, FACTORS mode) — the next
+ * member's rows are prefetched through shared memory: 40 B per cell-update at 0.93 of the measured HBM peak.
  * Limits of this on-chip variant: nx <= fbr_run_max_nx(), n_src <= 253, n_obs <= 64.
  * ------------------------------------------------------------------------------------------ */
 
