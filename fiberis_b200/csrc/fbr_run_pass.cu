@@ -115,15 +115,18 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     auto staged = [&](int64_t t) { return !SETUP && aligned && t >= 0 && (t + 1) * kPTile <= nx; };
-    auto stage_tile = [&](int64_t t) {  // thread 0, after everybody has read the previous tile out of the buffer
-        if (!staged(t)) return;
+    // (callers: every thread, after everybody has read the previous tile out of the buffer; lane 0 of warps 0 .. min(W, 4) - 1
+    //  issues — four copies from one thread kept warp 0 for ~470 cycles, scratch/k3p_prof.py)
+    auto stage_tile = [&](int64_t t) {
+        if (lane != 0 || !staged(t)) return;
         const int64_t c0 = t * kPTile;
+        const double *src[4] = {a.fl + c0, a.fr + c0, a.fg + c0, a.p_in + c0};
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before async-proxy writes
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * kPTile * 8u) : "memory");
-        bulk_g2s(smem_addr(s_stage) + 0 * kPTile * 8, a.fl + c0, kPTile * 8, bar);
-        bulk_g2s(smem_addr(s_stage) + 1 * kPTile * 8, a.fr + c0, kPTile * 8, bar);
-        bulk_g2s(smem_addr(s_stage) + 2 * kPTile * 8, a.fg + c0, kPTile * 8, bar);
-        bulk_g2s(smem_addr(s_stage) + 3 * kPTile * 8, a.p_in + c0, kPTile * 8, bar);
+        if (warp == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * kPTile * 8u) : "memory");
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (warp == (W >= 4 ? q : (q & 1))) bulk_g2s(smem_addr(s_stage) + q * kPTile * 8, src[q], kPTile * 8, bar);
     };
     unsigned n_staged = 0;  // staged tiles consumed so far: the mbarrier's phase
     // the source cells, once per CTA: which tiles hold one is then a shared-memory question
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
 
     if (tid == 0) s_ticket[0] = atomicAdd(a.ticket, 1u) - base;
     __syncthreads();
-    if (tid == 0 && s_ticket[0] < (unsigned)a.n_tiles) stage_tile(a.n_tiles - 1 - (int64_t)s_ticket[0]);
+    if (s_ticket[0] < (unsigned)a.n_tiles) stage_tile(a.n_tiles - 1 - (int64_t)s_ticket[0]);
     // Forward carry into tile t: fold the finished aggregates of the tiles on its left (exact: it stops at tile 0 or when
     // the running product underflows to 0).  One warp's job — warp 1 does it for the NEXT tile while warp 0 looks back for
     // the current one, so nobody waits for it (at the head of a tile it was 17 % of the stall samples).
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(32 * W, 16 / W) pass_kernel(const PassArgs a) 
         K3P_STAMP(9);
         const unsigned nt = s_ticket[(it & 1) ^ 1];
         const int64_t next_tile = nt < (unsigned)a.n_tiles ? a.n_tiles - 1 - (int64_t)nt : -1;
-        if (tid == 0) stage_tile(next_tile);  // (everybody passed the barrier above: the buffer is free)
+        stage_tile(next_tile);  // (everybody passed the barrier above: the buffer is free)
         K3P_STAMP(2);
         const ScanMultipliers sm = scan_multipliers<double>(chunk_product<double, 8>(l), chunk_product<double, 8>(g), lane);
         if (lane == 31) s_T[0][warp] = sm.tot_f;
