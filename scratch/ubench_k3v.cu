@@ -41,19 +41,39 @@ __device__ __forceinline__ Scan2<K> scan2(double cf, double cb, int lane) {
     return m;
 }
 
-// MODE 0: old scheme.  MODE 1: fused final, E via one FMA on the publishing lane.
-template <int W, int K, bool NEAR, int MINB, bool SPLIT, int MODE>
+// radix-4 scan, 2 levels (reach 16 chunks = 128 cells): multipliers are products over 1, 2, 3 and 4, 8, 12 chunks
+struct Scan4 {
+    double f[6], b[6];
+};
+__device__ __forceinline__ Scan4 scan4(double cf, double cb, int lane) {
+    Scan4 m;
+    const double f1 = cf, b1 = cb;
+    const double f2 = f1 * __shfl_up_sync(kAllLanes, f1, 1), b2 = b1 * __shfl_down_sync(kAllLanes, b1, 1);
+    const double f3 = f1 * __shfl_up_sync(kAllLanes, f2, 1), b3 = b1 * __shfl_down_sync(kAllLanes, b2, 1);
+    const double f4 = f2 * __shfl_up_sync(kAllLanes, f2, 2), b4 = b2 * __shfl_down_sync(kAllLanes, b2, 2);
+    const double f8 = f4 * __shfl_up_sync(kAllLanes, f4, 4), b8 = b4 * __shfl_down_sync(kAllLanes, b4, 4);
+    const double f12 = f4 * __shfl_up_sync(kAllLanes, f8, 4), b12 = b4 * __shfl_down_sync(kAllLanes, b8, 4);
+    const double fs[6] = {f1, f2, f3, f4, f8, f12}, bs[6] = {b1, b2, b3, b4, b8, b12};
+    const int d[6] = {1, 2, 3, 4, 8, 12};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { m.f[k] = lane >= d[k] ? fs[k] : 0.0; m.b[k] = lane + d[k] < 32 ? bs[k] : 0.0; }
+    return m;
+}
+
+// MODE 0: old scheme.  MODE 1: fused final, E via one FMA on the publishing lane.  MODE 2: radix-4, two levels + shift.
+template <int W, int K, bool NEAR, int MINB, bool SPLIT, int MODE, int CPT = 8>
 __global__ void __launch_bounds__(32 * W, MINB) k3v_kernel(const double *in, double *out, int n_steps) {
     __shared__ __align__(16) double s_K[2][W][W];
     __shared__ __align__(16) double s_E[2][W + 2];
     __shared__ double s_dummy;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double l[8], r[8], g[8], x[8];
+    double l[CPT], r[CPT], g[CPT], x[CPT];
     const double *p = in + ((size_t)(blockIdx.x % 64) * 32 * W + tid) * 32;
-    for (int j = 0; j < 8; ++j) { l[j] = p[j]; r[j] = p[8 + j]; g[j] = p[16 + j]; x[j] = p[24 + j]; }
-    const double cf = chunk_product<double, 8>(l), cb = chunk_product<double, 8>(g);
+    for (int j = 0; j < CPT; ++j) { l[j] = p[j]; r[j] = p[8 + j]; g[j] = p[16 + j]; x[j] = p[24 + j]; }
+    const double cf = chunk_product<double, CPT>(l), cb = chunk_product<double, CPT>(g);
     const ScanMultipliers sm = scan_multipliers<double>(cf, cb, lane);
     const Scan2<(K < 5 ? K : 4)> s2 = scan2<(K < 5 ? K : 4)>(cf, cb, lane);
+    const Scan4 s4 = scan4(cf, cb, lane);
     // exact table of warp-total products
     __shared__ double s_T[2][W];
     if (lane == 31) s_T[0][warp] = sm.tot_f;
@@ -76,18 +96,32 @@ __global__ void __launch_bounds__(32 * W, MINB) k3v_kernel(const double *in, dou
     for (int n = 0; n < n_steps; ++n) {
         {   // forward
             double e;
-            if (SPLIT) {
+            if constexpr (SPLIT && CPT == 8) {
                 double a = x[0], b = x[4];
                 a = fma(-l[1], a, x[1]); b = fma(-l[5], b, x[5]);
                 a = fma(-l[2], a, x[2]); b = fma(-l[6], b, x[6]);
                 a = fma(-l[3], a, x[3]); b = fma(-l[7], b, x[7]);
                 e = fma((l[4] * l[5]) * (l[6] * l[7]), a, b);  // (a register in the real kernel)
-            } else e = chunk_end_fwd_plain<double, 8>(x, l);
+            } else e = chunk_end_fwd_plain<double, CPT>(x, l);
             double c;
             if (MODE == 0) {
                 double y = e;
 #pragma unroll
-                for (int s = 0; s < 5; ++s) y = fma(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+                for (int s = 0; s < (K < 5 ? K : 5); ++s) y = fma(sm.f[s], __shfl_up_sync(kAllLanes, y, 1 << s), y);
+                c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
+                if (W > 1) sts_f64(st_f, y);
+            } else if (MODE == 2) {
+                double y = e;
+                {
+                    const double a1 = __shfl_up_sync(kAllLanes, e, 1), a2 = __shfl_up_sync(kAllLanes, e, 2),
+                                 a3 = __shfl_up_sync(kAllLanes, e, 3);
+                    y = fma(s4.f[0], a1, y); y = fma(s4.f[1], a2, y); y = fma(s4.f[2], a3, y);
+                }
+                {
+                    const double a1 = __shfl_up_sync(kAllLanes, y, 4), a2 = __shfl_up_sync(kAllLanes, y, 8),
+                                 a3 = __shfl_up_sync(kAllLanes, y, 12);
+                    y = fma(s4.f[3], a1, y); y = fma(s4.f[4], a2, y); y = fma(s4.f[5], a3, y);
+                }
                 c = and_mask(__shfl_up_sync(kAllLanes, y, 1), keep_f);
                 if (W > 1) sts_f64(st_f, y);
             } else {
@@ -109,22 +143,36 @@ __global__ void __launch_bounds__(32 * W, MINB) k3v_kernel(const double *in, dou
                     c = fma(sm.ex_f, cw, c);
                 }
             }
-            chunk_apply_fwd_plain<double, 8>(x, l, r, c);
+            chunk_apply_fwd_plain<double, CPT>(x, l, r, c);
         }
         {   // backward
             double e;
-            if (SPLIT) {
+            if constexpr (SPLIT && CPT == 8) {
                 double a = x[7], b = x[3];
                 a = fma(-g[6], a, x[6]); b = fma(-g[2], b, x[2]);
                 a = fma(-g[5], a, x[5]); b = fma(-g[1], b, x[1]);
                 a = fma(-g[4], a, x[4]); b = fma(-g[0], b, x[0]);
                 e = fma((g[3] * g[2]) * (g[1] * g[0]), a, b);
-            } else e = chunk_end_bwd_plain<double, 8>(x, g);
+            } else e = chunk_end_bwd_plain<double, CPT>(x, g);
             double c;
             if (MODE == 0) {
                 double z = e;
 #pragma unroll
-                for (int s = 0; s < 5; ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+                for (int s = 0; s < (K < 5 ? K : 5); ++s) z = fma(sm.b[s], __shfl_down_sync(kAllLanes, z, 1 << s), z);
+                c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
+                if (W > 1) sts_f64(st_b, z);
+            } else if (MODE == 2) {
+                double z = e;
+                {
+                    const double a1 = __shfl_down_sync(kAllLanes, e, 1), a2 = __shfl_down_sync(kAllLanes, e, 2),
+                                 a3 = __shfl_down_sync(kAllLanes, e, 3);
+                    z = fma(s4.b[0], a1, z); z = fma(s4.b[1], a2, z); z = fma(s4.b[2], a3, z);
+                }
+                {
+                    const double a1 = __shfl_down_sync(kAllLanes, z, 4), a2 = __shfl_down_sync(kAllLanes, z, 8),
+                                 a3 = __shfl_down_sync(kAllLanes, z, 12);
+                    z = fma(s4.b[3], a1, z); z = fma(s4.b[4], a2, z); z = fma(s4.b[5], a3, z);
+                }
                 c = and_mask(__shfl_down_sync(kAllLanes, z, 1), keep_b);
                 if (W > 1) sts_f64(st_b, z);
             } else {
@@ -146,18 +194,18 @@ __global__ void __launch_bounds__(32 * W, MINB) k3v_kernel(const double *in, dou
                     c = fma(sm.ex_b, cw, c);
                 }
             }
-            chunk_apply_bwd_plain<double, 8>(x, g, c);
+            chunk_apply_bwd_plain<double, CPT>(x, g, c);
         }
     }
-    double *q = out + ((size_t)blockIdx.x * 32 * W + tid) * 8;
-    for (int j = 0; j < 8; ++j) q[j] = x[j];
+    double *q = out + ((size_t)blockIdx.x * 32 * W + tid) * CPT;
+    for (int j = 0; j < CPT; ++j) q[j] = x[j];
 }
 
 static double *g_ref = nullptr;
 
-template <int W, int K, bool NEAR, int MINB, bool SPLIT, int MODE>
+template <int W, int K, bool NEAR, int MINB, bool SPLIT, int MODE, int CPT = 8>
 void run(const char *name, const double *in, double *out, int n_steps) {
-    auto kern = k3v_kernel<W, K, NEAR, MINB, SPLIT, MODE>;
+    auto kern = k3v_kernel<W, K, NEAR, MINB, SPLIT, MODE, CPT>;
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * W, 0);
     const int ctas = occ * 148;
@@ -175,15 +223,15 @@ void run(const char *name, const double *in, double *out, int n_steps) {
         best = ms < best ? ms : best;
     }
     // numerics: compare the first 64 CTAs' results after a short run with the first variant's
-    const size_t n = (size_t)64 * 32 * W * 8;
+    const size_t n = (size_t)64 * 32 * W * CPT;
     kern<<<64, 32 * W>>>(in, out, 50);
     double *h = (double *)malloc(n * 8);
     cudaMemcpy(h, out, n * 8, cudaMemcpyDeviceToHost);
     double err = 0.0, mx = 0.0;
     if (!g_ref) { g_ref = h; }
     else { for (size_t i = 0; i < n; ++i) { err = fmax(err, fabs(h[i] - g_ref[i])); mx = fmax(mx, fabs(g_ref[i])); } free(h); }
-    const double cells = (double)ctas * 256 * W;
-    printf("%-46s W=%d K=%d near=%d split=%d occ=%d regs=%3d  %7.3f us/step  %.3e cu/s  C3-equiv %.2f ms  relerr=%.1e %s\n", name, W, K,
+    const double cells = (double)ctas * 32 * CPT * W;
+    printf("%-46s CPT=%d W=%d K=%d near=%d split=%d occ=%d regs=%3d  %7.3f us/step  %.3e cu/s  C3-equiv %.2f ms  relerr=%.1e %s\n", name, CPT, W, K,
            (int)NEAR, (int)SPLIT, occ, fa.numRegs, best * 1e3 / n_steps, cells * n_steps / (best * 1e-3),
            2.097152e10 / (cells * n_steps / (best * 1e-3)) * 1e3, mx > 0 ? err / mx : 0.0, cudaGetErrorString(cudaGetLastError()));
 }
@@ -202,6 +250,21 @@ int main() {
     const int S = 3000;
     run<4, 5, false, 4, false, 0>("old: 5 stages + shift, K-table", in, out, S);
     run<4, 5, true, 4, false, 0>("old scan, near carry", in, out, S);
+    run<4, 4, true, 4, false, 0>("old scan 4 stages + shift, near (production NEAR4)", in, out, S);
+    run<4, 4, true, 4, false, 2>("radix-4 scan 2 levels + shift, near", in, out, S);
+    run<4, 4, true, 5, false, 2>("radix-4 scan 2 levels + shift, near, 5 CTAs/SM", in, out, S);
+    g_ref = nullptr;
+    run<8, 5, true, 4, false, 0, 4>("x4 W=8: 5 stages + shift, near, 4 CTAs/SM (64 regs)", in, out, S);
+    run<8, 5, true, 3, false, 0, 4>("x4 W=8: 5 stages + shift, near, 3 CTAs/SM (80 regs)", in, out, S);
+    run<8, 5, false, 4, false, 0, 4>("x4 W=8: 5 stages + shift, K-table, 4 CTAs/SM", in, out, S);
+    run<8, 5, false, 3, false, 0, 4>("x4 W=8: 5 stages + shift, K-table, 3 CTAs/SM", in, out, S);
+    run<8, 4, true, 4, false, 0, 4>("x4 W=8: 4 stages + shift (reach 64), near, 4 CTAs/SM", in, out, S);
+    run<8, 4, true, 3, false, 0, 4>("x4 W=8: 4 stages + shift (reach 64), near, 3 CTAs/SM", in, out, S);
+    run<4, 5, true, 8, false, 0, 4>("x4 W=4 (512 cells): 5 stages, near, 8 CTAs/SM", in, out, S);
+    run<4, 5, true, 6, false, 0, 4>("x4 W=4 (512 cells): 5 stages, near, 6 CTAs/SM", in, out, S);
+    run<2, 5, true, 8, false, 0, 8>("x8 W=2 (512 cells): 5 stages, near, 8 CTAs/SM", in, out, S);
+    run<2, 4, true, 10, false, 0, 8>("x8 W=2 (512 cells): 4 stages, near, 10 CTAs/SM", in, out, S);
+    g_ref = nullptr;
     run<4, 4, false, 4, false, 1>("fused K=4 (exact), K-table", in, out, S);
     run<4, 4, true, 4, false, 1>("fused K=4 (exact in warp), near", in, out, S);
     run<4, 3, true, 4, false, 1>("fused K=3 (reach 128 cells), near", in, out, S);
