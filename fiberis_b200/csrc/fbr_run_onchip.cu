@@ -27,6 +27,7 @@
 #include "fbr_sweep.cuh"
 #include "fbr_factor_reg.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <type_traits>
@@ -79,6 +80,7 @@ struct RunArgs {
     const int32_t *row_first_sample;
     int base_sample, first_sample, last_sample;
     int32_t *scan_mode;          // (M) or NULL: how each member was scanned
+    unsigned long long *ticket;  // zeroed word of this launch, or NULL: members beyond the first deal are handed out on demand
 };
 
 // Rows of A(dt) for CPT consecutive cells of member m, exactly K1's arithmetic (fbr_assemble.cu, matbuilder.py:21-81).
@@ -171,6 +173,10 @@ __device__ const double kZero = 0.0;
 
 constexpr unsigned kSlotNone = 0xFF, kSlotZero = 0xFE;
 
+// ticket words of the on-demand member schedule: one per launch in flight, zeroed on the launch's stream
+constexpr unsigned kTicketSlots = 1024;
+__device__ unsigned long long g_k3_ticket[kTicketSlots];
+
 // Order in which a CTA walks the models.  A recorded model (snapshots every few steps) takes about
 // twice as long as the others, so a recorded model picked up in the last round would be the tail of
 // the whole launch (C3: +3.5 ms of 27).  With A recorded models (short lists only) and G CTAs:
@@ -193,7 +199,7 @@ __device__ __forceinline__ ModelCursor model_cursor(const RunArgs &a) {
     const int64_t G = gridDim.x, cp = G - 1 - blockIdx.x;
     c.n_rec = (a.snap && a.snap_models && a.n_snap_models <= 16 && a.n_snap_models < G) ? a.n_snap_models : 0;
     if (c.n_rec == 0) {
-        c.j_rec = 0; c.k = blockIdx.x; c.p = 0; c.round0 = false; c.n_plain = a.M;
+        c.j_rec = 0; c.k = blockIdx.x; c.p = 0; c.round0 = true; c.n_plain = a.M;
         return c;
     }
     int64_t distinct = 0;
@@ -208,9 +214,20 @@ __device__ __forceinline__ ModelCursor model_cursor(const RunArgs &a) {
 __device__ __forceinline__ bool next_model(const RunArgs &a, ModelCursor &c, int64_t &m, long long &preset) {
     const int64_t G = gridDim.x;
     if (c.n_rec == 0) {
+        if (a.ticket && !c.round0) {
+            // Members cost differently (4 / 5 scan stages, the warp table: 940 / 1025 / 1150 cycles per step on C3), so a
+            // fixed deal leaves the CTAs that drew the expensive ones as the tail of the launch: after the first deal a
+            // CTA takes the next member when it is free.  Which CTA integrates a member does not change a bit of it.
+            __shared__ unsigned long long s_next;
+            __syncthreads();
+            if (threadIdx.x == 0) s_next = (unsigned long long)G + atomicAdd(a.ticket, 1ULL);
+            __syncthreads();
+            c.k = (int64_t)s_next;
+        }
         if (c.k >= a.M) return false;
         m = c.k;
         c.k += G;
+        c.round0 = false;
         preset = !a.snap ? -1 : !a.snap_models ? (long long)m : -2;
         return true;
     }
@@ -1396,6 +1413,15 @@ static int launch_onchipx(const RunArgs &a, cudaStream_t stream) {
     int64_t grid = (int64_t)occ * f.sm_count - a.reserve_ctas;  // fbr_run_opts::reserve_ctas
     if (grid < 1) grid = 1;
     if (grid > a.M) grid = a.M;
+    // long sweeps that record nothing: members after the first deal are handed out on demand (next_model)
+    b.ticket = nullptr;
+    if (!a.snap && !prefetch && a.M > grid && a.n_steps >= 64 && !getenv("FBR_K3_STATIC_DEAL")) {
+        static std::atomic<unsigned> next_slot{0};
+        unsigned long long *base = nullptr;
+        FBR_CUDA(cudaGetSymbolAddress((void **)&base, g_k3_ticket));
+        b.ticket = base + next_slot.fetch_add(1) % kTicketSlots;  // concurrent launches (streams, threads) never share a word
+        FBR_CUDA(cudaMemsetAsync(b.ticket, 0, sizeof(unsigned long long), stream));
+    }
     kern<<<(unsigned)grid, 32 * W, smem, stream>>>(b);
     return check_launch("fbr_run (on-chip, 64 B per thread)");
 }
@@ -1573,7 +1599,7 @@ extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
     a.snap_model_stride = snap_model_stride; a.snap = snap; a.p_final = p_final; a.obs_idx = obs_idx;             \
     a.n_obs = obs_idx ? n_obs : 0; a.obs = obs; a.obs_w = obs_w; a.misfit = misfit; a.blk_steps = 0; a.prefetch_rows = 0;     \
     a.z_mesh = nullptr; a.z_value = nullptr; a.z_of_cell = nullptr; a.z_n = 0; a.z_dt = 0.0;              \
-    a.z_sigma = nullptr; a.z_singular = nullptr;                                                         \
+    a.z_sigma = nullptr; a.z_singular = nullptr; a.ticket = nullptr;                                     \
     if (int rc_opts = apply_opts(a, opts)) return rc_opts;
 
 extern "C" int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,

@@ -146,6 +146,24 @@ def test_c3_full_shape_properties():
     npt.assert_array_equal(mis4, mis * 16.0)
 
 
+def test_members_handed_out_on_demand_equal_the_fixed_deal(monkeypatch):
+    """Sweeps that record nothing hand the members beyond the first deal to whichever CTA is free (a ticket word per
+    launch; `FBR_K3_STATIC_DEAL` keeps the fixed deal k, k + G, ..): which CTA integrates a member changes no bit of
+    its misfit, in either precision, and repeated launches (fresh ticket words) agree with each other."""
+    M, nx, n_steps = 3000, 512, 80  # 8 CTAs of 2 warps per SM: 1184 CTAs < M
+    e, c = make_ensemble(77, M, nx, n_steps, n_obs=6)
+    ref0, _ = O.solve_fixed(c["mesh"], c["zv"][5][c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                            c["srcs"], 0.0, 1.0, c["T"])
+    e.set_observations(c["obs_idx"], ref0[:, c["obs_idx"]])
+    for dtype in ("float64", "float32"):
+        monkeypatch.setenv("FBR_K3_STATIC_DEAL", "1")
+        fixed = e.solve(dt=1.0, t_total=c["T"], dtype=dtype).copy()
+        monkeypatch.delenv("FBR_K3_STATIC_DEAL")
+        for _ in range(3):
+            npt.assert_array_equal(e.solve(dt=1.0, t_total=c["T"], dtype=dtype), fixed)
+        assert np.all(np.isfinite(fixed)) and (dtype == "float32" or fixed[5] <= 1e-16)
+
+
 def test_sharded_blocks_equal_full_run():
     from fiberis_b200.simulator.core.ensemble import shard_bounds
     e, c = make_ensemble(8, 101, 128, 25)
