@@ -690,6 +690,8 @@ def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, 
         else:
             diag = E.assemble_zonal(mesh_d, zv_d, zone_d, M, nx, dt, "Neumann", "Neumann", sidx_d, n_src)
             fac, zonal = E.factorize(*diag, check_singular=False), None
+        # costly members first (what PDS1D_Ensemble.solve does): three small device kernels, inside the timed step
+        order_d = E.costly_members_first(zv_d, M, nx) if on_chip and split_audit and n_steps >= 64 else None
         if ev:
             ev[0].record()
         kw = dict(obs_idx=obs_idx_d, n_obs=n_obs, obs=obs_d, dtype="float32" if f32 else "float64")
@@ -708,7 +710,7 @@ def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, 
                       snap_out=snap_d, zonal=zon_a, singular_flags=flags_audit_d if on_chip else None, **kw)
             E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=0,
                   misfit_out=misfit_d, zonal=zonal, singular_flags=flags_d if on_chip else None, scan_mode_out=modes_d,
-                  reserve_ctas=n_audit, **kw)
+                  reserve_ctas=n_audit, member_order=order_d, **kw)
             main.wait_stream(side)
         else:
             E.run(fac, p0_d, M, nx, n_steps, "Neumann", "Neumann", sidx_d, n_src, table_d, snapshot_every=1 if n_audit else 0,

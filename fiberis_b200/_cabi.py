@@ -30,10 +30,10 @@ class RunOpts(C.Structure):
                 ("scan_log2_eps", C.c_double), ("n_samples", C.c_int64), ("sample_row", C.c_void_p),
                 ("sample_w", C.c_void_p), ("row_first_sample", C.c_void_p), ("base_sample", C.c_int32),
                 ("first_sample", C.c_int32), ("last_sample", C.c_int32), ("reserved_", C.c_int32),
-                ("scan_mode", C.c_void_p)]
+                ("scan_mode", C.c_void_p), ("member_order", C.c_void_p)]
 
 
-def run_opts(reserve_ctas=0, snap_cell_stride=0, scan_log2_eps=0.0, sampling=None, scan_mode=None):
+def run_opts(reserve_ctas=0, snap_cell_stride=0, scan_log2_eps=0.0, sampling=None, scan_mode=None, member_order=None):
     """Build an ``fbr_run_opts``.  ``sampling``: None, or a dict with device tensors ``sample_row`` (int32),
     ``sample_w`` (float64), ``row_first_sample`` (int32) and ints ``base_sample``, ``first_sample``, ``last_sample``."""
     o = RunOpts()
@@ -43,6 +43,8 @@ def run_opts(reserve_ctas=0, snap_cell_stride=0, scan_log2_eps=0.0, sampling=Non
     o.scan_log2_eps = float(scan_log2_eps)
     if scan_mode is not None:
         o.scan_mode = scan_mode.data_ptr()
+    if member_order is not None:  # device int32 permutation (a scheduling hint, see the header)
+        o.member_order = member_order.data_ptr()
     if sampling is not None:
         o.n_samples = int(sampling["sample_row"].numel())
         o.sample_row = sampling["sample_row"].data_ptr()
@@ -76,6 +78,7 @@ SIGNATURES = {
                                  _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, C.POINTER(RunOpts), _p]),
     "fbr_run_zonal_f32": (_i32, [_p, _p, _i32, _p, _f64, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _p, _i64, _p,
                                  _i64, _i64, _i64, _p, _p, _p, _i32, _p, _p, _p, C.POINTER(RunOpts), _p]),
+    "fbr_rank_members_f64": (_i32, [_p, _i64, _p, _p]),
     "fbr_run_max_nx": (_i64, []),
     "fbr_run_long_max_nx": (_i64, []),
     "fbr_run_long_work_bytes": (_i64, [_i64]),

@@ -6,6 +6,8 @@ host; without a CUDA device or without the built library the calls raise.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _cabi
@@ -186,10 +188,43 @@ def factorize(dl, d, du, check_singular=True, parallel=None):
     return out[0], out[1], out[2]
 
 
+_SM_COUNT = []
+
+
+def _sm_count():
+    if not _SM_COUNT:
+        _SM_COUNT.append(int(_cabi.device_info()["sm_count"]))
+    return _SM_COUNT[0]
+
+
+def costly_members_first(diffusivity_d, M, nx):
+    """Order in which a sweep should hand out its members (``fbr_run_opts.member_order``), or None when it cannot
+    matter.  The cost of a member in K3 is set by its decay horizon (4 / 5 scan stages, neighbour carry or the warp
+    table), which grows with the largest diffusivity of the member: members are ranked by it, largest first, so that
+    the last round of the on-demand schedule holds only cheap members.  ``diffusivity_d``: the (M, n_zones) or (M, nx)
+    device tensor the run kernel reads.  Worth its two small device kernels only while a CTA integrates a few dozen
+    members at most; a hint — no result depends on it."""
+    import torch
+    if os.environ.get("FBR_NO_MEMBER_ORDER"):  # tuning aid: members in index order
+        return None
+    if M < 1024 or nx <= 128 or nx > run_max_nx():  # a handful of members / the member-group kernel: no on-demand schedule
+        return None
+    warps = 1
+    while warps * 256 < nx:
+        warps *= 2  # team width of the 64-byte-per-thread kernel: 1, 2, 4, 8 or 16 warps; 16 warps per SM are resident
+    ctas = _sm_count() * (16 // warps)
+    if M <= ctas or M > 64 * ctas:
+        return None
+    cost = diffusivity_d.amax(dim=1)  # buffer plumbing; the ranking itself is the library's one-CTA counting sort
+    order = torch.empty(M, dtype=torch.int32, device=cost.device)
+    check(_cabi.load().fbr_rank_members_f64(ptr(cost), M, ptr(order), current_stream()))
+    return order
+
+
 def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapshot_every=1, snap_models=None,
         n_snap_models=None, want_final=False, obs_idx=None, n_obs=0, obs=None, obs_w=None, dtype="float64",
         with_initial_row=True, misfit_out=None, snap_out=None, zonal=None, singular_flags=None, reserve_ctas=0,
-        cell_major=False, scan_log2_eps=0.0, sampling=None, scan_mode_out=None):
+        cell_major=False, scan_log2_eps=0.0, sampling=None, scan_mode_out=None, member_order=None):
     """K3: persistent on-chip integration.
 
     ``factors`` = (fl, fr, fg) from ``factorize``; or ``factors=None`` and ``zonal=(mesh, zone_value (M, n_zones),
@@ -205,6 +240,8 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
     the initial state when ``with_initial_row``).  ``snapshot_every=0`` disables snapshots.
 
     ``sampling`` (from ``sample_plan``): the observations ``obs`` (n_samples, n_obs) sit on their own time axis.
+    ``member_order``: device int32 permutation, the order in which a sweep that records nothing hands out its members
+    (``fbr_run_opts.member_order``; see ``costly_members_first``).
     ``reserve_ctas``: CTA slots the persistent grid leaves free.  ``scan_log2_eps``: see ``fbr_run_opts``.
     """
     torch = _torch()
@@ -246,8 +283,9 @@ def run(factors, p0, M, nx, n_steps, lbc, rbc, src_idx, n_src, src_table, snapsh
         misfit = torch.empty(M, dtype=torch.float64, device=dev)
     p0_stride = 0 if p0.dim() == 1 else nx
     opts = None
-    if reserve_ctas or cell_stride or scan_log2_eps or sampling is not None or scan_mode_out is not None:
-        opts = _cabi.C.byref(_cabi.run_opts(reserve_ctas, cell_stride, scan_log2_eps, sampling, scan_mode_out))
+    if (reserve_ctas or cell_stride or scan_log2_eps or sampling is not None or scan_mode_out is not None
+            or member_order is not None):
+        opts = _cabi.C.byref(_cabi.run_opts(reserve_ctas, cell_stride, scan_log2_eps, sampling, scan_mode_out, member_order))
     tail = (ptr(p0), p0_stride, M, nx, n_steps, BC_CODES[lbc], BC_CODES[rbc],
             ptr(src_idx), n_src, ptr(src_table), max(int(snapshot_every), 1), ptr(snap_models),
             int(n_snap_models or 0), row_stride, model_stride, snap_ptr, ptr(p_final), ptr(obs_idx), int(n_obs),

@@ -81,6 +81,7 @@ struct RunArgs {
     int base_sample, first_sample, last_sample;
     int32_t *scan_mode;          // (M) or NULL: how each member was scanned
     unsigned long long *ticket;  // zeroed word of this launch, or NULL: members beyond the first deal are handed out on demand
+    const int32_t *order;        // (M) or NULL: with a ticket, the k-th member handed out is order[k] (fbr_run_opts::member_order)
 };
 
 // Rows of A(dt) for CPT consecutive cells of member m, exactly K1's arithmetic (fbr_assemble.cu, matbuilder.py:21-81).
@@ -225,7 +226,7 @@ __device__ __forceinline__ bool next_model(const RunArgs &a, ModelCursor &c, int
             c.k = (int64_t)s_next;
         }
         if (c.k >= a.M) return false;
-        m = c.k;
+        m = (a.ticket && a.order) ? (int64_t)__ldg(a.order + c.k) : c.k;
         c.k += G;
         c.round0 = false;
         preset = !a.snap ? -1 : !a.snap_models ? (long long)m : -2;
@@ -1573,6 +1574,7 @@ static int apply_opts(RunArgs &a, const fbr_run_opts *opts) {
     a.scan_eps = log2_eps > 0.0 ? -1.0 : exp2(log2_eps);
     if (getenv("FBR_K3_EXACT")) a.scan_eps = -1.0;  // tuning aid
     a.scan_mode = o.scan_mode;
+    a.order = o.member_order;
     a.n_samples = o.n_samples;
     if (o.n_samples > 0) {
         a.sample_row = o.sample_row; a.sample_w = o.sample_w; a.row_first_sample = o.row_first_sample;
@@ -1584,9 +1586,56 @@ static int apply_opts(RunArgs &a, const fbr_run_opts *opts) {
     return FBR_OK;
 }
 
+
+// fbr_rank_members_f64: members ranked by decreasing cost figure, in half-octave classes (counting sort, one CTA): the order
+// a sweep hands its members out in (fbr_run_opts::member_order).  Members of a class keep no particular order.
+constexpr int kRankBins = 4096;  // sign 0: 11 exponent bits + the leading mantissa bit
+__device__ __forceinline__ int rank_bin(double c) {
+    const long long bits = __double_as_longlong(c);
+    if (!(c > 0.0)) return kRankBins - 1;  // zero, negative, NaN: the last class
+    return kRankBins - 1 - (int)(bits >> 51);  // larger cost -> earlier class
+}
+__global__ void __launch_bounds__(1024) rank_members_kernel(const double *cost, int64_t M, int32_t *order) {
+    __shared__ int s_cnt[kRankBins];
+    __shared__ int s_warp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = tid; b < kRankBins; b += 1024) s_cnt[b] = 0;
+    __syncthreads();
+    for (int64_t m = tid; m < M; m += 1024) atomicAdd(&s_cnt[rank_bin(cost[m])], 1);
+    __syncthreads();
+    // exclusive prefix sum over the classes: 4 consecutive classes per thread
+    int c[4], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c[j] = s_cnt[4 * tid + j]; sum += c[j]; }
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(kFull, inc, d); if (lane >= d) inc += up; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(kFull, wi, d); if (lane >= d) wi += up; }
+        s_warp[lane] = wi - w;
+    }
+    __syncthreads();
+    int start = s_warp[warp] + inc - sum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_cnt[4 * tid + j] = start; start += c[j]; }
+    __syncthreads();
+    for (int64_t m = tid; m < M; m += 1024) order[atomicAdd(&s_cnt[rank_bin(cost[m])], 1)] = (int32_t)m;
+}
+
 }  // namespace fbr
 
 using namespace fbr;
+
+extern "C" int fbr_rank_members_f64(const double *cost, int64_t M, int32_t *order, void *stream) {
+    FBR_REQUIRE(cost && order, "NULL argument");
+    FBR_REQUIRE(M >= 1 && M <= 0x7fffffff, "M = %lld out of range", (long long)M);
+    rank_members_kernel<<<1, 1024, 0, as_stream(stream)>>>(cost, M, order);
+    return check_launch("fbr_rank_members_f64");
+}
 
 extern "C" int64_t fbr_run_max_nx(void) { return 8 * 32 * (int64_t)kMaxWarps; }
 

@@ -268,6 +268,8 @@ class PDS1D_Ensemble:
                       scan_log2_eps=scan_log2_eps, cell_major=cell_major)
         n_rows = n_steps // snapshot_every if n_audit else 0
         host_snap = None
+        # sweeps of a few members per CTA: the costly members (long decay horizons: large diffusivity) are handed out first
+        order_d = _engine.costly_members_first(zonal[1], M, nx) if on_chip and n_steps >= 64 else None
         if n_rows and M >= 8 * n_audit and M >= 512 and split_audit:
             # Large sweep, few audited members: integrate the audited ones as their own small launch on a
             # side stream and bring their snapshots home WHILE the big launch is still running (the
@@ -293,14 +295,14 @@ class PDS1D_Ensemble:
             # reserve_ctas: the audited members' CTAs stay resident next to the sweep's grid
             _, _, misfit_d = _engine.run(factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                                          snapshot_every=0, zonal=zonal, singular_flags=flags_d, reserve_ctas=n_audit,
-                                         **run_kw)
+                                         member_order=order_d, **run_kw)
             main.wait_stream(side)
             snap_d = snap_a
         else:
             snap_d, _, misfit_d = _engine.run(
                 factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                 snapshot_every=snapshot_every if n_audit else 0, snap_models=snap_models_d, n_snap_models=n_audit,
-                zonal=zonal, singular_flags=flags_d, **run_kw)
+                zonal=zonal, singular_flags=flags_d, member_order=None if n_audit else order_d, **run_kw)
         if flags_d is not None:
             _engine.raise_if_singular_zonal(flags_d)
 

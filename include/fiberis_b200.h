@@ -199,7 +199,19 @@ typedef struct fbr_run_opts {
     int32_t *scan_mode;              /* NULL, or device (M) int32: receives how each member's sweeps were scanned
                                         (0 exact, 1 neighbour-warp carry, 2 neighbour-warp carry + 4 scan stages);
                                         written by the 64-byte-per-thread kernels only */
+    const int32_t *member_order;     /* NULL, or device (M) int32: a permutation of 0 .. M-1, the order in which the
+                                        persistent CTAs of a sweep that records nothing take the members (they are handed
+                                        out on demand).  Most expensive first — e.g. by decreasing largest diffusivity: long
+                                        decay horizons take the slower scans — keeps the costly members out of the last
+                                        round (C3: 19.5 -> see DESIGN.md).  A scheduling hint only: results do not depend on
+                                        it, kernels without an on-demand schedule ignore it */
 } fbr_run_opts;
+
+/* Order for fbr_run_opts.member_order: members ranked by decreasing cost figure (e.g. the largest diffusivity of the
+ * member), in half-octave classes — a counting sort in one CTA, a few microseconds for the ensembles it matters for.
+ * cost: device (M) fp64; order: device (M) int32 out, a permutation of 0 .. M-1 (no particular order inside a class;
+ * non-positive / NaN figures come last).  No reference counterpart: scheduling of the sweep (north_star). */
+int fbr_rank_members_f64(const double *cost, int64_t M, int32_t *order, void *stream);
 
 int fbr_run_f64(const double *fl, const double *fr, const double *fg, const double *p0,
                 int64_t p0_stride, int64_t M, int64_t nx, int64_t n_steps, int lbc, int rbc,

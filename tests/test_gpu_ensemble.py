@@ -148,8 +148,9 @@ def test_c3_full_shape_properties():
 
 def test_members_handed_out_on_demand_equal_the_fixed_deal(monkeypatch):
     """Sweeps that record nothing hand the members beyond the first deal to whichever CTA is free (a ticket word per
-    launch; `FBR_K3_STATIC_DEAL` keeps the fixed deal k, k + G, ..): which CTA integrates a member changes no bit of
-    its misfit, in either precision, and repeated launches (fresh ticket words) agree with each other."""
+    launch; `FBR_K3_STATIC_DEAL` keeps the fixed deal k, k + G, ..), the costly ones first (`member_order`): which CTA
+    integrates a member, and when, changes no bit of its misfit, in either precision, and repeated launches (fresh
+    ticket words) agree with each other."""
     M, nx, n_steps = 3000, 512, 80  # 8 CTAs of 2 warps per SM: 1184 CTAs < M
     e, c = make_ensemble(77, M, nx, n_steps, n_obs=6)
     ref0, _ = O.solve_fixed(c["mesh"], c["zv"][5][c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
@@ -159,9 +160,34 @@ def test_members_handed_out_on_demand_equal_the_fixed_deal(monkeypatch):
         monkeypatch.setenv("FBR_K3_STATIC_DEAL", "1")
         fixed = e.solve(dt=1.0, t_total=c["T"], dtype=dtype).copy()
         monkeypatch.delenv("FBR_K3_STATIC_DEAL")
-        for _ in range(3):
+        for _ in range(3):  # default: costly members first (fbr_run_opts.member_order), handed out on demand
             npt.assert_array_equal(e.solve(dt=1.0, t_total=c["T"], dtype=dtype), fixed)
+        monkeypatch.setenv("FBR_NO_MEMBER_ORDER", "1")  # on demand, in index order
+        npt.assert_array_equal(e.solve(dt=1.0, t_total=c["T"], dtype=dtype), fixed)
+        monkeypatch.delenv("FBR_NO_MEMBER_ORDER")
         assert np.all(np.isfinite(fixed)) and (dtype == "float32" or fixed[5] <= 1e-16)
+
+
+def test_rank_members_orders_by_decreasing_cost_class():
+    """fbr_rank_members_f64 (the order a sweep hands its members out in): a permutation whose half-octave cost classes
+    never increase; zero / negative / NaN figures come last."""
+    import torch
+    from fiberis_b200 import _cabi, _engine
+    rng = np.random.default_rng(5)
+    for M in (1, 7, 1000, 4096, 70001):
+        cost = 10 ** rng.uniform(-6, 6, M)
+        if M > 100:
+            cost[[3, 50, 77]] = [0.0, -2.0, np.nan]
+        cost_d = _engine.to_device(cost)
+        order_d = torch.empty(M, dtype=torch.int32, device=cost_d.device)
+        _cabi.check(_cabi.load().fbr_rank_members_f64(_cabi.ptr(cost_d), M, _cabi.ptr(order_d), _cabi.current_stream()))
+        order = order_d.cpu().numpy()
+        npt.assert_array_equal(np.sort(order), np.arange(M))
+        c = cost[order]
+        good = c > 0
+        assert not np.any(good[np.argmin(good):]) or good.all()  # the unusable figures are a suffix
+        cls = np.frombuffer(c[good].tobytes(), dtype=np.int64) >> 51
+        assert np.all(np.diff(cls) <= 0)
 
 
 def test_sharded_blocks_equal_full_run():
