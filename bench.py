@@ -812,6 +812,8 @@ def ensemble_leg(args, w, world, rank, local_rank, steps, warmup, f32, on_chip, 
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "PDS1D_Ensemble.solve(host arrays) -> misfit + audit snapshots as numpy"},
         "gpu_launches": int(launches) * steps, "clocks": clocks.summary(), "parity": parity,
+        "members_ranked": bool(on_chip and split_audit and n_steps >= 64
+                               and E.costly_members_first(zv_d, M, nx) is not None),
         "audit_launch": ("the audited members are their own small launch on a side stream next to the sweep, which records nothing "
                          "and leaves their CTA slots free — what PDS1D_Ensemble.solve does (they are integrated twice: +0.1 % of "
                          "work, not counted)" if split_audit else "audited members inside the sweep's launch"),
@@ -875,6 +877,9 @@ def run_gpu_arm(args):
                        "diffusivity": "zonal, 8 zones, 10**U(-1,1)", "sources": 2, "obs_cells": res["n_obs"],
                        "audit_members_with_full_snapshots": res["n_audit"], "audit_launch": res["audit_launch"],
                        "bc": "Neumann/Neumann",
+                       "member_schedule": ("members handed out to free CTAs on demand" + (
+                           ", costly (largest diffusivity) first: ranked inside the timed step by fbr_rank_members_f64"
+                           if res.get("members_ranked") else "")) if not os.environ.get("FBR_K3_STATIC_DEAL") else "fixed deal",
                        "l2": "flushed between timed iterations (512 MiB memset)",
                        "timed_kernels": ("K3 run_onchip with on-chip assembly + factorisation (fbr_run_zonal_f64)" if on_chip
                                          else "K1 assemble_zonal + K1b factorize + K3 run_onchip")
