@@ -29,11 +29,11 @@ class RunOpts(C.Structure):
     _fields_ = [("struct_bytes", C.c_int32), ("reserve_ctas", C.c_int32), ("snap_cell_stride", C.c_int64),
                 ("scan_log2_eps", C.c_double), ("n_samples", C.c_int64), ("sample_row", C.c_void_p),
                 ("sample_w", C.c_void_p), ("row_first_sample", C.c_void_p), ("base_sample", C.c_int32),
-                ("first_sample", C.c_int32), ("last_sample", C.c_int32), ("reserved_", C.c_int32),
+                ("first_sample", C.c_int32), ("last_sample", C.c_int32), ("snap_f64", C.c_int32),
                 ("scan_mode", C.c_void_p), ("member_order", C.c_void_p)]
 
 
-def run_opts(reserve_ctas=0, snap_cell_stride=0, scan_log2_eps=0.0, sampling=None, scan_mode=None, member_order=None):
+def run_opts(reserve_ctas=0, snap_cell_stride=0, scan_log2_eps=0.0, sampling=None, scan_mode=None, member_order=None, snap_f64=False):
     """Build an ``fbr_run_opts``.  ``sampling``: None, or a dict with device tensors ``sample_row`` (int32),
     ``sample_w`` (float64), ``row_first_sample`` (int32) and ints ``base_sample``, ``first_sample``, ``last_sample``."""
     o = RunOpts()
@@ -43,6 +43,7 @@ def run_opts(reserve_ctas=0, snap_cell_stride=0, scan_log2_eps=0.0, sampling=Non
     o.scan_log2_eps = float(scan_log2_eps)
     if scan_mode is not None:
         o.scan_mode = scan_mode.data_ptr()
+    o.snap_f64 = 1 if snap_f64 else 0
     if member_order is not None:  # device int32 permutation (a scheduling hint, see the header)
         o.member_order = member_order.data_ptr()
     if sampling is not None:

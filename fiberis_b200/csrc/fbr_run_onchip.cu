@@ -81,6 +81,7 @@ struct RunArgs {
     int base_sample, first_sample, last_sample;
     int32_t *scan_mode;          // (M) or NULL: how each member was scanned
     unsigned long long *ticket;  // zeroed word of this launch, or NULL: members beyond the first deal are handed out on demand
+    int snap_wide;               // fp32 mode, a handful of recorded members: `snap` holds doubles, rows are widened at the store
     const int32_t *order;        // (M) or NULL: with a ticket, the k-th member handed out is order[k] (fbr_run_opts::member_order)
 };
 
@@ -615,6 +616,21 @@ __device__ __forceinline__ void store_row_direct(T *__restrict__ dst, int64_t ce
     }
 }
 
+// fp32 mode, fbr_run_opts::snap_f64: a thread's 16 floats go out as doubles (the audited members of a sweep: their launch
+// is a handful of CTAs, and a widening pass AFTER it would have to squeeze past the sweep's persistent grid — measured:
+// 4.6 ms for 82 MB on the four free CTA slots, which made the end-to-end figure of the fp32 mode wait for the audit chain).
+template <int CPT>
+__device__ __forceinline__ void store_row_wide(double *__restrict__ dst, int64_t cell0, int64_t nx, const float (&x)[CPT], int64_t cs) {
+    if (cs == 1 && cell0 + CPT <= nx && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < CPT / 2; ++q) reinterpret_cast<double2 *>(dst)[q] = make_double2((double)x[2 * q], (double)x[2 * q + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (cell0 + j < nx) dst[j * cs] = (double)x[j];
+    }
+}
+
 // One row of a warp's 32 * CPT cells to global memory with coalesced stores.  A thread holds CPT
 // consecutive cells (64 bytes); written directly, every store instruction would touch 32 half-filled
 // sectors 64 bytes apart (measured: 2.3 us per recorded row).  Instead the warp transposes through a
@@ -1127,8 +1143,18 @@ __global__ void __launch_bounds__(32 * W, MINB) run_onchipx_kernel(const RunArgs
                     // ---- sampled snapshot (CTA-uniform countdown; never fires for unrecorded members) ----
                     if (REC && --to_snap == 0) {
                         to_snap = snap_every;
-                        if (direct_rows) store_row_direct<T, CPT>(snap_row + cell0 * cs, cell0, nx, x, cs);
-                        else store_row_coalesced<T, CPT>(snap_row, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane, cs);
+                        bool stored = false;
+                        if constexpr (sizeof(T) == 4) {
+                            if (a.snap_wide) {  // same element offsets, 8-byte elements
+                                double *wide = reinterpret_cast<double *>(a.snap) + (snap_row - reinterpret_cast<T *>(a.snap));
+                                store_row_wide<CPT>(wide + cell0 * cs, cell0, nx, x, cs);
+                                stored = true;
+                            }
+                        }
+                        if (!stored) {
+                            if (direct_rows) store_row_direct<T, CPT>(snap_row + cell0 * cs, cell0, nx, x, cs);
+                            else store_row_coalesced<T, CPT>(snap_row, (int64_t)warp * 32 * CPT, nx, x, s_patch, lane, cs);
+                        }
                         snap_row += a.snap_row_stride;
                     }
                 }
@@ -1506,6 +1532,11 @@ static int run_dispatch(const RunArgs &a, cudaStream_t stream) {
             return step_factors_dispatch(a.fl, a.fr, a.fg, a.p0, reinterpret_cast<double *>(a.p_final), a.M, a.nx, a.lbc, a.rbc,
                                          a.src_idx, a.n_src, a.src_table, stream);
     }
+    if (a.snap_wide) {  // fbr_run_opts::snap_f64
+        FBR_REQUIRE(sizeof(T) == 4 && a.snap && a.M <= 64 && a.nx >= 512,
+                    "snap_f64 is an option of the fp32 variants for at most 64 recorded members of >= 512 cells");
+        return launch_x<T>(a, stream);
+    }
     int cpt = a.nx >= 256 ? 8 : a.nx >= 128 ? 4 : a.nx >= 64 ? 2 : 1;
     // a few members of 128..255 cells (C1: one model of 200 cells) are a latency problem: shorter chains over more warps
     // (2 cells per thread, 4 warps: 0.48 us per step against 0.52 with 4 cells per thread and 0.58 with 8)
@@ -1575,6 +1606,7 @@ static int apply_opts(RunArgs &a, const fbr_run_opts *opts) {
     if (getenv("FBR_K3_EXACT")) a.scan_eps = -1.0;  // tuning aid
     a.scan_mode = o.scan_mode;
     a.order = o.member_order;
+    a.snap_wide = o.snap_f64 != 0;
     a.n_samples = o.n_samples;
     if (o.n_samples > 0) {
         a.sample_row = o.sample_row; a.sample_w = o.sample_w; a.row_first_sample = o.row_first_sample;

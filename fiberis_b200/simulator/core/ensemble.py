@@ -21,7 +21,7 @@ from __future__ import annotations
 import numpy as np
 
 from fiberis_b200 import _engine
-from fiberis_b200.simulator.core.pds import PDS1D_MultiSource, _ALLOWED_BC, fixed_time_axis
+from fiberis_b200.simulator.core.pds import PDS1D_MultiSource, _ALLOWED_BC, fixed_time_axis, fixed_time_axis_array
 
 
 def shard_bounds(n_models: int, world_size: int, rank: int):
@@ -191,7 +191,7 @@ class PDS1D_Ensemble:
         nx = len(self.mesh)
         if t_total is None:
             t_total = self.source[0].taxis[-1] + self.t0
-        taxis = fixed_time_axis(self.t0, dt, t_total)  # same fp64 accumulation as the single-model path
+        taxis = fixed_time_axis_array(self.t0, dt, t_total)  # same fp64 accumulation as the single-model path
         n_steps = len(taxis) - 1
 
         dist = _dist(process_group)
@@ -216,51 +216,49 @@ class PDS1D_Ensemble:
         proto.source, proto.t0 = self.source, self.t0
         table = proto._source_table(taxis[:-1])
 
-        mesh_d = _engine.to_device(self.mesh)
-        sidx_d, n_src = _engine.index_tensor(self.sourceidx)
+        # Every small input goes up in ONE copy (a dozen pageable copies cost 0.5 ms of host time in front of the first launch)
+        audit = [int(a) for a in audit_models if lo <= int(a) < hi]
+        # the kernel records every listed model once: repeated entries share one recorded slot
+        audit_unique, audit_slot = np.unique(np.asarray(audit, dtype=np.int64), return_inverse=True)
+        n_audit = len(audit_unique)
+        sidx = np.atleast_1d(np.asarray(self.sourceidx)).astype(np.int64)
+        n_src = int(sidx.size)
+        init = self.initial if self.initial.ndim == 1 else self.initial[lo:hi]
+        member_values = self.zone_value[lo:hi] if self.diffusivity is None else self.diffusivity[lo:hi]
+        n_obs = 0
+        sampling = None
+        obs_items = [None, None, None]
+        if self.obs_idx is not None:
+            if self.obs_taxis is None and self.obs.shape[0] != n_steps + 1:
+                raise ValueError(f"obs has {self.obs.shape[0]} rows, the run has {n_steps + 1} time samples.")
+            oi = np.atleast_1d(np.asarray(self.obs_idx)).astype(np.int64)
+            n_obs = int(oi.size)
+            obs_items = [(oi, np.int64) if n_obs else None, (self.obs, np.float64),
+                         None if self.obs_weights is None else (self.obs_weights, np.float64)]
+        (mesh_d, sidx_d, values_d, zone_d, p0_d, table_d, snap_models_d, obs_idx_d, obs_d, w_d) = _engine.to_device_packed([
+            (self.mesh, np.float64), (sidx, np.int64) if n_src else None, (member_values, np.float64),
+            None if self.diffusivity is not None else (self.zone_of_cell, np.int32), (init, np.float64), (table, np.float64),
+            (audit_unique - lo, np.int64) if n_audit else None] + obs_items)
+        if self.obs_idx is not None and self.obs_taxis is not None:
+            # interpolation plan of the observed times on this run's time axis
+            sampling = _engine.sample_plan(np.asarray(taxis), self.obs_taxis, self.obs_baseline, self.obs_window)
         # fp64 ensembles on a shared mesh: the matrices are assembled and factorised inside the run kernel
         # (fbr_run_zonal_f64 / _f32), no (M, nx) coefficient array exists.  Short meshes: K1 + K1b + K3.
         zonal = flags_d = None
         on_chip = on_chip_assembly and nx <= _engine.run_max_nx() and (
             (dtype == "float64" and nx > 128 and (nx >= 256 or M >= 32)) or (dtype == "float32" and nx >= 512))
         if on_chip:
-            if self.diffusivity is None:
-                zonal = (mesh_d, _engine.to_device(self.zone_value[lo:hi]), _engine.to_device(self.zone_of_cell, np.int32),
-                         dt, None)
-            else:  # one diffusivity per cell and member: the (M, nx) array is read once, 8 B per cell
-                zonal = (mesh_d, _engine.to_device(self.diffusivity[lo:hi]), None, dt, None)
+            # zone_d is None: one diffusivity per cell and member, the (M, nx) array is read once, 8 B per cell
+            zonal = (mesh_d, values_d, zone_d, dt, None)
             flags_d = _engine.zonal_flags(M, mesh_d.device)
             factors = None
         else:
             if self.diffusivity is not None:
-                diag = _engine.assemble(mesh_d, _engine.to_device(self.diffusivity[lo:hi]), M, nx, dt, self.lbc, self.rbc,
-                                        sidx_d, n_src)
+                diag = _engine.assemble(mesh_d, values_d, M, nx, dt, self.lbc, self.rbc, sidx_d, n_src)
             else:
-                diag = _engine.assemble_zonal(mesh_d, _engine.to_device(self.zone_value[lo:hi]),
-                                              _engine.to_device(self.zone_of_cell, np.int32), M, nx, dt, self.lbc,
-                                              self.rbc, sidx_d, n_src)
+                diag = _engine.assemble_zonal(mesh_d, values_d, zone_d, M, nx, dt, self.lbc, self.rbc, sidx_d, n_src)
             factors = _engine.factorize(*diag)
             del diag
-        init = self.initial if self.initial.ndim == 1 else self.initial[lo:hi]
-        p0_d = _engine.to_device(init)
-        table_d = _engine.to_device(table)
-
-        audit = [int(a) for a in audit_models if lo <= int(a) < hi]
-        # the kernel records every listed model once: repeated entries share one recorded slot
-        audit_unique, audit_slot = np.unique(np.asarray(audit, dtype=np.int64), return_inverse=True)
-        snap_models_d, n_audit = _engine.index_tensor(audit_unique - lo) if audit else (None, 0)
-        obs_idx_d = obs_d = w_d = None
-        n_obs = 0
-        sampling = None
-        if self.obs_idx is not None:
-            if self.obs_taxis is not None:  # interpolation plan of the observed times on this run's time axis
-                sampling = _engine.sample_plan(np.asarray(taxis), self.obs_taxis, self.obs_baseline, self.obs_window)
-            elif self.obs.shape[0] != n_steps + 1:
-                raise ValueError(f"obs has {self.obs.shape[0]} rows, the run has {n_steps + 1} time samples.")
-            obs_idx_d, n_obs = _engine.index_tensor(self.obs_idx)
-            obs_d = _engine.to_device(self.obs)
-            w_d = None if self.obs_weights is None else _engine.to_device(self.obs_weights)
-
         if result_layout not in ("time_major", "cell_major"):
             raise ValueError("result_layout must be 'time_major' or 'cell_major'.")
         cell_major = result_layout == "cell_major"
@@ -289,8 +287,12 @@ class PDS1D_Ensemble:
                 # same observation arguments as the sweep: equal shared-memory footprints let CTAs of the two
                 # launches share an SM (with different footprints the audited CTAs kept their SMs to
                 # themselves and the sweep finished 2.5 ms later); the misfits computed here are discarded
+                # fp32 mode: the rows leave the kernel as doubles (a widening pass here would have to squeeze past the
+                # sweep's persistent grid: 4.6 ms for C3's 82 MB on the four free CTA slots)
+                wide = dtype == "float32" and on_chip and n_audit <= 64 and nx >= 512
                 snap_a, _, _ = _engine.run(fac_a, p0_a, n_audit, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
-                                           snapshot_every=snapshot_every, zonal=zon_a, singular_flags=flags_a, **run_kw)
+                                           snapshot_every=snapshot_every, zonal=zon_a, singular_flags=flags_a,
+                                           snap_f64=wide, **run_kw)
                 host_snap = _engine.to_host(_engine.as_f64(snap_a), sync=False)
             # reserve_ctas: the audited members' CTAs stay resident next to the sweep's grid
             _, _, misfit_d = _engine.run(factors, p0_d, M, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,

@@ -58,6 +58,28 @@ def _uses_stock_interp(src) -> bool:
 
 
 
+def fixed_time_axis_array(t0, dt, t_total):
+    """``fixed_time_axis`` as a float64 array, without the detour through a Python list (5000 steps: 0.02 instead of
+    0.1 ms, and ``np.interp`` of the source table no longer converts a list) — the same sequential ``np.cumsum``
+    accumulation, bit for bit (tests/test_host_logic.py)."""
+    try:
+        f0, fdt, ft = float(t0), float(dt), float(t_total)
+        plain = isinstance(t0, (int, float)) and isinstance(dt, (int, float)) and isinstance(t_total, (int, float))
+    except (TypeError, ValueError):
+        plain = False
+    if not plain or not (fdt > 0.0) or not np.isfinite(ft - f0) or (ft - f0) / fdt < 64:
+        return np.array(fixed_time_axis(t0, dt, t_total), dtype=np.float64)
+    parts, last = [np.array([f0])], f0
+    while last < ft:
+        guess = int(min(max((ft - last) / fdt, 1.0), 1e6)) + 2
+        block = np.cumsum(np.concatenate(([last], np.full(guess, fdt))))[1:]  # ((t + dt) + dt) + ... in order
+        stop = int(np.searchsorted(block, ft, side="left"))  # first entry >= t_total (the axis increases)
+        block = block[: stop + 1]
+        parts.append(block)
+        last = float(block[-1])
+    return np.concatenate(parts)
+
+
 def fixed_time_axis(t0, dt, t_total):
     """The time axis the reference's loop builds (``while taxis[-1] < t_total: taxis.append(taxis[-1] + dt)``,
     src/fiberis/simulator/core/pds.py:287,309), as a list.  The fp64 accumulation decides the step count (dt = 0.1,

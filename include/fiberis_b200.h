@@ -195,7 +195,10 @@ typedef struct fbr_run_opts {
     const int32_t *row_first_sample; /* device (n_steps + 2) */
     int32_t base_sample;             /* < 0: no baseline subtraction */
     int32_t first_sample, last_sample;
-    int32_t reserved_;
+    int32_t snap_f64;                /* fp32 variants only, M <= 64, nx >= 512: `snap` points to DOUBLES (same strides, in
+                                        elements) and the recorded rows are widened when they are stored — the few audited
+                                        members of an fp32 sweep then need no widening pass, which would have to squeeze
+                                        past the sweep's persistent grid (was the reserved word: 0 = off) */
     int32_t *scan_mode;              /* NULL, or device (M) int32: receives how each member's sweeps were scanned
                                         (0 exact, 1 neighbour-warp carry, 2 neighbour-warp carry + 4 scan stages);
                                         written by the 64-byte-per-thread kernels only */

@@ -190,6 +190,24 @@ def test_rank_members_orders_by_decreasing_cost_class():
         assert np.all(np.diff(cls) <= 0)
 
 
+@pytest.mark.parametrize("layout", ["time_major", "cell_major"])
+def test_fp32_audited_rows_leave_the_kernel_as_doubles(layout):
+    """fp32 sweeps: the audited members' launch stores its rows widened (fbr_run_opts.snap_f64) instead of a widening
+    pass behind it; the doubles are exactly the floats the single-launch path records."""
+    M, nx, n_steps = 600, 1024, 70
+    e, c = make_ensemble(91, M, nx, n_steps, n_obs=4)
+    audit = [599, 3, 3, 200]
+    e.solve(dt=1.0, t_total=c["T"], audit_models=audit, dtype="float32", split_audit=False, result_layout=layout)
+    want = e.snapshot.copy()
+    e.solve(dt=1.0, t_total=c["T"], audit_models=audit, dtype="float32", result_layout=layout)
+    assert e.snapshot.dtype == np.float64 and e.snapshot.shape == (4, n_steps + 1, nx)
+    npt.assert_array_equal(e.snapshot, want)
+    npt.assert_array_equal(e.snapshot, e.snapshot.astype(np.float32).astype(np.float64))
+    ref, _ = O.solve_fixed(c["mesh"], c["zv"][200][c["zone"]], np.zeros(nx), "Neumann", "Neumann", c["sidx"],
+                           c["srcs"], 0.0, 1.0, c["T"])
+    assert G.rel_max(e.snapshot[3], ref) <= 1e-5
+
+
 def test_sharded_blocks_equal_full_run():
     from fiberis_b200.simulator.core.ensemble import shard_bounds
     e, c = make_ensemble(8, 101, 128, 25)

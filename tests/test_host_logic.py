@@ -305,7 +305,7 @@ def test_sweep_candidate_generators():
 def test_fixed_time_axis_is_the_reference_loop_bit_for_bit():
     """pds.py:287,309 accumulates taxis[-1] + dt in fp64 and stops at the first value >= t_total; the chunked
     np.cumsum version must give the same list (length and every entry) for dyadic and non-dyadic steps."""
-    from fiberis_b200.simulator.core.pds import fixed_time_axis
+    from fiberis_b200.simulator.core.pds import fixed_time_axis, fixed_time_axis_array
     rng = np.random.default_rng(0)
 
     def loop(t0, dt, tt):
@@ -319,6 +319,8 @@ def test_fixed_time_axis_is_the_reference_loop_bit_for_bit():
         n = int(rng.integers(1, 3000))
         tt = float(rng.choice([t0 + n * dt, t0 + rng.uniform(0, 1) * n * dt, round(t0 + n * dt, 3)]))
         assert fixed_time_axis(t0, dt, tt) == loop(t0, dt, tt)
+        assert fixed_time_axis_array(t0, dt, tt).tolist() == loop(t0, dt, tt)  # the ensemble's array form
+    assert fixed_time_axis_array(0, 0.1, 1).tolist() == loop(0, 0.1, 1) and fixed_time_axis_array(0.0, 1.0, 5000.0).shape == (5001,)
     assert len(fixed_time_axis(0, 0.1, 1)) == 12 and fixed_time_axis(3.0, 1.0, 2.0) == [3.0]
     assert fixed_time_axis(0.0, 0.1, 100.0) == loop(0.0, 0.1, 100.0)
 
