@@ -301,20 +301,31 @@ class PDS1D_SingleSource:
         print("Problem solved.")
         return None
 
-    def _device_model(self, kwargs, initial=None):
-        """Model arrays on the device; with ``initial`` its tensor is appended to the result (long meshes upload
-        the three big arrays on parallel host threads, ``_engine.to_device_many``)."""
+    def _device_model(self, kwargs, initial=None, table=None):
+        """Model arrays on the device; with ``initial`` / ``table`` (per-step source values) their tensors are appended
+        to the result (long meshes upload the three big arrays on parallel host threads, ``_engine.to_device_many``)."""
         nx = len(self.mesh)
         sidx = self._source_indices()
         sidx = np.where(sidx < 0, sidx + nx, sidx)
+        pml = float(kwargs.get("pml_thickness", 0.0))
+        smax = float(kwargs.get("sigma_max", 10 if self._multi else 2))
+        if nx <= (1 << 16):
+            # short models: everything goes up in ONE copy through a cached pinned buffer (four or five pageable copies
+            # were 0.2 ms of C1's 0.9 ms end to end)
+            sidx = np.atleast_1d(np.asarray(sidx)).astype(np.int64)
+            n_src = int(sidx.size)
+            dev = _engine.to_device_packed([(self.mesh, np.float64), (self.diffusivity, np.float64),
+                                            (sidx, np.int64) if n_src else None,
+                                            None if initial is None else (initial, np.float64),
+                                            None if table is None else (table, np.float64)])
+            out = (nx, dev[0], dev[1], dev[2], n_src, pml, smax)
+            return out + (() if initial is None else (dev[3],)) + (() if table is None else (dev[4],))
         big = [self.mesh, self.diffusivity] + ([] if initial is None else [initial])
         dev = _engine.to_device_many(big)
         mesh_d, diff_d = dev[0], dev[1]
         sidx_d, n_src = _engine.index_tensor(sidx)
-        pml = float(kwargs.get("pml_thickness", 0.0))
-        smax = float(kwargs.get("sigma_max", 10 if self._multi else 2))
         out = (nx, mesh_d, diff_d, sidx_d, n_src, pml, smax)
-        return out if initial is None else out + (dev[2],)
+        return out + (() if initial is None else (dev[2],)) + (() if table is None else (_engine.to_device(table),))
 
     def _solve_fixed(self, dt, t_total, kwargs):
         mode = kwargs.get("mode", "implicit")
@@ -338,8 +349,8 @@ class PDS1D_SingleSource:
             self.snapshot = np.array([self.initial])
             self.taxis = np.array(taxis)
             return
-        nx, mesh_d, diff_d, sidx_d, n_src, pml, smax, p0_d = self._device_model(kwargs, initial[None, :])
         table = self._source_table(taxis[:-1])
+        nx, mesh_d, diff_d, sidx_d, n_src, pml, smax, p0_d, table_d = self._device_model(kwargs, initial[None, :], table)
         one_launch = (mode == "implicit" and dtype == "float64" and 2 <= nx <= _engine.run_max_nx()
                       and n_src <= _K3_MAX_SOURCES and kwargs.get("on_chip_assembly", True))
         if one_launch:
@@ -347,7 +358,6 @@ class PDS1D_SingleSource:
             # run kernel itself (fbr_run_zonal_f64 with one diffusivity per cell) — no (nx) coefficient arrays, no
             # separate assembly / factorisation launches (C1: 3 launches and a 44 us one-thread factorisation before)
             sigma_d = _engine.pml_sigma(mesh_d, pml, smax) if pml != 0.0 else None
-            table_d = _engine.to_device(table)
             try:
                 snap_d, _, _ = _engine.run(None, p0_d, 1, nx, n_steps, self.lbc, self.rbc, sidx_d, n_src, table_d,
                                            snapshot_every=every, cell_major=cell_major,
@@ -381,7 +391,6 @@ class PDS1D_SingleSource:
             return
         dl, d, du = _engine.assemble(mesh_d, diff_d, 1, nx, dt, self.lbc, self.rbc, sidx_d, n_src, pml, smax)
         if mode == "implicit":
-            table_d = _engine.to_device(table)
             try:
                 factors = _engine.factorize(dl, d, du)
             except np.linalg.LinAlgError:
