@@ -152,9 +152,15 @@ def to_device_packed(items, dev=None):
             buf.copy_(ent[0][:total], non_blocking=True)
             ent[1] = torch.cuda.Event()
             ent[1].record()
+        typed = {}  # one typed view of the buffer per element type; the results are slices of those
         for k, (a, off, pk) in enumerate(zip(arrs, offs, packed)):
             if pk:
-                outs[k] = buf[off:off + a.nbytes].view(torch.from_numpy(a.reshape(-1)[:0]).dtype).view(a.shape)
+                base = typed.get(a.dtype)
+                if base is None:
+                    base = typed[a.dtype] = buf.view(torch.from_numpy(a.reshape(-1)[:0]).dtype)
+                lo = off // a.itemsize
+                t = base[lo:lo + a.size]
+                outs[k] = t if a.ndim == 1 else t.view(a.shape)
     for k, (a, pk) in enumerate(zip(arrs, packed)):
         if a is not None and not pk:
             outs[k] = to_device(a, a.dtype, dev)
