@@ -80,6 +80,23 @@ def fixed_time_axis_array(t0, dt, t_total):
     return np.concatenate(parts)
 
 
+def fixed_time_axis_pair(t0, dt, t_total):
+    """``(list, array)``: the reference's time axis as the list its loop builds (what log lines print, ``t0`` kept as
+    given) and, for long plain axes, the same values as a float64 array built without the list detour (``None`` for
+    short or unusual axes, where the list is literally the reference's loop and ``np.array(list)`` keeps its dtype)."""
+    try:
+        f0, fdt, ft = float(t0), float(dt), float(t_total)
+        plain = isinstance(t0, (int, float)) and isinstance(dt, (int, float)) and isinstance(t_total, (int, float))
+    except (TypeError, ValueError):
+        plain = False
+    if not plain or not (fdt > 0.0) or not np.isfinite(ft - f0) or (ft - f0) / fdt < 64:
+        return fixed_time_axis(t0, dt, t_total), None
+    arr = fixed_time_axis_array(t0, dt, t_total)
+    lst = arr.tolist()
+    lst[0] = t0
+    return lst, arr
+
+
 def fixed_time_axis(t0, dt, t_total):
     """The time axis the reference's loop builds (``while taxis[-1] < t_total: taxis.append(taxis[-1] + dt)``,
     src/fiberis/simulator/core/pds.py:287,309), as a list.  The fp64 accumulation decides the step count (dt = 0.1,
@@ -341,7 +358,7 @@ class PDS1D_SingleSource:
         if every < 1:
             raise ValueError("snapshot_every must be >= 1.")
         # exact replica of the reference's time axis (fp64 accumulation decides the step count)
-        taxis = fixed_time_axis(self.t0, dt, t_total)
+        taxis, taxis_arr = fixed_time_axis_pair(self.t0, dt, t_total)  # the reference's list + (long axes) its float64 array
         n_steps = len(taxis) - 1
         self.record_log("Start to solve the problem.")
         initial = np.asarray(self.initial, dtype=np.float64)
@@ -349,7 +366,8 @@ class PDS1D_SingleSource:
             self.snapshot = np.array([self.initial])
             self.taxis = np.array(taxis)
             return
-        table = self._source_table(taxis[:-1])
+        table = self._source_table(taxis[:-1] if taxis_arr is None else taxis_arr[:-1])
+        taxis_out = np.array(taxis) if taxis_arr is None else taxis_arr
         nx, mesh_d, diff_d, sidx_d, n_src, pml, smax, p0_d, table_d = self._device_model(kwargs, initial[None, :], table)
         one_launch = (mode == "implicit" and dtype == "float64" and 2 <= nx <= _engine.run_max_nx()
                       and n_src <= _K3_MAX_SOURCES and kwargs.get("on_chip_assembly", True))
@@ -380,7 +398,7 @@ class PDS1D_SingleSource:
             else:
                 self.snapshot = _engine.to_host(snap_d[0])
             kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
-            self.taxis = np.array(taxis)[kept] if every > 1 else np.array(taxis)
+            self.taxis = taxis_out[kept] if every > 1 else taxis_out
             self._log_steps(taxis, table, kwargs)
             self.record_log(f"{n_steps} full steps solved on device (dt={dt}, mode={mode}, dtype={dtype}). "
                             f"taxis[-1]=", taxis[-1])
@@ -435,7 +453,7 @@ class PDS1D_SingleSource:
             rows = self._jacobi_loop(dl, d, du, p0_d, sidx_d, n_src, table, n_steps, every)
             self.snapshot = np.concatenate([initial[None, :], rows], axis=0)
         kept = np.arange(0, n_steps + 1, every)[: 1 + n_steps // every]
-        self.taxis = np.array(taxis)[kept] if every > 1 else np.array(taxis)
+        self.taxis = taxis_out[kept] if every > 1 else taxis_out
         self._log_steps(taxis, table, kwargs)
         self.record_log(f"{n_steps} full steps solved on device (dt={dt}, mode={mode}, dtype={dtype}). "
                         f"taxis[-1]=", taxis[-1])

@@ -22,6 +22,12 @@ for _ in range(20):
     with contextlib.redirect_stdout(io.StringIO()):
         p.solve(dt=w["dt"], t_total=w["T"])
 pr.disable()
-s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
-print(s.getvalue()[:6000])
+rows = []
+for e in pr.getstats():  # raw stats: microseconds per solve() call
+    code = e.code
+    name = code if isinstance(code, str) else f"{os.path.basename(code.co_filename)}:{code.co_firstlineno}({code.co_name})"
+    rows.append((e.inlinetime / 20 * 1e6, e.totaltime / 20 * 1e6, e.callcount / 20, name))
+rows.sort(reverse=True)
+print(f"{'inline us':>10s} {'total us':>10s} {'calls':>6s}  function   (per solve() call)")
+for r in rows[:36]:
+    print(f"{r[0]:10.1f} {r[1]:10.1f} {r[2]:6.1f}  {r[3][:100]}")
